@@ -1,0 +1,149 @@
+/*
+ * pn2_b200.h -- C ABI of libpn2_b200.so: the PointNet++ set-abstraction /
+ * feature-propagation op path of ero1311/Pointnet2.ScanNet as hand-written
+ * sm_100a CUDA.
+ *
+ * Boundary.  The reference's host bindings (pointnet2/_ext_src/src/*.cpp) call
+ * one plain-C++ launcher per kernel, `*_kernel_wrapper(int..., const float*,
+ * int*)`, declared at the top of each binding file.  Every entry point below
+ * replaces exactly one of those launchers: same scalar arguments in the same
+ * order, same pointer meaning, plus an explicit stream (the reference takes
+ * at::cuda::getCurrentCUDAStream() inside the launcher) and an int status
+ * instead of the reference's fprintf + exit(-1) (include/cuda_utils.h:30-39).
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers to contiguous fp32 / int32 arrays on the
+ *    current device; inputs are borrowed, outputs are caller-allocated.  The
+ *    library never allocates, frees or synchronises.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - return 0 on success; PN2_ERR_* (<0) for rejected arguments; a positive
+ *    value is the cudaError_t of a failed launch.  Nothing is written on error.
+ *  - outputs are fully written by the kernels: they need NOT be zero-filled by
+ *    the caller (the reference's bindings zero-fill because its kernels
+ *    accumulate with atomicAdd / leave empty balls untouched).  The results are
+ *    the same as the reference's on its zero-filled outputs.
+ *  - functions are re-entrant and thread-safe; no global state except the
+ *    launch counter.
+ *  - arithmetic: fp32, every distance evaluated as ((dx*dx)+(dy*dy))+(dz*dz)
+ *    with each operation rounded (no FMA contraction), so sampled / grouped /
+ *    neighbour indices are bit-identical to the reference built with
+ *    -fmad=false.
+ */
+#ifndef PN2_B200_H
+#define PN2_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN2_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PN2_API __attribute__((visibility("default")))
+#else
+#define PN2_API
+#endif
+
+#define PN2_OK 0
+#define PN2_ERR_INVALID_ARG (-1) /* null pointer, negative size */
+#define PN2_ERR_UNSUPPORTED (-2) /* size outside what the kernels handle */
+#define PN2_ERR_ALIGNMENT (-3)   /* pointer not 4-byte aligned */
+
+/* -- library ------------------------------------------------------------- */
+PN2_API int pn2_abi_version(void);
+/* kernels launched by this library since load / last reset (all threads) */
+PN2_API unsigned long long pn2_launch_count(void);
+PN2_API void pn2_reset_launch_count(void);
+/* static string for a status returned by any function below */
+PN2_API const char *pn2_status_string(int status);
+
+/* -- furthest point sampling ---------------------------------------------
+ * replaces furthest_point_sampling_kernel_wrapper (sampling.cpp:11-13,
+ * sampling_gpu.cu:175-229).
+ *   dataset (b, n, 3) f32   ->   idxs (b, m) i32
+ * idxs[.,0] = 0; then m-1 times: every point with |p|^2 > 1e-3 (compared in
+ * double, sampling_gpu.cu:100-101) lowers its running minimum squared distance
+ * to the last pick, and the next pick is the arg-max of those minima.  Ties
+ * are resolved as the reference's strided scan + shared-memory tree resolves
+ * them: minimise (bitrev_{log2 bs}(k mod bs), k div bs), bs = min(2^floor(log2
+ * n), 512).  If no point qualifies the pick is 0.
+ *   temp (b, n) f32: scratch.  The reference requires it pre-filled with 1e10
+ * (sampling.cpp:74-76) and streams it through global memory every iteration.
+ * Here the running minima live in registers; temp may be NULL and is left
+ * untouched when n <= PN2_FPS_MAX_RESIDENT_N.  For larger n it is REQUIRED
+ * (any contents; the kernel initialises it) and is used as the reference uses
+ * it.
+ */
+#define PN2_FPS_MAX_RESIDENT_N 8192
+PN2_API int pn2_furthest_point_sampling(int b, int n, int m, const float *dataset,
+                                float *temp, int *idxs, void *stream);
+
+/* -- gather ---------------------------------------------------------------
+ * replace gather_points(_grad)_kernel_wrapper (sampling.cpp:4-9,
+ * sampling_gpu.cu:22-30, 49-57).
+ *   fwd : points (b, c, n), idx (b, npoints)       -> out (b, c, npoints)
+ *   grad: grad_out (b, c, npoints), idx            -> grad_points (b, c, n)
+ *         (scatter-add; untouched entries are written as 0)
+ */
+PN2_API int pn2_gather_points(int b, int c, int n, int npoints, const float *points,
+                      const int *idx, float *out, void *stream);
+PN2_API int pn2_gather_points_grad(int b, int c, int n, int npoints,
+                           const float *grad_out, const int *idx,
+                           float *grad_points, void *stream);
+
+/* -- ball query -------------------------------------------------------------
+ * replaces query_ball_point_kernel_wrapper (ball_query.cpp:4-6,
+ * ball_query_gpu.cu:46-54).
+ *   new_xyz (b, m, 3) centres, xyz (b, n, 3) points -> idx (b, m, nsample)
+ * For each centre: the first `nsample` point indices k, ascending, with
+ * squared distance < radius*radius (fp32 product, strict); unused slots repeat
+ * the first hit; a centre without any hit gets all zeros.
+ */
+PN2_API int pn2_query_ball_point(int b, int n, int m, float radius, int nsample,
+                         const float *new_xyz, const float *xyz, int *idx,
+                         void *stream);
+
+/* -- grouping ---------------------------------------------------------------
+ * replace group_points(_grad)_kernel_wrapper (group_points.cpp:4-10,
+ * group_points_gpu.cu:30-39, 66-75).
+ *   fwd : points (b, c, n), idx (b, npoints, nsample)
+ *                                   -> out (b, c, npoints, nsample)
+ *   grad: grad_out (b, c, npoints, nsample), idx -> grad_points (b, c, n)
+ */
+PN2_API int pn2_group_points(int b, int c, int n, int npoints, int nsample,
+                     const float *points, const int *idx, float *out,
+                     void *stream);
+PN2_API int pn2_group_points_grad(int b, int c, int n, int npoints, int nsample,
+                          const float *grad_out, const int *idx,
+                          float *grad_points, void *stream);
+
+/* -- three nearest neighbours ----------------------------------------------
+ * replaces three_nn_kernel_wrapper (interpolate.cpp:4-5,
+ * interpolate_gpu.cu:61-68).
+ *   unknown (b, n, 3), known (b, m, 3) -> dist2 (b, n, 3) f32, idx (b, n, 3)
+ * SQUARED distances, ascending; scan order k ascending with strict '<' (the
+ * lower index keeps the better slot on ties); with fewer than 3 known points
+ * the missing slots are (+inf, 0).
+ */
+PN2_API int pn2_three_nn(int b, int n, int m, const float *unknown, const float *known,
+                 float *dist2, int *idx, void *stream);
+
+/* -- three-point interpolation ----------------------------------------------
+ * replace three_interpolate(_grad)_kernel_wrapper (interpolate.cpp:6-12,
+ * interpolate_gpu.cu:103-111, 145-154).
+ *   fwd : points (b, c, m), idx (b, n, 3), weight (b, n, 3) -> out (b, c, n)
+ *         out = ((p[i1]*w1) + (p[i2]*w2)) + (p[i3]*w3)
+ *   grad: grad_out (b, c, n), idx, weight -> grad_points (b, c, m)
+ */
+PN2_API int pn2_three_interpolate(int b, int c, int m, int n, const float *points,
+                          const int *idx, const float *weight, float *out,
+                          void *stream);
+PN2_API int pn2_three_interpolate_grad(int b, int c, int n, int m,
+                               const float *grad_out, const int *idx,
+                               const float *weight, float *grad_points,
+                               void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PN2_B200_H */

@@ -1,0 +1,125 @@
+// Shared device/host helpers for libpn2_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pn2_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libpn2_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace pn2 {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// Squared distance exactly as the reference evaluates it with FMA contraction
+// off: ((dx*dx) + (dy*dy)) + (dz*dz), one rounding per operation
+// (sampling_gpu.cu:103-104, ball_query_gpu.cu:31-32, interpolate_gpu.cu:33).
+// The intrinsics are never contracted, whatever -fmad says.
+__device__ __forceinline__ float sqdist_rn(float ax, float ay, float az,
+                                           float bx, float by, float bz) {
+  const float dx = __fsub_rn(ax, bx);
+  const float dy = __fsub_rn(ay, by);
+  const float dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)),
+                   __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ float sqnorm_rn(float x, float y, float z) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)),
+                   __fmul_rn(z, z));
+}
+
+// ---- mbarrier + 1-D TMA bulk copy (global -> shared::cta) -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+// bytes must be a multiple of 16; src and dst 16-byte aligned.
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem,
+                                            uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- streaming global accesses --------------------------------------------
+__device__ __forceinline__ void st_cs_f4(float *p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 ld_cs_f4(const float *p) {
+  float4 v;
+  asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int4 ld_nc_i4(const int *p) {
+  int4 v;
+  asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// ---- host side --------------------------------------------------------------
+void count_launch(int n = 1);
+
+// The reference's opt_n_threads (_ext_src/include/cuda_utils.h:15-19), same
+// double-precision log quotient so that the block size -- which fixes the FPS
+// tie-break -- is the one the reference would have launched.
+int ref_block_threads(int work);
+
+inline bool aligned16(const void *p) {
+  return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+inline bool aligned4(const void *p) {
+  return (reinterpret_cast<uintptr_t>(p) & 3u) == 0;
+}
+
+#define PN2_CHECK_PTRS(...)                                  \
+  do {                                                       \
+    const void *ptrs__[] = {__VA_ARGS__};                    \
+    for (const void *q__ : ptrs__) {                         \
+      if (q__ == nullptr) return PN2_ERR_INVALID_ARG;        \
+      if (!pn2::aligned4(q__)) return PN2_ERR_ALIGNMENT;     \
+    }                                                        \
+  } while (0)
+
+#define PN2_RETURN_LAUNCH_STATUS()          \
+  do {                                      \
+    cudaError_t e__ = cudaGetLastError();   \
+    return static_cast<int>(e__);           \
+  } while (0)
+
+}  // namespace pn2

@@ -1,0 +1,75 @@
+"""ctypes binding of libpn2_b200.so (C ABI: include/pn2_b200.h).
+
+The library is CUDA-only.  There is no CPU implementation behind it and no
+fallback: if the shared object is missing, loading raises ImportError; if a call
+is made without a CUDA device the wrappers in ``ext.py`` raise RuntimeError.
+"""
+import ctypes
+import os
+
+import torch  # noqa: F401  -- loads the CUDA runtime (libcudart.so.12) the library links to
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libpn2_b200.so")
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_f = ctypes.c_float
+
+# name -> argtypes; every data pointer is passed as a raw device address
+SIGNATURES = {
+    "pn2_furthest_point_sampling": [_i, _i, _i, _vp, _vp, _vp, _vp],
+    "pn2_gather_points": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "pn2_gather_points_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "pn2_query_ball_point": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
+    "pn2_group_points": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "pn2_group_points_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "pn2_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "pn2_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "pn2_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+}
+LIBRARY_SYMBOLS = ("pn2_abi_version", "pn2_launch_count", "pn2_reset_launch_count",
+                   "pn2_status_string")
+ABI_VERSION = 1
+
+_lib = None
+
+
+def load():
+    """Return the loaded library, loading it on first use."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "%s not found: build it with `python -m pointnet2.scannet_b200.build` "
+                "(or `python -c 'import __graft_entry__ as g; g.build()'`). "
+                "There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = _i
+        L.pn2_abi_version.restype = _i
+        L.pn2_launch_count.restype = ctypes.c_ulonglong
+        L.pn2_reset_launch_count.restype = None
+        L.pn2_status_string.argtypes = [_i]
+        L.pn2_status_string.restype = ctypes.c_char_p
+        if L.pn2_abi_version() != ABI_VERSION:
+            raise ImportError("libpn2_b200.so ABI %d != expected %d; rebuild"
+                              % (L.pn2_abi_version(), ABI_VERSION))
+        _lib = L
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        raise RuntimeError("%s failed: %s (status %d)"
+                           % (what, load().pn2_status_string(status).decode(), status))
+
+
+def launch_count():
+    return int(load().pn2_launch_count())
+
+
+def reset_launch_count():
+    load().pn2_reset_launch_count()

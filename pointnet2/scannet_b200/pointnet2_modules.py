@@ -1,0 +1,101 @@
+"""Set-abstraction and feature-propagation blocks -- mirror of
+/root/reference/pointnet2/pointnet2_modules.py for the classes the semseg models
+use: ``PointnetSAModuleMSG`` (ref :78-124), ``PointnetSAModule`` (:127-161) and
+``PointnetFPModule`` (:356-416).  Constructor keywords, child-module names
+(``groupers``, ``mlps``, ``mlp``) and tensor layouts are the reference's; the
+VoteNet leftovers (``*Votes``, ``PointnetLFPModuleMSG``) are out of scope.
+
+    SA:  xyz (B, N, 3), features (B, C, N)
+         -> new_xyz (B, npoint, 3), new_features (B, sum_k mlps[k][-1], npoint)
+    FP:  unknown (B, n, 3), known (B, m, 3), unknow_feats (B, C1, n), known_feats (B, C2, m)
+         -> (B, mlp[-1], n)
+"""
+from typing import List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import pointnet2_utils
+from . import pytorch_utils as pt_utils
+
+
+class _PointnetSAModuleBase(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.npoint = None
+        self.groupers = None
+        self.mlps = None
+
+    def forward(self, xyz, features=None):
+        new_xyz = None
+        if self.npoint is not None:
+            # FPS on (B, N, 3); the centres are gathered from the channel-major copy
+            picked = pointnet2_utils.furthest_point_sample(xyz, self.npoint)
+            new_xyz = pointnet2_utils.gather_operation(
+                xyz.transpose(1, 2).contiguous(), picked).transpose(1, 2).contiguous()
+
+        pooled = []
+        for grouper, mlp in zip(self.groupers, self.mlps):
+            grouped = grouper(xyz, new_xyz, features)        # (B, C, npoint, nsample)
+            grouped = mlp(grouped)                           # (B, mlp[-1], npoint, nsample)
+            grouped = F.max_pool2d(grouped, kernel_size=[1, grouped.size(3)])
+            pooled.append(grouped.squeeze(-1))               # (B, mlp[-1], npoint)
+        return new_xyz, torch.cat(pooled, dim=1)
+
+
+class PointnetSAModuleMSG(_PointnetSAModuleBase):
+    """Multi-scale grouping: one (radius, nsample, mlp) triple per scale, same centres.
+
+    As in the reference (ref :121-122) ``mlps[i][0]`` is incremented IN PLACE by 3
+    when ``use_xyz``.
+    """
+
+    def __init__(self, *, npoint: int, radii: List[float], nsamples: List[int],
+                 mlps: List[List[int]], bn: bool = True, use_xyz: bool = True,
+                 sample_uniformly: bool = False):
+        super().__init__()
+        assert len(radii) == len(nsamples) == len(mlps)
+        self.npoint = npoint
+        self.groupers = nn.ModuleList()
+        self.mlps = nn.ModuleList()
+        for radius, nsample, spec in zip(radii, nsamples, mlps):
+            if npoint is not None:
+                self.groupers.append(pointnet2_utils.QueryAndGroup(
+                    radius, nsample, use_xyz=use_xyz, sample_uniformly=sample_uniformly))
+            else:
+                self.groupers.append(pointnet2_utils.GroupAll(use_xyz))
+            if use_xyz:
+                spec[0] += 3
+            self.mlps.append(pt_utils.SharedMLP(spec, bn=bn))
+
+
+class PointnetSAModule(PointnetSAModuleMSG):
+    """Single-scale set abstraction."""
+
+    def __init__(self, *, mlp: List[int], npoint: int = None, radius: float = None,
+                 nsample: int = None, bn: bool = True, use_xyz: bool = True):
+        super().__init__(mlps=[mlp], npoint=npoint, radii=[radius], nsamples=[nsample],
+                         bn=bn, use_xyz=use_xyz)
+
+
+class PointnetFPModule(nn.Module):
+    """Feature propagation: inverse-distance interpolation from the 3 nearest known
+    points, concatenation with the skip features, shared MLP."""
+
+    def __init__(self, *, mlp: List[int], bn: bool = True):
+        super().__init__()
+        self.mlp = pt_utils.SharedMLP(mlp, bn=bn)
+
+    def forward(self, unknown, known, unknow_feats, known_feats):
+        if known is None:
+            interpolated = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
+        else:
+            dist, idx = pointnet2_utils.three_nn(unknown, known)
+            recip = 1.0 / (dist + 1e-8)                      # ref :395-397
+            weight = recip / torch.sum(recip, dim=2, keepdim=True)
+            interpolated = pointnet2_utils.three_interpolate(known_feats, idx, weight)
+
+        feats = interpolated if unknow_feats is None else torch.cat(
+            [interpolated, unknow_feats], dim=1)             # (B, C2 + C1, n)
+        return self.mlp(feats.unsqueeze(-1)).squeeze(-1)

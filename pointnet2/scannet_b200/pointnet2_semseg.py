@@ -1,0 +1,109 @@
+"""PointNet++ semantic-segmentation networks -- the CALLER of the hot path, mirrored
+from /root/reference/pointnet2/pointnet2_semseg.py (``get_model`` :7-23,
+``Pointnet2MSG`` :25-103, ``Pointnet2SSG`` :105-182) so that benchmarks and tests
+have the reference's architecture on a box where /root/reference does not exist.
+The reference file itself also runs unchanged over this package's ops (see
+INTEGRATION.md); parameter names and creation order are identical, so state
+dicts and seeded initialisations are interchangeable.
+
+    forward(pointcloud (B, N, 3 + input_channels)) -> (B, N, num_classes)
+"""
+import torch.nn as nn
+
+from . import pytorch_utils as pt_utils
+from .pointnet2_modules import PointnetFPModule, PointnetSAModule, PointnetSAModuleMSG
+
+NPOINTS = [1024, 256, 64, 16]
+
+SSG = dict(
+    radius=[0.1, 0.2, 0.4, 0.8],
+    nsample=[32, 32, 32, 32],
+    mlps=[[32, 32, 64], [64, 64, 128], [128, 128, 256], [256, 256, 512]],
+    fp_mlps=[[128, 128], [256, 128], [256, 256], [256, 256]],
+)
+MSG = dict(
+    radius=[[0.05, 0.1], [0.1, 0.2], [0.2, 0.4], [0.4, 0.8]],
+    nsample=[[16, 32], [16, 32], [16, 32], [16, 32]],
+    mlps=[[[16, 16, 32], [32, 32, 64]], [[64, 64, 128], [64, 96, 128]],
+          [[128, 196, 256], [128, 196, 256]], [[256, 256, 512], [256, 384, 512]]],
+    fp_mlps=[[128, 128], [256, 256], [512, 512], [512, 512]],
+)
+CLS_FC = [128]
+DP_RATIO = 0.5
+
+
+class _Pointnet2SemSeg(nn.Module):
+    """4 SA levels (8192 -> 1024 -> 256 -> 64 -> 16), 4 FP levels back up, 2-layer head."""
+
+    msg = False
+    cfg = SSG
+
+    def __init__(self, num_classes, input_channels=3, use_xyz=True, bn=True):
+        super().__init__()
+        cfg = self.cfg
+        self.SA_modules = nn.ModuleList()
+        channel_in = input_channels
+        skip_channels = [input_channels]
+        for k, npoint in enumerate(NPOINTS):
+            if self.msg:
+                specs = [[channel_in] + list(s) for s in cfg["mlps"][k]]
+                channel_out = sum(s[-1] for s in specs)
+                self.SA_modules.append(PointnetSAModuleMSG(
+                    npoint=npoint, radii=cfg["radius"][k], nsamples=cfg["nsample"][k],
+                    mlps=specs, use_xyz=use_xyz, bn=bn))
+            else:
+                spec = [channel_in] + list(cfg["mlps"][k])
+                channel_out = spec[-1]
+                self.SA_modules.append(PointnetSAModule(
+                    npoint=npoint, radius=cfg["radius"][k], nsample=cfg["nsample"][k],
+                    mlp=spec, use_xyz=use_xyz, bn=bn))
+            skip_channels.append(channel_out)
+            channel_in = channel_out
+
+        self.FP_modules = nn.ModuleList()
+        fp = cfg["fp_mlps"]
+        for k in range(len(fp)):
+            pre = fp[k + 1][-1] if k + 1 < len(fp) else channel_out
+            self.FP_modules.append(PointnetFPModule(mlp=[pre + skip_channels[k]] + fp[k], bn=bn))
+
+        layers = []
+        pre = fp[0][-1]
+        for width in CLS_FC:
+            layers.append(pt_utils.Conv1d(pre, width, bn=bn))
+            pre = width
+        layers.append(pt_utils.Conv1d(pre, num_classes, activation=None, bn=bn))
+        layers.insert(1, nn.Dropout(DP_RATIO))
+        self.cls_layer = nn.Sequential(*layers)
+
+    @staticmethod
+    def _break_up_pc(pc):
+        xyz = pc[..., 0:3].contiguous()
+        features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+        return xyz, features
+
+    def forward(self, pointcloud):
+        xyz, features = self._break_up_pc(pointcloud)
+        l_xyz, l_features = [xyz], [features]
+        for sa in self.SA_modules:
+            nxt_xyz, nxt_feat = sa(l_xyz[-1], l_features[-1])
+            l_xyz.append(nxt_xyz)
+            l_features.append(nxt_feat)
+        for i in range(-1, -(len(self.FP_modules) + 1), -1):  # coarse -> fine
+            l_features[i - 1] = self.FP_modules[i](
+                l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i])
+        return self.cls_layer(l_features[0]).transpose(1, 2).contiguous()
+
+
+class Pointnet2SSG(_Pointnet2SemSeg):
+    msg = False
+    cfg = SSG
+
+
+class Pointnet2MSG(_Pointnet2SemSeg):
+    msg = True
+    cfg = MSG
+
+
+def get_model(num_classes, is_msg=True, input_channels=6, use_xyz=True, bn=True):
+    cls = Pointnet2MSG if is_msg else Pointnet2SSG
+    return cls(num_classes=num_classes, input_channels=input_channels, use_xyz=use_xyz, bn=bn)
