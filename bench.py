@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the PointNet++ SA/FP hot path on B200 (BASELINE.json metric:
+8192-point chunks/sec, forward+backward, SSG semseg training step, batch 32 x 8192).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl product|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One JSON line on stdout (rank 0).  A "step" is one optimisation step -- forward, weighted
+cross-entropy, backward, gradient all-reduce (N > 1), Adam -- on one batch of synthetic
+ScanNet-shaped chunks.  `value` is timed with inputs resident in HBM; `e2e` is the same
+step called with HOST buffers (pinned), the host->device copies of the batch and the
+device->host read of the loss inside the timed region.
+
+--impl reference times the REFERENCE'S OWN kernels on the same box: oracle/_ref/stock is
+/root/reference/pointnet2/_ext_src compiled unmodified with the reference's flags for
+sm_100a (the reference has no CPU implementation -- every binding asserts "CPU not
+supported", e.g. ball_query.cpp:27-29 -- so its own implementation of the path IS CUDA;
+north_star's target is a ratio against exactly these kernels).  If that build is not
+present the arm falls back to the oracle's CPU port on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "8192-pt chunks/sec fwd+bwd (SSG semseg training step, 32x8192 per GPU)"
+UNIT = "chunks/s"
+CONFIG_ID = 2  # BASELINE.json configs[1]
+NUM_CLASSES = 20
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="product", choices=["product", "reference", "reference-cpu"])
+    p.add_argument("--batch", type=int, default=32, help="chunks per GPU")
+    p.add_argument("--npoints", type=int, default=8192)
+    p.add_argument("--msg", action="store_true", help="MSG model (BASELINE configs[2]) instead of SSG")
+    p.add_argument("--multiview", action="store_true", help="xyz+normal+128 features (configs[4])")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-per-op", action="store_true")
+    p.add_argument("--cpu-sample-chunks", type=int, default=2)
+    return p.parse_args()
+
+
+# --------------------------------------------------------------------------- plumbing
+def dist_setup(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def barrier_sync(world):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, world):
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9 or c[0] != str(self.index):
+                continue
+            try:
+                sm.append(float(c[1])), mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower() == "active":
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def host_batches(args, rank, count):
+    """`count` distinct pinned host batches for this rank (weak scaling: own chunks per rank)."""
+    from pointnet2.scannet_b200 import synthetic
+    kw = dict(use_color=not args.multiview, use_normal=True, use_multiview=args.multiview)
+    out = []
+    for i in range(count):
+        x, y, w = synthetic.make_batch(CONFIG_ID, args.batch, args.npoints,
+                                       first_chunk=(rank * count + i) * args.batch, **kw)
+        out.append(tuple(torch.from_numpy(a).pin_memory() if torch.cuda.is_available()
+                         else torch.from_numpy(a) for a in (x, y, w)))
+    return out, synthetic.input_channels(**kw)
+
+
+def build_step(args, in_ch, device):
+    from pointnet2.scannet_b200 import pointnet2_semseg, train
+    torch.manual_seed(0)  # same replica on every rank
+    model = pointnet2_semseg.get_model(NUM_CLASSES, is_msg=args.msg, input_channels=in_ch).to(device)
+    model.train()
+    return train.TrainStep(model, lr=1e-3)
+
+
+def time_steps(step, batches, steps, world, e2e):
+    """K steps bracketed by barrier+synchronize; CUDA events on the launching stream."""
+    dev_batches = None
+    if not e2e:
+        dev_batches = [tuple(t.cuda(non_blocking=True) for t in b) for b in batches]
+    else:
+        stage = tuple(torch.empty_like(t, device="cuda") for t in batches[0])
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = None
+    for i in range(steps):
+        if e2e:
+            for d, h in zip(stage, batches[i % len(batches)]):
+                d.copy_(h, non_blocking=True)          # host -> device, pinned source
+            last = float(step(*stage).item())          # device -> host read of the loss
+        else:
+            last = step(*dev_batches[i % len(dev_batches)])
+    e1.record()
+    barrier_sync(world)
+    ms = e0.elapsed_time(e1)
+    if not e2e:
+        last = float(last.item())
+    return max_over_ranks(ms, world), last
+
+
+# ------------------------------------------------------------------- cpu baseline (port)
+def cpu_baseline(args, in_ch):
+    """The oracle's C port of the nine ops (all host threads over clouds) under this
+    package's model code + torch CPU layers: forward+backward+Adam on a bounded sample."""
+    import oracle
+    from pointnet2.scannet_b200 import pointnet2_semseg, pointnet2_utils, synthetic, train
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oracle.set_threads(cores)
+    nb = args.cpu_sample_chunks
+    x, y, w = synthetic.make_batch(CONFIG_ID, nb, args.npoints, use_color=not args.multiview,
+                                   use_normal=True, use_multiview=args.multiview)
+    saved = pointnet2_utils._ext
+    pointnet2_utils._ext = oracle.ext_cpu
+    try:
+        torch.manual_seed(0)
+        model = pointnet2_semseg.get_model(NUM_CLASSES, is_msg=args.msg, input_channels=in_ch)
+        model.train()
+        step = train.TrainStep(model, lr=1e-3, fused_adam=False)
+        xs, ys, ws = torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(w)
+        step(xs, ys, ws)  # warm-up
+        times = []
+        t_end = time.time() + 20.0
+        while len(times) < 3 or (time.time() < t_end and len(times) < 10):
+            t0 = time.time()
+            step(xs, ys, ws)
+            times.append(time.time() - t0)
+    finally:
+        pointnet2_utils._ext = saved
+    sec = statistics.median(times)
+    return {"value": round(nb / sec, 3), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d chunks x %d pts, SSG fwd+bwd+Adam, oracle C ops (pthreads over clouds) + "
+                      "torch CPU layers, median of %d steps" % (nb, args.npoints, len(times))}
+
+
+# ------------------------------------------------------------------------------ arms
+def run_product(args, world, rank, local):
+    from pointnet2.scannet_b200 import lib, profiling
+    lib.load()  # fail loudly if the CUDA extension is missing
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU path")
+    batches, in_ch = host_batches(args, rank, 4)
+    step = build_step(args, in_ch, "cuda")
+    dev = [tuple(t.cuda() for t in b) for b in batches]
+    for i in range(args.warmup):
+        step(*dev[i % len(dev)])
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.reset_launch_count()
+    ms, loss = time_steps(step, batches, args.steps, world, e2e=False)
+    launches = lib.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = time_steps(step, batches, args.steps, world, e2e=True)
+
+    chunks = args.batch * world * args.steps
+    res = {
+        "metric": METRIC, "value": round(chunks / (ms * 1e-3), 2), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": "BASELINE configs[%d]: %s semseg training step (fwd + weighted CE + bwd + Adam%s), "
+                        "%d x %d-pt chunks per GPU, %d input channels" % (
+                            2 if args.msg else 1, "MSG" if args.msg else "SSG",
+                            " + NCCL grad all-reduce" if world > 1 else "", args.batch, args.npoints, in_ch),
+            "per_gpu_batch": args.batch, "global_batch": args.batch * world, "npoints": args.npoints,
+            "parallelism": "dp%d" % world,
+            "mlp": "torch.nn conv1x1+BN+ReLU (cuDNN/cuBLAS, cudnn.allow_tf32=%s as in the reference)"
+                   % torch.backends.cudnn.allow_tf32,
+            "l2": "no explicit flush: one step streams several GB of activations, far above the 126 MB L2; "
+                  "4 distinct input batches are cycled",
+        },
+        "e2e": {"value": round(chunks / (ms_e2e * 1e-3), 2), "unit": UNIT,
+                "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in batches[0])),
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "loss": loss,
+    }
+    if rank != 0:
+        return None
+    res["clocks"] = {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")}
+
+    # per-op timing (CUDA events around every call into libpn2_b200.so) -> roofline
+    if not args.no_per_op:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        nprof = min(args.steps, 5)
+        with profiling.ExtTimer() as timer:
+            for i in range(nprof):
+                step(*dev[i % len(dev)])
+        rows = timer.summary(nprof)
+        for r in rows:
+            r["frac_of_hbm_peak"] = round(r["gbs"] / peak, 4) if r["gbs"] else None
+        res["per_op"] = rows
+        res["ops_ms_per_step"] = round(sum(r["ms_per_step"] for r in rows), 4)
+        hbm_rows = [r for r in rows if r["op"] in profiling.HBM_BOUND]
+        top = hbm_rows[0]
+        res["roofline"] = {"bound": "hbm", "kernel": top["call"], "achieved": top["gbs"], "peak": peak,
+                           "unit": "GB/s", "frac": round(top["gbs"] / peak, 4), "traffic": None,
+                           "peak_source": which,
+                           "note": "dominant HBM-bound kernel of the step by time; algorithmic bytes per "
+                                   "SURVEY.md 8(d) / CUDA-event duration on the launching stream"}
+        fps = [r for r in rows if r["op"] == "furthest_point_sampling"]
+        if fps:
+            f = fps[0]
+            m = int(f["call"].rsplit(", ", 1)[1].rstrip(")"))
+            res["fps"] = {"call": f["call"], "us_per_call": f["us_per_call"],
+                          "ns_per_iteration": round(1e3 * f["us_per_call"] / max(m - 1, 1), 1),
+                          "note": "latency-bound (m-1 dependent iterations), not a bandwidth roofline"}
+    if not args.no_cpu_baseline:
+        try:
+            res["cpu_baseline"] = cpu_baseline(args, in_ch)
+        except Exception as e:  # noqa: BLE001
+            res["cpu_baseline"] = {"unavailable": repr(e)}
+    return res
+
+
+def run_reference(args, world, rank, local):
+    """Reference arm: rank 0 only; the reference is single-GPU."""
+    if rank != 0:
+        return None
+    from oracle import build_ref
+    from pointnet2.scannet_b200 import pointnet2_utils
+    use_cuda_ref = args.impl == "reference" and torch.cuda.is_available() and build_ref.available("stock")
+    batches, in_ch = host_batches(args, 0, 4)
+    if not use_cuda_ref:
+        base = cpu_baseline(args, in_ch)
+        return {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": 1,
+                "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(1e3 * args.cpu_sample_chunks / base["value"], 2),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": "SSG training step, CPU port on a bounded sample"},
+                "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+    ref = build_ref.load_ref("stock")
+    saved = pointnet2_utils._ext
+    pointnet2_utils._ext = ref  # the reference's own seam (pointnet2_utils.py:25-33)
+    try:
+        step = build_step(args, in_ch, "cuda")
+        dev = [tuple(t.cuda() for t in b) for b in batches]
+        for i in range(args.warmup):
+            step(*dev[i % len(dev)])
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ms, loss = time_steps(step, batches, args.steps, 1, e2e=False)
+        clocks = sampler.stop()
+        ms_e2e, _ = time_steps(step, batches, args.steps, 1, e2e=True)
+    finally:
+        pointnet2_utils._ext = saved
+    chunks = args.batch * args.steps
+    v, ve = round(chunks / (ms * 1e-3), 2), round(chunks / (ms_e2e * 1e-3), 2)
+    sample = ("the reference's own CUDA kernels (pointnet2/_ext_src compiled unmodified, -O3, sm_100a) on the "
+              "same B200, full workload, %d steps; the reference has no CPU implementation" % args.steps)
+    return {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[%d]: %s semseg training step, %d x %d-pt chunks, reference ops"
+                               % (2 if args.msg else 1, "MSG" if args.msg else "SSG", args.batch, args.npoints),
+                   "per_gpu_batch": args.batch, "npoints": args.npoints, "parallelism": "single GPU"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 0, "kind": "reference", "sample": sample},
+        "e2e": {"value": ve, "unit": UNIT,
+                "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in batches[0])),
+                "d2h_bytes_per_step": 4},
+        "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+        "loss": loss,
+    }
+
+
+def main():
+    args = parse()
+    if args.impl != "product":
+        rank = int(os.environ.get("RANK", "0"))
+        if rank != 0:
+            return 0
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        res = run_reference(args, 1, 0, int(os.environ.get("LOCAL_RANK", "0")))
+    else:
+        world, rank, local = dist_setup(args)
+        res = run_product(args, world, rank, local)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+    if res is not None:
+        print(json.dumps(res))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
