@@ -143,6 +143,74 @@ PN2_API int pn2_three_interpolate_grad(int b, int c, int n, int m,
                                const float *weight, float *grad_points,
                                void *stream);
 
+/* ==========================================================================
+ * Shared-MLP block in position-major ("rows") layout.
+ *
+ * Replaces what PointnetSAModule(MSG) / PointnetFPModule run around their 1x1
+ * convolutions through torch.nn / cuDNN on (B, C, npoint, nsample) tensors
+ * (pointnet2_modules.py:60-75, 395-416; pytorch_utils.py:11-36, 87-120):
+ * QueryAndGroup's gather + centring + concat, train-mode BatchNorm2d, ReLU and
+ * max_pool2d over nsample, forward and backward.  An activation is a row-major
+ * [P, C] fp32 matrix (P = b*npoint*nsample grouped positions, or b*n points;
+ * C % 4 == 0, C <= 1024, 16-byte aligned), so a 1x1 conv is Z = H * W^T.
+ * BatchNorm is carried as the per-channel fold  y = a*z + b  plus the saved
+ * (mean, invstd) of the batch.  All reductions are two-stage and
+ * order-deterministic.  `workspace`: pn2_bn_stats_workspace_floats(c) + 2*c
+ * floats, 16-byte aligned, private to the call while it runs.
+ * ========================================================================== */
+PN2_API int pn2_bn_stats_workspace_floats(int c);
+
+/* batch statistics of z [p, c]: biased variance; writes the fold (a, b), the saved
+ * (mean, invstd), and -- unless running_mean is NULL -- updates the running
+ * statistics like torch.nn.BatchNorm2d (momentum, unbiased variance). */
+PN2_API int pn2_bn_stats(int p, int c, const float *z, const float *gamma, const float *beta,
+                         float eps, float momentum, float *running_mean, float *running_var,
+                         float *a, float *b, float *mean, float *invstd, float *workspace,
+                         void *stream);
+/* eval mode: the fold from the running statistics */
+PN2_API int pn2_bn_fold_eval(int c, const float *gamma, const float *beta,
+                             const float *running_mean, const float *running_var, float eps,
+                             float *a, float *b, float *mean, float *invstd, void *stream);
+/* h = relu ? max(a*z + b, 0) : a*z + b            (h may alias z) */
+PN2_API int pn2_bn_relu_apply(int p, int c, const float *z, const float *a, const float *b,
+                              float *h, int relu, void *stream);
+/* out[g, c] = max over the ns rows of group g of relu(a*z + b); argmax[g, c] = first
+ * maximal row (F.max_pool2d's choice)              z [g*ns, c] -> out, argmax [g, c] */
+PN2_API int pn2_bn_relu_groupmax(int g, int ns, int c, const float *z, const float *a,
+                                 const float *b, float *out, int *argmax, void *stream);
+/* adjoint of pn2_bn_relu_groupmax through BatchNorm (training != 0: batch statistics):
+ * dout [g, c] -> dense dz [g*ns, c], dgamma [c], dbeta [c] */
+PN2_API int pn2_pool_bn_bwd(int g, int ns, int c, int training, const float *dout,
+                            const int *argmax, const float *z, const float *a, const float *b,
+                            const float *mean, const float *invstd, float *dz, float *dgamma,
+                            float *dbeta, float *workspace, void *stream);
+/* adjoint of pn2_bn_relu_apply through BatchNorm: dh [p, c] -> dz [p, c] (may alias dh) */
+PN2_API int pn2_relu_bn_bwd(int p, int c, int training, int relu, const float *dh, const float *z,
+                            const float *a, const float *b, const float *mean,
+                            const float *invstd, float *dz, float *dgamma, float *dbeta,
+                            float *workspace, void *stream);
+/* QueryAndGroup in rows layout (pointnet2_utils.py:317-359): table (b, n, ct) holds
+ * [xyz | features] per point (ct % 4 == 0, zero padded); rows[(b, j, s), :] =
+ * table[b, idx[b, j, s], :] with the first 3 columns minus new_xyz[b, j].
+ * _grad: scatter-add of grad_rows into grad_table (fully written). */
+PN2_API int pn2_sa_group_rows(int b, int n, int npoint, int nsample, int ct, const float *table,
+                              const float *new_xyz, const int *idx, float *rows, void *stream);
+PN2_API int pn2_sa_group_rows_grad(int b, int n, int npoint, int nsample, int ct,
+                                   const float *grad_rows, const int *idx, float *grad_table,
+                                   void *stream);
+
+/* PointnetFPModule's three_interpolate + concat in rows layout
+ * (pointnet2_modules.py:395-412): known (b, m, c2) and skip (b, n, c1) point-major,
+ * c2 % 4 == 0; rows[(b, j), :] = [ ((k1*w1)+(k2*w2))+(k3*w3) | skip[b, j, :] | 0 pad ],
+ * row width pad4(c2 + c1).  _grad: grad_known (fully written, scatter-add) and
+ * grad_skip (may be NULL). */
+PN2_API int pn2_fp_interp_rows(int b, int n, int m, int c2, int c1, const float *known,
+                               const float *skip, const int *idx, const float *weight,
+                               float *rows, void *stream);
+PN2_API int pn2_fp_interp_rows_grad(int b, int n, int m, int c2, int c1, const float *grad_rows,
+                                    const int *idx, const float *weight, float *grad_known,
+                                    float *grad_skip, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,593 @@
+// Shared-MLP block in POSITION-MAJOR layout for sm_100a: everything around the 1x1
+// convolutions of PointnetSAModule(MSG) / PointnetFPModule
+// (/root/reference/pointnet2/pointnet2_modules.py:60-75, 395-416;
+//  /root/reference/pointnet2/pytorch_utils.py:11-36,87-120).
+//
+// The reference materialises (B, C, npoint, nsample) tensors and runs cuDNN's NCHW
+// BatchNorm / ReLU / max_pool2d over them: on B200 55% of its training step is
+// cudnn::bn_fw_tr / bn_bw (profiles/r01_step_breakdown_baseline.md).  Here an activation
+// is a row-major [P, C] matrix -- P = B*npoint*nsample grouped positions (SA) or B*n
+// points (FP), channels contiguous -- so a 1x1 conv is a plain GEMM Z = H * W^T and
+// every kernel below streams rows with 128-bit accesses:
+//
+//   sa_group_rows        X0[p,:] = table[b, idx[p], :] - (centre, 0..)   (QueryAndGroup)
+//   bn_stats             per-channel batch mean / biased variance of Z (two-stage,
+//                        deterministic: per-CTA partials, then one fp64 finalise that also
+//                        folds BN into  y = a*z + b  and updates the running statistics)
+//   bn_relu_apply        H = relu(a*Z + b)
+//   bn_relu_groupmax     out[g,c] = max_s relu(a*Z[g*ns+s,c] + b), first arg-max kept
+//   pool_bn_bwd          adjoint of bn_relu_groupmax through train-mode BN -> dense dZ
+//   relu_bn_bwd          adjoint of bn_relu_apply through train-mode BN    -> dense dZ
+//   sa_group_rows_grad   scatter-add of dX0 into the point table (128-bit vector reds)
+//
+// Train-mode BN adjoint per channel (P rows, zhat = (z-mean)*invstd, a = gamma*invstd):
+//   dbeta = sum dY,  dgamma = sum dY*zhat,  dZ = a * (dY - dbeta/P - zhat*dgamma/P)
+#include "pn2_common.cuh"
+
+namespace pn2 {
+
+constexpr int kRowThreads = 256;
+constexpr int kMaxPartials = 4 * kNumSMs;  // CTAs of a column reduction (4 per SM)
+
+// ---------------------------------------------------------------------------------
+// generic per-channel reduction over the rows of [P, C]: every thread owns one float4
+// column group and a row lane; a CTA reduces its slab to one partial per channel
+// ---------------------------------------------------------------------------------
+struct ColGeom {
+  int P, C, C4, row_lanes, rows_per_cta;
+};
+
+static ColGeom col_geom(int P, int C, int *nblk) {
+  ColGeom g;
+  g.P = P, g.C = C, g.C4 = C / 4;
+  g.row_lanes = kRowThreads / g.C4 > 0 ? kRowThreads / g.C4 : 1;
+  int nb = (P + g.row_lanes * 8 - 1) / (g.row_lanes * 8);
+  if (nb > kMaxPartials) nb = kMaxPartials;
+  if (nb < 1) nb = 1;
+  g.rows_per_cta = (P + nb - 1) / nb;
+  *nblk = (P + g.rows_per_cta - 1) / g.rows_per_cta;
+  return g;
+}
+
+// F(row, col4, acc0, acc1): accumulates two float4 statistics for one (row, column group)
+template <class F>
+__device__ __forceinline__ void col_reduce2(const ColGeom &g, float *__restrict__ partials, F f) {
+  extern __shared__ float4 s_red[];  // [row_lanes][2][C4]
+  const int r0 = blockIdx.x * g.rows_per_cta;
+  const int r1 = min(r0 + g.rows_per_cta, g.P);
+  for (int c4 = threadIdx.x % g.C4; c4 < g.C4; c4 += kRowThreads) {  // C4 > 256 only if C > 1024
+    const int lane = threadIdx.x / g.C4;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    if (lane < g.row_lanes)
+      for (int r = r0 + lane; r < r1; r += g.row_lanes) f(r, c4, s0, s1);
+    if (lane < g.row_lanes) {
+      s_red[(lane * 2 + 0) * g.C4 + c4] = s0;
+      s_red[(lane * 2 + 1) * g.C4 + c4] = s1;
+    }
+    __syncthreads();
+    if (lane == 0) {
+      for (int l = 1; l < g.row_lanes; ++l) {
+        const float4 a = s_red[(l * 2 + 0) * g.C4 + c4], b = s_red[(l * 2 + 1) * g.C4 + c4];
+        s0.x += a.x, s0.y += a.y, s0.z += a.z, s0.w += a.w;
+        s1.x += b.x, s1.y += b.y, s1.z += b.z, s1.w += b.w;
+      }
+      float4 *dst = reinterpret_cast<float4 *>(partials + static_cast<size_t>(blockIdx.x) * 2 * g.C);
+      dst[c4] = s0;
+      dst[g.C4 + c4] = s1;
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ float4 ld4(const float *p, size_t i4) {
+  return __ldg(reinterpret_cast<const float4 *>(p) + i4);
+}
+
+// ------------------------------------------------------------------ forward statistics
+__global__ void __launch_bounds__(kRowThreads)
+bn_stats_partial_kernel(ColGeom g, const float *__restrict__ z, float *__restrict__ partials) {
+  col_reduce2(g, partials, [&](int r, int c4, float4 &s, float4 &q) {
+    const float4 v = ld4(z, static_cast<size_t>(r) * g.C4 + c4);
+    s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+    q.x += v.x * v.x, q.y += v.y * v.y, q.z += v.z * v.z, q.w += v.w * v.w;
+  });
+}
+
+// Fixed-order fp64 sum of the per-CTA partials of one channel by one warp: lane l adds
+// partials l, l+32, ... and a shuffle tree combines the lanes (same order every run).
+__device__ __forceinline__ void warp_sum_partials(int C, int c, int nblk, const float *__restrict__ partials,
+                                                  double &s, double &q) {
+  const int lane = threadIdx.x & 31;
+  s = 0.0, q = 0.0;
+  for (int k = lane; k < nblk; k += 32) {
+    s += __ldg(partials + static_cast<size_t>(k) * 2 * C + c);
+    q += __ldg(partials + static_cast<size_t>(k) * 2 * C + C + c);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+}
+
+constexpr int kFinalizeWarps = 8;  // channels per CTA of the finalise kernels
+
+// one WARP per channel, then the BN fold
+__global__ void __launch_bounds__(32 * kFinalizeWarps)
+bn_stats_finalize_kernel(int P, int C, int nblk, const float *__restrict__ partials,
+                         const float *__restrict__ gamma, const float *__restrict__ beta,
+                         float eps, float momentum, float *running_mean,
+                         float *running_var, float *__restrict__ a, float *__restrict__ b,
+                         float *__restrict__ mean_out, float *__restrict__ invstd_out) {
+  const int c = blockIdx.x * kFinalizeWarps + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s, q;
+  warp_sum_partials(C, c, nblk, partials, s, q);
+  if ((threadIdx.x & 31) != 0) return;
+  const double mean = s / P;
+  double var = q / P - mean * mean;  // biased, as BatchNorm normalises with
+  if (var < 0.0) var = 0.0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float ga = gamma[c] * invstd;
+  a[c] = ga;
+  b[c] = beta[c] - static_cast<float>(mean) * ga;
+  mean_out[c] = static_cast<float>(mean);
+  invstd_out[c] = invstd;
+  if (running_mean != nullptr) {  // torch: running = (1-m)*running + m*stat, unbiased variance
+    const double unbiased = P > 1 ? var * P / (P - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+// eval mode: fold the running statistics
+__global__ void bn_fold_eval_kernel(int C, const float *__restrict__ gamma, const float *__restrict__ beta,
+                                    const float *__restrict__ running_mean,
+                                    const float *__restrict__ running_var, float eps,
+                                    float *__restrict__ a, float *__restrict__ b,
+                                    float *__restrict__ mean_out, float *__restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = 1.0f / sqrtf(running_var[c] + eps);
+  const float ga = gamma[c] * invstd;
+  a[c] = ga;
+  b[c] = beta[c] - running_mean[c] * ga;
+  mean_out[c] = running_mean[c];
+  invstd_out[c] = invstd;
+}
+
+// -------------------------------------------------------------------------- apply
+__global__ void __launch_bounds__(kRowThreads)
+bn_relu_apply_kernel(size_t total4, int C4, const float *__restrict__ z, const float *__restrict__ a,
+                     const float *__restrict__ b, float *__restrict__ h, int relu) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * kRowThreads;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x; i < total4; i += stride) {
+    const int c4 = static_cast<int>(i % C4);
+    const float4 v = ld4(z, i), aa = ld4(a, c4), bb = ld4(b, c4);
+    float4 y = make_float4(fmaf(aa.x, v.x, bb.x), fmaf(aa.y, v.y, bb.y), fmaf(aa.z, v.z, bb.z),
+                           fmaf(aa.w, v.w, bb.w));
+    if (relu) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
+    reinterpret_cast<float4 *>(h)[i] = y;
+  }
+}
+
+// out[g, c] = max over the ns rows of group g of relu(a*z + b); first maximal row kept
+__global__ void __launch_bounds__(kRowThreads)
+bn_relu_groupmax_kernel(int G, int ns, int C4, const float *__restrict__ z, const float *__restrict__ a,
+                        const float *__restrict__ b, float *__restrict__ out, int *__restrict__ argmax) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
+  if (i >= static_cast<size_t>(G) * C4) return;
+  const int c4 = static_cast<int>(i % C4);
+  const size_t g = i / C4;
+  const float4 aa = ld4(a, c4), bb = ld4(b, c4);
+  float4 best = make_float4(-1.f, -1.f, -1.f, -1.f);  // relu output is >= 0
+  int4 arg = make_int4(0, 0, 0, 0);
+  for (int s = 0; s < ns; ++s) {
+    const float4 v = ld4(z, (g * ns + s) * C4 + c4);
+    const float y0 = fmaxf(fmaf(aa.x, v.x, bb.x), 0.f), y1 = fmaxf(fmaf(aa.y, v.y, bb.y), 0.f);
+    const float y2 = fmaxf(fmaf(aa.z, v.z, bb.z), 0.f), y3 = fmaxf(fmaf(aa.w, v.w, bb.w), 0.f);
+    if (y0 > best.x) best.x = y0, arg.x = s;
+    if (y1 > best.y) best.y = y1, arg.y = s;
+    if (y2 > best.z) best.z = y2, arg.z = s;
+    if (y3 > best.w) best.w = y3, arg.w = s;
+  }
+  reinterpret_cast<float4 *>(out)[i] = best;
+  reinterpret_cast<int4 *>(argmax)[i] = arg;
+}
+
+// ------------------------------------------------------------- adjoint of the pooled layer
+// sparse statistics: only the arg-max row of every (group, channel) carries a gradient
+__global__ void __launch_bounds__(kRowThreads)
+pool_bwd_stats_kernel(ColGeom g, int ns, const float *__restrict__ dout, const int *__restrict__ argmax,
+                      const float *__restrict__ z, const float *__restrict__ a, const float *__restrict__ b,
+                      const float *__restrict__ mean, const float *__restrict__ invstd,
+                      float *__restrict__ partials) {
+  // rows here are GROUPS (g.P = G)
+  col_reduce2(g, partials, [&](int grp, int c4, float4 &s, float4 &q) {
+    const size_t i = static_cast<size_t>(grp) * g.C4 + c4;
+    const float4 d = ld4(dout, i);
+    const int4 am = __ldg(reinterpret_cast<const int4 *>(argmax) + i);
+    const float4 aa = ld4(a, c4), bb = ld4(b, c4), mu = ld4(mean, c4), is = ld4(invstd, c4);
+    const size_t base = static_cast<size_t>(grp) * ns;
+    const float z0 = __ldg(z + (base + am.x) * g.C + 4 * c4 + 0);
+    const float z1 = __ldg(z + (base + am.y) * g.C + 4 * c4 + 1);
+    const float z2 = __ldg(z + (base + am.z) * g.C + 4 * c4 + 2);
+    const float z3 = __ldg(z + (base + am.w) * g.C + 4 * c4 + 3);
+    const float d0 = fmaf(aa.x, z0, bb.x) > 0.f ? d.x : 0.f, d1 = fmaf(aa.y, z1, bb.y) > 0.f ? d.y : 0.f;
+    const float d2 = fmaf(aa.z, z2, bb.z) > 0.f ? d.z : 0.f, d3 = fmaf(aa.w, z3, bb.w) > 0.f ? d.w : 0.f;
+    s.x += d0, s.y += d1, s.z += d2, s.w += d3;
+    q.x += d0 * (z0 - mu.x) * is.x, q.y += d1 * (z1 - mu.y) * is.y;
+    q.z += d2 * (z2 - mu.z) * is.z, q.w += d3 * (z3 - mu.w) * is.w;
+  });
+}
+
+// sums the partials (fp64, fixed order, one warp per channel): dbeta, dgamma, and the two
+// per-channel constants c1 = dbeta/P, c2 = dgamma/P used by the dense dZ kernels (0 in eval mode)
+__global__ void __launch_bounds__(32 * kFinalizeWarps)
+bwd_stats_finalize_kernel(int P, int C, int nblk, int training, const float *__restrict__ partials,
+                          float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ c1,
+                          float *__restrict__ c2) {
+  const int c = blockIdx.x * kFinalizeWarps + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s, q;
+  warp_sum_partials(C, c, nblk, partials, s, q);
+  if ((threadIdx.x & 31) != 0) return;
+  dbeta[c] = static_cast<float>(s);
+  dgamma[c] = static_cast<float>(q);
+  c1[c] = training ? static_cast<float>(s / P) : 0.f;
+  c2[c] = training ? static_cast<float>(q / P) : 0.f;
+}
+
+// dense dZ of the pooled layer: dZ[p,c] = a*(dY - c1 - zhat*c2), dY nonzero at the arg-max row
+__global__ void __launch_bounds__(kRowThreads)
+pool_bwd_dz_kernel(int G, int ns, int C4, const float *__restrict__ dout, const int *__restrict__ argmax,
+                   const float *__restrict__ z, const float *__restrict__ a, const float *__restrict__ b,
+                   const float *__restrict__ mean, const float *__restrict__ invstd,
+                   const float *__restrict__ c1, const float *__restrict__ c2, float *__restrict__ dz) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
+  if (i >= static_cast<size_t>(G) * C4) return;
+  const int c4 = static_cast<int>(i % C4);
+  const size_t g = i / C4;
+  const float4 d = ld4(dout, i);
+  const int4 am = __ldg(reinterpret_cast<const int4 *>(argmax) + i);
+  const float4 aa = ld4(a, c4), bb = ld4(b, c4), mu = ld4(mean, c4), is = ld4(invstd, c4);
+  const float4 k1 = ld4(c1, c4), k2 = ld4(c2, c4);
+  for (int s = 0; s < ns; ++s) {
+    const size_t r = (g * ns + s) * C4 + c4;
+    const float4 v = ld4(z, r);
+    float4 o;
+    {
+      const float dy = (s == am.x && fmaf(aa.x, v.x, bb.x) > 0.f) ? d.x : 0.f;
+      o.x = aa.x * (dy - k1.x - (v.x - mu.x) * is.x * k2.x);
+    }
+    {
+      const float dy = (s == am.y && fmaf(aa.y, v.y, bb.y) > 0.f) ? d.y : 0.f;
+      o.y = aa.y * (dy - k1.y - (v.y - mu.y) * is.y * k2.y);
+    }
+    {
+      const float dy = (s == am.z && fmaf(aa.z, v.z, bb.z) > 0.f) ? d.z : 0.f;
+      o.z = aa.z * (dy - k1.z - (v.z - mu.z) * is.z * k2.z);
+    }
+    {
+      const float dy = (s == am.w && fmaf(aa.w, v.w, bb.w) > 0.f) ? d.w : 0.f;
+      o.w = aa.w * (dy - k1.w - (v.w - mu.w) * is.w * k2.w);
+    }
+    reinterpret_cast<float4 *>(dz)[r] = o;
+  }
+}
+
+// ------------------------------------------------------- adjoint of a hidden BN+ReLU layer
+__global__ void __launch_bounds__(kRowThreads)
+relu_bwd_stats_kernel(ColGeom g, int relu, const float *__restrict__ dh, const float *__restrict__ z,
+                      const float *__restrict__ a, const float *__restrict__ b,
+                      const float *__restrict__ mean, const float *__restrict__ invstd,
+                      float *__restrict__ partials) {
+  col_reduce2(g, partials, [&](int r, int c4, float4 &s, float4 &q) {
+    const size_t i = static_cast<size_t>(r) * g.C4 + c4;
+    const float4 d = ld4(dh, i), v = ld4(z, i);
+    const float4 aa = ld4(a, c4), bb = ld4(b, c4), mu = ld4(mean, c4), is = ld4(invstd, c4);
+    const float d0 = (!relu || fmaf(aa.x, v.x, bb.x) > 0.f) ? d.x : 0.f;
+    const float d1 = (!relu || fmaf(aa.y, v.y, bb.y) > 0.f) ? d.y : 0.f;
+    const float d2 = (!relu || fmaf(aa.z, v.z, bb.z) > 0.f) ? d.z : 0.f;
+    const float d3 = (!relu || fmaf(aa.w, v.w, bb.w) > 0.f) ? d.w : 0.f;
+    s.x += d0, s.y += d1, s.z += d2, s.w += d3;
+    q.x += d0 * (v.x - mu.x) * is.x, q.y += d1 * (v.y - mu.y) * is.y;
+    q.z += d2 * (v.z - mu.z) * is.z, q.w += d3 * (v.w - mu.w) * is.w;
+  });
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+relu_bwd_dz_kernel(size_t total4, int C4, int relu, const float *__restrict__ dh, const float *__restrict__ z,
+                   const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ mean,
+                   const float *__restrict__ invstd, const float *__restrict__ c1,
+                   const float *__restrict__ c2, float *__restrict__ dz) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * kRowThreads;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x; i < total4; i += stride) {
+    const int c4 = static_cast<int>(i % C4);
+    const float4 d = ld4(dh, i), v = ld4(z, i);
+    const float4 aa = ld4(a, c4), bb = ld4(b, c4), mu = ld4(mean, c4), is = ld4(invstd, c4);
+    const float4 k1 = ld4(c1, c4), k2 = ld4(c2, c4);
+    float4 o;
+    o.x = aa.x * (((!relu || fmaf(aa.x, v.x, bb.x) > 0.f) ? d.x : 0.f) - k1.x - (v.x - mu.x) * is.x * k2.x);
+    o.y = aa.y * (((!relu || fmaf(aa.y, v.y, bb.y) > 0.f) ? d.y : 0.f) - k1.y - (v.y - mu.y) * is.y * k2.y);
+    o.z = aa.z * (((!relu || fmaf(aa.z, v.z, bb.z) > 0.f) ? d.z : 0.f) - k1.z - (v.z - mu.z) * is.z * k2.z);
+    o.w = aa.w * (((!relu || fmaf(aa.w, v.w, bb.w) > 0.f) ? d.w : 0.f) - k1.w - (v.w - mu.w) * is.w * k2.w);
+    reinterpret_cast<float4 *>(dz)[i] = o;
+  }
+}
+
+// --------------------------------------------------------------- grouping in row layout
+// rows[(b*np + j)*ns + s, :] = table[b, idx[b,j,s], :]; the first 3 columns (xyz) are centred
+// on new_xyz[b, j] (pointnet2_utils.py:348-350).  One thread per (row, float4 column group).
+__global__ void __launch_bounds__(kRowThreads)
+sa_group_rows_kernel(size_t total4, int n, int np_ns, int ns, int ct4, const float *__restrict__ table,
+                     const float *__restrict__ new_xyz, const int *__restrict__ idx,
+                     float *__restrict__ rows) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = static_cast<int>(i % ct4);
+  const size_t p = i / ct4;
+  const size_t cloud = p / np_ns;
+  const int k = __ldg(idx + p);
+  float4 v = ld4(table, (cloud * n + k) * ct4 + c4);
+  if (c4 == 0) {
+    const float *ctr = new_xyz + (p / ns) * 3;
+    v.x -= __ldg(ctr), v.y -= __ldg(ctr + 1), v.z -= __ldg(ctr + 2);
+  }
+  reinterpret_cast<float4 *>(rows)[i] = v;
+}
+
+__device__ __forceinline__ void red_add_v4(float *p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// grad_table[b, idx[p], :] += grad_rows[p, :]   (grad_table zero-filled by the launcher)
+__global__ void __launch_bounds__(kRowThreads)
+sa_group_rows_grad_kernel(size_t total4, int n, int np_ns, int ct4, const float *__restrict__ grad_rows,
+                          const int *__restrict__ idx, float *__restrict__ grad_table) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = static_cast<int>(i % ct4);
+  const size_t p = i / ct4;
+  const size_t cloud = p / np_ns;
+  const int k = __ldg(idx + p);
+  red_add_v4(grad_table + ((cloud * n + k) * ct4 + c4) * 4, ld4(grad_rows, i));
+}
+
+// ------------------------------------------------------ feature propagation in row layout
+// rows[(b, j), :] = [ ((k1*w1) + (k2*w2)) + (k3*w3) | skip[b, j, :] | 0 ]   with k_t = known[b, idx[b,j,t], :]
+// (three_interpolate + torch.cat of PointnetFPModule.forward, pointnet2_modules.py:395-412).
+// known (b, m, c2) and skip (b, n, c1) are point-major; c2 % 4 == 0; ct = pad4(c2 + c1).
+__global__ void __launch_bounds__(kRowThreads)
+fp_interp_rows_kernel(size_t total4, int n, int m, int c2, int c1, int ct4, const float *__restrict__ known,
+                      const float *__restrict__ skip, const int *__restrict__ idx,
+                      const float *__restrict__ weight, float *__restrict__ rows) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = static_cast<int>(i % ct4);
+  const size_t p = i / ct4;  // = b*n + j
+  float4 v;
+  if (c4 * 4 < c2) {
+    const size_t cloud = p / n;
+    const int i1 = __ldg(idx + 3 * p), i2 = __ldg(idx + 3 * p + 1), i3 = __ldg(idx + 3 * p + 2);
+    const float w1 = __ldg(weight + 3 * p), w2 = __ldg(weight + 3 * p + 1), w3 = __ldg(weight + 3 * p + 2);
+    const int k4 = c2 / 4;
+    const float4 a = ld4(known, (cloud * m + i1) * k4 + c4);
+    const float4 b = ld4(known, (cloud * m + i2) * k4 + c4);
+    const float4 c = ld4(known, (cloud * m + i3) * k4 + c4);
+    v.x = __fadd_rn(__fadd_rn(__fmul_rn(a.x, w1), __fmul_rn(b.x, w2)), __fmul_rn(c.x, w3));
+    v.y = __fadd_rn(__fadd_rn(__fmul_rn(a.y, w1), __fmul_rn(b.y, w2)), __fmul_rn(c.y, w3));
+    v.z = __fadd_rn(__fadd_rn(__fmul_rn(a.z, w1), __fmul_rn(b.z, w2)), __fmul_rn(c.z, w3));
+    v.w = __fadd_rn(__fadd_rn(__fmul_rn(a.w, w1), __fmul_rn(b.w, w2)), __fmul_rn(c.w, w3));
+  } else {
+    const int c = c4 * 4 - c2;
+    const float *sr = skip + p * c1;
+    v.x = c + 0 < c1 ? __ldg(sr + c + 0) : 0.f;
+    v.y = c + 1 < c1 ? __ldg(sr + c + 1) : 0.f;
+    v.z = c + 2 < c1 ? __ldg(sr + c + 2) : 0.f;
+    v.w = c + 3 < c1 ? __ldg(sr + c + 3) : 0.f;
+  }
+  reinterpret_cast<float4 *>(rows)[i] = v;
+}
+
+// adjoint: grad_known[b, idx_t, :] += w_t * grad_rows[p, :c2] (vector reds into a zeroed buffer);
+// grad_skip[b, j, :] = grad_rows[p, c2:c2+c1]
+__global__ void __launch_bounds__(kRowThreads)
+fp_interp_rows_grad_kernel(size_t total4, int n, int m, int c2, int c1, int ct4,
+                           const float *__restrict__ grad_rows, const int *__restrict__ idx,
+                           const float *__restrict__ weight, float *__restrict__ grad_known,
+                           float *__restrict__ grad_skip) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = static_cast<int>(i % ct4);
+  const size_t p = i / ct4;
+  const float4 g = ld4(grad_rows, i);
+  if (c4 * 4 < c2) {
+    const size_t cloud = p / n;
+    const int k4 = c2 / 4;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const int it = __ldg(idx + 3 * p + t);
+      const float w = __ldg(weight + 3 * p + t);
+      red_add_v4(grad_known + ((cloud * m + it) * k4 + c4) * 4,
+                 make_float4(__fmul_rn(g.x, w), __fmul_rn(g.y, w), __fmul_rn(g.z, w), __fmul_rn(g.w, w)));
+    }
+  } else if (grad_skip != nullptr) {
+    const int c = c4 * 4 - c2;
+    float *sr = grad_skip + p * c1;
+    if (c + 0 < c1) sr[c + 0] = g.x;
+    if (c + 1 < c1) sr[c + 1] = g.y;
+    if (c + 2 < c1) sr[c + 2] = g.z;
+    if (c + 3 < c1) sr[c + 3] = g.w;
+  }
+}
+
+static inline int blocks_for(size_t total, int cap = 0) {
+  size_t nb = (total + kRowThreads - 1) / kRowThreads;
+  if (cap > 0 && nb > static_cast<size_t>(cap)) nb = cap;
+  return static_cast<int>(nb < 1 ? 1 : nb);
+}
+
+static inline bool rows_ok(int C, const void *p0) { return C > 0 && C % 4 == 0 && C <= 1024 && aligned16(p0); }
+
+}  // namespace pn2
+
+using namespace pn2;
+
+extern "C" int pn2_bn_stats_workspace_floats(int c) { return kMaxPartials * 2 * c; }
+
+extern "C" int pn2_bn_stats(int p, int c, const float *z, const float *gamma, const float *beta, float eps,
+                            float momentum, float *running_mean, float *running_var, float *a, float *b,
+                            float *mean, float *invstd, float *workspace, void *stream) {
+  if (p <= 0 || c <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(z, gamma, beta, a, b, mean, invstd, workspace);
+  if (!rows_ok(c, z) || !aligned16(workspace)) return PN2_ERR_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int nblk;
+  const ColGeom g = col_geom(p, c, &nblk);
+  const size_t smem = sizeof(float4) * 2 * g.row_lanes * g.C4;
+  bn_stats_partial_kernel<<<nblk, kRowThreads, smem, s>>>(g, z, workspace);
+  bn_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(p, c, nblk, workspace, gamma, beta, eps, momentum,
+                                                           running_mean, running_var, a, b, mean, invstd);
+  count_launch(2);
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_bn_fold_eval(int c, const float *gamma, const float *beta, const float *running_mean,
+                                const float *running_var, float eps, float *a, float *b, float *mean,
+                                float *invstd, void *stream) {
+  if (c <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(gamma, beta, running_mean, running_var, a, b, mean, invstd);
+  bn_fold_eval_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      c, gamma, beta, running_mean, running_var, eps, a, b, mean, invstd);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_bn_relu_apply(int p, int c, const float *z, const float *a, const float *b, float *h,
+                                 int relu, void *stream) {
+  if (p <= 0 || c <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(z, a, b, h);
+  if (!rows_ok(c, z) || !aligned16(h) || !aligned16(a) || !aligned16(b)) return PN2_ERR_UNSUPPORTED;
+  const size_t total4 = static_cast<size_t>(p) * (c / 4);
+  bn_relu_apply_kernel<<<blocks_for(total4, 16 * kNumSMs), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      total4, c / 4, z, a, b, h, relu);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_bn_relu_groupmax(int g, int ns, int c, const float *z, const float *a, const float *b,
+                                    float *out, int *argmax, void *stream) {
+  if (g <= 0 || ns <= 0 || c <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(z, a, b, out, argmax);
+  if (!rows_ok(c, z) || !aligned16(out) || !aligned16(argmax) || !aligned16(a) || !aligned16(b))
+    return PN2_ERR_UNSUPPORTED;
+  const size_t total4 = static_cast<size_t>(g) * (c / 4);
+  bn_relu_groupmax_kernel<<<blocks_for(total4), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      g, ns, c / 4, z, a, b, out, argmax);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_pool_bn_bwd(int g, int ns, int c, int training, const float *dout, const int *argmax,
+                               const float *z, const float *a, const float *b, const float *mean,
+                               const float *invstd, float *dz, float *dgamma, float *dbeta,
+                               float *workspace, void *stream) {
+  if (g <= 0 || ns <= 0 || c <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(dout, argmax, z, a, b, mean, invstd, dz, dgamma, dbeta, workspace);
+  if (!rows_ok(c, z) || !aligned16(dout) || !aligned16(argmax) || !aligned16(dz) || !aligned16(workspace))
+    return PN2_ERR_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int nblk;
+  const ColGeom geom = col_geom(g, c, &nblk);
+  float *c1 = workspace + static_cast<size_t>(kMaxPartials) * 2 * c, *c2 = c1 + c;
+  const size_t smem = sizeof(float4) * 2 * geom.row_lanes * geom.C4;
+  pool_bwd_stats_kernel<<<nblk, kRowThreads, smem, s>>>(geom, ns, dout, argmax, z, a, b, mean, invstd, workspace);
+  bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(g * ns, c, nblk, training, workspace, dgamma,
+                                                            dbeta, c1, c2);
+  const size_t total4 = static_cast<size_t>(g) * (c / 4);
+  pool_bwd_dz_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(g, ns, c / 4, dout, argmax, z, a, b, mean,
+                                                               invstd, c1, c2, dz);
+  count_launch(3);
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_relu_bn_bwd(int p, int c, int training, int relu, const float *dh, const float *z,
+                               const float *a, const float *b, const float *mean, const float *invstd,
+                               float *dz, float *dgamma, float *dbeta, float *workspace, void *stream) {
+  if (p <= 0 || c <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(dh, z, a, b, mean, invstd, dz, dgamma, dbeta, workspace);
+  if (!rows_ok(c, z) || !aligned16(dh) || !aligned16(dz) || !aligned16(workspace)) return PN2_ERR_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int nblk;
+  const ColGeom geom = col_geom(p, c, &nblk);
+  float *c1 = workspace + static_cast<size_t>(kMaxPartials) * 2 * c, *c2 = c1 + c;
+  const size_t smem = sizeof(float4) * 2 * geom.row_lanes * geom.C4;
+  relu_bwd_stats_kernel<<<nblk, kRowThreads, smem, s>>>(geom, relu, dh, z, a, b, mean, invstd, workspace);
+  bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(p, c, nblk, training, workspace, dgamma, dbeta,
+                                                            c1, c2);
+  const size_t total4 = static_cast<size_t>(p) * (c / 4);
+  relu_bwd_dz_kernel<<<blocks_for(total4, 16 * kNumSMs), kRowThreads, 0, s>>>(total4, c / 4, relu, dh, z, a, b,
+                                                                             mean, invstd, c1, c2, dz);
+  count_launch(3);
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_sa_group_rows(int b, int n, int npoint, int nsample, int ct, const float *table,
+                                 const float *new_xyz, const int *idx, float *rows, void *stream) {
+  if (b <= 0 || n <= 0 || npoint <= 0 || nsample <= 0 || ct < 4) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(table, new_xyz, idx, rows);
+  if (!rows_ok(ct, table) || !aligned16(rows)) return PN2_ERR_UNSUPPORTED;
+  const size_t total4 = static_cast<size_t>(b) * npoint * nsample * (ct / 4);
+  sa_group_rows_kernel<<<blocks_for(total4), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      total4, n, npoint * nsample, nsample, ct / 4, table, new_xyz, idx, rows);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_sa_group_rows_grad(int b, int n, int npoint, int nsample, int ct, const float *grad_rows,
+                                      const int *idx, float *grad_table, void *stream) {
+  if (b <= 0 || n <= 0 || npoint <= 0 || nsample <= 0 || ct < 4) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(grad_rows, idx, grad_table);
+  if (!rows_ok(ct, grad_rows) || !aligned16(grad_table)) return PN2_ERR_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(grad_table, 0, sizeof(float) * static_cast<size_t>(b) * n * ct, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const size_t total4 = static_cast<size_t>(b) * npoint * nsample * (ct / 4);
+  sa_group_rows_grad_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(total4, n, npoint * nsample, ct / 4,
+                                                                      grad_rows, idx, grad_table);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_fp_interp_rows(int b, int n, int m, int c2, int c1, const float *known, const float *skip,
+                                  const int *idx, const float *weight, float *rows, void *stream) {
+  if (b <= 0 || n <= 0 || m <= 0 || c2 <= 0 || c1 < 0 || c2 % 4 != 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(known, idx, weight, rows);
+  if (c1 > 0) PN2_CHECK_PTRS(skip);
+  const int ct = (c2 + c1 + 3) / 4 * 4;
+  if (!aligned16(known) || !aligned16(rows) || ct > 4096) return PN2_ERR_UNSUPPORTED;
+  const size_t total4 = static_cast<size_t>(b) * n * (ct / 4);
+  fp_interp_rows_kernel<<<blocks_for(total4), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      total4, n, m, c2, c1, ct / 4, known, skip, idx, weight, rows);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_fp_interp_rows_grad(int b, int n, int m, int c2, int c1, const float *grad_rows,
+                                       const int *idx, const float *weight, float *grad_known,
+                                       float *grad_skip, void *stream) {
+  if (b <= 0 || n <= 0 || m <= 0 || c2 <= 0 || c1 < 0 || c2 % 4 != 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(grad_rows, idx, weight, grad_known);
+  const int ct = (c2 + c1 + 3) / 4 * 4;
+  if (!aligned16(grad_known) || !aligned16(grad_rows) || ct > 4096) return PN2_ERR_UNSUPPORTED;
+  if (grad_skip != nullptr && !aligned4(grad_skip)) return PN2_ERR_ALIGNMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(grad_known, 0, sizeof(float) * static_cast<size_t>(b) * m * c2, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const size_t total4 = static_cast<size_t>(b) * n * (ct / 4);
+  fp_interp_rows_grad_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(total4, n, m, c2, c1, ct / 4, grad_rows,
+                                                                       idx, weight, grad_known, grad_skip);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}

@@ -1,0 +1,310 @@
+"""Fused shared-MLP blocks in position-major ("rows") layout.
+
+What the reference's SA / FP modules compute around their 1x1 convolutions
+(/root/reference/pointnet2/pointnet2_modules.py:60-75 and 395-416: QueryAndGroup ->
+SharedMLP [Conv2d 1x1 + BatchNorm2d + ReLU]* -> max_pool2d over nsample), restated on
+[P, C] row-major activations so that each conv is one GEMM and BatchNorm / ReLU / max /
+their adjoints are the streaming kernels of csrc/mlp_rows.cu (C ABI: include/pn2_b200.h,
+"Shared-MLP block").  The module parameters and BatchNorm buffers are used as they are
+(no new parameters: state dicts stay the reference's); running statistics and
+num_batches_tracked are updated exactly like torch.nn.BatchNorm2d does in train mode.
+
+Numerics: BatchNorm statistics fp32 partials + fp64 finalise; GEMMs in TF32 when
+``GEMM_TF32`` (the arithmetic class of the reference's own cuDNN convs, whose
+``cudnn.allow_tf32`` defaults to True) or in fp32 otherwise.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.autograd import Function
+
+from . import lib as _lib
+
+GEMM_TF32 = True   # tensor-core TF32 GEMMs, like the reference's cuDNN convs on Ampere+
+ENABLED = True     # module forward()s take the fused path when eligible
+
+
+def _mm(a, b):
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = GEMM_TF32
+    try:
+        return torch.mm(a, b)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def _mm_tn_splitk(dz, h):
+    """dz^T @ h for tall-skinny operands ([P, Cout]^T [P, Cin], P up to 10^6): a single GEMM
+    offers only Cout*Cin/tile CTAs, so the reduction over P is split into S slabs computed as
+    one batched GEMM and summed (fixed order)."""
+    P, cout = dz.shape
+    cin = h.shape[1]
+    tiles = ((cout + 127) // 128) * ((cin + 63) // 64)
+    S = min((2 * 148 + tiles - 1) // tiles, P // 2048)
+    while S > 1 and P % S:
+        S -= 1
+    if S <= 1:
+        return _mm(dz.t(), h)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = GEMM_TF32
+    try:
+        part = torch.bmm(dz.view(S, P // S, cout).transpose(1, 2), h.view(S, P // S, cin))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return part.sum(dim=0)
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ws(c, dev):
+    n = _lib.load().pn2_bn_stats_workspace_floats(c) + 2 * c
+    return torch.empty(n, dtype=torch.float32, device=dev)
+
+
+class _BNLayer(object):
+    """Per-layer state shared between forward and backward."""
+    __slots__ = ("z", "a", "b", "mean", "invstd", "cout")
+
+
+def _bn_forward(z, gamma, beta, rm, rv, eps, momentum, training):
+    """-> (a, b, mean, invstd); updates rm / rv in place when training."""
+    L = _lib.load()
+    P, C = z.shape
+    dev = z.device
+    a, b, mean, invstd = (torch.empty(C, dtype=torch.float32, device=dev) for _ in range(4))
+    if training:
+        _lib.check(L.pn2_bn_stats(P, C, z.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, momentum,
+                                  rm.data_ptr() if rm is not None else None,
+                                  rv.data_ptr() if rv is not None else None,
+                                  a.data_ptr(), b.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                  _ws(C, dev).data_ptr(), _stream(dev)), "bn_stats")
+    else:
+        _lib.check(L.pn2_bn_fold_eval(C, gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                                      eps, a.data_ptr(), b.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                      _stream(dev)), "bn_fold_eval")
+    return a, b, mean, invstd
+
+
+class SharedMLPRows(Function):
+    """x0 [P, Cin] -> out [P/ns, C_L] (max over each run of ns rows) or [P, C_L] (ns == 0).
+
+    args: x0, ns, training, eps, momentum, buffers, relus, then (W, gamma, beta) per layer.
+    ``buffers`` is a list of (running_mean, running_var) per layer (updated in place);
+    ``relus`` one flag per layer (the pooled last layer always has its ReLU).
+    """
+
+    @staticmethod
+    def forward(ctx, x0, ns, training, eps, momentum, buffers, relus, *params):
+        L = _lib.load()
+        dev = x0.device
+        nl = len(params) // 3
+        P = x0.shape[0]
+        layers, hs = [], [x0]
+        out = argmax = None
+        with torch.cuda.device(dev):
+            for l in range(nl):
+                W, gamma, beta = params[3 * l:3 * l + 3]
+                W2 = W.reshape(W.shape[0], -1)
+                cin = hs[-1].shape[1]
+                if W2.shape[1] != cin:  # first layer: rows are zero-padded to a multiple of 4
+                    W2 = F.pad(W2, (0, cin - W2.shape[1]))
+                st = _BNLayer()
+                st.cout = W2.shape[0]
+                st.z = _mm(hs[-1], W2.t())
+                rm, rv = buffers[l]
+                st.a, st.b, st.mean, st.invstd = _bn_forward(st.z, gamma, beta, rm, rv, eps, momentum, training)
+                layers.append(st)
+                C = st.cout
+                if l < nl - 1 or ns == 0:
+                    h = torch.empty_like(st.z)
+                    _lib.check(L.pn2_bn_relu_apply(P, C, st.z.data_ptr(), st.a.data_ptr(), st.b.data_ptr(),
+                                                   h.data_ptr(), int(relus[l]), _stream(dev)), "bn_relu_apply")
+                    if l < nl - 1:
+                        hs.append(h)
+                    else:
+                        out = h
+                else:
+                    G = P // ns
+                    out = torch.empty(G, C, dtype=torch.float32, device=dev)
+                    argmax = torch.empty(G, C, dtype=torch.int32, device=dev)
+                    _lib.check(L.pn2_bn_relu_groupmax(G, ns, C, st.z.data_ptr(), st.a.data_ptr(),
+                                                      st.b.data_ptr(), out.data_ptr(), argmax.data_ptr(),
+                                                      _stream(dev)), "bn_relu_groupmax")
+        ctx.layers, ctx.hs, ctx.argmax = layers, hs, argmax
+        ctx.ns, ctx.training, ctx.nl, ctx.relus = ns, training, nl, relus
+        ctx.weights = [params[3 * l] for l in range(nl)]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.load()
+        layers, hs, nl, ns = ctx.layers, ctx.hs, ctx.nl, ctx.ns
+        dev = dout.device
+        dout = dout.contiguous()
+        grads = [None] * (3 * nl)
+        training = 1 if ctx.training else 0
+        with torch.cuda.device(dev):
+            dh = dout
+            for l in range(nl - 1, -1, -1):
+                st = layers[l]
+                P, C = st.z.shape
+                dz = torch.empty_like(st.z)
+                dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+                dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+                ws = _ws(C, dev)
+                if l == nl - 1 and ns > 0:
+                    _lib.check(L.pn2_pool_bn_bwd(P // ns, ns, C, training, dh.data_ptr(),
+                                                 ctx.argmax.data_ptr(), st.z.data_ptr(), st.a.data_ptr(),
+                                                 st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
+                                                 dz.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                                 ws.data_ptr(), _stream(dev)), "pool_bn_bwd")
+                else:
+                    _lib.check(L.pn2_relu_bn_bwd(P, C, training, int(ctx.relus[l]), dh.data_ptr(), st.z.data_ptr(),
+                                                 st.a.data_ptr(), st.b.data_ptr(), st.mean.data_ptr(),
+                                                 st.invstd.data_ptr(), dz.data_ptr(), dgamma.data_ptr(),
+                                                 dbeta.data_ptr(), ws.data_ptr(), _stream(dev)), "relu_bn_bwd")
+                W = ctx.weights[l]
+                W2 = W.reshape(W.shape[0], -1)
+                h_prev = hs[l]
+                dW = _mm_tn_splitk(dz, h_prev)                 # [Cout, Cin(_pad)]
+                if dW.shape[1] != W2.shape[1]:
+                    dW = dW[:, :W2.shape[1]]
+                grads[3 * l] = dW.reshape(W.shape)
+                grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
+                if l > 0 or ctx.needs_input_grad[0]:
+                    if W2.shape[1] != h_prev.shape[1]:
+                        W2 = F.pad(W2, (0, h_prev.shape[1] - W2.shape[1]))
+                    dh = _mm(dz, W2)                           # [P, Cin]
+                else:
+                    dh = None
+        return (dh if ctx.needs_input_grad[0] else None, None, None, None, None, None, None) + tuple(grads)
+
+
+class SAGroupRows(Function):
+    """QueryAndGroup in rows layout: table (B, N, ct) [xyz | features | 0 pad], new_xyz (B, np, 3),
+    idx (B, np, ns) -> rows (B*np*ns, ct) with the xyz columns centred on their query point."""
+
+    @staticmethod
+    def forward(ctx, table, new_xyz, idx):
+        B, N, ct = table.shape
+        _, npoint, ns = idx.shape
+        dev = table.device
+        rows = torch.empty(B * npoint * ns, ct, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().pn2_sa_group_rows(B, N, npoint, ns, ct, table.data_ptr(),
+                                                     new_xyz.data_ptr(), idx.data_ptr(), rows.data_ptr(),
+                                                     _stream(dev)), "sa_group_rows")
+        ctx.idx, ctx.shape = idx, (B, N, ct, npoint, ns)
+        return rows
+
+    @staticmethod
+    def backward(ctx, grad_rows):
+        B, N, ct, npoint, ns = ctx.shape
+        dev = grad_rows.device
+        grad_rows = grad_rows.contiguous()
+        grad_table = torch.empty(B, N, ct, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().pn2_sa_group_rows_grad(B, N, npoint, ns, ct, grad_rows.data_ptr(),
+                                                          ctx.idx.data_ptr(), grad_table.data_ptr(),
+                                                          _stream(dev)), "sa_group_rows_grad")
+        # new_xyz is a gather of input coordinates; like the reference's semseg models this path
+        # does not propagate a gradient into it
+        return grad_table, None, None
+
+
+class FPInterpRows(Function):
+    """three_interpolate + concat of PointnetFPModule in rows layout: known (B, m, C2) and skip
+    (B, n, C1) point-major, idx / weight (B, n, 3) -> rows (B*n, pad4(C2 + C1))."""
+
+    @staticmethod
+    def forward(ctx, known, skip, idx, weight):
+        B, m, c2 = known.shape
+        n = idx.shape[1]
+        c1 = skip.shape[2] if skip is not None else 0
+        dev = known.device
+        rows = torch.empty(B * n, pad4(c2 + c1), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().pn2_fp_interp_rows(
+                B, n, m, c2, c1, known.data_ptr(), skip.data_ptr() if skip is not None else None,
+                idx.data_ptr(), weight.data_ptr(), rows.data_ptr(), _stream(dev)), "fp_interp_rows")
+        ctx.saved = (idx, weight, B, n, m, c2, c1)
+        return rows
+
+    @staticmethod
+    def backward(ctx, grad_rows):
+        idx, weight, B, n, m, c2, c1 = ctx.saved
+        dev = grad_rows.device
+        grad_rows = grad_rows.contiguous()
+        gk = torch.empty(B, m, c2, dtype=torch.float32, device=dev)
+        gs = None
+        if c1 > 0 and ctx.needs_input_grad[1]:
+            gs = torch.empty(B, n, c1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().pn2_fp_interp_rows_grad(
+                B, n, m, c2, c1, grad_rows.data_ptr(), idx.data_ptr(), weight.data_ptr(), gk.data_ptr(),
+                gs.data_ptr() if gs is not None else None, _stream(dev)), "fp_interp_rows_grad")
+        return gk, gs, None, None
+
+
+def rows_of(t):
+    """Point-major (B, N, C) contiguous alias of a channel-major (B, C, N) feature tensor: the
+    rows tensor a fused module produced it from when there is one, else a transposed copy."""
+    r = getattr(t, "_pn2_rows", None)
+    if r is not None:
+        return r
+    return t.transpose(1, 2).contiguous()
+
+
+def channel_major(rows3):
+    """(B, N, C) rows -> the (B, C, N) contiguous tensor the op surface promises, remembering the
+    rows it came from so that the next fused block can skip the transpose back."""
+    out = rows3.transpose(1, 2).contiguous()
+    out._pn2_rows = rows3
+    return out
+
+
+# ------------------------------------------------------------------------ module glue
+def mlp_eligible(mlp, x_like):
+    """True when ``mlp`` (a pytorch_utils.SharedMLP) is conv1x1(no bias) + BatchNorm2d + ReLU
+    throughout and the data is fp32 on CUDA -- the configuration of every semseg block."""
+    if not ENABLED or not x_like.is_cuda or x_like.dtype != torch.float32:
+        return False
+    for layer in mlp:
+        conv = getattr(layer, "conv", None)
+        bn = getattr(layer, "bn", None)
+        act = getattr(layer, "activation", None)
+        if conv is None or bn is None or not (act is None or isinstance(act, nn.ReLU)):
+            return False
+        if conv.bias is not None or conv.weight.shape[0] % 4 != 0 or conv.weight.shape[0] > 1024:
+            return False
+        if list(layer._modules.keys())[0] != "conv":  # preact ordering is not handled here
+            return False
+        norm = bn.bn
+        if norm.momentum is None or not norm.affine or not norm.track_running_stats:
+            return False
+    return True
+
+
+def run_mlp_rows(mlp, x0, ns):
+    """Apply a SharedMLP (or any sequence of conv+BN[+ReLU] units) to rows ``x0`` [P, Cin(_pad)];
+    ns > 0 pools every run of ns rows after the last layer."""
+    params, buffers, relus = [], [], []
+    layers = list(mlp)
+    training = layers[0].training
+    norms = [layer.bn.bn for layer in layers]
+    for layer, norm in zip(layers, norms):
+        params += [layer.conv.weight, norm.weight, norm.bias]
+        buffers.append((norm.running_mean, norm.running_var))
+        relus.append(getattr(layer, "activation", None) is not None)
+    out = SharedMLPRows.apply(x0, ns, training, float(norms[0].eps), float(norms[0].momentum), buffers,
+                              tuple(relus), *params)
+    if training:
+        for norm in norms:
+            norm.num_batches_tracked.add_(1)
+    return out
+
+
+def pad4(c):
+    return (c + 3) // 4 * 4

@@ -27,6 +27,18 @@ SIGNATURES = {
     "pn2_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    # shared-MLP block, rows layout
+    "pn2_bn_stats_workspace_floats": [_i],
+    "pn2_bn_stats": [_i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pn2_bn_fold_eval": [_i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp],
+    "pn2_bn_relu_apply": [_i, _i, _vp, _vp, _vp, _vp, _i, _vp],
+    "pn2_bn_relu_groupmax": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pn2_pool_bn_bwd": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pn2_relu_bn_bwd": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pn2_sa_group_rows": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "pn2_sa_group_rows_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "pn2_fp_interp_rows": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pn2_fp_interp_rows_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
 }
 LIBRARY_SYMBOLS = ("pn2_abi_version", "pn2_launch_count", "pn2_reset_launch_count",
                    "pn2_status_string")

@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fused
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 
@@ -35,6 +36,9 @@ class _PointnetSAModuleBase(nn.Module):
             new_xyz = pointnet2_utils.gather_operation(
                 xyz.transpose(1, 2).contiguous(), picked).transpose(1, 2).contiguous()
 
+        if self._fused_ok(xyz, features):
+            return new_xyz, self._forward_rows(xyz, new_xyz, features)
+
         pooled = []
         for grouper, mlp in zip(self.groupers, self.mlps):
             grouped = grouper(xyz, new_xyz, features)        # (B, C, npoint, nsample)
@@ -42,6 +46,36 @@ class _PointnetSAModuleBase(nn.Module):
             grouped = F.max_pool2d(grouped, kernel_size=[1, grouped.size(3)])
             pooled.append(grouped.squeeze(-1))               # (B, mlp[-1], npoint)
         return new_xyz, torch.cat(pooled, dim=1)
+
+    # -- fused path: same arithmetic on [positions, channels] rows (fused.py) -----------
+    def _fused_ok(self, xyz, features):
+        if self.npoint is None or (features is not None and features.dtype != torch.float32):
+            return False
+        for grouper, mlp in zip(self.groupers, self.mlps):
+            if not isinstance(grouper, pointnet2_utils.QueryAndGroup):
+                return False
+            if (not grouper.use_xyz or grouper.normalize_xyz or grouper.sample_uniformly
+                    or grouper.ret_grouped_xyz or grouper.ret_unique_cnt):
+                return False
+            if not fused.mlp_eligible(mlp, xyz):
+                return False
+        return True
+
+    def _forward_rows(self, xyz, new_xyz, features):
+        B, N, _ = xyz.shape
+        cols = [xyz] if features is None else [xyz, fused.rows_of(features)]
+        width = sum(c.size(2) for c in cols)
+        if fused.pad4(width) != width:
+            cols.append(xyz.new_zeros(B, N, fused.pad4(width) - width))
+        table = torch.cat(cols, dim=2)                       # (B, N, 3 + C [+ pad]) per-point rows
+        pooled = []
+        for grouper, mlp in zip(self.groupers, self.mlps):
+            idx = pointnet2_utils.ball_query(grouper.radius, grouper.nsample, xyz, new_xyz)
+            rows = fused.SAGroupRows.apply(table, new_xyz, idx)          # (B*npoint*nsample, ct)
+            out = fused.run_mlp_rows(mlp, rows, grouper.nsample)          # (B*npoint, mlp[-1])
+            pooled.append(out.view(B, self.npoint, -1))
+        rows = torch.cat(pooled, dim=2) if len(pooled) > 1 else pooled[0]   # (B, npoint, sum C)
+        return fused.channel_major(rows)
 
 
 class PointnetSAModuleMSG(_PointnetSAModuleBase):
@@ -88,6 +122,10 @@ class PointnetFPModule(nn.Module):
         self.mlp = pt_utils.SharedMLP(mlp, bn=bn)
 
     def forward(self, unknown, known, unknow_feats, known_feats):
+        if known is not None and fused.mlp_eligible(self.mlp, known_feats) \
+                and known_feats.size(1) % 4 == 0:
+            return fused.channel_major(self.forward_rows(unknown, known, unknow_feats, known_feats))
+
         if known is None:
             interpolated = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
         else:
@@ -99,3 +137,14 @@ class PointnetFPModule(nn.Module):
         feats = interpolated if unknow_feats is None else torch.cat(
             [interpolated, unknow_feats], dim=1)             # (B, C2 + C1, n)
         return self.mlp(feats.unsqueeze(-1)).squeeze(-1)
+
+    def forward_rows(self, unknown, known, unknow_feats, known_feats):
+        """Fused path, point-major result (B, n, mlp[-1]): interpolation + concat written straight
+        into [positions, channels] rows, then the shared MLP on rows (fused.py)."""
+        B, n, _ = unknown.shape
+        dist, idx = pointnet2_utils.three_nn(unknown, known)
+        recip = 1.0 / (dist + 1e-8)                          # ref :395-397
+        weight = recip / torch.sum(recip, dim=2, keepdim=True)
+        skip = fused.rows_of(unknow_feats) if unknow_feats is not None else None
+        rows = fused.FPInterpRows.apply(fused.rows_of(known_feats), skip, idx, weight)
+        return fused.run_mlp_rows(self.mlp, rows, 0).view(B, n, -1)

@@ -9,7 +9,9 @@ dicts and seeded initialisations are interchangeable.
     forward(pointcloud (B, N, 3 + input_channels)) -> (B, N, num_classes)
 """
 import torch.nn as nn
+import torch.nn.functional as F
 
+from . import fused
 from . import pytorch_utils as pt_utils
 from .pointnet2_modules import PointnetFPModule, PointnetSAModule, PointnetSAModuleMSG
 
@@ -88,10 +90,40 @@ class _Pointnet2SemSeg(nn.Module):
             nxt_xyz, nxt_feat = sa(l_xyz[-1], l_features[-1])
             l_xyz.append(nxt_xyz)
             l_features.append(nxt_feat)
-        for i in range(-1, -(len(self.FP_modules) + 1), -1):  # coarse -> fine
+        nfp = len(self.FP_modules)
+        for i in range(-1, -nfp, -1):  # coarse -> fine, all but the finest level
             l_features[i - 1] = self.FP_modules[i](
                 l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i])
+        fp0 = self.FP_modules[0]
+        if self._head_rows_ok(l_features[1]):
+            # finest FP level and the classifier head stay in [points, channels] rows: the head's
+            # output rows ARE the (B, N, num_classes) result, no transpose anywhere
+            rows = fp0.forward_rows(l_xyz[0], l_xyz[1], l_features[0], l_features[1])
+            return self._head_rows(rows)
+        l_features[0] = fp0(l_xyz[0], l_xyz[1], l_features[0], l_features[1])
         return self.cls_layer(l_features[0]).transpose(1, 2).contiguous()
+
+    def _head_rows_ok(self, known_feats):
+        units = [m for m in self.cls_layer if not isinstance(m, nn.Dropout)]
+        return (fused.mlp_eligible(units, known_feats) and fused.mlp_eligible(self.FP_modules[0].mlp, known_feats)
+                and known_feats.size(1) % 4 == 0)
+
+    def _head_rows(self, rows):
+        """cls_layer (Conv1d+BN+ReLU, Dropout, Conv1d+BN -- ref :152-159) on (B, N, C) rows."""
+        B, N, C = rows.shape
+        x = rows.reshape(B * N, C)
+        run = []
+        for m in self.cls_layer:
+            if isinstance(m, nn.Dropout):
+                if run:
+                    x = fused.run_mlp_rows(run, x, 0)
+                    run = []
+                x = F.dropout(x, m.p, self.training)
+            else:
+                run.append(m)
+        if run:
+            x = fused.run_mlp_rows(run, x, 0)
+        return x.view(B, N, -1)
 
 
 class Pointnet2SSG(_Pointnet2SemSeg):

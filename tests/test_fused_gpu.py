@@ -1,0 +1,175 @@
+"""GPU parity of the fused shared-MLP blocks (rows layout, csrc/mlp_rows.cu + GEMM) against
+the SAME module run through the reference's formulation (torch.nn Conv2d + BatchNorm2d +
+ReLU + max_pool2d on (B, C, npoint, nsample)).
+
+Tolerances.  With fp32 GEMMs on both sides (TF32 off) the two paths differ only by
+summation order: outputs, input gradients and parameter gradients within 2e-4 of the
+tensor's max magnitude, BatchNorm running statistics within 1e-5.  With TF32 GEMMs (the
+reference's default arithmetic for its convs) the bar is 5e-3 of the max magnitude.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from pointnet2.scannet_b200 import fused, pointnet2_modules as M, pointnet2_semseg
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+
+
+class precision(object):
+    def __init__(self, tf32):
+        self.tf32 = tf32
+
+    def __enter__(self):
+        self.saved = (fused.GEMM_TF32, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        fused.GEMM_TF32 = self.tf32
+        torch.backends.cudnn.allow_tf32 = self.tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.tf32
+
+    def __exit__(self, *a):
+        fused.GEMM_TF32, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.saved
+
+
+def run(module, enabled, *inputs, train=True):
+    module = copy.deepcopy(module)
+    module.train(train)
+    ins = [i.clone().requires_grad_(r) for i, r in inputs]
+    fused.ENABLED = enabled
+    try:
+        out = module(*ins)
+        out = out[1] if isinstance(out, tuple) else out
+        torch.manual_seed(1)
+        w = torch.randn_like(out)
+        (out * w).sum().backward()
+    finally:
+        fused.ENABLED = True
+    grads = {n: p.grad for n, p in module.named_parameters()}
+    bufs = {n: b.clone() for n, b in module.named_buffers()}
+    in_grads = [i.grad if i.requires_grad else None for i in ins]
+    return out.detach(), grads, bufs, in_grads
+
+
+def compare(module, inputs, tol, stat_tol):
+    out_f, g_f, b_f, ig_f = run(module, True, *inputs)
+    out_r, g_r, b_r, ig_r = run(module, False, *inputs)
+    assert out_f.shape == out_r.shape
+    assert rel_err(out_f, out_r) < tol, "output %g" % rel_err(out_f, out_r)
+    for n in g_r:
+        assert rel_err(g_f[n], g_r[n]) < tol, "grad %s %g" % (n, rel_err(g_f[n], g_r[n]))
+    for n in b_r:
+        if b_r[n].dtype == torch.long:
+            assert torch.equal(b_f[n], b_r[n]), n
+        else:
+            assert rel_err(b_f[n], b_r[n]) < stat_tol, "buffer %s %g" % (n, rel_err(b_f[n], b_r[n]))
+    for a, b in zip(ig_f, ig_r):
+        if b is not None:
+            assert rel_err(a, b) < tol, "input grad %g" % rel_err(a, b)
+
+
+def sa_inputs(B, N, C, seed=0):
+    xyz, full = cases.chunk_xyz(B, npoints=N, first=seed)
+    rng = np.random.default_rng(seed)
+    feats = rng.standard_normal((B, C, N)).astype(np.float32)
+    return [(cases.t(xyz, DEV), False), (cases.t(feats, DEV), True)]
+
+
+def test_sa_module_ssg():
+    torch.manual_seed(0)
+    sa = M.PointnetSAModule(npoint=256, radius=0.2, nsample=32, mlp=[6, 32, 32, 64]).to(DEV)
+    with precision(False):
+        compare(sa, sa_inputs(2, 2048, 6), 2e-4, 1e-5)
+
+
+def test_sa_module_tf32_error_is_the_references_class():
+    """TF32 GEMMs: the fused path's deviation from the fp32 result must be of the size of the
+    deviation the reference's own formulation shows when ITS convs run in TF32 (the torch
+    default): no worse than 3x that, or 5e-3 of the max magnitude, whichever is larger."""
+    torch.manual_seed(0)
+    sa = M.PointnetSAModule(npoint=256, radius=0.2, nsample=32, mlp=[6, 32, 32, 64]).to(DEV)
+    ins = sa_inputs(2, 2048, 6)
+    with precision(False):
+        out_t, g_t, _, ig_t = run(sa, False, *ins)
+    with precision(True):
+        out_f, g_f, _, ig_f = run(sa, True, *ins)
+        out_r, g_r, _, ig_r = run(sa, False, *ins)
+    pairs = [(out_f, out_r, out_t)] + [(g_f[n], g_r[n], g_t[n]) for n in g_t] + [(ig_f[1], ig_r[1], ig_t[1])]
+    for f, r, t in pairs:
+        assert rel_err(f, t) <= max(3 * rel_err(r, t), 5e-3), (rel_err(f, t), rel_err(r, t))
+
+
+def test_sa_module_msg_odd_widths():
+    torch.manual_seed(0)
+    sa = M.PointnetSAModuleMSG(npoint=128, radii=[0.1, 0.2], nsamples=[16, 32],
+                               mlps=[[64, 64, 96, 128], [64, 128, 196, 256]]).to(DEV)
+    with precision(False):
+        compare(sa, sa_inputs(2, 1024, 64, seed=3), 2e-4, 1e-5)
+
+
+def test_fp_module():
+    torch.manual_seed(0)
+    fp = M.PointnetFPModule(mlp=[128 + 6, 128, 128]).to(DEV)
+    xyz, _ = cases.chunk_xyz(2, npoints=2048)
+    unknown = cases.t(xyz, DEV)
+    known = unknown[:, :256].contiguous()
+    rng = np.random.default_rng(1)
+    uf = cases.t(rng.standard_normal((2, 6, 2048)).astype(np.float32), DEV)
+    kf = cases.t(rng.standard_normal((2, 128, 256)).astype(np.float32), DEV)
+    with precision(False):
+        compare(fp, [(unknown, False), (known, False), (uf, True), (kf, True)], 2e-4, 1e-5)
+
+
+def test_eval_mode_uses_running_stats():
+    torch.manual_seed(0)
+    sa = M.PointnetSAModule(npoint=64, radius=0.3, nsample=16, mlp=[6, 16, 32]).to(DEV)
+    for m in sa.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(), m.running_var.uniform_(0.5, 2.0)
+    ins = sa_inputs(2, 512, 6)
+    with precision(False), torch.no_grad():
+        out_f = run_noback(sa, True, ins)
+        out_r = run_noback(sa, False, ins)
+    assert rel_err(out_f, out_r) < 2e-4
+
+
+def run_noback(module, enabled, inputs):
+    module = copy.deepcopy(module).eval()
+    fused.ENABLED = enabled
+    try:
+        return module(*[i for i, _ in inputs])[1]
+    finally:
+        fused.ENABLED = True
+
+
+def test_full_ssg_model_step_matches_unfused():
+    """Whole SSG network, one forward/backward: fused vs torch.nn formulation."""
+    torch.manual_seed(0)
+    model = pointnet2_semseg.get_model(20, is_msg=False, input_channels=6).to(DEV)
+    x, _, _ = __import__("pointnet2.scannet_b200.synthetic", fromlist=["x"]).make_batch(2, 2, 8192)
+    pc = cases.t(x, DEV)
+    with precision(False):
+        outs = []
+        for enabled in (True, False):
+            m = copy.deepcopy(model).train()
+            m.cls_layer[1].p = 0.0  # the dropout mask is drawn per layout; keep the comparison deterministic
+            fused.ENABLED = enabled
+            try:
+                torch.manual_seed(5)  # dropout mask
+                logits = m(pc)
+                torch.manual_seed(6)
+                (logits * torch.randn_like(logits)).sum().backward()  # (a mean of squares after the
+                # final BatchNorm would be constant: every gradient would be rounding noise)
+            finally:
+                fused.ENABLED = True
+            outs.append((logits.detach(), {n: p.grad for n, p in m.named_parameters()}))
+    (lf, gf), (lr, gr) = outs
+    assert rel_err(lf, lr) < 1e-3, rel_err(lf, lr)
+    worst = max(rel_err(gf[n], gr[n]) for n in gr)
+    assert worst < 5e-3, worst
