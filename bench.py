@@ -51,6 +51,7 @@ def parse():
     p.add_argument("--npoints", type=int, default=8192)
     p.add_argument("--msg", action="store_true", help="MSG model (BASELINE configs[2]) instead of SSG")
     p.add_argument("--multiview", action="store_true", help="xyz+normal+128 features (configs[4])")
+    p.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of from a CUDA graph")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-per-op", action="store_true")
     p.add_argument("--cpu-sample-chunks", type=int, default=2)
@@ -149,12 +150,12 @@ def host_batches(args, rank, count):
     return out, synthetic.input_channels(**kw)
 
 
-def build_step(args, in_ch, device):
+def build_step(args, in_ch, device, capturable=False):
     from pointnet2.scannet_b200 import pointnet2_semseg, train
     torch.manual_seed(0)  # same replica on every rank
     model = pointnet2_semseg.get_model(NUM_CLASSES, is_msg=args.msg, input_channels=in_ch).to(device)
     model.train()
-    return train.TrainStep(model, lr=1e-3)
+    return train.TrainStep(model, lr=1e-3, capturable=capturable)
 
 
 def time_steps(step, batches, steps, world, e2e):
@@ -162,8 +163,8 @@ def time_steps(step, batches, steps, world, e2e):
     dev_batches = None
     if not e2e:
         dev_batches = [tuple(t.cuda(non_blocking=True) for t in b) for b in batches]
-    else:
-        stage = tuple(torch.empty_like(t, device="cuda") for t in batches[0])
+    else:  # a graphed step owns static input buffers: copy host batches straight into them
+        stage = getattr(step, "static", None) or tuple(torch.empty_like(t, device="cuda") for t in batches[0])
     barrier_sync(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -224,9 +225,19 @@ def run_product(args, world, rank, local):
     lib.load()  # fail loudly if the CUDA extension is missing
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU path")
+    from pointnet2.scannet_b200 import train
     batches, in_ch = host_batches(args, rank, 4)
-    step = build_step(args, in_ch, "cuda")
+    eager = build_step(args, in_ch, "cuda", capturable=not args.no_graph)
     dev = [tuple(t.cuda() for t in b) for b in batches]
+    step, launch_mode = eager, "eager"
+    if not args.no_graph:
+        try:  # single GPU: the whole step; DP: forward+backward in the graph, NCCL + Adam after it
+            step = train.GraphedTrainStep(eager, dev[0], scope="step" if world == 1 else "fwd_bwd")
+            launch_mode = "cuda-graph(%s)" % step.scope
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write("CUDA graph capture failed, running eagerly: %r\n" % (e,))
+            torch.cuda.synchronize()
+            step, launch_mode = eager, "eager (graph capture failed)"
     for i in range(args.warmup):
         step(*dev[i % len(dev)])
     torch.cuda.synchronize()
@@ -237,6 +248,12 @@ def run_product(args, world, rank, local):
     lib.reset_launch_count()
     ms, loss = time_steps(step, batches, args.steps, world, e2e=False)
     launches = lib.launch_count()
+    if launch_mode.startswith("cuda-graph"):
+        # replayed kernels do not pass through the library's launchers: count them once, eagerly
+        lib.reset_launch_count()
+        eager.forward_backward(*dev[0])
+        torch.cuda.synchronize()
+        launches = lib.launch_count() * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = time_steps(step, batches, args.steps, world, e2e=True)
 
@@ -252,7 +269,7 @@ def run_product(args, world, rank, local):
                             2 if args.msg else 1, "MSG" if args.msg else "SSG",
                             " + NCCL grad all-reduce" if world > 1 else "", args.batch, args.npoints, in_ch),
             "per_gpu_batch": args.batch, "global_batch": args.batch * world, "npoints": args.npoints,
-            "parallelism": "dp%d" % world,
+            "parallelism": "dp%d" % world, "launch": launch_mode,
             "mlp": "torch.nn conv1x1+BN+ReLU (cuDNN/cuBLAS, cudnn.allow_tf32=%s as in the reference)"
                    % torch.backends.cudnn.allow_tf32,
             "l2": "no explicit flush: one step streams several GB of activations, far above the 126 MB L2; "
@@ -280,7 +297,7 @@ def run_product(args, world, rank, local):
         nprof = min(args.steps, 5)
         with profiling.ExtTimer() as timer:
             for i in range(nprof):
-                step(*dev[i % len(dev)])
+                eager(*dev[i % len(dev)])
         rows = timer.summary(nprof)
         for r in rows:
             r["frac_of_hbm_peak"] = round(r["gbs"] / peak, 4) if r["gbs"] else None

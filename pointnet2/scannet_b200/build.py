@@ -49,7 +49,19 @@ def _compile(src, force, verbose):
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("nvcc failed on %s:\n%s\n%s" % (src, p.stdout, p.stderr))
+    if os.path.basename(src) in NO_FMA:
+        _assert_no_contraction(obj)
     return obj, p.stderr
+
+
+def _assert_no_contraction(obj):
+    """Index parity depends on un-contracted fp32 distances: the only fused multiply-adds allowed
+    in these objects are the packed squares written as fma(d, d, +0) (addend RZ)."""
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    bad = [l for l in sass.splitlines()
+           if (" FFMA " in l or " FFMA2 " in l or " FFMA." in l) and "RZ" not in l.split(";")[0].split(",")[-1]]
+    if bad:
+        raise RuntimeError("contracted FMA in %s:\n%s" % (obj, "\n".join(bad[:5])))
 
 
 def build(force=False, verbose=False):

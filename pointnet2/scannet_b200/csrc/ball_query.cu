@@ -4,11 +4,11 @@
 // (/root/reference/pointnet2/_ext_src/src/ball_query_gpu.cu:9-54): one CTA per
 // cloud, one THREAD per centre scanning up to n points from global memory.
 //
-// Here a WARP owns a centre: 32 lanes test 32 consecutive points,
-// __ballot_sync + popc ranks the hits in ascending index order (the
-// reference's order), and the warp leaves the scan as soon as nsample hits are
-// found -- per centre, not per slowest-of-32-centres as in a thread-per-centre
-// layout.  The result row is assembled in shared memory and written with one
+// Here a WARP owns four centres: 32 lanes test 32 consecutive points against
+// all four (packed fp32: two distances per instruction), __ballot_sync + popc
+// ranks the hits in ascending index order (the reference's order), and the warp
+// leaves the scan as soon as its centres have nsample hits each -- not when
+// the slowest of 32 centres has, as in a thread-per-centre layout.  The result row is assembled in shared memory and written with one
 // coalesced store, including the reference's padding (first hit repeated; all
 // zeros when the ball is empty, ball_query.cpp:19-21 + ball_query_gpu.cu:34-38).
 //
@@ -20,7 +20,7 @@
 
 namespace pn2 {
 
-constexpr int kBqThreads = 256;
+constexpr int kBqThreads = 512;
 constexpr int kBqWarps = kBqThreads / 32;
 constexpr int kBqStagePts = 8192;  // 96 KB -> two CTAs resident per SM
 
@@ -31,24 +31,46 @@ struct BqParams {
   float radius2;
 };
 
-// Scan points [0, n) of `pts` (shared or global, (n,3) fp32) for centre q.
-// On return row[0..min(cnt,nsample)) holds the hits in ascending index order.
-__device__ __forceinline__ void bq_scan(const float *pts, int n, float qx, float qy,
-                                        float qz, float radius2, int nsample,
-                                        int lane, int *row, int &cnt, int &first) {
-  cnt = 0, first = 0;
-  for (int base = 0; base < n && cnt < nsample; base += 32) {
+constexpr int kBqQ = 4;  // centres a warp tests against every point it loads
+
+// A warp scans points [0, n) of `pts` (shared or global, (n,3) fp32) for kBqQ centres at
+// once: each lane loads ONE point per step and evaluates it against the four centres with
+// two packed distance evaluations (centres 0|1 and 2|3 share an instruction), so the point
+// load, the loop and the address arithmetic are amortised 4x.  rows[q][0..min(cnt,nsample))
+// receive the hits of centre q in ascending index order.
+__device__ __forceinline__ void bq_scan4(const float *pts, int n, const float2 (&qx)[2],
+                                         const float2 (&qy)[2], const float2 (&qz)[2], float radius2,
+                                         int nsample, int nq, int lane, int *rows, int (&cnt)[kBqQ],
+                                         int (&first)[kBqQ]) {
+#pragma unroll
+  for (int q = 0; q < kBqQ; ++q) cnt[q] = q < nq ? 0 : nsample, first[q] = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int base = 0; base < n; base += 32) {
     const int k = base + lane;
-    bool hit = false;
-    if (k < n)
-      hit = sqdist_rn(qx, qy, qz, pts[3 * k], pts[3 * k + 1], pts[3 * k + 2]) < radius2;
-    const unsigned mask = __ballot_sync(0xffffffffu, hit);
-    if (mask) {
-      if (cnt == 0) first = base + __ffs(mask) - 1;
-      const int rank = cnt + __popc(mask & ((1u << lane) - 1u));
-      if (hit && rank < nsample) row[rank] = k;
-      cnt += __popc(mask);
+    const bool in = k < n;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (in) px = pts[3 * k], py = pts[3 * k + 1], pz = pts[3 * k + 2];
+    const float2 p2x = make_float2(px, px), p2y = make_float2(py, py), p2z = make_float2(pz, pz);
+    const float2 d01 = sqdist2_rn(qx[0], qy[0], qz[0], p2x, p2y, p2z);
+    const float2 d23 = sqdist2_rn(qx[1], qy[1], qz[1], p2x, p2y, p2z);
+    const bool h0 = in && d01.x < radius2, h1 = in && d01.y < radius2;
+    const bool h2 = in && d23.x < radius2, h3 = in && d23.y < radius2;
+    // hits are rare (tens per centre among thousands of points): one vote decides the step
+    if (!__any_sync(0xffffffffu, h0 | h1 | h2 | h3)) continue;
+    const bool hit[kBqQ] = {h0, h1, h2, h3};
+    bool open = false;
+#pragma unroll
+    for (int q = 0; q < kBqQ; ++q) {
+      const unsigned mask = __ballot_sync(0xffffffffu, hit[q]);
+      if (mask && cnt[q] < nsample) {
+        if (cnt[q] == 0) first[q] = base + __ffs(mask) - 1;
+        const int rank = cnt[q] + __popc(mask & lt);
+        if (hit[q] && rank < nsample) rows[q * nsample + rank] = k;
+        cnt[q] += __popc(mask);
+      }
+      open |= cnt[q] < nsample;
     }
+    if (!open) break;  // every centre of this warp has its nsample hits
   }
 }
 
@@ -66,7 +88,7 @@ ball_query_kernel(BqParams p, const float *__restrict__ new_xyz,
   const float *pts = xyz + static_cast<size_t>(cloud) * p.n * 3;
   const float *ctr = new_xyz + static_cast<size_t>(cloud) * p.m * 3;
   int *out = idx + static_cast<size_t>(cloud) * p.m * p.nsample;
-  int *row = s_rows + warp * p.nsample;
+  int *rows = s_rows + warp * kBqQ * p.nsample;
 
   if (kStaged && p.n > 0) {
     const uint32_t bytes = static_cast<uint32_t>(p.n) * 12u;
@@ -89,14 +111,28 @@ ball_query_kernel(BqParams p, const float *__restrict__ new_xyz,
 
   const int c_begin = blockIdx.x * p.centres_per_cta;
   const int c_end = min(c_begin + p.centres_per_cta, p.m);
-  for (int j = c_begin + warp; j < c_end; j += kBqWarps) {
-    const float qx = __ldg(ctr + 3 * j), qy = __ldg(ctr + 3 * j + 1), qz = __ldg(ctr + 3 * j + 2);
-    int cnt, first;
-    bq_scan(src, p.n, qx, qy, qz, p.radius2, p.nsample, lane, row, cnt, first);
+  for (int j0 = c_begin + warp * kBqQ; j0 < c_end; j0 += kBqWarps * kBqQ) {
+    const int nq = min(kBqQ, c_end - j0);
+    float c[kBqQ][3];
+#pragma unroll
+    for (int q = 0; q < kBqQ; ++q) {
+      const int j = j0 + (q < nq ? q : 0);
+      c[q][0] = __ldg(ctr + 3 * j), c[q][1] = __ldg(ctr + 3 * j + 1), c[q][2] = __ldg(ctr + 3 * j + 2);
+    }
+    const float2 qx[2] = {make_float2(c[0][0], c[1][0]), make_float2(c[2][0], c[3][0])};
+    const float2 qy[2] = {make_float2(c[0][1], c[1][1]), make_float2(c[2][1], c[3][1])};
+    const float2 qz[2] = {make_float2(c[0][2], c[1][2]), make_float2(c[2][2], c[3][2])};
+    int cnt[kBqQ], first[kBqQ];
+    bq_scan4(src, p.n, qx, qy, qz, p.radius2, p.nsample, nq, lane, rows, cnt, first);
     __syncwarp();
-    int *dst = out + static_cast<size_t>(j) * p.nsample;
-    const int filled = min(cnt, p.nsample);
-    for (int l = lane; l < p.nsample; l += 32) dst[l] = l < filled ? row[l] : first;
+#pragma unroll
+    for (int q = 0; q < kBqQ; ++q) {
+      if (q < nq) {
+        int *dst = out + static_cast<size_t>(j0 + q) * p.nsample;
+        const int filled = min(cnt[q], p.nsample);
+        for (int l = lane; l < p.nsample; l += 32) dst[l] = l < filled ? rows[q * p.nsample + l] : first[q];
+      }
+    }
     __syncwarp();
   }
 }
@@ -111,21 +147,22 @@ extern "C" int pn2_query_ball_point(int b, int n, int m, float radius,
   if (b == 0 || m == 0 || nsample == 0) return PN2_OK;
   PN2_CHECK_PTRS(new_xyz, idx);
   if (n > 0) PN2_CHECK_PTRS(xyz);
-  if (nsample > 2048 || b > 65535) return PN2_ERR_UNSUPPORTED;
+  if (nsample > 512 || b > 65535) return PN2_ERR_UNSUPPORTED;
 
   BqParams p;
   p.n = n, p.m = m, p.nsample = nsample;
   p.radius2 = radius * radius;  // fp32 product, ball_query_gpu.cu:22
-  // two CTAs resident per SM; at least one centre per warp of a CTA
-  int ctas_per_cloud = (2 * kNumSMs + b - 1) / b;
-  const int max_ctas = (m + kBqWarps - 1) / kBqWarps;
+  // one wave: at most two CTAs resident per SM (shared-memory stage), never a second, partial wave
+  int ctas_per_cloud = 2 * kNumSMs / b;
+  if (ctas_per_cloud < 1) ctas_per_cloud = 1;
+  const int max_ctas = (m + kBqWarps * kBqQ - 1) / (kBqWarps * kBqQ);
   if (ctas_per_cloud > max_ctas) ctas_per_cloud = max_ctas;
   p.centres_per_cta = (m + ctas_per_cloud - 1) / ctas_per_cloud;
   ctas_per_cloud = (m + p.centres_per_cta - 1) / p.centres_per_cta;
 
   const bool staged = n <= kBqStagePts;
   p.stage_floats = staged ? (3 * n + 3) / 4 * 4 : 0;  // keeps the row buffers 16-byte aligned
-  const size_t smem = sizeof(float) * p.stage_floats + sizeof(int) * kBqWarps * nsample;
+  const size_t smem = sizeof(float) * p.stage_floats + sizeof(int) * kBqWarps * kBqQ * nsample;
   auto kern = staged ? ball_query_kernel<true> : ball_query_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));

@@ -83,11 +83,14 @@ fps_resident_kernel(FpsGeom g, const float *__restrict__ dataset,
   const float *pts = dataset + static_cast<size_t>(blockIdx.x) * g.n * 3;
   int *out = idxs + static_cast<size_t>(blockIdx.x) * g.m;
 
-  float x[P], y[P], z[P], t[P];
+  // points are held as PAIRS (slots 2h, 2h+1 of this thread) so that one packed FADD2/FFMA2
+  // updates two running minima; odd P (= 1) keeps a dummy second half
+  constexpr int H = (P + 1) / 2;
+  float2 x[H], y[H], z[H], t[H];
 #pragma unroll
-  for (int i = 0; i < P; ++i) {
+  for (int i = 0; i < 2 * H; ++i) {
     const int p = tid * P + i;
-    const int k = p < npos ? fps_pos_to_index(p, g) : g.n;
+    const int k = (i < P && p < npos) ? fps_pos_to_index(p, g) : g.n;
     float px = 0.f, py = 0.f, pz = 0.f;
     bool live = false;
     if (k < g.n) {
@@ -96,26 +99,33 @@ fps_resident_kernel(FpsGeom g, const float *__restrict__ dataset,
       pz = __ldg(pts + 3 * k + 2);
       live = !(static_cast<double>(sqnorm_rn(px, py, pz)) <= 1e-3);
     }
-    x[i] = px, y[i] = py, z[i] = pz;
-    t[i] = live ? 1e10f : -1.0f;
-    if (p < npos) s_pts[p] = make_float4(px, py, pz, __int_as_float(k < g.n ? k : 0));
+    const float t0 = live ? 1e10f : -1.0f;
+    if (i & 1) x[i / 2].y = px, y[i / 2].y = py, z[i / 2].y = pz, t[i / 2].y = t0;
+    else x[i / 2].x = px, y[i / 2].x = py, z[i / 2].x = pz, t[i / 2].x = t0;
+    if (i < P && p < npos) s_pts[p] = make_float4(px, py, pz, __int_as_float(k < g.n ? k : 0));
   }
   if (tid == 0) out[0] = 0;
   __syncthreads();
 
   float4 c = s_pts[0];  // position 0 <-> index 0
   for (int j = 1; j < g.m; ++j) {
+    const float2 cx = make_float2(c.x, c.x), cy = make_float2(c.y, c.y), cz = make_float2(c.z, c.z);
     float best;
     int bi = 0;
 #pragma unroll
-    for (int i = 0; i < P; ++i) {
-      const float d = sqdist_rn(x[i], y[i], z[i], c.x, c.y, c.z);
-      t[i] = fminf(d, t[i]);
-      if (i == 0) {
-        best = t[0];
-      } else if (t[i] > best) {  // strict: lowest position of a thread's ties
-        best = t[i];
-        bi = i;
+    for (int h = 0; h < H; ++h) {
+      const float2 d = sqdist2_rn(x[h], y[h], z[h], cx, cy, cz);
+      t[h].x = fminf(d.x, t[h].x);
+      t[h].y = fminf(d.y, t[h].y);
+      if (h == 0) {
+        best = t[0].x;
+      } else if (t[h].x > best) {  // strict: lowest position of a thread's ties
+        best = t[h].x;
+        bi = 2 * h;
+      }
+      if (2 * h + 1 < P && t[h].y > best) {
+        best = t[h].y;
+        bi = 2 * h + 1;
       }
     }
     const unsigned win =

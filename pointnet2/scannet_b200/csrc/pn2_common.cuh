@@ -26,6 +26,42 @@ __device__ __forceinline__ float sqdist_rn(float ax, float ay, float az,
                    __fmul_rn(dz, dz));
 }
 
+// ---- two distances per instruction: Blackwell packed fp32 (FADD2 / FFMA2) ------------
+// Same IEEE operations as sqdist_rn on each half, so the results are bit-identical.  The
+// squares are written as fma(d, d, +0): ptxas fuses a packed mul.rn + add.rn pair into one
+// FFMA2 even with --fmad=false (which would skip a rounding), but it cannot fuse an fma
+// into an add, and fma(d, d, +0) rounds exactly like mul(d, d).  build.py checks the SASS.
+__device__ __forceinline__ float2 sub2_rn(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; "
+      "mov.b64 {%0,%1}, rc;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; "
+      "mov.b64 {%0,%1}, rc;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 sq2_rn(float2 a) {
+  float2 r;
+  asm("{.reg .b64 ra, rz, rc; mov.b64 ra, {%2,%3}; mov.b64 rz, {%4,%4}; fma.rn.f32x2 rc, ra, ra, rz; "
+      "mov.b64 {%0,%1}, rc;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(0.0f));
+  return r;
+}
+// (ax.x,ay.x,az.x)-(bx.x,..) and (ax.y,..)-(bx.y,..): ((dx*dx)+(dy*dy))+(dz*dz) per half
+__device__ __forceinline__ float2 sqdist2_rn(float2 ax, float2 ay, float2 az, float2 bx,
+                                             float2 by, float2 bz) {
+  const float2 dx = sub2_rn(ax, bx), dy = sub2_rn(ay, by), dz = sub2_rn(az, bz);
+  return add2_rn(add2_rn(sq2_rn(dx), sq2_rn(dy)), sq2_rn(dz));
+}
+
 __device__ __forceinline__ float sqnorm_rn(float x, float y, float z) {
   return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)),
                    __fmul_rn(z, z));

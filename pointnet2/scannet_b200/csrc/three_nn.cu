@@ -6,8 +6,9 @@
 // fp64 compares (running bests are `double`, :27).
 //
 // Here the grid covers (query tile, cloud); the known points are staged in
-// shared memory by a 1-D TMA bulk copy, tile by tile, and every lane reads the
-// same known point (one broadcast LDS per coordinate) while owning one query.
+// shared memory tile by tile, re-laid out as pairs [x0 x1 y0 y1 z0 z1]; every lane
+// owns one query and reads the same pair (broadcast LDS.64), evaluating both
+// distances with packed fp32 instructions.
 // The compares are fp32: a float candidate compared with a double that holds
 // either 1e40 or an earlier float candidate orders exactly like the same
 // compare in fp32 against +inf -- and (float)1e40, which the reference stores
@@ -25,8 +26,7 @@ __global__ void __launch_bounds__(kNnThreads)
 three_nn_kernel(int n, int m, const float *__restrict__ unknown,
                 const float *__restrict__ known, float *__restrict__ dist2,
                 int *__restrict__ idx) {
-  extern __shared__ __align__(16) float s_known[];  // [min(m, kNnTilePts)][3]
-  __shared__ uint64_t s_bar;
+  extern __shared__ __align__(16) float s_known[];  // [ceil(min(m, kNnTilePts) / 2)][6]
 
   const int tid = threadIdx.x;
   const int cloud = blockIdx.y;
@@ -40,43 +40,45 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown,
   float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
   int i1 = 0, i2 = 0, i3 = 0;
 
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  uint32_t phase = 0;
+  // known points are staged as PAIRS in structure-of-arrays form, [x0 x1 y0 y1 z0 z1] per pair,
+  // so that three LDS.64 deliver the register pairs the packed distance evaluation consumes
   for (int t0 = 0; t0 < m; t0 += kNnTilePts) {
     const int tn = min(kNnTilePts, m - t0);
     const float *src = kn + static_cast<size_t>(t0) * 3;
-    const uint32_t bytes = static_cast<uint32_t>(tn) * 12u;
     if (t0 > 0) __syncthreads();  // previous tile fully consumed
-    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0 && bytes % 16u == 0) {
-      if (tid == 0) {
-        mbar_expect_tx(&s_bar, bytes);
-        tma_load_1d(s_known, src, bytes, &s_bar);
-      }
-      mbar_wait(&s_bar, phase);
-      phase ^= 1u;
-    } else {
-      for (int i = tid; i < tn * 3; i += kNnThreads) s_known[i] = __ldg(src + i);
-      __syncthreads();
+    for (int i = tid; i < tn * 3; i += kNnThreads) {
+      const int k = i / 3, c = i - 3 * k;
+      s_known[6 * (k >> 1) + 2 * c + (k & 1)] = __ldg(src + i);
     }
+    if (tn & 1) {  // odd tail: duplicate the last point into the unused half (re-insertion of an
+      if (tid < 3) s_known[6 * (tn >> 1) + 2 * tid + 1] = __ldg(src + 3 * (tn - 1) + tid);  // equal
+    }                                                                 // (d, later index) is a no-op)
+    __syncthreads();
+    const float2 u2x = make_float2(ux, ux), u2y = make_float2(uy, uy), u2z = make_float2(uz, uz);
+    const int pairs = (tn + 1) >> 1;
 #pragma unroll 4
-    for (int k = 0; k < tn; ++k) {
-      const float d = sqdist_rn(ux, uy, uz, s_known[3 * k], s_known[3 * k + 1], s_known[3 * k + 2]);
-      if (d < b3) {  // interpolate_gpu.cu:34-49, slots kept sorted, strict '<'
-        const int kk = t0 + k;
-        if (d < b1) {
-          b3 = b2, i3 = i2;
-          b2 = b1, i2 = i1;
-          b1 = d, i1 = kk;
-        } else if (d < b2) {
-          b3 = b2, i3 = i2;
-          b2 = d, i2 = kk;
-        } else {
-          b3 = d, i3 = kk;
+    for (int h = 0; h < pairs; ++h) {
+      const float2 kx = *reinterpret_cast<const float2 *>(s_known + 6 * h);
+      const float2 ky = *reinterpret_cast<const float2 *>(s_known + 6 * h + 2);
+      const float2 kz = *reinterpret_cast<const float2 *>(s_known + 6 * h + 4);
+      const float2 d = sqdist2_rn(u2x, u2y, u2z, kx, ky, kz);
+      if (fminf(d.x, d.y) < b3) {  // rare after the first few dozen points
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {  // ascending index order, as the reference scans
+          const float dd = e ? d.y : d.x;
+          const int kk = min(t0 + 2 * h + e, t0 + tn - 1);
+          if (dd < b3 && !(e == 1 && 2 * h + 1 >= tn)) {  // interpolate_gpu.cu:34-49, strict '<'
+            if (dd < b1) {
+              b3 = b2, i3 = i2;
+              b2 = b1, i2 = i1;
+              b1 = dd, i1 = kk;
+            } else if (dd < b2) {
+              b3 = b2, i3 = i2;
+              b2 = dd, i2 = kk;
+            } else {
+              b3 = dd, i3 = kk;
+            }
+          }
         }
       }
     }
@@ -100,7 +102,7 @@ extern "C" int pn2_three_nn(int b, int n, int m, const float *unknown,
   PN2_CHECK_PTRS(unknown, dist2, idx);
   if (m > 0) PN2_CHECK_PTRS(known);
   if (b > 65535) return PN2_ERR_UNSUPPORTED;
-  const size_t smem = sizeof(float) * 3 * static_cast<size_t>(m < kNnTilePts ? m : kNnTilePts);
+  const size_t smem = sizeof(float) * 6 * ((static_cast<size_t>(m < kNnTilePts ? m : kNnTilePts) + 1) / 2);
   cudaError_t e = cudaFuncSetAttribute(three_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(sizeof(float) * 3 * kNnTilePts));
   if (e != cudaSuccess) return static_cast<int>(e);

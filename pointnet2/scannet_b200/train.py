@@ -60,14 +60,26 @@ class GradBucket(object):
 class TrainStep(object):
     """One optimisation step on a (B, N, 3+C) batch; call it with device tensors."""
 
-    def __init__(self, model, lr=1e-3, weight_decay=0.0, group=None, fused_adam=None):
+    def __init__(self, model, lr=1e-3, weight_decay=0.0, group=None, fused_adam=None, capturable=False):
         self.model = model
         self.group = group
         self.bucket = GradBucket(model.parameters())
         if fused_adam is None:
             fused_adam = self.bucket.flat.is_cuda
         self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, weight_decay=weight_decay,
-                                          fused=fused_adam)
+                                          fused=fused_adam, capturable=capturable)
+
+    def forward_backward(self, pointcloud, targets, weights):
+        self.bucket.zero()
+        logits = self.model(pointcloud)
+        loss = weighted_cross_entropy(logits.reshape(-1, logits.size(-1)),
+                                      targets.reshape(-1), weights.reshape(-1))
+        loss.backward()
+        return loss
+
+    def reduce_and_update(self):
+        self.bucket.all_reduce_mean(self.group)
+        self.optimizer.step()
 
     def __call__(self, pointcloud, targets, weights):
         self.bucket.zero()
@@ -78,3 +90,45 @@ class TrainStep(object):
         self.bucket.all_reduce_mean(self.group)
         self.optimizer.step()
         return loss
+
+
+class GraphedTrainStep(object):
+    """The same step replayed from a CUDA graph: the ~470 kernel launches of one SSG step
+    (libpn2_b200.so kernels, cuBLAS GEMMs, the fused Adam) become one graph launch, which removes
+    the host launch gaps between the many short kernels of the coarse levels.
+
+    ``scope="step"`` captures forward + backward + all-reduce + Adam (single GPU, or NCCL in the
+    graph); ``scope="fwd_bwd"`` captures forward + backward only and runs the gradient all-reduce
+    and Adam eagerly after the replay.  Inputs are copied into static device buffers."""
+
+    def __init__(self, step, example, scope="step", warmup=3):
+        assert scope in ("step", "fwd_bwd")
+        self.step, self.scope = step, scope
+        self.static = tuple(torch.empty_like(t) for t in example)
+        for s, t in zip(self.static, example):
+            s.copy_(t)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # allocator / cuBLAS workspaces / lazy inits outside capture
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+
+    def _body(self):
+        loss = self.step.forward_backward(*self.static)
+        if self.scope == "step":
+            self.step.reduce_and_update()
+        return loss
+
+    def __call__(self, pointcloud, targets, weights):
+        for s, t in zip(self.static, (pointcloud, targets, weights)):
+            if s.data_ptr() != t.data_ptr():
+                s.copy_(t, non_blocking=True)
+        self.graph.replay()
+        if self.scope == "fwd_bwd":
+            self.step.reduce_and_update()
+        return self.loss
