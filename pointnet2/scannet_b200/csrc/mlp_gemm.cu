@@ -1,0 +1,428 @@
+// Shared-MLP layer on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// One 1x1-conv layer of a PointNet++ shared MLP in rows layout
+// (/root/reference/pointnet2/pytorch_utils.py:11-36: Conv2d 1x1 -> BatchNorm2d -> ReLU,
+//  as used by pointnet2_modules.py:65-67 and :414):
+//
+//     Z[P, N] = act(A)[P, K] * W[N, K]^T           act(x) = relu(a_in * x + b_in) | x
+//
+// fused with what surrounds it in the reference:
+//   * PROLOGUE  the PREVIOUS layer's BatchNorm fold + ReLU is applied to the A tile after it
+//               lands in shared memory (the normalised activation H is never read back from
+//               HBM; optionally it is written out once, for the weight-gradient GEMM);
+//   * EPILOGUE  per-channel sum / sum-of-squares of Z (this layer's BatchNorm batch
+//               statistics) are reduced from the accumulator while it is stored, so Z is not
+//               re-read for them.
+//
+// Structure (one persistent CTA per SM, 288 threads):
+//   warps 0-3  loaders: cp.async 16-byte chunks of A straight into the 128B-swizzled K-major
+//              UMMA tile (3 stages in flight), then transform the landed stage in place
+//              (fold + ReLU + round-to-TF32), fence.proxy.async, arrive on the stage's
+//              mbarrier; lane 0 of warp 0 also issues ONE 1-D TMA bulk copy per stage for the
+//              pre-packed weight tile (pack_weights_kernel lays W out as ready tile images);
+//   warp  8    one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) into a
+//              double-buffered TMEM accumulator and commits to the stage / accumulator
+//              mbarriers;
+//   warps 4-7  epilogue: tcgen05.ld 32 lanes x 32 columns, coalesced 128-byte row stores of
+//              Z, butterfly transpose-reduction of the column sums.
+//
+// Precision: TF32 operands (round-to-nearest), fp32 accumulation -- the arithmetic class of
+// the reference's own convolutions (torch.backends.cudnn.allow_tf32 defaults to True).
+#include "pn2_common.cuh"
+
+namespace pn2 {
+namespace gemm {
+
+constexpr int BM = 128;          // rows (positions) per tile = UMMA M
+constexpr int BK = 32;           // fp32 per K block = one 128-byte swizzle row
+constexpr int STAGES = 4;
+constexpr int kLoadWarps = 4, kEpiWarps = 4;
+constexpr int kThreads = 32 * (kLoadWarps + kEpiWarps + 1);
+constexpr int kMaxBN = 256;
+constexpr int A_STAGE_BYTES = BM * BK * 4;        // 16 KB
+constexpr int B_STAGE_BYTES = kMaxBN * BK * 4;    // 32 KB
+constexpr int kTmemCols = 512;                    // 2 accumulators x 256 columns
+
+struct Params {
+  const float *A;        // [P, lda]
+  const float *a_in;     // [>= K] fold scale of the previous BatchNorm (nullptr: identity)
+  const float *b_in;     // [>= K]
+  float *H_out;          // optional [P, lda]: act(A) written once (fp32, not TF32-rounded)
+  const float *Wp;       // packed weight tiles [n_tiles][k_blocks][BN][32] (swizzled, TF32)
+  float *Z;              // [P, ldz] (nullptr: not stored)
+  float *partials;       // [gridDim.x][2][n_tiles * BN] column sums / sums of squares, or nullptr
+  int P, lda, K, k_blocks;
+  int N, ldz, BN, n_tiles;
+  int relu_in;
+};
+
+// ------------------------------------------------------------------ small PTX wrappers
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of
+// 128 bytes, 8-row swizzle atoms 1024 bytes apart; start address / offsets in 16-byte units.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffff) >> 4);       // start address, bits [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                          // leading byte offset (unused for SW128 K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                  // stride byte offset: next 8-row atom
+  d |= static_cast<uint64_t>(1) << 46;                          // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                          // layout type: SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major
+__host__ __device__ inline uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// sum over the 32 lanes of v[c] for every c: after the butterfly lane l holds column l
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+struct __align__(8) Barriers {
+  uint64_t raw[STAGES];    // cp.async chunks of A landed            (128 arrivals)
+  uint64_t full[STAGES];   // A transformed + weight tile landed     (128 arrivals + 1 expect_tx)
+  uint64_t empty[STAGES];  // MMAs that read the stage have retired  (1 commit)
+  uint64_t acc_full[2];    // accumulator complete                   (1 commit)
+  uint64_t acc_empty[2];   // accumulator drained by the epilogue    (128 arrivals)
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tf32_fwd_kernel(Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *smem_a = smem;                                  // STAGES x 16 KB
+  unsigned char *smem_b = smem + STAGES * A_STAGE_BYTES;         // STAGES x 32 KB
+  Barriers *bars = reinterpret_cast<Barriers *>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  float *s_stats = reinterpret_cast<float *>(bars + 1);          // [kEpiWarps][2][kMaxBN]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tile = blockIdx.y;
+  const int m_tiles = (p.P + BM - 1) / BM;
+  const int my_tiles = blockIdx.x < m_tiles ? (m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * BK * 4;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bars->raw[s], 32 * kLoadWarps);
+      mbar_init(&bars->full[s], 32 * kLoadWarps + 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars->acc_full[a], 1);
+      mbar_init(&bars->acc_empty[a], 32 * kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kLoadWarps + kEpiWarps) {  // the MMA warp owns the tensor memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&bars->tmem_base)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  const int total_kb = my_tiles * p.k_blocks;  // K blocks this CTA streams, over all its tiles
+
+  if (warp < kLoadWarps) {
+    // =============================== loaders / transformers ===============================
+    const int chunk = tid & 7;            // 16-byte chunk of the 128-byte K-block row
+    const int row0 = tid >> 3;            // rows row0 + 16*i, i = 0..7
+    auto issue = [&](int it) {            // cp.async of K block `it` into stage it % STAGES
+      const int s = it % STAGES;
+      const int tile = blockIdx.x + (it / p.k_blocks) * gridDim.x;
+      const int kb = it % p.k_blocks;
+      mbar_wait(&bars->empty[s], ((it / STAGES) & 1) ^ 1);
+      if (tid == 0) {  // weight tile: one contiguous, pre-swizzled image
+        mbar_expect_tx(&bars->full[s], b_bytes);
+        tma_load_1d(smem_b + s * B_STAGE_BYTES,
+                    p.Wp + (static_cast<size_t>(n_tile) * p.k_blocks + kb) * p.BN * BK, b_bytes,
+                    &bars->full[s]);
+      }
+      const int col = kb * BK + chunk * 4;
+      const uint32_t dst0 = smem_u32(smem_a + s * A_STAGE_BYTES);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = row0 + 16 * i;
+        const int grow = tile * BM + r;
+        const bool ok = grow < p.P && col < p.lda;
+        const float *src = ok ? p.A + static_cast<size_t>(grow) * p.lda + col : p.A;
+        cp_async16(dst0 + r * 128 + ((chunk ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+      }
+      cp_async_arrive(&bars->raw[s]);
+    };
+    constexpr int AHEAD = STAGES - 1;
+    for (int it = 0; it < min(AHEAD, total_kb); ++it) issue(it);
+    for (int it = 0; it < total_kb; ++it) {
+      if (it + AHEAD < total_kb) issue(it + AHEAD);
+      const int s = it % STAGES;
+      const int tile = blockIdx.x + (it / p.k_blocks) * gridDim.x;
+      const int kb = it % p.k_blocks;
+      const int col = kb * BK + chunk * 4;
+      mbar_wait(&bars->raw[s], (it / STAGES) & 1);
+      float4 fa = make_float4(1.f, 1.f, 1.f, 1.f), fb = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool fold = p.a_in != nullptr && col < p.K;
+      if (fold) {
+        fa = __ldg(reinterpret_cast<const float4 *>(p.a_in + col));
+        fb = __ldg(reinterpret_cast<const float4 *>(p.b_in + col));
+      }
+      unsigned char *base = smem_a + s * A_STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = row0 + 16 * i;
+        float4 *q = reinterpret_cast<float4 *>(base + r * 128 + ((chunk ^ (r & 7)) << 4));
+        float4 v = *q;
+        if (fold) {
+          v.x = fmaf(fa.x, v.x, fb.x), v.y = fmaf(fa.y, v.y, fb.y);
+          v.z = fmaf(fa.z, v.z, fb.z), v.w = fmaf(fa.w, v.w, fb.w);
+          if (p.relu_in) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+          const int grow = tile * BM + r;
+          if (grow >= p.P) v = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past the end stay zero: the
+          else if (p.H_out != nullptr && n_tile == 0)             // epilogue statistics rely on it
+            *reinterpret_cast<float4 *>(p.H_out + static_cast<size_t>(grow) * p.lda + col) = v;
+        }
+        *q = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      }
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
+      mbar_arrive(&bars->full[s]);
+    }
+  } else if (warp == kLoadWarps + kEpiWarps) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BM, p.BN);
+      for (int it = 0; it < total_kb; ++it) {
+        const int s = it % STAGES;
+        const int t = it / p.k_blocks, kb = it % p.k_blocks;
+        const int acc = t & 1;
+        if (kb == 0) {
+          mbar_wait(&bars->acc_empty[acc], ((t >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        mbar_wait(&bars->full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        const uint64_t da = make_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
+        const uint64_t db = make_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k)  // 32 bytes (8 x tf32) further along K per instruction
+          tc_mma_tf32(tmem_base + acc * kMaxBN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+        tc_commit(&bars->empty[s]);                       // stage reusable once these MMAs retire
+        if (kb == p.k_blocks - 1) tc_commit(&bars->acc_full[acc]);
+      }
+    }
+  } else {
+    // ====================================== epilogue ======================================
+    const int wq = warp & 3;  // TMEM lane quarter this warp may read
+    const int chunks = p.BN / 32 + (p.BN % 32 ? 1 : 0);
+    float csum[kMaxBN / 32], csq[kMaxBN / 32];
+#pragma unroll
+    for (int c = 0; c < kMaxBN / 32; ++c) csum[c] = 0.f, csq[c] = 0.f;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = blockIdx.x + t * gridDim.x;
+      const int acc = t & 1;
+      mbar_wait(&bars->acc_full[acc], (t >> 1) & 1);
+      tc_fence_after();
+      const int grow = tile * BM + wq * 32 + lane;
+#pragma unroll
+      for (int c = 0; c < kMaxBN / 32; ++c) {
+        if (c < chunks) {
+          float v[32];
+          tc_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * kMaxBN + c * 32, v);
+          const int n0 = n_tile * p.BN + c * 32;
+          if (p.Z != nullptr && grow < p.P) {
+            float *dst = p.Z + static_cast<size_t>(grow) * p.ldz + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (n0 + j + 3 < p.N) {
+                *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (n0 + j + e < p.N) dst[j + e] = v[j + e];
+              }
+          }
+          if (p.partials != nullptr) {  // rows past P are zero (zero-filled A): they add nothing
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+            csum[c] += warp_colsum32(v, lane);
+            csq[c] += warp_colsum32(sq, lane);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bars->acc_empty[acc]);
+    }
+    if (p.partials != nullptr) {
+#pragma unroll
+      for (int c = 0; c < kMaxBN / 32; ++c)
+        if (c < chunks) {
+          s_stats[(wq * 2 + 0) * kMaxBN + c * 32 + lane] = csum[c];
+          s_stats[(wq * 2 + 1) * kMaxBN + c * 32 + lane] = csq[c];
+        }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (p.partials != nullptr && tid < p.BN) {  // combine the four epilogue warps, fixed order
+    const int ntot = p.n_tiles * p.BN;
+    float s = 0.f, q = 0.f;
+    if (my_tiles > 0)
+      for (int w = 0; w < kEpiWarps; ++w) s += s_stats[(w * 2) * kMaxBN + tid], q += s_stats[(w * 2 + 1) * kMaxBN + tid];
+    float *dst = p.partials + static_cast<size_t>(blockIdx.x) * 2 * ntot;
+    dst[n_tile * p.BN + tid] = s;
+    dst[ntot + n_tile * p.BN + tid] = q;
+  }
+  if (warp == kLoadWarps + kEpiWarps) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols)
+                 : "memory");
+  }
+}
+
+// W [N, K] row-major (a 1x1 conv weight) -> tile images [n_tiles][k_blocks][BN][32], each row's
+// 16-byte chunks XOR-swizzled by (row & 7) exactly as the UMMA SWIZZLE_128B layout expects,
+// rounded to TF32, zero padded.
+__global__ void pack_weights_kernel(const float *__restrict__ W, int N, int K, int ldw, int BN, int n_tiles,
+                                    int k_blocks, float *__restrict__ Wp) {
+  const size_t total = static_cast<size_t>(n_tiles) * k_blocks * BN * BK;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int e = static_cast<int>(i % 4);
+    const int pc = static_cast<int>((i / 4) % 8);  // physical chunk
+    const int r = static_cast<int>((i / BK) % BN);
+    const size_t blk = i / (static_cast<size_t>(BK) * BN);
+    const int kb = static_cast<int>(blk % k_blocks), nt = static_cast<int>(blk / k_blocks);
+    const int n = nt * BN + r;
+    const int k = kb * BK + ((pc ^ (r & 7)) * 4) + e;
+    float v = (n < N && k < K) ? W[static_cast<size_t>(n) * ldw + k] : 0.f;
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+    Wp[i] = __uint_as_float(t);
+  }
+}
+
+inline int pick_bn(int n) {  // UMMA N: multiple of 16 in [16, 256]
+  if (n > kMaxBN) return kMaxBN;
+  return (n + 15) / 16 * 16;
+}
+
+}  // namespace gemm
+}  // namespace pn2
+
+using namespace pn2;
+
+// geometry helpers for the caller (sizes of the packed weights / the partials buffer)
+extern "C" int pn2_mlp_gemm_bn(int n) { return gemm::pick_bn(n); }
+extern "C" int pn2_mlp_gemm_n_tiles(int n) { return (n + gemm::pick_bn(n) - 1) / gemm::pick_bn(n); }
+extern "C" int pn2_mlp_gemm_k_blocks(int k) { return (k + gemm::BK - 1) / gemm::BK; }
+extern "C" int pn2_mlp_gemm_grid(int p, int n) {
+  const int m_tiles = (p + gemm::BM - 1) / gemm::BM;
+  const int per = kNumSMs / pn2_mlp_gemm_n_tiles(n);
+  return m_tiles < per ? m_tiles : (per < 1 ? 1 : per);
+}
+
+extern "C" int pn2_mlp_pack_weights(int n, int k, int ldw, const float *w, float *packed, void *stream) {
+  if (n <= 0 || k <= 0 || ldw < k) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(w, packed);
+  const int bn = gemm::pick_bn(n), nt = pn2_mlp_gemm_n_tiles(n), kb = pn2_mlp_gemm_k_blocks(k);
+  const size_t total = static_cast<size_t>(nt) * kb * bn * gemm::BK;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  gemm::pack_weights_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, n, k, ldw, bn, nt, kb, packed);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const float *a, const float *a_in,
+                                const float *b_in, int relu_in, float *h_out, const float *w_packed,
+                                float *z, float *partials, void *stream) {
+  if (p <= 0 || k <= 0 || n <= 0 || lda < 4 || lda % 4 != 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(a, w_packed);
+  if (!aligned16(a) || !aligned16(w_packed)) return PN2_ERR_UNSUPPORTED;
+  if (z != nullptr && (!aligned16(z) || ldz % 4 != 0 || ldz < n)) return PN2_ERR_UNSUPPORTED;
+  if (a_in != nullptr && (b_in == nullptr || !aligned16(a_in) || !aligned16(b_in))) return PN2_ERR_UNSUPPORTED;
+  if (h_out != nullptr && !aligned16(h_out)) return PN2_ERR_UNSUPPORTED;
+  gemm::Params prm;
+  prm.A = a, prm.a_in = a_in, prm.b_in = b_in, prm.H_out = h_out, prm.Wp = w_packed, prm.Z = z;
+  prm.partials = partials;
+  prm.P = p, prm.lda = lda, prm.K = k, prm.k_blocks = pn2_mlp_gemm_k_blocks(k);
+  prm.N = n, prm.ldz = ldz, prm.BN = gemm::pick_bn(n), prm.n_tiles = pn2_mlp_gemm_n_tiles(n);
+  prm.relu_in = relu_in;
+  const size_t smem = gemm::STAGES * (gemm::A_STAGE_BYTES + gemm::B_STAGE_BYTES) + sizeof(gemm::Barriers) +
+                      sizeof(float) * gemm::kEpiWarps * 2 * gemm::kMaxBN;
+  cudaError_t e = cudaFuncSetAttribute(gemm::gemm_tf32_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  dim3 grid(pn2_mlp_gemm_grid(p, n), prm.n_tiles);
+  gemm::gemm_tf32_fwd_kernel<<<grid, gemm::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(prm);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}

@@ -95,13 +95,13 @@ bn_stats_partial_kernel(ColGeom g, const float *__restrict__ z, float *__restric
 
 // Fixed-order fp64 sum of the per-CTA partials of one channel by one warp: lane l adds
 // partials l, l+32, ... and a shuffle tree combines the lanes (same order every run).
-__device__ __forceinline__ void warp_sum_partials(int C, int c, int nblk, const float *__restrict__ partials,
+__device__ __forceinline__ void warp_sum_partials(int ld, int c, int nblk, const float *__restrict__ partials,
                                                   double &s, double &q) {
   const int lane = threadIdx.x & 31;
   s = 0.0, q = 0.0;
-  for (int k = lane; k < nblk; k += 32) {
-    s += __ldg(partials + static_cast<size_t>(k) * 2 * C + c);
-    q += __ldg(partials + static_cast<size_t>(k) * 2 * C + C + c);
+  for (int k = lane; k < nblk; k += 32) {  // partials: [nblk][2][ld]
+    s += __ldg(partials + static_cast<size_t>(k) * 2 * ld + c);
+    q += __ldg(partials + static_cast<size_t>(k) * 2 * ld + ld + c);
   }
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -113,7 +113,7 @@ constexpr int kFinalizeWarps = 8;  // channels per CTA of the finalise kernels
 
 // one WARP per channel, then the BN fold
 __global__ void __launch_bounds__(32 * kFinalizeWarps)
-bn_stats_finalize_kernel(int P, int C, int nblk, const float *__restrict__ partials,
+bn_stats_finalize_kernel(int P, int C, int ld, int nblk, const float *__restrict__ partials,
                          const float *__restrict__ gamma, const float *__restrict__ beta,
                          float eps, float momentum, float *running_mean,
                          float *running_var, float *__restrict__ a, float *__restrict__ b,
@@ -121,7 +121,7 @@ bn_stats_finalize_kernel(int P, int C, int nblk, const float *__restrict__ parti
   const int c = blockIdx.x * kFinalizeWarps + (threadIdx.x >> 5);
   if (c >= C) return;
   double s, q;
-  warp_sum_partials(C, c, nblk, partials, s, q);
+  warp_sum_partials(ld, c, nblk, partials, s, q);
   if ((threadIdx.x & 31) != 0) return;
   const double mean = s / P;
   double var = q / P - mean * mean;  // biased, as BatchNorm normalises with
@@ -447,7 +447,7 @@ extern "C" int pn2_bn_stats(int p, int c, const float *z, const float *gamma, co
   const ColGeom g = col_geom(p, c, &nblk);
   const size_t smem = sizeof(float4) * 2 * g.row_lanes * g.C4;
   bn_stats_partial_kernel<<<nblk, kRowThreads, smem, s>>>(g, z, workspace);
-  bn_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(p, c, nblk, workspace, gamma, beta, eps, momentum,
+  bn_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(p, c, c, nblk, workspace, gamma, beta, eps, momentum,
                                                            running_mean, running_var, a, b, mean, invstd);
   count_launch(2);
   PN2_RETURN_LAUNCH_STATUS();
@@ -588,6 +588,22 @@ extern "C" int pn2_fp_interp_rows_grad(int b, int n, int m, int c2, int c1, cons
   const size_t total4 = static_cast<size_t>(b) * n * (ct / 4);
   fp_interp_rows_grad_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(total4, n, m, c2, c1, ct / 4, grad_rows,
                                                                        idx, weight, grad_known, grad_skip);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+// Finalise BatchNorm batch statistics from per-CTA partial sums produced elsewhere (the
+// tensor-core GEMM's epilogue): partials [nblk][2][ld], first c of every ld columns valid.
+extern "C" int pn2_bn_finalize(int p, int c, int ld, int nblk, const float *partials, const float *gamma,
+                               const float *beta, float eps, float momentum, float *running_mean,
+                               float *running_var, float *a, float *b, float *mean, float *invstd,
+                               void *stream) {
+  if (p <= 0 || c <= 0 || ld < c || nblk <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(partials, gamma, beta, a, b, mean, invstd);
+  bn_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0,
+                             static_cast<cudaStream_t>(stream)>>>(p, c, ld, nblk, partials, gamma, beta, eps,
+                                                                  momentum, running_mean, running_var, a, b,
+                                                                  mean, invstd);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

@@ -22,6 +22,9 @@ from . import lib as _lib
 
 GEMM_TF32 = True   # tensor-core TF32 GEMMs, like the reference's cuDNN convs on Ampere+
 ENABLED = True     # module forward()s take the fused path when eligible
+TC_GEMM = True     # forward layers on the hand-written tcgen05 kernel (csrc/mlp_gemm.cu) when
+                   # GEMM_TF32: BN fold + ReLU of the previous layer in its prologue, BN batch
+                   # statistics in its epilogue; off: cuBLAS GEMM + separate streaming kernels
 
 
 def _mm(a, b):
@@ -87,6 +90,42 @@ def _bn_forward(z, gamma, beta, rm, rv, eps, momentum, training):
     return a, b, mean, invstd
 
 
+def _tc_layer(A, k, W2, fold, relu_in, want_h, want_stats):
+    """One layer on the tcgen05 kernel: z = act(A)[:, :k] @ W2^T.  fold = (a_in, b_in) or None.
+    -> (z, h_out or None, partials or None, (ld, nblk))"""
+    L = _lib.load()
+    dev = A.device
+    P, lda = A.shape
+    N = W2.shape[0]
+    s = _stream(dev)
+    bn, nt, kb = L.pn2_mlp_gemm_bn(N), L.pn2_mlp_gemm_n_tiles(N), L.pn2_mlp_gemm_k_blocks(k)
+    grid = L.pn2_mlp_gemm_grid(P, N)
+    W2 = W2.contiguous()
+    Wp = torch.empty(nt * kb * bn * 32, dtype=torch.float32, device=dev)
+    _lib.check(L.pn2_mlp_pack_weights(N, k, W2.shape[1], W2.data_ptr(), Wp.data_ptr(), s), "mlp_pack_weights")
+    z = torch.empty(P, N, dtype=torch.float32, device=dev)
+    h = torch.empty_like(A) if (want_h and fold is not None) else None
+    part = torch.empty(grid, 2, nt * bn, dtype=torch.float32, device=dev) if want_stats else None
+    _lib.check(L.pn2_mlp_gemm_fwd(
+        P, k, lda, N, N, A.data_ptr(),
+        fold[0].data_ptr() if fold is not None else None,
+        fold[1].data_ptr() if fold is not None else None, int(relu_in),
+        h.data_ptr() if h is not None else None, Wp.data_ptr(), z.data_ptr(),
+        part.data_ptr() if part is not None else None, s), "mlp_gemm_fwd")
+    return z, h, part, (nt * bn, grid)
+
+
+def _bn_finalize(P, C, part, ld, nblk, gamma, beta, rm, rv, eps, momentum):
+    L = _lib.load()
+    dev = part.device
+    a, b, mean, invstd = (torch.empty(C, dtype=torch.float32, device=dev) for _ in range(4))
+    _lib.check(L.pn2_bn_finalize(P, C, ld, nblk, part.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps,
+                                 momentum, rm.data_ptr() if rm is not None else None,
+                                 rv.data_ptr() if rv is not None else None, a.data_ptr(), b.data_ptr(),
+                                 mean.data_ptr(), invstd.data_ptr(), _stream(dev)), "bn_finalize")
+    return a, b, mean, invstd
+
+
 class SharedMLPRows(Function):
     """x0 [P, Cin] -> out [P/ns, C_L] (max over each run of ns rows) or [P, C_L] (ns == 0).
 
@@ -103,20 +142,43 @@ class SharedMLPRows(Function):
         P = x0.shape[0]
         layers, hs = [], [x0]
         out = argmax = None
+        use_tc = TC_GEMM and GEMM_TF32
+        want_h = any(ctx.needs_input_grad)
         with torch.cuda.device(dev):
             for l in range(nl):
                 W, gamma, beta = params[3 * l:3 * l + 3]
                 W2 = W.reshape(W.shape[0], -1)
-                cin = hs[-1].shape[1]
-                if W2.shape[1] != cin:  # first layer: rows are zero-padded to a multiple of 4
-                    W2 = F.pad(W2, (0, cin - W2.shape[1]))
                 st = _BNLayer()
                 st.cout = W2.shape[0]
-                st.z = _mm(hs[-1], W2.t())
                 rm, rv = buffers[l]
-                st.a, st.b, st.mean, st.invstd = _bn_forward(st.z, gamma, beta, rm, rv, eps, momentum, training)
-                layers.append(st)
-                C = st.cout
+                if use_tc:
+                    # tensor-core layer: the previous layer's BN fold + ReLU is applied to the A tile
+                    # on chip (its normalised output is only written out, once, for the backward
+                    # weight-gradient GEMM); this layer's BN statistics come out of the epilogue
+                    prev = layers[l - 1] if l > 0 else None
+                    A = prev.z if prev is not None else x0
+                    fold = (prev.a, prev.b) if prev is not None else None
+                    st.z, h, part, (ld, nblk) = _tc_layer(A, W2.shape[1], W2, fold,
+                                                          relus[l - 1] if l > 0 else False, want_h, training)
+                    if l > 0:
+                        hs.append(h)
+                    if training:
+                        st.a, st.b, st.mean, st.invstd = _bn_finalize(P, st.cout, part, ld, nblk, gamma, beta,
+                                                                      rm, rv, eps, momentum)
+                    else:
+                        st.a, st.b, st.mean, st.invstd = _bn_forward(st.z, gamma, beta, rm, rv, eps, momentum, False)
+                    layers.append(st)
+                    C = st.cout
+                    if l < nl - 1:
+                        continue
+                else:
+                    cin = hs[-1].shape[1]
+                    if W2.shape[1] != cin:  # first layer: rows are zero-padded to a multiple of 4
+                        W2 = F.pad(W2, (0, cin - W2.shape[1]))
+                    st.z = _mm(hs[-1], W2.t())
+                    st.a, st.b, st.mean, st.invstd = _bn_forward(st.z, gamma, beta, rm, rv, eps, momentum, training)
+                    layers.append(st)
+                    C = st.cout
                 if l < nl - 1 or ns == 0:
                     h = torch.empty_like(st.z)
                     _lib.check(L.pn2_bn_relu_apply(P, C, st.z.data_ptr(), st.a.data_ptr(), st.b.data_ptr(),

@@ -1,0 +1,80 @@
+"""GPU parity of the tcgen05 shared-MLP layer (csrc/mlp_gemm.cu) through the C ABI.
+
+Reference: the same product in fp64 on operands rounded to TF32 exactly as the kernel rounds
+them (cvt.rna: nearest, ties away from zero).  What remains is fp32 accumulation order, so the
+tolerance is 2e-5 of the output's max magnitude; the fused BatchNorm statistics (column sums and
+sums of squares) within 1e-4 relative; the side-output act(A) within 1e-6.
+"""
+import numpy as np
+import pytest
+import torch
+
+from pointnet2.scannet_b200 import lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def tf32_rna(x):
+    u = x.astype(np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def run_gemm(A, W, k, a_in=None, b_in=None, relu=False, want_h=False):
+    L = lib.load()
+    P, lda = A.shape
+    N = W.shape[0]
+    s = torch.cuda.current_stream().cuda_stream
+    bn, nt, kb = L.pn2_mlp_gemm_bn(N), L.pn2_mlp_gemm_n_tiles(N), L.pn2_mlp_gemm_k_blocks(k)
+    grid = L.pn2_mlp_gemm_grid(P, N)
+    assert A.dtype == np.float32 and W.dtype == np.float32
+    Wd = torch.from_numpy(W).to(DEV)
+    Wp = torch.empty(nt * kb * bn * 32, dtype=torch.float32, device=DEV)
+    lib.check(L.pn2_mlp_pack_weights(N, k, W.shape[1], Wd.data_ptr(), Wp.data_ptr(), s), "pack")
+    Ad = torch.from_numpy(A).to(DEV)
+    Z = torch.full((P, N), float("nan"), dtype=torch.float32, device=DEV)
+    part = torch.zeros(grid, 2, nt * bn, dtype=torch.float32, device=DEV)
+    H = torch.zeros_like(Ad) if want_h else None
+    ad = torch.from_numpy(a_in).to(DEV) if a_in is not None else None
+    bd = torch.from_numpy(b_in).to(DEV) if b_in is not None else None
+    lib.check(L.pn2_mlp_gemm_fwd(P, k, lda, N, N, Ad.data_ptr(),
+                                 ad.data_ptr() if ad is not None else None,
+                                 bd.data_ptr() if bd is not None else None, int(relu),
+                                 H.data_ptr() if H is not None else None, Wp.data_ptr(), Z.data_ptr(),
+                                 part.data_ptr(), s), "gemm")
+    torch.cuda.synchronize()
+    return Z.cpu().numpy(), part.cpu().numpy().sum(0)[:, :N], (H.cpu().numpy() if want_h else None)
+
+
+@pytest.mark.parametrize("P,K,lda,N", [
+    (1000, 9, 12, 32), (4096, 32, 32, 32), (5000, 64, 64, 128), (3000, 131, 132, 128),
+    (2048, 256, 256, 512), (777, 64, 64, 20), (1024, 128, 128, 196), (70000, 32, 32, 64),
+    (128, 8, 8, 16), (130, 260, 260, 256)])
+def test_gemm_plain(P, K, lda, N):
+    rng = np.random.default_rng(P + N)
+    A = np.zeros((P, lda), np.float32)
+    A[:, :K] = rng.standard_normal((P, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    Z, stats, _ = run_gemm(A, W, K)
+    ref = tf32_rna(A[:, :K]).astype(np.float64) @ tf32_rna(W).astype(np.float64).T
+    assert np.isfinite(Z).all()
+    assert np.abs(Z - ref).max() <= 2e-5 * np.abs(ref).max()
+    np.testing.assert_allclose(stats[0], ref.sum(0), rtol=1e-4, atol=1e-4 * np.abs(ref).sum(0).max())
+    np.testing.assert_allclose(stats[1], (ref * ref).sum(0), rtol=1e-4)
+
+
+@pytest.mark.parametrize("P,K,N,relu", [(3000, 64, 128, True), (9000, 32, 64, True), (500, 128, 256, False)])
+def test_gemm_fused_bn_relu_prologue(P, K, N, relu):
+    rng = np.random.default_rng(N)
+    A = rng.standard_normal((P, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    a_in = rng.uniform(0.5, 1.5, K).astype(np.float32) * rng.choice([-1, 1], K).astype(np.float32)
+    b_in = rng.standard_normal(K).astype(np.float32)
+    Z, stats, H = run_gemm(A, W, K, a_in, b_in, relu, want_h=True)
+    act = a_in.astype(np.float64) * A + b_in
+    if relu:
+        act = np.maximum(act, 0)
+    np.testing.assert_allclose(H, act, rtol=1e-6, atol=1e-6)
+    ref = tf32_rna(H).astype(np.float64) @ tf32_rna(W).astype(np.float64).T
+    assert np.abs(Z - ref).max() <= 2e-5 * np.abs(ref).max()
+    np.testing.assert_allclose(stats[1], (ref * ref).sum(0), rtol=1e-4)
