@@ -35,12 +35,12 @@ namespace gemm {
 
 constexpr int BM = 128;          // rows (positions) per tile = UMMA M
 constexpr int BK = 32;           // fp32 per K block = one 128-byte swizzle row
-constexpr int STAGES = 4;
+constexpr int kMaxStages = 12;   // stage count is chosen per launch: as many as fit (see launcher)
 constexpr int kLoadWarps = 4, kEpiWarps = 4;
 constexpr int kThreads = 32 * (kLoadWarps + kEpiWarps + 1);
 constexpr int kMaxBN = 256;
 constexpr int A_STAGE_BYTES = BM * BK * 4;        // 16 KB
-constexpr int B_STAGE_BYTES = kMaxBN * BK * 4;    // 32 KB
+constexpr int kSmemBudget = 200 * 1024;           // A + B stages
 constexpr int kTmemCols = 512;                    // 2 accumulators x 256 columns
 
 struct Params {
@@ -54,6 +54,7 @@ struct Params {
   int P, lda, K, k_blocks;
   int N, ldz, BN, n_tiles;
   int relu_in;
+  int stages, b_stage_bytes;  // pipeline depth; bytes reserved per weight stage (multiple of 1024)
 };
 
 // ------------------------------------------------------------------ small PTX wrappers
@@ -144,9 +145,9 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 }
 
 struct __align__(8) Barriers {
-  uint64_t raw[STAGES];    // cp.async chunks of A landed            (128 arrivals)
-  uint64_t full[STAGES];   // A transformed + weight tile landed     (128 arrivals + 1 expect_tx)
-  uint64_t empty[STAGES];  // MMAs that read the stage have retired  (1 commit)
+  uint64_t raw[kMaxStages];    // cp.async chunks of A landed            (128 arrivals)
+  uint64_t full[kMaxStages];   // A transformed + weight tile landed     (128 arrivals + 1 expect_tx)
+  uint64_t empty[kMaxStages];  // MMAs that read the stage have retired  (1 commit)
   uint64_t acc_full[2];    // accumulator complete                   (1 commit)
   uint64_t acc_empty[2];   // accumulator drained by the epilogue    (128 arrivals)
   uint32_t tmem_base;
@@ -154,8 +155,9 @@ struct __align__(8) Barriers {
 
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_fwd_kernel(Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  const int STAGES = p.stages, B_STAGE_BYTES = p.b_stage_bytes;
   unsigned char *smem_a = smem;                                  // STAGES x 16 KB
-  unsigned char *smem_b = smem + STAGES * A_STAGE_BYTES;         // STAGES x 32 KB
+  unsigned char *smem_b = smem + STAGES * A_STAGE_BYTES;         // STAGES x b_stage_bytes
   Barriers *bars = reinterpret_cast<Barriers *>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
   float *s_stats = reinterpret_cast<float *>(bars + 1);          // [kEpiWarps][2][kMaxBN]
 
@@ -195,11 +197,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_fwd_kernel(Params p) {
     // =============================== loaders / transformers ===============================
     const int chunk = tid & 7;            // 16-byte chunk of the 128-byte K-block row
     const int row0 = tid >> 3;            // rows row0 + 16*i, i = 0..7
-    auto issue = [&](int it) {            // cp.async of K block `it` into stage it % STAGES
-      const int s = it % STAGES;
-      const int tile = blockIdx.x + (it / p.k_blocks) * gridDim.x;
-      const int kb = it % p.k_blocks;
-      mbar_wait(&bars->empty[s], ((it / STAGES) & 1) ^ 1);
+    // (stage, use parity, tile, k block) of the next K block to ISSUE and the next to CONSUME are
+    // tracked incrementally (no divisions in the loop)
+    int is_s = 0, is_par = 1, is_tile = blockIdx.x, is_kb = 0;
+    auto issue = [&]() {                  // cp.async of the next K block into stage is_s
+      const int s = is_s, tile = is_tile, kb = is_kb;
+      mbar_wait(&bars->empty[s], is_par);
       if (tid == 0) {  // weight tile: one contiguous, pre-swizzled image
         mbar_expect_tx(&bars->full[s], b_bytes);
         tma_load_1d(smem_b + s * B_STAGE_BYTES,
@@ -217,16 +220,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_fwd_kernel(Params p) {
         cp_async16(dst0 + r * 128 + ((chunk ^ (r & 7)) << 4), src, ok ? 16u : 0u);
       }
       cp_async_arrive(&bars->raw[s]);
+      if (++is_s == STAGES) is_s = 0, is_par ^= 1;
+      if (++is_kb == p.k_blocks) is_kb = 0, is_tile += gridDim.x;
     };
-    constexpr int AHEAD = STAGES - 1;
-    for (int it = 0; it < min(AHEAD, total_kb); ++it) issue(it);
+    // Run AHEAD K blocks in front of the consumer, but refill only stages whose MMAs were issued
+    // >= 3 iterations ago: the empty-barrier wait then never sits on the critical path (with
+    // AHEAD = STAGES-1 every iteration would include a full loader -> MMA -> commit round trip).
+    const int AHEAD = STAGES > 4 ? STAGES - 3 : STAGES - 1;
+    int issued = 0;
+    for (; issued < min(AHEAD, total_kb); ++issued) issue();
+    int s = 0, par = 0, tile = blockIdx.x, kb = 0;
     for (int it = 0; it < total_kb; ++it) {
-      if (it + AHEAD < total_kb) issue(it + AHEAD);
-      const int s = it % STAGES;
-      const int tile = blockIdx.x + (it / p.k_blocks) * gridDim.x;
-      const int kb = it % p.k_blocks;
+      if (issued < total_kb) issue(), ++issued;
       const int col = kb * BK + chunk * 4;
-      mbar_wait(&bars->raw[s], (it / STAGES) & 1);
+      mbar_wait(&bars->raw[s], par);
       float4 fa = make_float4(1.f, 1.f, 1.f, 1.f), fb = make_float4(0.f, 0.f, 0.f, 0.f);
       const bool fold = p.a_in != nullptr && col < p.K;
       if (fold) {
@@ -252,20 +259,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_fwd_kernel(Params p) {
       }
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
       mbar_arrive(&bars->full[s]);
+      if (++s == STAGES) s = 0, par ^= 1;
+      if (++kb == p.k_blocks) kb = 0, tile += gridDim.x;
     }
   } else if (warp == kLoadWarps + kEpiWarps) {
     // ===================================== MMA issuer =====================================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BM, p.BN);
+      int s = 0, par = 0, t = 0, kb = 0;
       for (int it = 0; it < total_kb; ++it) {
-        const int s = it % STAGES;
-        const int t = it / p.k_blocks, kb = it % p.k_blocks;
         const int acc = t & 1;
         if (kb == 0) {
           mbar_wait(&bars->acc_empty[acc], ((t >> 1) & 1) ^ 1);
           tc_fence_after();
         }
-        mbar_wait(&bars->full[s], (it / STAGES) & 1);
+        mbar_wait(&bars->full[s], par);
         tc_fence_after();
         const uint64_t da = make_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
         const uint64_t db = make_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
@@ -274,6 +282,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_fwd_kernel(Params p) {
           tc_mma_tf32(tmem_base + acc * kMaxBN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
         tc_commit(&bars->empty[s]);                       // stage reusable once these MMAs retire
         if (kb == p.k_blocks - 1) tc_commit(&bars->acc_full[acc]);
+        if (++s == STAGES) s = 0, par ^= 1;
+        if (++kb == p.k_blocks) kb = 0, ++t;
       }
     }
   } else {
@@ -416,8 +426,14 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   prm.P = p, prm.lda = lda, prm.K = k, prm.k_blocks = pn2_mlp_gemm_k_blocks(k);
   prm.N = n, prm.ldz = ldz, prm.BN = gemm::pick_bn(n), prm.n_tiles = pn2_mlp_gemm_n_tiles(n);
   prm.relu_in = relu_in;
-  const size_t smem = gemm::STAGES * (gemm::A_STAGE_BYTES + gemm::B_STAGE_BYTES) + sizeof(gemm::Barriers) +
-                      sizeof(float) * gemm::kEpiWarps * 2 * gemm::kMaxBN;
+  // as many stages as fit: the narrow layers (BN = 32..64) are pure streaming and need >100 KB of
+  // loads in flight per SM to cover HBM latency; the wide ones get 4 x 48 KB
+  prm.b_stage_bytes = (prm.BN * gemm::BK * 4 + 1023) / 1024 * 1024;
+  prm.stages = gemm::kSmemBudget / (gemm::A_STAGE_BYTES + prm.b_stage_bytes);
+  if (prm.stages > gemm::kMaxStages) prm.stages = gemm::kMaxStages;
+  if (prm.stages < 2) return PN2_ERR_UNSUPPORTED;
+  const size_t smem = static_cast<size_t>(prm.stages) * (gemm::A_STAGE_BYTES + prm.b_stage_bytes) +
+                      sizeof(gemm::Barriers) + sizeof(float) * gemm::kEpiWarps * 2 * gemm::kMaxBN;
   cudaError_t e = cudaFuncSetAttribute(gemm::gemm_tf32_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
