@@ -1,0 +1,229 @@
+"""CPU-side tests: the drop-in boundary, the host mirror against the reference's own Python
+(imported from /root/reference where it exists), the C ABI's symbol table, the DP gradient bucket
+over gloo with world_size 2, and the synthetic workload."""
+import builtins
+import importlib
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/pointnet2"
+have_ref = os.path.isdir(REF)
+
+
+def _import_reference(name):
+    """Import one of the reference's top-level modules (pointnet2_utils, ...) from /root/reference."""
+    builtins.__POINTNET2_SETUP__ = False
+    if REF not in sys.path:
+        sys.path.append(REF)
+    return importlib.import_module(name)
+
+
+# ------------------------------------------------------------------ boundary
+def test_abi_exports_every_declared_symbol():
+    import ctypes
+    from pointnet2.scannet_b200 import build
+    build.build()
+    header = open(os.path.join(ROOT, "include", "pn2_b200.h")).read()
+    declared = set(re.findall(r"PN2_API[^;(]*?\b(pn2_\w+)\s*\(", header))
+    assert len(declared) >= 30, declared
+    L = ctypes.CDLL(build.LIB)
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    assert L.pn2_abi_version() == 1
+    L.pn2_status_string.restype = ctypes.c_char_p
+    assert L.pn2_status_string(0) == b"ok" and b"invalid" in L.pn2_status_string(-1)
+    # argument validation happens before any CUDA call: no GPU needed
+    assert L.pn2_furthest_point_sampling(-1, 8, 2, None, None, None, None) == -1
+    assert L.pn2_three_nn(1, 8, 2, None, None, None, None, None) == -1
+    assert L.pn2_query_ball_point(0, 8, 2, ctypes.c_float(0.1), 4, None, None, None, None) == 0
+
+
+def test_ctypes_signatures_cover_the_header():
+    from pointnet2.scannet_b200 import lib
+    header = open(os.path.join(ROOT, "include", "pn2_b200.h")).read()
+    declared = set(re.findall(r"PN2_API[^;(]*?\b(pn2_\w+)\s*\(", header))
+    assert declared == set(lib.SIGNATURES) | set(lib.LIBRARY_SYMBOLS)
+
+
+def test_no_cpu_fallback_and_loud_failure():
+    from pointnet2.scannet_b200 import ext
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ext.furthest_point_sampling(torch.rand(1, 16, 3), 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ext.ball_query(torch.rand(1, 4, 3), torch.rand(1, 16, 3), 0.1, 4)
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "pointnet2")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle", src, re.M), f
+                assert "pn2o_" not in src, f
+
+
+@pytest.mark.skipif(not have_ref, reason="/root/reference not present")
+def test_reference_op_layer_resolves_to_the_dropin():
+    """`import pointnet2._ext` inside the reference's unchanged pointnet2_utils.py finds this repo's."""
+    ref_utils = _import_reference("pointnet2_utils")
+    import pointnet2._ext as dropin
+    assert ref_utils._ext is dropin
+    from pointnet2.scannet_b200 import ext
+    for name in ext.__all__:
+        assert getattr(dropin, name) is getattr(ext, name)
+
+
+@pytest.mark.skipif(not have_ref, reason="/root/reference not present")
+@pytest.mark.parametrize("msg,channels", [(False, 6), (True, 6), (False, 131), (True, 131)])
+def test_state_dict_matches_reference(msg, channels):
+    from pointnet2.scannet_b200 import pointnet2_semseg as mine
+    ref = _import_reference("pointnet2_semseg")
+    torch.manual_seed(0)
+    a = mine.get_model(20, msg, channels).state_dict()
+    torch.manual_seed(0)
+    b = ref.get_model(20, msg, channels).state_dict()
+    assert list(a) == list(b)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    expect = {(False, 6): 949384, (False, 131): 969384, (True, 6): 3027752, (True, 131): 3049752}
+    assert sum(v.numel() for k, v in a.items() if "running" not in k and "tracked" not in k) == expect[(msg, channels)]
+
+
+@pytest.mark.skipif(not have_ref, reason="/root/reference not present")
+def test_mirror_modules_equal_reference_modules_on_cpu(oracle):
+    """Same ops table (the oracle's CPU one), same seed: the mirror's SA / FP modules and whole SSG
+    model reproduce the reference's Python modules bit for bit, forward and backward."""
+    from pointnet2.scannet_b200 import pointnet2_semseg as mine, pointnet2_utils as my_utils, synthetic
+    ref = _import_reference("pointnet2_semseg")
+    ref_utils = _import_reference("pointnet2_utils")
+    saved = (my_utils._ext, ref_utils._ext)
+    my_utils._ext = ref_utils._ext = oracle.ext_cpu
+    try:
+        x, _, _ = synthetic.make_batch(2, 2, npoints=2048)
+        pc = torch.from_numpy(x)
+        outs = []
+        for mod in (mine, ref):
+            torch.manual_seed(0)
+            model = mod.get_model(20, is_msg=False, input_channels=6).train()
+            torch.manual_seed(1)
+            logits = model(pc)
+            torch.manual_seed(2)
+            (logits * torch.randn_like(logits)).sum().backward()
+            outs.append((logits.detach(), [p.grad for p in model.parameters()], model.state_dict()))
+    finally:
+        my_utils._ext, ref_utils._ext = saved
+    (la, ga, sa), (lb, gb, sb) = outs
+    assert torch.equal(la, lb)
+    assert all(torch.equal(x, y) for x, y in zip(ga, gb))
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+
+
+def test_groupall_and_surface_names():
+    from pointnet2.scannet_b200 import pointnet2_utils as U
+    for name in ("furthest_point_sample", "gather_operation", "three_nn", "three_interpolate",
+                 "grouping_operation", "ball_query", "QueryAndGroup", "GroupAll", "RandomDropout",
+                 "FurthestPointSampling", "GatherOperation", "ThreeNN", "ThreeInterpolate",
+                 "GroupingOperation", "BallQuery"):
+        assert hasattr(U, name), name
+    xyz, feats = torch.rand(2, 10, 3), torch.rand(2, 4, 10)
+    out = U.GroupAll()(xyz, None, feats)
+    assert out.shape == (2, 7, 1, 10)
+    out, gx = U.GroupAll(ret_grouped_xyz=True)(xyz, None, feats)  # the reference raises here (ref :422)
+    assert gx.shape == (2, 3, 1, 10)
+
+
+# ------------------------------------------------------------------ workload / accounting
+def test_synthetic_chunks_are_scannet_shaped():
+    from pointnet2.scannet_b200 import synthetic
+    x, y, w = synthetic.make_batch(2, 2)
+    assert x.shape == (2, 8192, 9) and x.dtype == np.float32 and y.shape == (2, 8192)
+    x2, _, _ = synthetic.make_batch(2, 2)
+    assert np.array_equal(x, x2)  # seeded
+    uniq = len(np.unique(x[0, :, :3], axis=0)) / 8192.0
+    assert 0.6 < uniq < 0.9, uniq  # drawn with replacement: many exact duplicates (dataset.py:248)
+    assert np.abs(np.linalg.norm(x[0, :, 6:9], axis=1) - 1).max() < 1e-5  # unit normals
+    xm, _, _ = synthetic.make_batch(5, 1, use_color=False, use_multiview=True)
+    assert xm.shape == (1, 8192, 3 + 128 + 3)
+    scene = synthetic.make_scene(0, npoints=20000)
+    tiles = synthetic.tile_scene(scene)
+    assert tiles.shape[1:] == (8192, 9) and tiles.shape[0] >= 12
+
+
+def test_algorithmic_bytes_match_survey_totals():
+    """compulsory traffic of the custom ops of one SSG 32x8192 forward = 437 MB."""
+    from pointnet2.scannet_b200 import profiling
+    B = 32
+    lv = [(8192, 1024, 6), (1024, 256, 64), (256, 64, 128), (64, 16, 256)]
+    t = lambda *s: torch.empty(*s, device="meta")  # noqa: E731
+    total = 0
+    for n, m, c in lv:
+        total += profiling.algorithmic_bytes("furthest_point_sampling", (t(B, n, 3), m), None)
+        total += profiling.algorithmic_bytes("gather_points", (t(B, 3, n), t(B, m)), None)
+        total += profiling.algorithmic_bytes("ball_query", (t(B, m, 3), t(B, n, 3), 0.1, 32), None)
+        total += profiling.algorithmic_bytes("group_points", (t(B, 3, n), t(B, m, 32)), None)
+        total += profiling.algorithmic_bytes("group_points", (t(B, c, n), t(B, m, 32)), None)
+    for n, m, c in [(64, 16, 512), (256, 64, 256), (1024, 256, 256), (8192, 1024, 128)]:
+        total += profiling.algorithmic_bytes("three_nn", (t(B, n, 3), t(B, m, 3)), None)
+        total += profiling.algorithmic_bytes("three_interpolate", (t(B, c, m), t(B, n, 3), t(B, n, 3)), None)
+    assert abs(total / 1e6 - 437) < 15, total / 1e6
+
+
+# ------------------------------------------------------------------ data parallel (gloo, 2 ranks)
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from pointnet2.scannet_b200.train import GradBucket, TrainStep
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo")
+torch.manual_seed(0)
+model = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+bucket = GradBucket(model.parameters())
+assert bucket.attached()
+torch.manual_seed(100 + rank)
+x = torch.randn(4, 5)
+model(x).square().sum().backward()
+local = bucket.flat.clone()
+bucket.all_reduce_mean()
+gathered = [torch.zeros_like(local) for _ in range(2)]
+dist.all_gather(gathered, local)
+assert torch.allclose(bucket.flat, (gathered[0] + gathered[1]) / 2, atol=1e-7)
+assert bucket.attached() and all(torch.equal(p.grad.flatten(), bucket.flat[o:o + p.numel()])
+                                 for p, o in zip(bucket.params, [0, 35, 42, 63]))
+# a full TrainStep keeps the replicas identical
+class Tiny(torch.nn.Module):
+    def __init__(s):
+        super().__init__(); s.l = torch.nn.Linear(9, 20)
+    def forward(s, pc):
+        return s.l(pc)
+torch.manual_seed(0)
+step = TrainStep(Tiny(), lr=1e-2, fused_adam=False)
+for i in range(3):
+    torch.manual_seed(10 * rank + i)
+    pc = torch.randn(2, 16, 9); y = torch.randint(0, 20, (2, 16)); w = torch.ones(2, 16)
+    step(pc, y, w)
+flat = torch.cat([p.detach().flatten() for p in step.model.parameters()])
+both = [torch.zeros_like(flat) for _ in range(2)]
+dist.all_gather(both, flat)
+assert torch.equal(both[0], both[1]), "replicas diverged"
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_grad_bucket_all_reduce_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert "rank %d ok" % r in o
