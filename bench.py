@@ -52,6 +52,8 @@ def parse():
     p.add_argument("--msg", action="store_true", help="MSG model (BASELINE configs[2]) instead of SSG")
     p.add_argument("--multiview", action="store_true", help="xyz+normal+128 features (configs[4])")
     p.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of from a CUDA graph")
+    p.add_argument("--no-prefetch", action="store_true",
+                   help="compute each batch's sampling/grouping geometry inline instead of one batch ahead")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-per-op", action="store_true")
     p.add_argument("--cpu-sample-chunks", type=int, default=2)
@@ -155,7 +157,7 @@ def build_step(args, in_ch, device, capturable=False):
     torch.manual_seed(0)  # same replica on every rank
     model = pointnet2_semseg.get_model(NUM_CLASSES, is_msg=args.msg, input_channels=in_ch).to(device)
     model.train()
-    return train.TrainStep(model, lr=1e-3, capturable=capturable)
+    return train.TrainStep(model, lr=1e-3)
 
 
 def time_steps(step, batches, steps, world, e2e):
@@ -163,14 +165,23 @@ def time_steps(step, batches, steps, world, e2e):
     dev_batches = None
     if not e2e:
         dev_batches = [tuple(t.cuda(non_blocking=True) for t in b) for b in batches]
-    else:  # a graphed step owns static input buffers: copy host batches straight into them
+    elif not hasattr(step, "prefetch"):  # a graphed step owns static input buffers: copy straight into them
         stage = getattr(step, "static", None) or tuple(torch.empty_like(t, device="cuda") for t in batches[0])
+    pipelined = hasattr(step, "prefetch")
+    src = batches if e2e else dev_batches
+    if pipelined:  # batch 0 is staged before the clock starts; every timed step stages the next one,
+        step.prefetch(*src[0])  # so K batches are staged + K geometries computed inside the region
     barrier_sync(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     last = None
     for i in range(steps):
-        if e2e:
+        if pipelined:
+            last = step()                                   # trains on the batch staged one step ago
+            step.prefetch(*src[(i + 1) % len(src)])         # host->device copy (e2e) + geometry, side stream
+            if e2e:
+                last = float(last.item())                   # device -> host read of the loss
+        elif e2e:
             for d, h in zip(stage, batches[i % len(batches)]):
                 d.copy_(h, non_blocking=True)          # host -> device, pinned source
             last = float(step(*stage).item())          # device -> host read of the loss
@@ -179,7 +190,7 @@ def time_steps(step, batches, steps, world, e2e):
     e1.record()
     barrier_sync(world)
     ms = e0.elapsed_time(e1)
-    if not e2e:
+    if torch.is_tensor(last):
         last = float(last.item())
     return max_over_ranks(ms, world), last
 
@@ -232,8 +243,10 @@ def run_product(args, world, rank, local):
     step, launch_mode = eager, "eager"
     if not args.no_graph:
         try:  # single GPU: the whole step; DP: forward+backward in the graph, NCCL + Adam after it
-            step = train.GraphedTrainStep(eager, dev[0], scope="step" if world == 1 else "fwd_bwd")
-            launch_mode = "cuda-graph(%s)" % step.scope
+            cls = train.GraphedTrainStep if args.no_prefetch else train.PipelinedTrainStep
+            step = cls(eager, dev[0], scope="step" if world == 1 else "fwd_bwd")
+            launch_mode = "cuda-graph(%s)%s" % (step.scope, "" if args.no_prefetch else
+                                                 " + geometry of batch i+1 prefetched on a side stream")
         except Exception as e:  # noqa: BLE001
             sys.stderr.write("CUDA graph capture failed, running eagerly: %r\n" % (e,))
             torch.cuda.synchronize()

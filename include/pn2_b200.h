@@ -77,6 +77,12 @@ PN2_API const char *pn2_status_string(int status);
 #define PN2_FPS_MAX_RESIDENT_N 8192
 PN2_API int pn2_furthest_point_sampling(int b, int n, int m, const float *dataset,
                                 float *temp, int *idxs, void *stream);
+/* Identical results through the variant that Morton-sorts the cloud inside the kernel and lets a
+ * warp skip an iteration when the exactly-rounded lower bound of the distance from the new pick
+ * to its bounding box cannot lower any of its minima (applies to 2048 < n <= 8192; otherwise the
+ * same as above).  Not the default: see DESIGN.md section 4. */
+PN2_API int pn2_furthest_point_sampling_pruned(int b, int n, int m, const float *dataset,
+                                       float *temp, int *idxs, void *stream);
 
 /* -- gather ---------------------------------------------------------------
  * replace gather_points(_grad)_kernel_wrapper (sampling.cpp:4-9,
@@ -162,11 +168,12 @@ PN2_API int pn2_bn_stats_workspace_floats(int c);
 
 /* batch statistics of z [p, c]: biased variance; writes the fold (a, b), the saved
  * (mean, invstd), and -- unless running_mean is NULL -- updates the running
- * statistics like torch.nn.BatchNorm2d (momentum, unbiased variance). */
+ * statistics like torch.nn.BatchNorm2d (momentum, unbiased variance);
+ * num_batches_tracked (int64, may be NULL) is incremented by one. */
 PN2_API int pn2_bn_stats(int p, int c, const float *z, const float *gamma, const float *beta,
                          float eps, float momentum, float *running_mean, float *running_var,
-                         float *a, float *b, float *mean, float *invstd, float *workspace,
-                         void *stream);
+                         long long *num_batches_tracked, float *a, float *b, float *mean,
+                         float *invstd, float *workspace, void *stream);
 /* eval mode: the fold from the running statistics */
 PN2_API int pn2_bn_fold_eval(int c, const float *gamma, const float *beta,
                              const float *running_mean, const float *running_var, float eps,
@@ -236,8 +243,22 @@ PN2_API int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const float 
                              const float *w_packed, float *z, float *partials, void *stream);
 PN2_API int pn2_bn_finalize(int p, int c, int ld, int nblk, const float *partials,
                             const float *gamma, const float *beta, float eps, float momentum,
-                            float *running_mean, float *running_var, float *a, float *b,
-                            float *mean, float *invstd, void *stream);
+                            float *running_mean, float *running_var, long long *num_batches_tracked,
+                            float *a, float *b, float *mean, float *invstd, void *stream);
+
+/* ==========================================================================
+ * Training-step utilities on flat fp32 buffers (the step the reference's solver
+ * runs after backward, lib/solver.py:171-176, as one launch instead of one per
+ * parameter tensor).
+ * pn2_sum_partials: out[m] = sum over s of in[s, m] (fixed order; m % 4 == 0).
+ * pn2_adam_flat: torch.optim.Adam's update (scripts/train.py:44) over one flat
+ * parameter buffer; `step` is a device int64 incremented by the call, so the
+ * launch is CUDA-graph replayable; the gradient is multiplied by grad_scale first.
+ * ========================================================================== */
+PN2_API int pn2_sum_partials(int s, int m, const float *in, float *out, void *stream);
+PN2_API int pn2_adam_flat(long long n, float *param, const float *grad, float *exp_avg,
+                          float *exp_avg_sq, long long *step, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, float grad_scale, void *stream);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,7 @@
 //     candidate (>= 0) -- exactly the reference's `best = -1` initial value --
 //     and if nothing else exists position 0 (= index 0) wins, as `besti = 0`.
 #include <math.h>
+#include <stdlib.h>
 
 #include "pn2_common.cuh"
 
@@ -137,6 +138,235 @@ fps_resident_kernel(FpsGeom g, const float *__restrict__ dataset,
 }
 
 // ---------------------------------------------------------------------------
+// pruned register-resident kernel (2048 < positions <= 8192)
+//
+// Same arithmetic, same answer, fewer updates.  Points are Morton-sorted inside the kernel
+// (bitonic sort in shared memory, ~7 us) so that every WARP owns 256 spatially compact points
+// and their bounding box.  After a new centre c is picked, a warp first evaluates the lower
+// bound  lb = ((ex*ex)+(ey*ey))+(ez*ez),  e = max(lo - c, c - hi, 0) per axis, with the very
+// operations the distance uses.  fp32 rounding is monotone, so lb <= d(p, c) for EVERY point p of
+// the box, bit for bit; if lb >= the warp's current maximum of the running minima, no minimum
+// in the warp can change (min(d, t) = t for all of them) and the warp's arg-max candidate from the
+// previous iteration is still exact: the warp skips the iteration.  Once a few dozen samples
+// are placed the running minima are small and a new centre only touches nearby warps.
+//
+// The tie-break can no longer be encoded in the register order (slots are spatial now): a thread
+// resolves equal minima by comparing the reference positions pos(k) kept in shared memory --
+// rare, except in the first iterations when every minimum is still 1e10.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned morton_expand10(unsigned v) {  // 10 bits -> every third bit
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+#ifdef PN2_FPS_DEBUG
+__device__ unsigned long long g_fps_active[1024];  // per-iteration count of non-skipping warps
+#endif
+
+template <int P, int T>
+__global__ void __launch_bounds__(T, 1)
+fps_pruned_kernel(FpsGeom g, const float *__restrict__ dataset, int *__restrict__ idxs) {
+  constexpr int M = T * P;          // sorted slots (power of two)
+  constexpr int NW = T / 32;
+  extern __shared__ __align__(16) unsigned char fps_smem[];
+  float4 *s_pts = reinterpret_cast<float4 *>(fps_smem);                              // [M] by reference position
+  unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(s_pts + M);    // [M] (morton << 32) | position
+  float4 *s_box = reinterpret_cast<float4 *>(s_keys + M);                            // [NW][2] lo, hi
+  __shared__ int2 s_slots[2][32];
+  __shared__ float s_ext[6][32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int npos = g.bs * g.q;
+  const float *pts = dataset + static_cast<size_t>(blockIdx.x) * g.n * 3;
+  int *out = idxs + static_cast<size_t>(blockIdx.x) * g.m;
+
+  // ---- 1. load by reference position, cloud bounding box over the live points
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  unsigned state[P];  // 0 live, 1 real but skipped by the reference (never a candidate), 2 padding
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    const int p = tid * P + i;
+    const int k = p < npos ? fps_pos_to_index(p, g) : g.n;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    state[i] = 2;
+    if (k < g.n) {
+      px = __ldg(pts + 3 * k), py = __ldg(pts + 3 * k + 1), pz = __ldg(pts + 3 * k + 2);
+      state[i] = (static_cast<double>(sqnorm_rn(px, py, pz)) <= 1e-3) ? 1 : 0;
+      if (state[i] == 0) {
+        lo[0] = fminf(lo[0], px), lo[1] = fminf(lo[1], py), lo[2] = fminf(lo[2], pz);
+        hi[0] = fmaxf(hi[0], px), hi[1] = fmaxf(hi[1], py), hi[2] = fmaxf(hi[2], pz);
+      }
+    }
+    s_pts[p] = make_float4(px, py, pz, __int_as_float(k < g.n ? k : 0));
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(kFull, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(kFull, hi[a], o));
+    }
+    if (lane == 0) s_ext[a][warp] = lo[a], s_ext[3 + a][warp] = hi[a];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float l = lane < NW ? s_ext[a][lane] : 3.0e38f, h = lane < NW ? s_ext[3 + a][lane] : -3.0e38f;
+    for (int o = 16; o > 0; o >>= 1) {
+      l = fminf(l, __shfl_xor_sync(kFull, l, o));
+      h = fmaxf(h, __shfl_xor_sync(kFull, h, o));
+    }
+    lo[a] = l, hi[a] = h;
+  }
+  // ---- 2. sort keys: Morton code of the live points; skipped and padding slots go last
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    const int p = tid * P + i;
+    unsigned code = state[i] == 0 ? 0u : (state[i] == 1 ? 0xFFFFFFFEu : 0xFFFFFFFFu);
+    if (state[i] == 0) {
+      const float4 v = s_pts[p];
+      const float q[3] = {v.x, v.y, v.z};
+      unsigned c3[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float span = hi[a] - lo[a];
+        const float u = span > 0.f ? (q[a] - lo[a]) / span : 0.f;
+        c3[a] = static_cast<unsigned>(fminf(fmaxf(u * 1023.f, 0.f), 1023.f));
+      }
+      code = morton_expand10(c3[0]) | (morton_expand10(c3[1]) << 1) | (morton_expand10(c3[2]) << 2);
+    }
+    s_keys[p] = (static_cast<unsigned long long>(code) << 32) |
+                static_cast<unsigned>(state[i] == 2 ? 0x7fffffff : p);
+  }
+  __syncthreads();
+  for (int size = 2; size <= M; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int e = tid; e < M / 2; e += T) {
+        const int i0 = 2 * e - (e & (stride - 1));  // lower element of the pair
+        const int i1 = i0 + stride;
+        const bool up = (i0 & size) == 0;
+        const unsigned long long a = s_keys[i0], b = s_keys[i1];
+        if ((a > b) == up) s_keys[i0] = b, s_keys[i1] = a;
+      }
+      __syncthreads();
+    }
+  }
+  // ---- 3. this thread's P sorted slots -> registers (pairs), warp bounding box
+  constexpr int H = P / 2;
+  float2 x[H], y[H], z[H], t[H];
+  float wl[3] = {3.0e38f, 3.0e38f, 3.0e38f}, wh[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    const unsigned long long key = s_keys[tid * P + i];
+    const unsigned code = static_cast<unsigned>(key >> 32), pos = static_cast<unsigned>(key);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pos < static_cast<unsigned>(npos)) v = s_pts[pos];
+    const bool live = code < 0xFFFFFFFEu;
+    if (live) {
+      wl[0] = fminf(wl[0], v.x), wl[1] = fminf(wl[1], v.y), wl[2] = fminf(wl[2], v.z);
+      wh[0] = fmaxf(wh[0], v.x), wh[1] = fmaxf(wh[1], v.y), wh[2] = fmaxf(wh[2], v.z);
+    }
+    const float t0 = live ? 1e10f : -1.0f;
+    if (i & 1) x[i / 2].y = v.x, y[i / 2].y = v.y, z[i / 2].y = v.z, t[i / 2].y = t0;
+    else x[i / 2].x = v.x, y[i / 2].x = v.y, z[i / 2].x = v.z, t[i / 2].x = t0;
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    for (int o = 16; o > 0; o >>= 1) {
+      wl[a] = fminf(wl[a], __shfl_xor_sync(kFull, wl[a], o));
+      wh[a] = fmaxf(wh[a], __shfl_xor_sync(kFull, wh[a], o));
+    }
+  if (lane == 0) {
+    s_box[2 * warp] = make_float4(wl[0], wl[1], wl[2], 0.f);
+    s_box[2 * warp + 1] = make_float4(wh[0], wh[1], wh[2], 0.f);
+  }
+  if (tid == 0) out[0] = 0;
+  __syncthreads();
+
+  const unsigned *s_pos = reinterpret_cast<const unsigned *>(s_keys);  // low word of key e: 2*e
+  auto pos_of = [&](int i) { return s_pos[2 * (tid * P + i)]; };
+  int wval = __float_as_int(1e10f);  // the warp's cached arg-max candidate: (value bits, position)
+  unsigned wpos = 0xffffffffu;
+  bool fresh = false;                // becomes true once the warp has evaluated an iteration
+  float4 c = s_pts[0];               // position 0 <-> index 0
+  for (int j = 1; j < g.m; ++j) {
+    // exact lower bound of the distance from c to any point of this warp's box
+    const float4 bl = s_box[2 * warp], bh = s_box[2 * warp + 1];
+    const float ex = fmaxf(fmaxf(__fsub_rn(bl.x, c.x), __fsub_rn(c.x, bh.x)), 0.f);
+    const float ey = fmaxf(fmaxf(__fsub_rn(bl.y, c.y), __fsub_rn(c.y, bh.y)), 0.f);
+    const float ez = fmaxf(fmaxf(__fsub_rn(bl.z, c.z), __fsub_rn(c.z, bh.z)), 0.f);
+    const float lb = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+    if (!(fresh && lb >= __int_as_float(wval))) {
+#ifdef PN2_FPS_DEBUG
+      if (lane == 0 && j < 1024) atomicAdd(&g_fps_active[j], 1ull);
+#endif
+      // Only a few warps survive the bounding-box test, so what matters here is the length of the
+      // dependency chain, not the instruction count: all P updates are independent, the maximum
+      // is a tree, and the tie-break positions are fetched only when a thread really has a tie.
+      const float2 cx = make_float2(c.x, c.x), cy = make_float2(c.y, c.y), cz = make_float2(c.z, c.z);
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float2 d = sqdist2_rn(x[h], y[h], z[h], cx, cy, cz);
+        t[h].x = fminf(d.x, t[h].x);
+        t[h].y = fminf(d.y, t[h].y);
+      }
+      float pm[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) pm[h] = fmaxf(t[h].x, t[h].y);
+#pragma unroll
+      for (int w = H; w > 1; w = (w + 1) / 2)
+#pragma unroll
+        for (int h = 0; h < w / 2; ++h) pm[h] = fmaxf(pm[h], pm[w - 1 - h]);
+      const float best = pm[0];
+      int bi = 0, ties = 0;
+#pragma unroll
+      for (int i = P - 1; i >= 0; --i) {  // lowest slot holding the maximum, and how many hold it
+        const bool e = ((i & 1) ? t[i / 2].y : t[i / 2].x) == best;
+        bi = e ? i : bi;
+        ties += e ? 1 : 0;
+      }
+      if (ties > 1) {  // equal minima inside one thread: the reference position decides
+        unsigned bp = 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+          if (((i & 1) ? t[i / 2].y : t[i / 2].x) == best) {
+            const unsigned q = pos_of(i);
+            if (q < bp) bp = q, bi = i;
+          }
+      }
+      const int v = __float_as_int(best);
+      wval = __reduce_max_sync(kFull, v);
+      wpos = __reduce_min_sync(kFull, v == wval ? pos_of(bi) : 0xffffffffu);
+      fresh = true;
+    }
+    if (lane == 0) s_slots[j & 1][warp] = make_int2(wval, static_cast<int>(wpos));
+    __syncthreads();
+    int2 r = make_int2(INT_MIN, -1);
+    if (lane < NW) r = s_slots[j & 1][lane];
+    const int gmax = __reduce_max_sync(kFull, r.x);
+    const unsigned win = __reduce_min_sync(kFull, r.x == gmax ? static_cast<unsigned>(r.y) : 0xffffffffu);
+    c = s_pts[win < static_cast<unsigned>(npos) ? win : 0];
+    if (tid == 0) out[j] = __float_as_int(c.w);
+  }
+}
+
+template <int P, int T>
+static cudaError_t launch_pruned(const FpsGeom &g, int b, const float *dataset, int *idxs,
+                                 cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(T) * P * (sizeof(float4) + sizeof(unsigned long long)) +
+                      sizeof(float4) * 2 * (T / 32);
+  auto kern = fps_pruned_kernel<P, T>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  kern<<<b, T, smem, stream>>>(g, dataset, idxs);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // streaming fallback for n > PN2_FPS_MAX_RESIDENT_N: minima in the caller's
 // `temp` like the reference.  1024 threads; thread t scans k = t, t+1024, ...
 // (k mod bs is constant per thread because 1024 % bs == 0, so a thread's
@@ -196,9 +426,18 @@ static cudaError_t launch_resident(const FpsGeom &g, int b, int threads,
 
 }  // namespace pn2
 
-extern "C" int pn2_furthest_point_sampling(int b, int n, int m,
-                                           const float *dataset, float *temp,
-                                           int *idxs, void *stream) {
+#ifdef PN2_FPS_DEBUG
+extern "C" __attribute__((visibility("default"))) int pn2_debug_fps_active(unsigned long long *host1024) {
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(host1024, pn2::g_fps_active, sizeof(unsigned long long) * 1024);
+  unsigned long long zeros[1024] = {0};
+  cudaMemcpyToSymbol(pn2::g_fps_active, zeros, sizeof(zeros));
+  return static_cast<int>(e);
+}
+#endif
+
+static int fps_dispatch(int b, int n, int m, const float *dataset, float *temp, int *idxs, void *stream,
+                        bool force_pruned) {
   using namespace pn2;
   if (b < 0 || n < 0 || m < 0) return PN2_ERR_INVALID_ARG;
   if (b == 0 || m == 0) return PN2_OK;
@@ -223,7 +462,15 @@ extern "C" int pn2_furthest_point_sampling(int b, int n, int m,
       return t < 128 ? (npos < 128 ? (npos + 31) / 32 * 32 : 128) : t;
     };
     cudaError_t e;
-    if (npos <= 128 * 1) e = launch_resident<1, 1024>(g, b, threads_for(1), dataset, idxs, s);
+    // Measured on B200 (8192 -> 1024, B = 32): the bounding-box variant leaves only 19% of the warps
+    // active per iteration yet runs 708 us against 635 us for the plain resident kernel -- at this
+    // size the iteration is bound by what EVERY warp executes (winner fetch, box test, slot,
+    // barrier, second-stage arg-max), not by the distance updates.  It is therefore opt-in
+    // (pn2_furthest_point_sampling_pruned / PN2_FPS_PRUNE=1); see DESIGN.md section 4.
+    static const bool prune = getenv("PN2_FPS_PRUNE") != nullptr;
+    if ((prune || force_pruned) && npos > 4096 && m > 2) e = launch_pruned<8, 1024>(g, b, dataset, idxs, s);
+    else if ((prune || force_pruned) && npos > 2048 && m > 2) e = launch_pruned<8, 512>(g, b, dataset, idxs, s);
+    else if (npos <= 128 * 1) e = launch_resident<1, 1024>(g, b, threads_for(1), dataset, idxs, s);
     else if (npos <= 128 * 2) e = launch_resident<2, 1024>(g, b, threads_for(2), dataset, idxs, s);
     else if (npos <= 128 * 4) e = launch_resident<4, 1024>(g, b, threads_for(4), dataset, idxs, s);
     else if (npos <= 1024 * 8) e = launch_resident<8, 1024>(g, b, threads_for(8), dataset, idxs, s);
@@ -235,4 +482,15 @@ extern "C" int pn2_furthest_point_sampling(int b, int n, int m,
   fps_streaming_kernel<<<b, 1024, 0, s>>>(g, dataset, temp, idxs);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_furthest_point_sampling(int b, int n, int m, const float *dataset, float *temp,
+                                           int *idxs, void *stream) {
+  return fps_dispatch(b, n, m, dataset, temp, idxs, stream, false);
+}
+
+// Same result through the bounding-box-pruned kernel where it applies (2048 < n <= 8192).
+extern "C" int pn2_furthest_point_sampling_pruned(int b, int n, int m, const float *dataset, float *temp,
+                                                  int *idxs, void *stream) {
+  return fps_dispatch(b, n, m, dataset, temp, idxs, stream, true);
 }

@@ -116,9 +116,11 @@ __global__ void __launch_bounds__(32 * kFinalizeWarps)
 bn_stats_finalize_kernel(int P, int C, int ld, int nblk, const float *__restrict__ partials,
                          const float *__restrict__ gamma, const float *__restrict__ beta,
                          float eps, float momentum, float *running_mean,
-                         float *running_var, float *__restrict__ a, float *__restrict__ b,
-                         float *__restrict__ mean_out, float *__restrict__ invstd_out) {
+                         float *running_var, long long *num_batches_tracked, float *__restrict__ a,
+                         float *__restrict__ b, float *__restrict__ mean_out,
+                         float *__restrict__ invstd_out) {
   const int c = blockIdx.x * kFinalizeWarps + (threadIdx.x >> 5);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
   if (c >= C) return;
   double s, q;
   warp_sum_partials(ld, c, nblk, partials, s, q);
@@ -437,8 +439,9 @@ using namespace pn2;
 extern "C" int pn2_bn_stats_workspace_floats(int c) { return kMaxPartials * 2 * c; }
 
 extern "C" int pn2_bn_stats(int p, int c, const float *z, const float *gamma, const float *beta, float eps,
-                            float momentum, float *running_mean, float *running_var, float *a, float *b,
-                            float *mean, float *invstd, float *workspace, void *stream) {
+                            float momentum, float *running_mean, float *running_var,
+                            long long *num_batches_tracked, float *a, float *b, float *mean, float *invstd,
+                            float *workspace, void *stream) {
   if (p <= 0 || c <= 0) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(z, gamma, beta, a, b, mean, invstd, workspace);
   if (!rows_ok(c, z) || !aligned16(workspace)) return PN2_ERR_UNSUPPORTED;
@@ -448,7 +451,7 @@ extern "C" int pn2_bn_stats(int p, int c, const float *z, const float *gamma, co
   const size_t smem = sizeof(float4) * 2 * g.row_lanes * g.C4;
   bn_stats_partial_kernel<<<nblk, kRowThreads, smem, s>>>(g, z, workspace);
   bn_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(p, c, c, nblk, workspace, gamma, beta, eps, momentum,
-                                                           running_mean, running_var, a, b, mean, invstd);
+                                                           running_mean, running_var, num_batches_tracked, a, b, mean, invstd);
   count_launch(2);
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -596,14 +599,79 @@ extern "C" int pn2_fp_interp_rows_grad(int b, int n, int m, int c2, int c1, cons
 // tensor-core GEMM's epilogue): partials [nblk][2][ld], first c of every ld columns valid.
 extern "C" int pn2_bn_finalize(int p, int c, int ld, int nblk, const float *partials, const float *gamma,
                                const float *beta, float eps, float momentum, float *running_mean,
-                               float *running_var, float *a, float *b, float *mean, float *invstd,
-                               void *stream) {
+                               float *running_var, long long *num_batches_tracked, float *a, float *b,
+                               float *mean, float *invstd, void *stream) {
   if (p <= 0 || c <= 0 || ld < c || nblk <= 0) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(partials, gamma, beta, a, b, mean, invstd);
   bn_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0,
                              static_cast<cudaStream_t>(stream)>>>(p, c, ld, nblk, partials, gamma, beta, eps,
-                                                                  momentum, running_mean, running_var, a, b,
-                                                                  mean, invstd);
+                                                                  momentum, running_mean, running_var,
+                                                                  num_batches_tracked, a, b, mean, invstd);
   count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+// ---------------------------------------------------------------------------------------
+// Small training-step utilities on flat fp32 buffers (one launch each instead of one per tensor)
+// ---------------------------------------------------------------------------------------
+// out[j] = sum_s in[s, j]  (fixed order): the S partial weight gradients of a split-K GEMM
+__global__ void __launch_bounds__(kRowThreads)
+sum_partials_kernel(int S, int M4, const float *__restrict__ in, float *__restrict__ out) {
+  const int j = blockIdx.x * kRowThreads + threadIdx.x;
+  if (j >= M4) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < S; ++s) {
+    const float4 v = ld4(in, static_cast<size_t>(s) * M4 + j);
+    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+  }
+  reinterpret_cast<float4 *>(out)[j] = acc;
+}
+
+extern "C" int pn2_sum_partials(int s, int m, const float *in, float *out, void *stream) {
+  if (s <= 0 || m <= 0 || m % 4 != 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(in, out);
+  if (!aligned16(in) || !aligned16(out)) return PN2_ERR_UNSUPPORTED;
+  sum_partials_kernel<<<blocks_for(m / 4), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(s, m / 4, in, out);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+// Adam (torch.optim.Adam semantics: L2 weight decay added to the gradient, bias correction,
+// eps outside the square root) over ONE flat parameter buffer; the step count lives on the
+// device so that the launch can be replayed from a CUDA graph.  grad_scale multiplies the
+// gradient first (1/world after a summed all-reduce).
+__global__ void __launch_bounds__(kRowThreads)
+adam_flat_kernel(size_t n, float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                 float *__restrict__ v, const long long *__restrict__ step, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, float grad_scale) {
+  const double t = static_cast<double>(*step);
+  const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), t));
+  const float bc2s = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)));
+  const float step_size = lr / bc1;
+  const size_t stride = static_cast<size_t>(gridDim.x) * kRowThreads;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x; i < n; i += stride) {
+    float grad = g[i] * grad_scale;
+    const float w = p[i];
+    if (weight_decay != 0.f) grad = fmaf(weight_decay, w, grad);
+    const float mi = beta1 * m[i] + (1.f - beta1) * grad;
+    const float vi = beta2 * v[i] + (1.f - beta2) * grad * grad;
+    m[i] = mi, v[i] = vi;
+    p[i] = w - step_size * mi / (sqrtf(vi) / bc2s + eps);
+  }
+}
+__global__ void bump_step_kernel(long long *step) { *step += 1; }
+
+extern "C" int pn2_adam_flat(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
+                             long long *step, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, float grad_scale, void *stream) {
+  if (n <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(param, grad, exp_avg, exp_avg_sq);
+  if (step == nullptr) return PN2_ERR_INVALID_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bump_step_kernel<<<1, 1, 0, s>>>(step);
+  adam_flat_kernel<<<blocks_for(static_cast<size_t>(n), 8 * kNumSMs), kRowThreads, 0, s>>>(
+      static_cast<size_t>(n), param, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, weight_decay,
+      grad_scale);
+  count_launch(2);
   PN2_RETURN_LAUNCH_STATUS();
 }

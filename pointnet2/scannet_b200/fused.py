@@ -54,7 +54,12 @@ def _mm_tn_splitk(dz, h):
         part = torch.bmm(dz.view(S, P // S, cout).transpose(1, 2), h.view(S, P // S, cin))
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    return part.sum(dim=0)
+    if (cout * cin) % 4:
+        return part.sum(dim=0)
+    out = torch.empty(cout, cin, dtype=torch.float32, device=dz.device)
+    _lib.check(_lib.load().pn2_sum_partials(S, cout * cin, part.data_ptr(), out.data_ptr(), _stream(dz.device)),
+               "sum_partials")
+    return out
 
 
 def _stream(dev):
@@ -71,8 +76,8 @@ class _BNLayer(object):
     __slots__ = ("z", "a", "b", "mean", "invstd", "cout")
 
 
-def _bn_forward(z, gamma, beta, rm, rv, eps, momentum, training):
-    """-> (a, b, mean, invstd); updates rm / rv in place when training."""
+def _bn_forward(z, gamma, beta, rm, rv, eps, momentum, training, nbt=None):
+    """-> (a, b, mean, invstd); updates rm / rv / num_batches_tracked in place when training."""
     L = _lib.load()
     P, C = z.shape
     dev = z.device
@@ -81,6 +86,7 @@ def _bn_forward(z, gamma, beta, rm, rv, eps, momentum, training):
         _lib.check(L.pn2_bn_stats(P, C, z.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, momentum,
                                   rm.data_ptr() if rm is not None else None,
                                   rv.data_ptr() if rv is not None else None,
+                                  nbt.data_ptr() if nbt is not None else None,
                                   a.data_ptr(), b.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
                                   _ws(C, dev).data_ptr(), _stream(dev)), "bn_stats")
     else:
@@ -115,13 +121,14 @@ def _tc_layer(A, k, W2, fold, relu_in, want_h, want_stats):
     return z, h, part, (nt * bn, grid)
 
 
-def _bn_finalize(P, C, part, ld, nblk, gamma, beta, rm, rv, eps, momentum):
+def _bn_finalize(P, C, part, ld, nblk, gamma, beta, rm, rv, eps, momentum, nbt=None):
     L = _lib.load()
     dev = part.device
     a, b, mean, invstd = (torch.empty(C, dtype=torch.float32, device=dev) for _ in range(4))
     _lib.check(L.pn2_bn_finalize(P, C, ld, nblk, part.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps,
                                  momentum, rm.data_ptr() if rm is not None else None,
-                                 rv.data_ptr() if rv is not None else None, a.data_ptr(), b.data_ptr(),
+                                 rv.data_ptr() if rv is not None else None,
+                                 nbt.data_ptr() if nbt is not None else None, a.data_ptr(), b.data_ptr(),
                                  mean.data_ptr(), invstd.data_ptr(), _stream(dev)), "bn_finalize")
     return a, b, mean, invstd
 
@@ -130,7 +137,8 @@ class SharedMLPRows(Function):
     """x0 [P, Cin] -> out [P/ns, C_L] (max over each run of ns rows) or [P, C_L] (ns == 0).
 
     args: x0, ns, training, eps, momentum, buffers, relus, then (W, gamma, beta) per layer.
-    ``buffers`` is a list of (running_mean, running_var) per layer (updated in place);
+    ``buffers`` is a list of (running_mean, running_var, num_batches_tracked) per layer (updated
+    in place, as torch.nn.BatchNorm does in train mode);
     ``relus`` one flag per layer (the pooled last layer always has its ReLU).
     """
 
@@ -150,7 +158,7 @@ class SharedMLPRows(Function):
                 W2 = W.reshape(W.shape[0], -1)
                 st = _BNLayer()
                 st.cout = W2.shape[0]
-                rm, rv = buffers[l]
+                rm, rv, nbt = buffers[l]
                 if use_tc:
                     # tensor-core layer: the previous layer's BN fold + ReLU is applied to the A tile
                     # on chip (its normalised output is only written out, once, for the backward
@@ -164,7 +172,7 @@ class SharedMLPRows(Function):
                         hs.append(h)
                     if training:
                         st.a, st.b, st.mean, st.invstd = _bn_finalize(P, st.cout, part, ld, nblk, gamma, beta,
-                                                                      rm, rv, eps, momentum)
+                                                                      rm, rv, eps, momentum, nbt)
                     else:
                         st.a, st.b, st.mean, st.invstd = _bn_forward(st.z, gamma, beta, rm, rv, eps, momentum, False)
                     layers.append(st)
@@ -176,7 +184,7 @@ class SharedMLPRows(Function):
                     if W2.shape[1] != cin:  # first layer: rows are zero-padded to a multiple of 4
                         W2 = F.pad(W2, (0, cin - W2.shape[1]))
                     st.z = _mm(hs[-1], W2.t())
-                    st.a, st.b, st.mean, st.invstd = _bn_forward(st.z, gamma, beta, rm, rv, eps, momentum, training)
+                    st.a, st.b, st.mean, st.invstd = _bn_forward(st.z, gamma, beta, rm, rv, eps, momentum, training, nbt)
                     layers.append(st)
                     C = st.cout
                 if l < nl - 1 or ns == 0:
@@ -358,14 +366,11 @@ def run_mlp_rows(mlp, x0, ns):
     norms = [layer.bn.bn for layer in layers]
     for layer, norm in zip(layers, norms):
         params += [layer.conv.weight, norm.weight, norm.bias]
-        buffers.append((norm.running_mean, norm.running_var))
+        buffers.append((norm.running_mean, norm.running_var, norm.num_batches_tracked))
         relus.append(getattr(layer, "activation", None) is not None)
-    out = SharedMLPRows.apply(x0, ns, training, float(norms[0].eps), float(norms[0].momentum), buffers,
-                              tuple(relus), *params)
-    if training:
-        for norm in norms:
-            norm.num_batches_tracked.add_(1)
-    return out
+    # running statistics AND num_batches_tracked are updated inside the finalise kernels
+    return SharedMLPRows.apply(x0, ns, training, float(norms[0].eps), float(norms[0].momentum), buffers,
+                               tuple(relus), *params)
 
 
 def pad4(c):

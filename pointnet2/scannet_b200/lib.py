@@ -19,6 +19,7 @@ _f = ctypes.c_float
 # name -> argtypes; every data pointer is passed as a raw device address
 SIGNATURES = {
     "pn2_furthest_point_sampling": [_i, _i, _i, _vp, _vp, _vp, _vp],
+    "pn2_furthest_point_sampling_pruned": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_gather_points": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_gather_points_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_query_ball_point": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
@@ -29,7 +30,7 @@ SIGNATURES = {
     "pn2_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     # shared-MLP block, rows layout
     "pn2_bn_stats_workspace_floats": [_i],
-    "pn2_bn_stats": [_i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pn2_bn_stats": [_i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_bn_fold_eval": [_i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp],
     "pn2_bn_relu_apply": [_i, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "pn2_bn_relu_groupmax": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -46,7 +47,10 @@ SIGNATURES = {
     "pn2_mlp_gemm_grid": [_i, _i],
     "pn2_mlp_pack_weights": [_i, _i, _i, _vp, _vp, _vp],
     "pn2_mlp_gemm_fwd": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],
-    "pn2_bn_finalize": [_i, _i, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pn2_bn_finalize": [_i, _i, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    # flat-buffer training-step utilities
+    "pn2_sum_partials": [_i, _i, _vp, _vp, _vp],
+    "pn2_adam_flat": [ctypes.c_longlong, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp],
 }
 LIBRARY_SYMBOLS = ("pn2_abi_version", "pn2_launch_count", "pn2_reset_launch_count",
                    "pn2_status_string")

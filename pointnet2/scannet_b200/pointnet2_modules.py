@@ -28,7 +28,10 @@ class _PointnetSAModuleBase(nn.Module):
         self.groupers = None
         self.mlps = None
 
-    def forward(self, xyz, features=None):
+    def forward(self, xyz, features=None, geometry=None):
+        """``geometry`` (optional) = (new_xyz, [idx per scale]) computed ahead by geometry.build_plan."""
+        if geometry is not None and self._fused_ok(xyz, features):
+            return geometry[0], self._forward_rows(xyz, geometry[0], features, geometry[1])
         new_xyz = None
         if self.npoint is not None:
             # FPS on (B, N, 3); the centres are gathered from the channel-major copy
@@ -61,7 +64,7 @@ class _PointnetSAModuleBase(nn.Module):
                 return False
         return True
 
-    def _forward_rows(self, xyz, new_xyz, features):
+    def _forward_rows(self, xyz, new_xyz, features, idxs=None):
         B, N, _ = xyz.shape
         cols = [xyz] if features is None else [xyz, fused.rows_of(features)]
         width = sum(c.size(2) for c in cols)
@@ -69,8 +72,9 @@ class _PointnetSAModuleBase(nn.Module):
             cols.append(xyz.new_zeros(B, N, fused.pad4(width) - width))
         table = torch.cat(cols, dim=2)                       # (B, N, 3 + C [+ pad]) per-point rows
         pooled = []
-        for grouper, mlp in zip(self.groupers, self.mlps):
-            idx = pointnet2_utils.ball_query(grouper.radius, grouper.nsample, xyz, new_xyz)
+        for i, (grouper, mlp) in enumerate(zip(self.groupers, self.mlps)):
+            idx = idxs[i] if idxs is not None else pointnet2_utils.ball_query(
+                grouper.radius, grouper.nsample, xyz, new_xyz)
             rows = fused.SAGroupRows.apply(table, new_xyz, idx)          # (B*npoint*nsample, ct)
             out = fused.run_mlp_rows(mlp, rows, grouper.nsample)          # (B*npoint, mlp[-1])
             pooled.append(out.view(B, self.npoint, -1))
@@ -121,10 +125,11 @@ class PointnetFPModule(nn.Module):
         super().__init__()
         self.mlp = pt_utils.SharedMLP(mlp, bn=bn)
 
-    def forward(self, unknown, known, unknow_feats, known_feats):
+    def forward(self, unknown, known, unknow_feats, known_feats, geometry=None):
+        """``geometry`` (optional) = (idx, weight) of the three nearest known points, computed ahead."""
         if known is not None and fused.mlp_eligible(self.mlp, known_feats) \
                 and known_feats.size(1) % 4 == 0:
-            return fused.channel_major(self.forward_rows(unknown, known, unknow_feats, known_feats))
+            return fused.channel_major(self.forward_rows(unknown, known, unknow_feats, known_feats, geometry))
 
         if known is None:
             interpolated = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
@@ -138,13 +143,16 @@ class PointnetFPModule(nn.Module):
             [interpolated, unknow_feats], dim=1)             # (B, C2 + C1, n)
         return self.mlp(feats.unsqueeze(-1)).squeeze(-1)
 
-    def forward_rows(self, unknown, known, unknow_feats, known_feats):
+    def forward_rows(self, unknown, known, unknow_feats, known_feats, geometry=None):
         """Fused path, point-major result (B, n, mlp[-1]): interpolation + concat written straight
         into [positions, channels] rows, then the shared MLP on rows (fused.py)."""
         B, n, _ = unknown.shape
-        dist, idx = pointnet2_utils.three_nn(unknown, known)
-        recip = 1.0 / (dist + 1e-8)                          # ref :395-397
-        weight = recip / torch.sum(recip, dim=2, keepdim=True)
+        if geometry is not None:
+            idx, weight = geometry
+        else:
+            dist, idx = pointnet2_utils.three_nn(unknown, known)
+            recip = 1.0 / (dist + 1e-8)                      # ref :395-397
+            weight = recip / torch.sum(recip, dim=2, keepdim=True)
         skip = fused.rows_of(unknow_feats) if unknow_feats is not None else None
         rows = fused.FPInterpRows.apply(fused.rows_of(known_feats), skip, idx, weight)
         return fused.run_mlp_rows(self.mlp, rows, 0).view(B, n, -1)

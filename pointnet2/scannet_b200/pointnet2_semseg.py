@@ -83,24 +83,28 @@ class _Pointnet2SemSeg(nn.Module):
         features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
         return xyz, features
 
-    def forward(self, pointcloud):
+    def forward(self, pointcloud, plan=None):
+        """``plan`` (optional): a geometry.GeometryPlan built from this pointcloud's xyz; the
+        sampling / grouping / neighbour indices are then taken from it instead of being
+        recomputed inline (identical values, see geometry.py)."""
         xyz, features = self._break_up_pc(pointcloud)
         l_xyz, l_features = [xyz], [features]
-        for sa in self.SA_modules:
-            nxt_xyz, nxt_feat = sa(l_xyz[-1], l_features[-1])
+        for k, sa in enumerate(self.SA_modules):
+            nxt_xyz, nxt_feat = sa(l_xyz[-1], l_features[-1], plan.sa[k] if plan is not None else None)
             l_xyz.append(nxt_xyz)
             l_features.append(nxt_feat)
         nfp = len(self.FP_modules)
+        geo = (lambda k: plan.fp[k]) if plan is not None else (lambda k: None)
         for i in range(-1, -nfp, -1):  # coarse -> fine, all but the finest level
             l_features[i - 1] = self.FP_modules[i](
-                l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i])
+                l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i], geo(nfp + i))
         fp0 = self.FP_modules[0]
         if self._head_rows_ok(l_features[1]):
             # finest FP level and the classifier head stay in [points, channels] rows: the head's
             # output rows ARE the (B, N, num_classes) result, no transpose anywhere
-            rows = fp0.forward_rows(l_xyz[0], l_xyz[1], l_features[0], l_features[1])
+            rows = fp0.forward_rows(l_xyz[0], l_xyz[1], l_features[0], l_features[1], geo(0))
             return self._head_rows(rows)
-        l_features[0] = fp0(l_xyz[0], l_xyz[1], l_features[0], l_features[1])
+        l_features[0] = fp0(l_xyz[0], l_xyz[1], l_features[0], l_features[1], geo(0))
         return self.cls_layer(l_features[0]).transpose(1, 2).contiguous()
 
     def _head_rows_ok(self, known_feats):

@@ -17,6 +17,11 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
+# graph capture runs backward on the capture stream while the AccumulateGrad nodes were created
+# on the warm-up stream: intended here, so silence the per-step warning
+if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+
 
 def weighted_cross_entropy(logits, targets, weights=None):
     """logits (P, classes), targets (P,), weights (P,) -> scalar  (lib/loss.py:10-18)."""
@@ -57,38 +62,103 @@ class GradBucket(object):
             self.flat.div_(dist.get_world_size(group))
 
 
+class FlatAdam(object):
+    """torch.optim.Adam's update over ONE flat buffer, CUDA only (libpn2_b200.so: pn2_adam_flat).
+
+    All parameters are re-pointed at views of a single fp32 buffer (state dicts are unaffected);
+    gradients are handed over by autograd as it produces them (``.grad = None`` before backward,
+    so there is no accumulate kernel per tensor), packed into one flat gradient with a single
+    concatenation, all-reduced once when data-parallel, and applied by one kernel whose step
+    counter lives on the device (replayable from a CUDA graph).  This replaces ~75 accumulate
+    launches, the per-tensor-list fused-Adam launches and the gradient bucket zero-fill."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params and all(p.is_cuda and p.dtype == torch.float32 for p in self.params)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        dev = self.params[0].device
+        with torch.no_grad():
+            self.flat = torch.cat([p.detach().reshape(-1) for p in self.params])
+            off = 0
+            for p in self.params:
+                p.data = self.flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    @property
+    def nbytes(self):
+        return self.flat.numel() * 4
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    def pack_grads(self):
+        torch.cat([p.grad.reshape(-1) for p in self.params], out=self.grad)
+
+    def step(self, grad_scale=1.0):
+        from . import lib
+        dev = self.flat.device
+        with torch.cuda.device(dev):
+            lib.check(lib.load().pn2_adam_flat(
+                self.flat.numel(), self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(), self.lr, self.betas[0],
+                self.betas[1], self.eps, self.weight_decay, grad_scale,
+                torch.cuda.current_stream(dev).cuda_stream), "adam_flat")
+
+
 class TrainStep(object):
-    """One optimisation step on a (B, N, 3+C) batch; call it with device tensors."""
+    """One optimisation step on a (B, N, 3+C) batch; call it with device tensors.
+
+    On CUDA the update runs through ``FlatAdam``; on the CPU (the benchmark's cpu_baseline leg and
+    the gloo tests) through ``GradBucket`` + ``torch.optim.Adam``."""
 
     def __init__(self, model, lr=1e-3, weight_decay=0.0, group=None, fused_adam=None, capturable=False):
         self.model = model
         self.group = group
-        self.bucket = GradBucket(model.parameters())
-        if fused_adam is None:
-            fused_adam = self.bucket.flat.is_cuda
-        self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, weight_decay=weight_decay,
-                                          fused=fused_adam, capturable=capturable)
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.flat_mode = params[0].is_cuda and fused_adam is not False
+        if self.flat_mode:
+            self.opt = FlatAdam(params, lr=lr, weight_decay=weight_decay)
+            self.bucket = None
+        else:
+            self.bucket = GradBucket(params)
+            self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, weight_decay=weight_decay)
 
-    def forward_backward(self, pointcloud, targets, weights):
-        self.bucket.zero()
-        logits = self.model(pointcloud)
+    def _world(self):
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.group)
+        return 1
+
+    def forward_backward(self, pointcloud, targets, weights, plan=None):
+        if self.flat_mode:
+            self.opt.zero_grad()
+        else:
+            self.bucket.zero()
+        logits = self.model(pointcloud, plan) if plan is not None else self.model(pointcloud)
         loss = weighted_cross_entropy(logits.reshape(-1, logits.size(-1)),
                                       targets.reshape(-1), weights.reshape(-1))
         loss.backward()
+        if self.flat_mode:
+            self.opt.pack_grads()
         return loss
 
     def reduce_and_update(self):
-        self.bucket.all_reduce_mean(self.group)
-        self.optimizer.step()
+        if not self.flat_mode:
+            self.bucket.all_reduce_mean(self.group)
+            self.optimizer.step()
+            return
+        world = self._world()
+        if world > 1:  # the one collective of the step: the whole gradient, summed
+            dist.all_reduce(self.opt.grad, op=dist.ReduceOp.SUM, group=self.group)
+        self.opt.step(grad_scale=1.0 / world)
 
     def __call__(self, pointcloud, targets, weights):
-        self.bucket.zero()
-        logits = self.model(pointcloud)                                   # (B, N, classes)
-        loss = weighted_cross_entropy(logits.reshape(-1, logits.size(-1)),
-                                      targets.reshape(-1), weights.reshape(-1))
-        loss.backward()
-        self.bucket.all_reduce_mean(self.group)
-        self.optimizer.step()
+        loss = self.forward_backward(pointcloud, targets, weights)
+        self.reduce_and_update()
         return loss
 
 
@@ -128,6 +198,83 @@ class GraphedTrainStep(object):
         for s, t in zip(self.static, (pointcloud, targets, weights)):
             if s.data_ptr() != t.data_ptr():
                 s.copy_(t, non_blocking=True)
+        self.graph.replay()
+        if self.scope == "fwd_bwd":
+            self.step.reduce_and_update()
+        return self.loss
+
+
+class PipelinedTrainStep(object):
+    """GraphedTrainStep + geometry prefetch: while the graph of batch i runs on the main stream,
+    the coordinates-only part of batch i+1 (geometry.build_plan: FPS chain, ball queries, 3-NN) is
+    computed by a second graph on a side stream.  Every batch still gets its own geometry,
+    computed by the same kernels; only WHEN it is computed changes.  Call ``prefetch(batch)`` with
+    the next batch before (or right after) calling the step on the current one."""
+
+    def __init__(self, step, example, scope="step", warmup=3):
+        from . import geometry
+        assert scope in ("step", "fwd_bwd")
+        self.step, self.scope = step, scope
+        self.static = tuple(torch.empty_like(t) for t in example)        # batch being trained on
+        self.next = tuple(torch.empty_like(t) for t in example)          # batch being prefetched
+        self.side = torch.cuda.Stream()
+        self.copied = torch.cuda.Event()
+        self.ready = torch.cuda.Event()
+        for s, t in zip(self.next, example):
+            s.copy_(t)
+        for s, t in zip(self.static, example):
+            s.copy_(t)
+        model = step.model
+        warm = torch.cuda.Stream()
+        warm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(warm):
+            self.plan = geometry.build_plan(model, self.static[0][..., 0:3].contiguous())
+            self.plan_next = geometry.build_plan(model, self.next[0][..., 0:3].contiguous())
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(warm)
+        torch.cuda.synchronize()
+        # graph 1 (side stream): next batch's coordinates -> plan_next
+        self.geo_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.geo_graph, stream=self.side):
+            fresh = geometry.build_plan(model, self.next[0][..., 0:3].contiguous())
+            self.plan_next.copy_from(fresh)
+        # graph 2 (main stream): the training step on (static, plan)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+        self._have_next = False
+        torch.cuda.synchronize()
+
+    def _body(self):
+        loss = self.step.forward_backward(*self.static, plan=self.plan)
+        if self.scope == "step":
+            self.step.reduce_and_update()
+        return loss
+
+    def prefetch(self, pointcloud, targets, weights):
+        """Stage the NEXT batch (host or device tensors) and compute its geometry on the side stream."""
+        main = torch.cuda.current_stream()
+        self.side.wait_event(self.copied)        # the previous contents of `next` were consumed
+        with torch.cuda.stream(self.side):
+            for s, t in zip(self.next, (pointcloud, targets, weights)):
+                s.copy_(t, non_blocking=True)
+            self.geo_graph.replay()
+            self.ready.record(self.side)
+        self._have_next = True
+        del main
+
+    def __call__(self, pointcloud=None, targets=None, weights=None):
+        """Train on the prefetched batch (arguments are only used when nothing was prefetched)."""
+        main = torch.cuda.current_stream()
+        if not self._have_next:
+            self.prefetch(pointcloud, targets, weights)
+        main.wait_event(self.ready)
+        for d, s in zip(self.static, self.next):   # next -> current (device copies, ~12 MB)
+            d.copy_(s, non_blocking=True)
+        self.plan.copy_from(self.plan_next)
+        self.copied.record(main)
+        self._have_next = False
         self.graph.replay()
         if self.scope == "fwd_bwd":
             self.step.reduce_and_update()

@@ -211,3 +211,61 @@ def test_tensor_core_path_matches_cublas_path():
         for n in b2:
             if b2[n].dtype != torch.long:
                 assert rel_err(b1[n], b2[n]) < 2e-3, n
+
+
+def test_flat_adam_matches_torch_adam():
+    """pn2_adam_flat over one flat buffer == torch.optim.Adam (eps outside the root, bias correction,
+    L2 weight decay) step for step: parameters within 1e-6 after 5 steps."""
+    from pointnet2.scannet_b200 import train
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Linear(17, 33), torch.nn.ReLU(), torch.nn.Linear(33, 5)).to(DEV)
+    mine = copy.deepcopy(ref)
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-2, weight_decay=1e-3)
+    opt = train.FlatAdam(mine.parameters(), lr=1e-2, weight_decay=1e-3)
+    for i in range(5):
+        torch.manual_seed(i)
+        x = torch.randn(64, 17, device=DEV)
+        opt_ref.zero_grad()
+        ref(x).square().sum().backward()
+        opt_ref.step()
+        opt.zero_grad()
+        mine(x).square().sum().backward()
+        opt.pack_grads()
+        opt.step()
+    for a, b in zip(mine.parameters(), ref.parameters()):
+        assert (a - b).abs().max() < 1e-6, (a - b).abs().max()
+    assert int(opt.step_count.item()) == 5
+    assert set(mine.state_dict()) == set(ref.state_dict())
+
+
+def test_pipelined_step_equals_eager_step():
+    """CUDA-graph replay with the geometry of the next batch prefetched on a side stream: (1) the plan
+    a step trains with is, bit for bit, the plan of ITS batch (not a stale one); (2) losses follow the
+    eager step's (5e-3: Adam's first steps amplify the atomics-order noise of the scatter-adds)."""
+    from pointnet2.scannet_b200 import geometry, synthetic, train
+    batches = []
+    for i in range(3):
+        x, y, w = synthetic.make_batch(2, 2, 4096, first_chunk=10 * i)
+        batches.append(tuple(torch.from_numpy(a).to(DEV) for a in (x, y, w)))
+
+    def make():
+        torch.manual_seed(0)
+        m = pointnet2_semseg.get_model(20, is_msg=False, input_channels=6).to(DEV).train()
+        m.cls_layer[1].p = 0.0
+        return train.TrainStep(m, lr=1e-3)
+
+    eager = make()
+    want = [float(eager(*batches[i % 3]).item()) for i in range(5)]
+    piped = train.PipelinedTrainStep(make(), batches[2], warmup=0)
+    piped.prefetch(*batches[0])
+    got = []
+    for i in range(5):
+        loss = piped()
+        piped.prefetch(*batches[(i + 1) % 3])
+        got.append(float(loss.item()))
+        torch.cuda.synchronize()
+        assert torch.equal(piped.static[0], batches[i % 3][0])
+        fresh = geometry.build_plan(piped.step.model, batches[i % 3][0][..., 0:3].contiguous())
+        for a, b in zip(piped.plan.tensors(), fresh.tensors()):
+            assert torch.equal(a, b), "step %d trained with a plan that is not its batch's" % i
+    assert np.allclose(got, want, rtol=5e-3), (got, want)

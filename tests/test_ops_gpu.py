@@ -66,6 +66,20 @@ def test_fps_sizes(ext, oracle, n):
     np.testing.assert_array_equal(got, want)
 
 
+@pytest.mark.parametrize("n", [2049, 4096, 4097, 8191, 8192])
+def test_fps_pruned_variant_bit_exact(oracle, n):
+    """The bounding-box-skipping kernel (pn2_furthest_point_sampling_pruned) picks the same indices."""
+    from pointnet2.scannet_b200 import lib
+    xyz, _ = cases.chunk_xyz(3, first=40, npoints=n)
+    m = 300
+    want = oracle.ext_cpu.furthest_point_sampling(cases.t(xyz), m).numpy()
+    pts = g(xyz)
+    out = torch.empty(3, m, dtype=torch.int32, device=DEV)
+    lib.check(lib.load().pn2_furthest_point_sampling_pruned(
+        3, n, m, pts.data_ptr(), None, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "fps_pruned")
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
 def test_fps_more_samples_than_points(ext, oracle):
     pts = np.random.default_rng(5).uniform(1, 2, (2, 50, 3)).astype(np.float32)
     want = oracle.ext_cpu.furthest_point_sampling(cases.t(pts), 80).numpy()
