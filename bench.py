@@ -298,7 +298,7 @@ def run_product(args, world, rank, local):
         return None
     res["clocks"] = {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")}
 
-    # per-op timing (CUDA events around every call into libpn2_b200.so) -> roofline
+    # per-kernel timing: CUDA events around every call into libpn2_b200.so -> roofline
     if not args.no_per_op:
         peaks = {}
         try:
@@ -308,25 +308,42 @@ def run_product(args, world, rank, local):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         nprof = min(args.steps, 5)
-        with profiling.ExtTimer() as timer:
+        with profiling.LibTimer() as timer:
             for i in range(nprof):
                 eager(*dev[i % len(dev)])
         rows = timer.summary(nprof)
         for r in rows:
-            r["frac_of_hbm_peak"] = round(r["gbs"] / peak, 4) if r["gbs"] else None
-        res["per_op"] = rows
-        res["ops_ms_per_step"] = round(sum(r["ms_per_step"] for r in rows), 4)
-        hbm_rows = [r for r in rows if r["op"] in profiling.HBM_BOUND]
-        top = hbm_rows[0]
+            if r.get("gbs"):
+                r["frac_of_hbm_peak"] = round(r["gbs"] / peak, 4)
+        res["per_kernel"] = rows
+        res["lib_ms_per_step_eager"] = round(sum(r["ms_per_step"] for r in rows), 4)
+        by_kernel = {}
+        for r in rows:
+            by_kernel[r["kernel"]] = by_kernel.get(r["kernel"], 0.0) + r["ms_per_step"]
+        res["lib_ms_per_step_by_kernel"] = {k: round(v, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1])}
+        # dominant kernel of the step among those bounded by HBM bandwidth (FPS, ball query and
+        # three_nn are latency / issue bound: reported in per_kernel and "fps", not as a roofline)
+        not_hbm = ("pn2_furthest_point_sampling", "pn2_query_ball_point", "pn2_three_nn")
+        dom = max((k for k in by_kernel if k not in not_hbm), key=lambda k: by_kernel[k])
+        top = max((r for r in rows if r["kernel"] == dom and r.get("gbs")), key=lambda r: r["ms_per_step"])
+        traffic = None
+        try:  # DRAM bytes of this very call from the committed ncu --set full capture, if there is one
+            tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic = tr.get(top["call"])
+        except Exception:  # noqa: BLE001
+            pass
         res["roofline"] = {"bound": "hbm", "kernel": top["call"], "achieved": top["gbs"], "peak": peak,
-                           "unit": "GB/s", "frac": round(top["gbs"] / peak, 4), "traffic": None,
-                           "peak_source": which,
-                           "note": "dominant HBM-bound kernel of the step by time; algorithmic bytes per "
-                                   "SURVEY.md 8(d) / CUDA-event duration on the launching stream"}
-        fps = [r for r in rows if r["op"] == "furthest_point_sampling"]
+                           "unit": "GB/s", "frac": round(top["gbs"] / peak, 4), "traffic": traffic,
+                           "peak_source": which, "kernel_share_of_lib_time": round(by_kernel[dom] / sum(by_kernel.values()), 3),
+                           "note": "dominant HBM-bound kernel of the step (by total time over its launches); its "
+                                   "largest launch: algorithmic bytes (read A, write H and Z once) / CUDA-event "
+                                   "duration on the launching stream"}
+        if top.get("tflops"):
+            res["roofline"]["tensor_tflops"] = top["tflops"]
+        fps = [r for r in rows if r["kernel"] == "pn2_furthest_point_sampling"]
         if fps:
             f = fps[0]
-            m = int(f["call"].rsplit(", ", 1)[1].rstrip(")"))
+            m = int(f["call"].split("(")[1].split(",")[2].strip(" )"))
             res["fps"] = {"call": f["call"], "us_per_call": f["us_per_call"],
                           "ns_per_iteration": round(1e3 * f["us_per_call"] / max(m - 1, 1), 1),
                           "note": "latency-bound (m-1 dependent iterations), not a bandwidth roofline"}

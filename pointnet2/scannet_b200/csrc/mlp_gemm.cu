@@ -14,7 +14,7 @@
 //               statistics) are reduced from the accumulator while it is stored, so Z is not
 //               re-read for them.
 //
-// Structure (one persistent CTA per SM, 288 threads):
+// Structure (persistent CTAs, 288 threads; two per SM when BN <= 128, else one):
 //   warps 0-3  loaders: cp.async 16-byte chunks of A straight into the 128B-swizzled K-major
 //              UMMA tile (3 stages in flight), then transform the landed stage in place
 //              (fold + ReLU + round-to-TF32), fence.proxy.async, arrive on the stage's
@@ -40,8 +40,8 @@ constexpr int kLoadWarps = 4, kEpiWarps = 4;
 constexpr int kThreads = 32 * (kLoadWarps + kEpiWarps + 1);
 constexpr int kMaxBN = 256;
 constexpr int A_STAGE_BYTES = BM * BK * 4;        // 16 KB
-constexpr int kSmemBudget = 200 * 1024;           // A + B stages
-constexpr int kTmemCols = 512;                    // 2 accumulators x 256 columns
+constexpr int kSmemBudget = 200 * 1024;           // A + B stages, one CTA per SM (BN > 128)
+constexpr int kSmemBudgetHalf = 96 * 1024;        // two CTAs per SM (BN <= 128: 256 TMEM columns each)
 
 struct Params {
   const float *A;        // [P, lda]
@@ -55,6 +55,7 @@ struct Params {
   int N, ldz, BN, n_tiles;
   int relu_in;
   int stages, b_stage_bytes;  // pipeline depth; bytes reserved per weight stage (multiple of 1024)
+  int tmem_cols;              // 512 (one CTA per SM) or 256 (two): two accumulators of tmem_cols / 2
 };
 
 // ------------------------------------------------------------------ small PTX wrappers
@@ -106,6 +107,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 256-bit store (Blackwell STG.256): a full 32-byte sector per thread
+__device__ __forceinline__ void st_global_v8(float *p, const float *v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -153,7 +160,7 @@ struct __align__(8) Barriers {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) gemm_tf32_fwd_kernel(Params p) {
+__global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int STAGES = p.stages, B_STAGE_BYTES = p.b_stage_bytes;
   unsigned char *smem_a = smem;                                  // STAGES x 16 KB
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_fwd_kernel(Params p) {
   if (warp == kLoadWarps + kEpiWarps) {  // the MMA warp owns the tensor memory
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&bars->tmem_base)),
-                 "n"(kTmemCols)
+                 "r"(static_cast<uint32_t>(p.tmem_cols))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -190,6 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_fwd_kernel(Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  const int acc_cols = p.tmem_cols / 2;  // column stride between the two accumulators
 
   const int total_kb = my_tiles * p.k_blocks;  // K blocks this CTA streams, over all its tiles
 
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_fwd_kernel(Params p) {
         const uint64_t db = make_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k)  // 32 bytes (8 x tf32) further along K per instruction
-          tc_mma_tf32(tmem_base + acc * kMaxBN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          tc_mma_tf32(tmem_base + acc * acc_cols, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
         tc_commit(&bars->empty[s]);                       // stage reusable once these MMAs retire
         if (kb == p.k_blocks - 1) tc_commit(&bars->acc_full[acc]);
         if (++s == STAGES) s = 0, par ^= 1;
@@ -303,10 +311,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_fwd_kernel(Params p) {
       for (int c = 0; c < kMaxBN / 32; ++c) {
         if (c < chunks) {
           float v[32];
-          tc_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * kMaxBN + c * 32, v);
+          tc_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * acc_cols + c * 32, v);
           const int n0 = n_tile * p.BN + c * 32;
           if (p.Z != nullptr && grow < p.P) {
             float *dst = p.Z + static_cast<size_t>(grow) * p.ldz + n0;
+            if (n0 + 32 <= p.N && (p.ldz & 7) == 0) {  // the thread's 128-byte row segment: 4 x STG.256
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, v + j);
+            } else
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               if (n0 + j + 3 < p.N) {
@@ -352,7 +364,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32_fwd_kernel(Params p) {
   }
   if (warp == kLoadWarps + kEpiWarps) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(p.tmem_cols))
                  : "memory");
   }
 }
@@ -395,7 +408,8 @@ extern "C" int pn2_mlp_gemm_n_tiles(int n) { return (n + gemm::pick_bn(n) - 1) /
 extern "C" int pn2_mlp_gemm_k_blocks(int k) { return (k + gemm::BK - 1) / gemm::BK; }
 extern "C" int pn2_mlp_gemm_grid(int p, int n) {
   const int m_tiles = (p + gemm::BM - 1) / gemm::BM;
-  const int per = kNumSMs / pn2_mlp_gemm_n_tiles(n);
+  const int ctas_per_sm = gemm::pick_bn(n) <= 128 ? 2 : 1;
+  const int per = ctas_per_sm * kNumSMs / pn2_mlp_gemm_n_tiles(n);
   return m_tiles < per ? m_tiles : (per < 1 ? 1 : per);
 }
 
@@ -429,7 +443,11 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   // as many stages as fit: the narrow layers (BN = 32..64) are pure streaming and need >100 KB of
   // loads in flight per SM to cover HBM latency; the wide ones get 4 x 48 KB
   prm.b_stage_bytes = (prm.BN * gemm::BK * 4 + 1023) / 1024 * 1024;
-  prm.stages = gemm::kSmemBudget / (gemm::A_STAGE_BYTES + prm.b_stage_bytes);
+  // Narrow layers (BN <= 128) are pure streaming: two CTAs per SM (256 TMEM columns and <= 96 KB of
+  // stages each) double the loads in flight and the warps available to hide latency.
+  const bool two_per_sm = prm.BN <= 128;
+  prm.tmem_cols = two_per_sm ? 256 : 512;
+  prm.stages = (two_per_sm ? gemm::kSmemBudgetHalf : gemm::kSmemBudget) / (gemm::A_STAGE_BYTES + prm.b_stage_bytes);
   if (prm.stages > gemm::kMaxStages) prm.stages = gemm::kMaxStages;
   if (prm.stages < 2) return PN2_ERR_UNSUPPORTED;
   const size_t smem = static_cast<size_t>(prm.stages) * (gemm::A_STAGE_BYTES + prm.b_stage_bytes) +
@@ -437,7 +455,7 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   cudaError_t e = cudaFuncSetAttribute(gemm::gemm_tf32_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  dim3 grid(pn2_mlp_gemm_grid(p, n), prm.n_tiles);
+  dim3 grid(pn2_mlp_gemm_grid(p, n), prm.n_tiles);  // the partials buffer is sized by the same function
   gemm::gemm_tf32_fwd_kernel<<<grid, gemm::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(prm);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();

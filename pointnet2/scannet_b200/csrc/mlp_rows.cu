@@ -614,24 +614,33 @@ extern "C" int pn2_bn_finalize(int p, int c, int ld, int nblk, const float *part
 // ---------------------------------------------------------------------------------------
 // Small training-step utilities on flat fp32 buffers (one launch each instead of one per tensor)
 // ---------------------------------------------------------------------------------------
-// out[j] = sum_s in[s, j]  (fixed order): the S partial weight gradients of a split-K GEMM
+// out[j] = sum_s in[s, j]  (fixed order): the S partial weight gradients of a split-K GEMM.
+// One WARP per float4 of the output: lane l adds partials l, l+32, ... and a shuffle tree
+// combines the lanes, so even a 32x32 weight gradient summed over ~300 slabs uses 256 warps.
 __global__ void __launch_bounds__(kRowThreads)
 sum_partials_kernel(int S, int M4, const float *__restrict__ in, float *__restrict__ out) {
-  const int j = blockIdx.x * kRowThreads + threadIdx.x;
+  const int j = blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (j >= M4) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < S; ++s) {
+  for (int s = lane; s < S; s += 32) {
     const float4 v = ld4(in, static_cast<size_t>(s) * M4 + j);
     acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
   }
-  reinterpret_cast<float4 *>(out)[j] = acc;
+  for (int o = 16; o > 0; o >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o), acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o), acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+  }
+  if (lane == 0) reinterpret_cast<float4 *>(out)[j] = acc;
 }
 
 extern "C" int pn2_sum_partials(int s, int m, const float *in, float *out, void *stream) {
   if (s <= 0 || m <= 0 || m % 4 != 0) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(in, out);
   if (!aligned16(in) || !aligned16(out)) return PN2_ERR_UNSUPPORTED;
-  sum_partials_kernel<<<blocks_for(m / 4), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(s, m / 4, in, out);
+  const int warps_per_cta = kRowThreads / 32;
+  sum_partials_kernel<<<(m / 4 + warps_per_cta - 1) / warps_per_cta, kRowThreads, 0,
+                        static_cast<cudaStream_t>(stream)>>>(s, m / 4, in, out);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

@@ -106,3 +106,109 @@ class ExtTimer(object):
                              ms_per_step=round(d["ms"] / steps, 4)))
         rows.sort(key=lambda r: -r["ms_per_step"])
         return rows
+
+
+# ---------------------------------------------------------------------------------------------
+# every launch through libpn2_b200.so (the fused-block kernels are called straight from fused.py,
+# not through the nine-function table): bracket the C-ABI calls themselves
+# ---------------------------------------------------------------------------------------------
+def _lib_bytes(name, a):
+    """Algorithmic bytes (and flops) of one C-ABI call from its scalar arguments; None = not modelled.
+    Same convention as SURVEY.md 8(d): inputs read once, outputs written once, 4 bytes per element."""
+    if name == "pn2_mlp_gemm_fwd":
+        p, k, lda, n = a[0], a[1], a[2], a[3]
+        h_out, z = a[9], a[11]
+        return 4 * p * lda + (4 * p * lda if h_out else 0) + (4 * p * n if z else 0) + 4 * n * k, 2 * p * k * n
+    if name == "pn2_bn_stats":
+        return 4 * a[0] * a[1], 0
+    if name == "pn2_bn_relu_apply":
+        return 8 * a[0] * a[1], 0
+    if name == "pn2_bn_relu_groupmax":
+        g, ns, c = a[0], a[1], a[2]
+        return 4 * g * ns * c + 8 * g * c, 0
+    if name == "pn2_pool_bn_bwd":
+        g, ns, c = a[0], a[1], a[2]
+        return 8 * g * ns * c + 12 * g * c, 0                 # read z, write dz (+ dout, argmax, z at argmax)
+    if name == "pn2_relu_bn_bwd":
+        return 20 * a[0] * a[1], 0                            # stats pass reads dh, z; dz pass reads both, writes dz
+    if name in ("pn2_sa_group_rows", "pn2_sa_group_rows_grad"):
+        b, n, npoint, ns, ct = a[:5]
+        rows = b * npoint * ns
+        return 4 * rows + 4 * ct * min(b * n, rows) + 4 * rows * ct, 0
+    if name in ("pn2_fp_interp_rows", "pn2_fp_interp_rows_grad"):
+        b, n, m, c2, c1 = a[:5]
+        ct = (c2 + c1 + 3) // 4 * 4
+        return 24 * b * n + 4 * b * min(m, 3 * n) * c2 + 4 * b * n * c1 + 4 * b * n * ct, 0
+    if name == "pn2_furthest_point_sampling":
+        return 12 * a[0] * a[1] + 4 * a[0] * a[2], 0
+    if name == "pn2_query_ball_point":
+        b, n, m, ns = a[0], a[1], a[2], a[4]
+        return 12 * b * n + 12 * b * m + 4 * b * m * ns, 0
+    if name == "pn2_three_nn":
+        b, n, m = a[0], a[1], a[2]
+        return 36 * b * n + 12 * b * m, 0
+    if name in ("pn2_gather_points", "pn2_gather_points_grad"):
+        b, c, n, m = a[:4]
+        return 4 * b * m + 4 * b * c * min(n, m) + 4 * b * c * m, 0
+    if name == "pn2_adam_flat":
+        return 28 * a[0], 0
+    return None
+
+
+class LibTimer(object):
+    """Context manager: CUDA events around EVERY call into libpn2_b200.so (on the stream the kernels
+    launch on).  summary() aggregates by (entry point, scalar arguments)."""
+
+    def __init__(self):
+        from . import lib
+        self.lib = lib.load()
+        self.records = []
+        self._saved = {}
+
+    def __enter__(self):
+        from . import lib
+        names = [n for n in lib.SIGNATURES if not n.endswith(("_bn", "_n_tiles", "_k_blocks", "_grid",
+                                                              "_workspace_floats"))]
+        for name in names:
+            fn = getattr(self.lib, name)
+            self._saved[name] = fn
+
+            def wrapped(*args, _fn=fn, _name=name):
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                st = _fn(*args)
+                e1.record()
+                scal = tuple(x for x in args[:6] if isinstance(x, float) or (isinstance(x, int) and 0 <= x < 2 ** 31))
+                self.records.append((_name, scal, _lib_bytes(_name, args), e0, e1))
+                return st
+            setattr(self.lib, name, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        for name, fn in self._saved.items():
+            setattr(self.lib, name, fn)
+        return False
+
+    def summary(self, steps):
+        torch.cuda.synchronize()
+        agg = collections.OrderedDict()
+        for name, scal, model, e0, e1 in self.records:
+            key = "%s%s" % (name, scal)
+            d = agg.setdefault(key, dict(kernel=name, call=key, calls=0, ms=0.0, model=model))
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+        rows = []
+        for d in agg.values():
+            us = 1e3 * d["ms"] / d["calls"]
+            row = dict(kernel=d["kernel"], call=d["call"], calls_per_step=d["calls"] / float(steps),
+                       us_per_call=round(us, 2), ms_per_step=round(d["ms"] / steps, 4))
+            if d["model"] is not None and us > 0:
+                nbytes, flops = d["model"]
+                row["bytes_per_call"] = int(nbytes)
+                row["gbs"] = round(nbytes / (us * 1e-6) / 1e9, 1)
+                if flops:
+                    row["tflops"] = round(flops / (us * 1e-6) / 1e12, 2)
+            rows.append(row)
+        rows.sort(key=lambda r: -r["ms_per_step"])
+        return rows
