@@ -50,7 +50,11 @@ def _compile(src, force, verbose):
     if p.returncode != 0:
         raise RuntimeError("nvcc failed on %s:\n%s\n%s" % (src, p.stdout, p.stderr))
     if os.path.basename(src) in NO_FMA:
-        _assert_no_contraction(obj)
+        try:
+            _assert_no_contraction(obj)
+        except RuntimeError:
+            os.remove(obj)  # never leave an object behind that a later incremental build would link
+            raise
     return obj, p.stderr
 
 

@@ -24,6 +24,7 @@
 //     minimum -1.0f: fminf(d, -1) stays -1, which never beats a real
 //     candidate (>= 0) -- exactly the reference's `best = -1` initial value --
 //     and if nothing else exists position 0 (= index 0) wins, as `besti = 0`.
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -51,6 +52,8 @@ __device__ __forceinline__ int fps_index_to_pos(int k, const FpsGeom &g) {
   const int trev = g.log2bs ? static_cast<int>(__brev(t) >> (32 - g.log2bs)) : 0;
   return trev * g.q + (k >> g.log2bs);
 }
+
+namespace cg = cooperative_groups;
 
 // Block-wide arg-max of (value desc, position asc).  `v` = float bits of this
 // thread's best minimum distance (as signed int: -1.0f < every float >= 0),
@@ -232,7 +235,7 @@ fps_pruned_kernel(FpsGeom g, const float *__restrict__ dataset, int *__restrict_
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         const float span = hi[a] - lo[a];
-        const float u = span > 0.f ? (q[a] - lo[a]) / span : 0.f;
+        const float u = span > 0.f ? __fdividef(q[a] - lo[a], span) : 0.f;  // sort key only: no parity role
         c3[a] = static_cast<unsigned>(fminf(fmaxf(u * 1023.f, 0.f), 1023.f));
       }
       code = morton_expand10(c3[0]) | (morton_expand10(c3[1]) << 1) | (morton_expand10(c3[2]) << 2);
@@ -367,6 +370,139 @@ static cudaError_t launch_pruned(const FpsGeom &g, int b, const float *dataset, 
 }
 
 // ---------------------------------------------------------------------------
+// thread-block-cluster kernel: one cloud per CLUSTER of C CTAs (8192 < positions <= 16 * T * P,
+// i.e. whole scenes of up to ~160k points, or smaller clouds split for latency).
+//
+// CTA r keeps positions [r*S, (r+1)*S), S = T*P, in registers exactly like the resident kernel.
+// Per iteration: local block arg-max (one __syncthreads), then lane r of warp 0 writes this CTA's
+// candidate -- (value bits, position, x, y, z, original index), 32 bytes -- into slot [parity][rank]
+// of CTA r's shared memory (distributed shared memory store), ONE cluster barrier, and every warp
+// of every CTA reduces the C candidates with the same REDUX pair.  The exchanged record carries the
+// winner's coordinates, so no CTA ever reads another CTA's point table.  Slots are double buffered
+// by iteration parity, which makes one cluster barrier per iteration sufficient (a CTA can only run
+// one barrier ahead of the slowest reader).
+// ---------------------------------------------------------------------------
+struct __align__(16) FpsCand {
+  int val;        // float bits of the running minimum (as int: -1.0f sorts below every value >= 0)
+  unsigned pos;   // reference position (tie-break key)
+  int idx;        // original point index
+  int pad;
+  float x, y, z, w;
+};
+
+template <int P, int T>
+__global__ void __launch_bounds__(T, 1)
+fps_cluster_kernel(FpsGeom g, int csize, const float *__restrict__ dataset, int *__restrict__ idxs) {
+  constexpr int S = T * P;
+  extern __shared__ float4 s_pts[];  // [S] this CTA's slice (x, y, z, bits(index)), by local position
+  __shared__ int2 s_slots[2][32];
+  __shared__ FpsCand s_xchg[2][16];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int cloud = blockIdx.x / csize;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T / 32;
+  const int npos = g.bs * g.q;
+  const float *pts = dataset + static_cast<size_t>(cloud) * g.n * 3;
+  int *out = idxs + static_cast<size_t>(cloud) * g.m;
+  const int base = rank * S;
+
+  constexpr int H = (P + 1) / 2;
+  float2 x[H], y[H], z[H], t[H];
+#pragma unroll
+  for (int i = 0; i < 2 * H; ++i) {
+    const int p = base + tid * P + i;
+    const int k = (i < P && p < npos) ? fps_pos_to_index(p, g) : g.n;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    bool live = false;
+    if (k < g.n) {
+      px = __ldg(pts + 3 * k), py = __ldg(pts + 3 * k + 1), pz = __ldg(pts + 3 * k + 2);
+      live = !(static_cast<double>(sqnorm_rn(px, py, pz)) <= 1e-3);
+    }
+    const float t0 = live ? 1e10f : -1.0f;
+    if (i & 1) x[i / 2].y = px, y[i / 2].y = py, z[i / 2].y = pz, t[i / 2].y = t0;
+    else x[i / 2].x = px, y[i / 2].x = py, z[i / 2].x = pz, t[i / 2].x = t0;
+    if (i < P) s_pts[tid * P + i] = make_float4(px, py, pz, __int_as_float(k < g.n ? k : 0));
+  }
+  if (rank == 0 && tid == 0) out[0] = 0;
+  // first centre = index 0 = position 0, owned by CTA 0: fetch it from global memory
+  float cx0 = __ldg(pts + 0), cy0 = __ldg(pts + 1), cz0 = __ldg(pts + 2);
+  cluster.sync();  // every CTA's shared memory (exchange slots) exists before anyone writes to it
+
+  float c_x = cx0, c_y = cy0, c_z = cz0;
+  for (int j = 1; j < g.m; ++j) {
+    const float2 cx = make_float2(c_x, c_x), cy = make_float2(c_y, c_y), cz = make_float2(c_z, c_z);
+    float best;
+    int bi = 0;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float2 d = sqdist2_rn(x[h], y[h], z[h], cx, cy, cz);
+      t[h].x = fminf(d.x, t[h].x);
+      t[h].y = fminf(d.y, t[h].y);
+      if (h == 0) {
+        best = t[0].x;
+      } else if (t[h].x > best) {
+        best = t[h].x, bi = 2 * h;
+      }
+      if (2 * h + 1 < P && t[h].y > best) best = t[h].y, bi = 2 * h + 1;
+    }
+    // local arg-max (value, lowest global position)
+    const int v = __float_as_int(best);
+    const int wmax = __reduce_max_sync(kFull, v);
+    const unsigned wpos = __reduce_min_sync(kFull, v == wmax ? static_cast<unsigned>(base + tid * P + bi) : 0xffffffffu);
+    if (lane == 0) s_slots[j & 1][warp] = make_int2(wmax, static_cast<int>(wpos));
+    __syncthreads();
+    if (warp == 0) {
+      int2 r = make_int2(INT_MIN, -1);
+      if (lane < nwarps) r = s_slots[j & 1][lane];
+      const int lmax = __reduce_max_sync(kFull, r.x);
+      const unsigned lpos = __reduce_min_sync(kFull, r.x == lmax ? static_cast<unsigned>(r.y) : 0xffffffffu);
+      if (lane < csize) {  // lane r publishes this CTA's candidate in CTA r's exchange slot
+        const float4 pw = s_pts[lpos - base];
+        FpsCand cand;
+        cand.val = lmax, cand.pos = lpos, cand.idx = __float_as_int(pw.w), cand.pad = 0;
+        cand.x = pw.x, cand.y = pw.y, cand.z = pw.z, cand.w = 0.f;
+        FpsCand *remote = cluster.map_shared_rank(&s_xchg[j & 1][rank], lane);
+        *remote = cand;
+      }
+    }
+    cluster.sync();  // release the stores / acquire everyone else's
+    int cv = INT_MIN;
+    unsigned cp = 0xffffffffu;
+    if (lane < csize) cv = s_xchg[j & 1][lane].val, cp = s_xchg[j & 1][lane].pos;
+    const int gmax = __reduce_max_sync(kFull, cv);
+    const unsigned gpos = __reduce_min_sync(kFull, cv == gmax ? cp : 0xffffffffu);
+    const unsigned who = __ballot_sync(kFull, cv == gmax && cp == gpos);
+    const FpsCand &win = s_xchg[j & 1][__ffs(who) - 1];
+    c_x = win.x, c_y = win.y, c_z = win.z;
+    if (rank == 0 && tid == 0) out[j] = win.idx;
+  }
+  cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
+}
+
+template <int P, int T>
+static cudaError_t launch_cluster(const FpsGeom &g, int b, int csize, const float *dataset, int *idxs,
+                                  cudaStream_t stream) {
+  auto kern = fps_cluster_kernel<P, T>;
+  const size_t smem = static_cast<size_t>(T) * P * sizeof(float4);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  if (csize > 8) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(b * csize), cfg.blockDim = dim3(T), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, g, csize, dataset, idxs);
+  count_launch();
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // streaming fallback for n > PN2_FPS_MAX_RESIDENT_N: minima in the caller's
 // `temp` like the reference.  1024 threads; thread t scans k = t, t+1024, ...
 // (k mod bs is constant per thread because 1024 % bs == 0, so a thread's
@@ -468,6 +604,16 @@ static int fps_dispatch(int b, int n, int m, const float *dataset, float *temp, 
     // barrier, second-stage arg-max), not by the distance updates.  It is therefore opt-in
     // (pn2_furthest_point_sampling_pruned / PN2_FPS_PRUNE=1); see DESIGN.md section 4.
     static const bool prune = getenv("PN2_FPS_PRUNE") != nullptr;
+    // PN2_FPS_SPLIT=c (2, 4, 8): split every resident-size cloud over a cluster of c CTAs (more SMs
+    // per cloud, fewer points per thread, one cluster barrier per iteration extra).  Measured, not
+    // the default: see DESIGN.md section 4.
+    const int split = getenv("PN2_FPS_SPLIT") != nullptr ? atoi(getenv("PN2_FPS_SPLIT")) : 0;
+    if (split >= 2 && split <= 8 && !force_pruned && npos > 1024 && m > 1) {
+      const int per = (npos + split - 1) / split;
+      if (per <= 8 * 128) return static_cast<int>(launch_cluster<8, 128>(g, b, split, dataset, idxs, s));
+      if (per <= 8 * 256) return static_cast<int>(launch_cluster<8, 256>(g, b, split, dataset, idxs, s));
+      if (per <= 8 * 512) return static_cast<int>(launch_cluster<8, 512>(g, b, split, dataset, idxs, s));
+    }
     if ((prune || force_pruned) && npos > 4096 && m > 2) e = launch_pruned<8, 1024>(g, b, dataset, idxs, s);
     else if ((prune || force_pruned) && npos > 2048 && m > 2) e = launch_pruned<8, 512>(g, b, dataset, idxs, s);
     else if (npos <= 128 * 1) e = launch_resident<1, 1024>(g, b, threads_for(1), dataset, idxs, s);
@@ -475,6 +621,15 @@ static int fps_dispatch(int b, int n, int m, const float *dataset, float *temp, 
     else if (npos <= 128 * 4) e = launch_resident<4, 1024>(g, b, threads_for(4), dataset, idxs, s);
     else if (npos <= 1024 * 8) e = launch_resident<8, 1024>(g, b, threads_for(8), dataset, idxs, s);
     else return PN2_ERR_UNSUPPORTED;
+    return static_cast<int>(e);
+  }
+  // whole scenes: one CLUSTER per cloud, the slices register-resident in 2..16 CTAs
+  const bool no_cluster = getenv("PN2_FPS_NO_CLUSTER") != nullptr;
+  if (!no_cluster && npos <= 16 * 768 * 13) {
+    int csize = 2;
+    while (csize < 16 && csize * 8192 < npos) csize *= 2;
+    cudaError_t e = csize * 8192 >= npos ? launch_cluster<8, 1024>(g, b, csize, dataset, idxs, s)
+                                         : launch_cluster<13, 768>(g, b, 16, dataset, idxs, s);
     return static_cast<int>(e);
   }
   if (temp == nullptr) return PN2_ERR_INVALID_ARG;

@@ -6,6 +6,8 @@ the op is a copy or an un-contracted fp32 expression; scatter-add gradients with
 1e-5 relative (the reference's atomicAdd order is itself nondeterministic; the
 oracle accumulates in double).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -94,6 +96,46 @@ def test_fps_streaming_large_cloud(ext, oracle):
     pts[:, 5000:9000] = pts[:, 1000:5000]
     want = oracle.ext_cpu.furthest_point_sampling(cases.t(pts), 128).numpy()
     got = ext.furthest_point_sampling(g(pts), 128).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("n,m,b", [(150000, 96, 1), (40000, 64, 3), (8200, 40, 2)])
+def test_fps_cluster_whole_scene(ext, oracle, n, m, b):
+    """8192 < n <= 159744: one thread-block CLUSTER per cloud (2..16 CTAs, register-resident slices,
+    one distributed-shared-memory exchange + cluster barrier per iteration)."""
+    rng = np.random.default_rng(n)
+    pts = rng.uniform(0.5, 6.0, (b, n, 3)).astype(np.float32)
+    pts[:, n // 2:n // 2 + 3000] = pts[:, 100:3100]          # exact duplicates -> ties
+    pts[:, 7] = 0.01                                         # near-origin skip
+    want = oracle.ext_cpu.furthest_point_sampling(cases.t(pts), m).numpy()
+    got = ext.furthest_point_sampling(g(pts), m).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    os.environ["PN2_FPS_NO_CLUSTER"] = "1"                   # the streaming kernel, same answer
+    try:
+        got2 = ext.furthest_point_sampling(g(pts), m).cpu().numpy()
+    finally:
+        del os.environ["PN2_FPS_NO_CLUSTER"]
+    np.testing.assert_array_equal(got2, want)
+
+
+def test_fps_streaming_beyond_cluster_capacity(ext, oracle):
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(0.5, 9.0, (1, 170000, 3)).astype(np.float32)
+    want = oracle.ext_cpu.furthest_point_sampling(cases.t(pts), 24).numpy()
+    got = ext.furthest_point_sampling(g(pts), 24).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("split", [2, 4, 8])
+def test_fps_split_over_cluster(ext, oracle, split):
+    """PN2_FPS_SPLIT: resident-size clouds split over a cluster, same indices."""
+    xyz, _ = cases.chunk_xyz(2)
+    want = oracle.ext_cpu.furthest_point_sampling(cases.t(xyz), 300).numpy()
+    os.environ["PN2_FPS_SPLIT"] = str(split)
+    try:
+        got = ext.furthest_point_sampling(g(xyz), 300).cpu().numpy()
+    finally:
+        del os.environ["PN2_FPS_SPLIT"]
     np.testing.assert_array_equal(got, want)
 
 
