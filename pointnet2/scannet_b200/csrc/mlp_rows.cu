@@ -225,13 +225,13 @@ pool_bwd_stats_kernel(ColGeom g, int ns, const float *__restrict__ dout, const i
 // sums the partials (fp64, fixed order, one warp per channel): dbeta, dgamma, and the two
 // per-channel constants c1 = dbeta/P, c2 = dgamma/P used by the dense dZ kernels (0 in eval mode)
 __global__ void __launch_bounds__(32 * kFinalizeWarps)
-bwd_stats_finalize_kernel(int P, int C, int nblk, int training, const float *__restrict__ partials,
+bwd_stats_finalize_kernel(int P, int C, int ld, int nblk, int training, const float *__restrict__ partials,
                           float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ c1,
                           float *__restrict__ c2) {
   const int c = blockIdx.x * kFinalizeWarps + (threadIdx.x >> 5);
   if (c >= C) return;
   double s, q;
-  warp_sum_partials(C, c, nblk, partials, s, q);
+  warp_sum_partials(ld, c, nblk, partials, s, q);
   if ((threadIdx.x & 31) != 0) return;
   dbeta[c] = static_cast<float>(s);
   dgamma[c] = static_cast<float>(q);
@@ -506,7 +506,7 @@ extern "C" int pn2_pool_bn_bwd(int g, int ns, int c, int training, const float *
   float *c1 = workspace + static_cast<size_t>(kMaxPartials) * 2 * c, *c2 = c1 + c;
   const size_t smem = sizeof(float4) * 2 * geom.row_lanes * geom.C4;
   pool_bwd_stats_kernel<<<nblk, kRowThreads, smem, s>>>(geom, ns, dout, argmax, z, a, b, mean, invstd, workspace);
-  bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(g * ns, c, nblk, training, workspace, dgamma,
+  bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(g * ns, c, c, nblk, training, workspace, dgamma,
                                                             dbeta, c1, c2);
   const size_t total4 = static_cast<size_t>(g) * (c / 4);
   pool_bwd_dz_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(g, ns, c / 4, dout, argmax, z, a, b, mean,
@@ -527,12 +527,62 @@ extern "C" int pn2_relu_bn_bwd(int p, int c, int training, int relu, const float
   float *c1 = workspace + static_cast<size_t>(kMaxPartials) * 2 * c, *c2 = c1 + c;
   const size_t smem = sizeof(float4) * 2 * geom.row_lanes * geom.C4;
   relu_bwd_stats_kernel<<<nblk, kRowThreads, smem, s>>>(geom, relu, dh, z, a, b, mean, invstd, workspace);
-  bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(p, c, nblk, training, workspace, dgamma, dbeta,
+  bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(p, c, c, nblk, training, workspace, dgamma, dbeta,
                                                             c1, c2);
   const size_t total4 = static_cast<size_t>(p) * (c / 4);
   relu_bwd_dz_kernel<<<blocks_for(total4, 16 * kNumSMs), kRowThreads, 0, s>>>(total4, c / 4, relu, dh, z, a, b,
                                                                              mean, invstd, c1, c2, dz);
   count_launch(3);
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+// Statistics halves of the two adjoints above, for the fused tensor-core backward layer
+// (mlp_bwd.cu), which forms dZ on chip: dgamma, dbeta and c1c2 = [dbeta / P | dgamma / P].
+extern "C" int pn2_pool_bn_bwd_stats(int g, int ns, int c, int training, const float *dout, const int *argmax,
+                                     const float *z, const float *a, const float *b, const float *mean,
+                                     const float *invstd, float *dgamma, float *dbeta, float *c1c2,
+                                     float *workspace, void *stream) {
+  if (g <= 0 || ns <= 0 || c <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(dout, argmax, z, a, b, mean, invstd, dgamma, dbeta, c1c2, workspace);
+  if (!rows_ok(c, z) || !aligned16(dout) || !aligned16(argmax) || !aligned16(workspace)) return PN2_ERR_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int nblk;
+  const ColGeom geom = col_geom(g, c, &nblk);
+  const size_t smem = sizeof(float4) * 2 * geom.row_lanes * geom.C4;
+  pool_bwd_stats_kernel<<<nblk, kRowThreads, smem, s>>>(geom, ns, dout, argmax, z, a, b, mean, invstd, workspace);
+  bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(
+      g * ns, c, c, nblk, training, workspace, dgamma, dbeta, c1c2, c1c2 + c);
+  count_launch(2);
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_relu_bn_bwd_stats(int p, int c, int training, int relu, const float *dh, const float *z,
+                                     const float *a, const float *b, const float *mean, const float *invstd,
+                                     float *dgamma, float *dbeta, float *c1c2, float *workspace, void *stream) {
+  if (p <= 0 || c <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(dh, z, a, b, mean, invstd, dgamma, dbeta, c1c2, workspace);
+  if (!rows_ok(c, z) || !aligned16(dh) || !aligned16(workspace)) return PN2_ERR_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int nblk;
+  const ColGeom geom = col_geom(p, c, &nblk);
+  const size_t smem = sizeof(float4) * 2 * geom.row_lanes * geom.C4;
+  relu_bwd_stats_kernel<<<nblk, kRowThreads, smem, s>>>(geom, relu, dh, z, a, b, mean, invstd, workspace);
+  bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(
+      p, c, c, nblk, training, workspace, dgamma, dbeta, c1c2, c1c2 + c);
+  count_launch(2);
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+// partials [nblk][2][ld] (column sums of dY and dY * zhat from pn2_mlp_bwd_layer's epilogue) ->
+// dgamma, dbeta, c1c2 of the layer below
+extern "C" int pn2_bwd_stats_finalize(int p, int c, int ld, int nblk, int training, const float *partials,
+                                      float *dgamma, float *dbeta, float *c1c2, void *stream) {
+  if (p <= 0 || c <= 0 || ld < c || nblk <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(partials, dgamma, dbeta, c1c2);
+  bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0,
+                              static_cast<cudaStream_t>(stream)>>>(p, c, ld, nblk, training, partials, dgamma,
+                                                                   dbeta, c1c2, c1c2 + c);
+  count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
 

@@ -22,6 +22,8 @@ from . import lib as _lib
 
 GEMM_TF32 = True   # tensor-core TF32 GEMMs, like the reference's cuDNN convs on Ampere+
 ENABLED = True     # module forward()s take the fused path when eligible
+TC_BWD = False     # backward layers on the fused tcgen05 kernel (csrc/mlp_bwd.cu: BN adjoint + dH + dW +
+                   # next statistics in one pass) where the shape is supported and TC_GEMM is on
 TC_GEMM = True     # forward layers on the hand-written tcgen05 kernel (csrc/mlp_gemm.cu) when
                    # GEMM_TF32: BN fold + ReLU of the previous layer in its prologue, BN batch
                    # statistics in its epilogue; off: cuBLAS GEMM + separate streaming kernels
@@ -151,11 +153,16 @@ class SharedMLPRows(Function):
         layers, hs = [], [x0]
         out = argmax = None
         use_tc = TC_GEMM and GEMM_TF32
-        want_h = any(ctx.needs_input_grad)
+        want_grad = any(ctx.needs_input_grad)
+        bwd_fused = [False] * nl
         with torch.cuda.device(dev):
             for l in range(nl):
                 W, gamma, beta = params[3 * l:3 * l + 3]
                 W2 = W.reshape(W.shape[0], -1)
+                lda = x0.shape[1] if l == 0 else layers[l - 1].cout
+                bwd_fused[l] = bool(use_tc and TC_BWD and want_grad and
+                                    L.pn2_mlp_bwd_supported(P, W2.shape[0], W2.shape[1], lda))
+                want_h = want_grad and not bwd_fused[l]   # the fused adjoint recomputes H_{l-1} from Z_{l-1}
                 st = _BNLayer()
                 st.cout = W2.shape[0]
                 rm, rv, nbt = buffers[l]
@@ -169,7 +176,7 @@ class SharedMLPRows(Function):
                     st.z, h, part, (ld, nblk) = _tc_layer(A, W2.shape[1], W2, fold,
                                                           relus[l - 1] if l > 0 else False, want_h, training)
                     if l > 0:
-                        hs.append(h)
+                        hs.append(h)          # None when the fused backward layer will recompute it
                     if training:
                         st.a, st.b, st.mean, st.invstd = _bn_finalize(P, st.cout, part, ld, nblk, gamma, beta,
                                                                       rm, rv, eps, momentum, nbt)
@@ -202,7 +209,7 @@ class SharedMLPRows(Function):
                     _lib.check(L.pn2_bn_relu_groupmax(G, ns, C, st.z.data_ptr(), st.a.data_ptr(),
                                                       st.b.data_ptr(), out.data_ptr(), argmax.data_ptr(),
                                                       _stream(dev)), "bn_relu_groupmax")
-        ctx.layers, ctx.hs, ctx.argmax = layers, hs, argmax
+        ctx.layers, ctx.hs, ctx.argmax, ctx.bwd_fused = layers, hs, argmax, bwd_fused
         ctx.ns, ctx.training, ctx.nl, ctx.relus = ns, training, nl, relus
         ctx.weights = [params[3 * l] for l in range(nl)]
         return out
@@ -215,35 +222,105 @@ class SharedMLPRows(Function):
         dout = dout.contiguous()
         grads = [None] * (3 * nl)
         training = 1 if ctx.training else 0
+        s = _stream(dev)
+
+        def f32(*shape):
+            return torch.empty(*shape, dtype=torch.float32, device=dev)
+
         with torch.cuda.device(dev):
             dh = dout
+            pending = None   # (dgamma, dbeta, c1c2) of layer l, produced by layer l+1's fused kernel
             for l in range(nl - 1, -1, -1):
                 st = layers[l]
                 P, C = st.z.shape
+                W = ctx.weights[l]
+                W2 = W.reshape(W.shape[0], -1)
+                K = W2.shape[1]
+                pooled = l == nl - 1 and ns > 0
+                need_dh = l > 0 or ctx.needs_input_grad[0]
+                if ctx.bwd_fused[l]:
+                    # ---- one tensor-core pass: BN adjoint + dH_prev + dW + the next layer's statistics ----
+                    if pending is None:
+                        dgamma, dbeta, c1c2 = f32(C), f32(C), f32(2 * C)
+                        if pooled:
+                            _lib.check(L.pn2_pool_bn_bwd_stats(
+                                P // ns, ns, C, training, dh.data_ptr(), ctx.argmax.data_ptr(), st.z.data_ptr(),
+                                st.a.data_ptr(), st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
+                                dgamma.data_ptr(), dbeta.data_ptr(), c1c2.data_ptr(), _ws(C, dev).data_ptr(), s),
+                                "pool_bn_bwd_stats")
+                        else:
+                            _lib.check(L.pn2_relu_bn_bwd_stats(
+                                P, C, training, int(ctx.relus[l]), dh.data_ptr(), st.z.data_ptr(), st.a.data_ptr(),
+                                st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), dgamma.data_ptr(),
+                                dbeta.data_ptr(), c1c2.data_ptr(), _ws(C, dev).data_ptr(), s), "relu_bn_bwd_stats")
+                    else:
+                        dgamma, dbeta, c1c2 = pending
+                    prev = layers[l - 1] if l > 0 else None
+                    a_prev = prev.z if prev is not None else hs[0]
+                    lda = a_prev.shape[1]
+                    nb, kb, kpad = L.pn2_mlp_bwd_nb(C), L.pn2_mlp_bwd_kb(lda), L.pn2_mlp_bwd_kpad(lda)
+                    grid = L.pn2_mlp_bwd_grid(P)
+                    wtp = dh_prev = sp = None
+                    if need_dh:
+                        W2c = W2.contiguous()
+                        wtp = f32(nb * kpad * 32)
+                        _lib.check(L.pn2_mlp_pack_weights_t(C, K, lda, W2c.shape[1], W2c.data_ptr(), wtp.data_ptr(), s),
+                                   "mlp_pack_weights_t")
+                        dh_prev = f32(P, lda)
+                        if prev is not None:
+                            sp = f32(grid, 2, kb * 32)
+                    dwp = f32(grid, nb * 32 * kb * 32)
+                    _lib.check(L.pn2_mlp_bwd_layer(
+                        P, C, K, lda, ns if pooled else 0, 1 if pooled else int(ctx.relus[l]),
+                        int(ctx.relus[l - 1]) if prev is not None else 0,
+                        None if pooled else dh.data_ptr(), dh.data_ptr() if pooled else None,
+                        ctx.argmax.data_ptr() if pooled else None, st.z.data_ptr(), st.a.data_ptr(),
+                        st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), c1c2.data_ptr(),
+                        a_prev.data_ptr(), prev.a.data_ptr() if prev is not None else None,
+                        prev.b.data_ptr() if prev is not None else None,
+                        prev.mean.data_ptr() if prev is not None else None,
+                        prev.invstd.data_ptr() if prev is not None else None,
+                        wtp.data_ptr() if wtp is not None else None,
+                        dh_prev.data_ptr() if dh_prev is not None else None, dwp.data_ptr(),
+                        sp.data_ptr() if sp is not None else None, s), "mlp_bwd_layer")
+                    dW = f32(nb * 32, kb * 32)
+                    _lib.check(L.pn2_sum_partials(grid, nb * 32 * kb * 32, dwp.data_ptr(), dW.data_ptr(), s),
+                               "sum_partials")
+                    grads[3 * l] = dW[:C, :K].reshape(W.shape)
+                    grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
+                    pending = None
+                    if sp is not None:
+                        Kc = prev.cout
+                        pg, pb, pc = f32(Kc), f32(Kc), f32(2 * Kc)
+                        _lib.check(L.pn2_bwd_stats_finalize(P, Kc, kb * 32, grid, training, sp.data_ptr(),
+                                                            pg.data_ptr(), pb.data_ptr(), pc.data_ptr(), s),
+                                   "bwd_stats_finalize")
+                        pending = (pg, pb, pc)
+                    dh = dh_prev
+                    continue
+                # ---- streaming adjoint kernels + cuBLAS GEMMs ----
+                pending = None
                 dz = torch.empty_like(st.z)
-                dgamma = torch.empty(C, dtype=torch.float32, device=dev)
-                dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+                dgamma, dbeta = f32(C), f32(C)
                 ws = _ws(C, dev)
-                if l == nl - 1 and ns > 0:
+                if pooled:
                     _lib.check(L.pn2_pool_bn_bwd(P // ns, ns, C, training, dh.data_ptr(),
                                                  ctx.argmax.data_ptr(), st.z.data_ptr(), st.a.data_ptr(),
                                                  st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
                                                  dz.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                                                 ws.data_ptr(), _stream(dev)), "pool_bn_bwd")
+                                                 ws.data_ptr(), s), "pool_bn_bwd")
                 else:
                     _lib.check(L.pn2_relu_bn_bwd(P, C, training, int(ctx.relus[l]), dh.data_ptr(), st.z.data_ptr(),
                                                  st.a.data_ptr(), st.b.data_ptr(), st.mean.data_ptr(),
                                                  st.invstd.data_ptr(), dz.data_ptr(), dgamma.data_ptr(),
-                                                 dbeta.data_ptr(), ws.data_ptr(), _stream(dev)), "relu_bn_bwd")
-                W = ctx.weights[l]
-                W2 = W.reshape(W.shape[0], -1)
+                                                 dbeta.data_ptr(), ws.data_ptr(), s), "relu_bn_bwd")
                 h_prev = hs[l]
                 dW = _mm_tn_splitk(dz, h_prev)                 # [Cout, Cin(_pad)]
                 if dW.shape[1] != W2.shape[1]:
                     dW = dW[:, :W2.shape[1]]
                 grads[3 * l] = dW.reshape(W.shape)
                 grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
-                if l > 0 or ctx.needs_input_grad[0]:
+                if need_dh:
                     if W2.shape[1] != h_prev.shape[1]:
                         W2 = F.pad(W2, (0, h_prev.shape[1] - W2.shape[1]))
                     dh = _mm(dz, W2)                           # [P, Cin]

@@ -1,0 +1,166 @@
+"""GPU parity of the fused tensor-core backward layer (csrc/mlp_bwd.cu) through the C ABI.
+
+Reference: the layer adjoint in numpy -- dZ and H_prev formed in fp32 exactly as the kernel forms
+them, rounded to TF32 (cvt.rna), the two products in fp64.  What remains is fp32 accumulation
+order (and an occasional TF32 rounding flip where the compiler contracts the dZ expression), so
+the tolerance is 1e-4 of each output's max magnitude; the BatchNorm-adjoint column sums of the
+layer below within 2e-4.
+"""
+import numpy as np
+import pytest
+import torch
+
+from pointnet2.scannet_b200 import lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def tf32_rna(x):
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV) if x is not None else None
+
+
+def ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def make_case(rng, P, N, K, lda, ns, relu, fold, relu_in):
+    f32 = np.float32
+    z = rng.standard_normal((P, N)).astype(f32)
+    gamma = rng.uniform(0.5, 1.5, N).astype(f32) * rng.choice([-1, 1], N).astype(f32)
+    beta = (0.3 * rng.standard_normal(N)).astype(f32)
+    mean = z.mean(0).astype(f32)
+    invstd = (1.0 / np.sqrt(z.var(0) + 1e-5)).astype(f32)
+    a = (gamma * invstd).astype(f32)
+    b = (beta - mean * a).astype(f32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(f32)
+    aprev = np.zeros((P, lda), f32)
+    aprev[:, :K] = rng.standard_normal((P, K)).astype(f32)
+    if fold:
+        a_in = rng.uniform(0.5, 1.5, K).astype(f32) * rng.choice([-1, 1], K).astype(f32)
+        b_in = (0.2 * rng.standard_normal(K)).astype(f32)
+        mean_in = aprev[:, :K].mean(0).astype(f32)
+        invstd_in = (1.0 / np.sqrt(aprev[:, :K].var(0) + 1e-5)).astype(f32)
+    else:
+        a_in = b_in = mean_in = invstd_in = None
+    if ns:
+        G = P // ns
+        dout = rng.standard_normal((G, N)).astype(f32)
+        argmax = rng.integers(0, ns, (G, N)).astype(np.int32)
+        dh = np.zeros((P, N), f32)
+        gi, ci = np.meshgrid(np.arange(G), np.arange(N), indexing="ij")
+        dh[gi * ns + argmax, ci] = dout
+        dense = None
+    else:
+        dout = argmax = None
+        dh = rng.standard_normal((P, N)).astype(f32)
+        dense = dh
+    # this layer's adjoint in fp32, as the kernel evaluates it
+    y = a * z + b
+    dy = np.where((y > 0) | (not relu), dh, f32(0)).astype(f32)
+    zhat = ((z - mean) * invstd).astype(f32)
+    c1 = (dy.astype(np.float64).sum(0) / P).astype(f32)
+    c2 = ((dy.astype(np.float64) * zhat).sum(0) / P).astype(f32)
+    dz = (a * (dy - c1 - zhat * c2)).astype(f32)
+    if fold:
+        h = a_in * aprev[:, :K] + b_in
+        if relu_in:
+            h = np.maximum(h, 0)
+        h = h.astype(f32)
+    else:
+        h = aprev[:, :K]
+    dz64, h64, w64 = (tf32_rna(t).astype(np.float64) for t in (dz, h, W))
+    ref = {"dh_prev": dz64 @ w64, "dw": dz64.T @ h64}
+    if fold:
+        yp = a_in * aprev[:, :K] + b_in
+        mask = (yp > 0) | (not relu_in)
+        dyp = np.where(mask, ref["dh_prev"], 0.0)
+        zhp = (aprev[:, :K].astype(np.float64) - mean_in) * invstd_in
+        ref["s"], ref["q"] = dyp.sum(0), (dyp * zhp).sum(0)
+    case = dict(P=P, N=N, K=K, lda=lda, ns=ns, relu=relu, relu_in=relu_in, dh=dense, dout=dout, argmax=argmax,
+                z=z, a=a, b=b, mean=mean, invstd=invstd, c1c2=np.concatenate([c1, c2]), aprev=aprev, a_in=a_in,
+                b_in=b_in, mean_in=mean_in, invstd_in=invstd_in, W=W)
+    return case, ref
+
+
+def run_layer(c, dgrad=True, stats=True):
+    L = lib.load()
+    s = torch.cuda.current_stream().cuda_stream
+    P, N, K, lda = c["P"], c["N"], c["K"], c["lda"]
+    assert L.pn2_mlp_bwd_supported(P, N, K, lda) == 1
+    nb, kb, kpad, grid = L.pn2_mlp_bwd_nb(N), L.pn2_mlp_bwd_kb(lda), L.pn2_mlp_bwd_kpad(lda), L.pn2_mlp_bwd_grid(P)
+    t = {k: dev(c[k]) for k in ("dh", "dout", "argmax", "z", "a", "b", "mean", "invstd", "c1c2", "aprev", "a_in",
+                                "b_in", "mean_in", "invstd_in", "W")}
+    wtp = None
+    if dgrad:
+        wtp = torch.empty(nb * kpad * 32, dtype=torch.float32, device=DEV)
+        lib.check(L.pn2_mlp_pack_weights_t(N, K, lda, K, ptr(t["W"]), ptr(wtp), s), "pack_t")
+    dh_prev = torch.full((P, lda), float("nan"), dtype=torch.float32, device=DEV) if dgrad else None
+    dwp = torch.full((grid, nb * 32, kb * 32), float("nan"), dtype=torch.float32, device=DEV)
+    stats = stats and dgrad and c["a_in"] is not None
+    sp = torch.full((grid, 2, kb * 32), float("nan"), dtype=torch.float32, device=DEV) if stats else None
+    lib.check(L.pn2_mlp_bwd_layer(P, N, K, lda, c["ns"], int(c["relu"]), int(c["relu_in"]), ptr(t["dh"]),
+                                  ptr(t["dout"]), ptr(t["argmax"]), ptr(t["z"]), ptr(t["a"]), ptr(t["b"]),
+                                  ptr(t["mean"]), ptr(t["invstd"]), ptr(t["c1c2"]), ptr(t["aprev"]), ptr(t["a_in"]),
+                                  ptr(t["b_in"]), ptr(t["mean_in"]), ptr(t["invstd_in"]), ptr(wtp), ptr(dh_prev),
+                                  ptr(dwp), ptr(sp), s), "mlp_bwd_layer")
+    torch.cuda.synchronize()
+    out = {"dw": dwp.double().sum(0).cpu().numpy()[:N, :K]}
+    if dgrad:
+        out["dh_prev"] = dh_prev.cpu().numpy()
+    if stats:
+        sq = sp.double().sum(0).cpu().numpy()
+        out["s"], out["q"] = sq[0, :K], sq[1, :K]
+    return out
+
+
+def check(out, ref, K):
+    for key, tol in (("dw", 1e-4), ("dh_prev", 1e-4), ("s", 2e-4), ("q", 2e-4)):
+        if key not in out:
+            continue
+        got, want = out[key], ref[key]
+        if key == "dh_prev":
+            assert np.isfinite(got).all()
+            assert np.abs(got[:, K:]).max(initial=0.0) == 0.0     # padding columns are written as zeros
+            got = got[:, :K]
+        err = np.abs(got - want).max()
+        assert err <= tol * np.abs(want).max(), "%s: err %g vs max %g" % (key, err, np.abs(want).max())
+
+
+@pytest.mark.parametrize("P,N,K,lda", [
+    (4096, 32, 32, 32), (5000, 64, 32, 32), (3000, 128, 64, 64), (2500, 128, 128, 128),
+    (70000, 64, 64, 64), (1000, 128, 132, 132), (777, 20, 128, 128), (130, 96, 40, 40)])
+def test_bwd_layer_hidden(P, N, K, lda):
+    """dense upstream gradient, BN + ReLU below: dH_prev, dW and the statistics of the layer below"""
+    rng = np.random.default_rng(P + N + K)
+    c, ref = make_case(rng, P, N, K, lda, 0, True, True, True)
+    check(run_layer(c), ref, K)
+
+
+@pytest.mark.parametrize("P,N,K,lda,dgrad", [
+    (4096, 32, 9, 12, False), (4096, 64, 67, 68, True), (2048, 128, 134, 136, True), (999, 128, 131, 132, True)])
+def test_bwd_layer_first(P, N, K, lda, dgrad):
+    """first layer of a block: the input rows are used as they are (zero-padded to lda), no BN below"""
+    rng = np.random.default_rng(P + K)
+    c, ref = make_case(rng, P, N, K, lda, 0, True, False, False)
+    check(run_layer(c, dgrad=dgrad), ref, K)
+
+
+@pytest.mark.parametrize("G,ns,N,K", [(128, 32, 64, 32), (100, 32, 128, 64), (64, 16, 128, 128), (37, 64, 32, 32)])
+def test_bwd_layer_pooled(G, ns, N, K):
+    """pooled last layer: the upstream gradient is the arg-max scatter of dOut"""
+    rng = np.random.default_rng(G + N)
+    c, ref = make_case(rng, G * ns, N, K, K, ns, True, True, True)
+    check(run_layer(c), ref, K)
+
+
+def test_bwd_layer_no_relu_head():
+    """the classifier's last unit has no activation (pointnet2_semseg.py:157-158)"""
+    rng = np.random.default_rng(3)
+    c, ref = make_case(rng, 3000, 20, 128, 128, 0, False, False, False)
+    check(run_layer(c), ref, 128)
