@@ -257,16 +257,18 @@ PN2_API int pn2_bn_finalize(int p, int c, int ld, int nblk, const float *partial
  *     dW      = dZ^T * H_prev               per-CTA partials [pn2_mlp_bwd_grid(p)][nb*32][kb*32],
  *                                           nb = pn2_mlp_bwd_nb(n), kb = pn2_mlp_bwd_kb(lda)
  *     stats   = column sums of dY_prev and dY_prev * zhat_prev, per-CTA partials
- *               [grid][2][kb*32] for pn2_bwd_stats_finalize (stats_part NULL: skipped)
+ *               [grid][2][kb*32] for pn2_bwd_stats_finalize (stats_part NULL: skipped);
+ *               they are obtained as sum_n w[n,c] * (dZ^T M)[n,c] from two tensor-core
+ *               products with the ReLU mask M of the layer below (w [n, k] fp32)
  * with H_prev = relu_in ? max(a_in * a_prev + b_in, 0) : ... recomputed from the previous
  * layer's pre-BN output a_prev [p, lda] (a_in NULL: a_prev is used as it is, e.g. the
  * block's grouped input rows).  z [p, n], a/b/mean/invstd [n] are this layer's saved
  * forward state, c1c2 = [dbeta/P | dgamma/P] from pn2_*_bwd_stats or
- * pn2_bwd_stats_finalize.  Supported: n <= 128, n % 4 == 0, lda <= 160, lda % 4 == 0
- * (pn2_mlp_bwd_supported); wt_packed from pn2_mlp_pack_weights_t (nb * kpad * 32 floats,
+ * pn2_bwd_stats_finalize.  Supported: n <= 128, n % 4 == 0, lda <= 160 (128 with
+ * statistics), lda % 4 == 0 (pn2_mlp_bwd_supported); wt_packed from pn2_mlp_pack_weights_t (nb * kpad * 32 floats,
  * kpad = pn2_mlp_bwd_kpad(lda)).  TF32 operands, fp32 accumulation.
  * ========================================================================== */
-PN2_API int pn2_mlp_bwd_supported(int p, int n, int k, int lda);
+PN2_API int pn2_mlp_bwd_supported(int p, int n, int k, int lda, int with_stats);
 PN2_API int pn2_mlp_bwd_grid(int p);
 PN2_API int pn2_mlp_bwd_nb(int n);
 PN2_API int pn2_mlp_bwd_kb(int lda);
@@ -276,7 +278,7 @@ PN2_API int pn2_mlp_pack_weights_t(int n, int k, int lda, int ldw, const float *
 PN2_API int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu, int relu_in,
                               const float *dh, const float *dout, const int *argmax, const float *z,
                               const float *a, const float *b, const float *mean, const float *invstd,
-                              const float *c1c2, const float *a_prev, const float *a_in,
+                              const float *c1c2, const float *w, const float *a_prev, const float *a_in,
                               const float *b_in, const float *mean_in, const float *invstd_in,
                               const float *wt_packed, float *dh_prev, float *dw_part,
                               float *stats_part, void *stream);

@@ -9,30 +9,44 @@
 //   dZ      = a * (dY - c1 - zhat * c2)      dY = dH masked by this layer's ReLU (or, for the
 //                                            pooled last layer, the arg-max scatter of dOut)
 //   dH_prev = dZ * W                          GEMM 1  (M = 128 rows, N = K channels, reduce over N)
-//   dW     += dZ^T * H_prev                   GEMM 2  (M = N, N = K, reduce over the 128 rows)
-//   s, q   += column sums of dY_prev, dY_prev * zhat_prev    (the NEXT layer adjoint's BN constants)
+//   dW      = dZ^T * H_prev                   GEMM 2  (M = N, N = K, reduce over the rows)
+//   s, q    = column sums of dY_prev, dY_prev * zhat_prev   (BN-adjoint constants of the layer below)
 //
-// dZ is formed on chip from (dH, Z) and never written; H_prev = relu(a_in * Z_prev + b_in) is
-// recomputed from Z_prev (the forward pass does not store it); dW accumulates in tensor memory over
-// all of a CTA's tiles and leaves the SM once.  HBM traffic per layer: read dH, Z, Z_prev, write
-// dH_prev -- against 7 reads/writes of [P, N] plus 2 of [P, K] for the unfused sequence.
+// dZ is formed on chip from (dH, Z) and never written; H_prev is recomputed from Z_prev (the
+// forward pass does not store it); dW accumulates in tensor memory over all of a CTA's tiles and
+// leaves the SM once.  HBM traffic per layer: read dH, Z, Z_prev, write dH_prev -- against 7
+// reads/writes of [P, N] plus 2 of [P, K] for the unfused sequence.
+//
+// Statistics without an epilogue pass.  With M = relu mask of the layer below and
+// H_prev = M .* (g1 * zhat_prev + g0)  (g1 = gamma, g0 = beta per column), GEMM 2 is run on the two
+// operands M and M .* zhat_prev instead of H_prev:
+//     S = dZ^T * M,   Q = dZ^T * (M .* zhat_prev)          (both [N, K], accumulated in TMEM)
+//     dW = g1 .* Q + g0 .* S                                 (column scaling at the final read-out)
+//     s[c] = sum_n W[n,c] S[n,c],   q[c] = sum_n W[n,c] Q[n,c]
+// because dY_prev = M .* (dZ * W): the column sums the next adjoint needs are linear in S and Q.
+// The per-tile epilogue is then only TMEM -> HBM of dH_prev.
 //
 // GEMM 2 reduces over ROWS, so its operands are read MN-major straight from row-major slabs
-// ([128 rows][32 fp32], slab stride = leading byte offset): dZ^T and H_prev are never transposed in
-// memory.  MN-major TF32 operands must use the 32-byte-atom 128-byte swizzle, GEMM 1's K-major A
-// operand the ordinary 16-byte-atom one, so a dZ slab is written twice by its loader: once into the
-// tile's dZ set (GEMM 2) and once into the group's small staging slot (GEMM 1, freed one step later).
+// ([128 rows][32 fp32], slab stride = leading byte offset): nothing is transposed in memory.
+// MN-major TF32 operands must use the 32-byte-atom 128-byte swizzle, GEMM 1's K-major A operand the
+// ordinary 16-byte-atom one, so a dZ slab is written twice by its loader: into the tile's dZ set
+// (GEMM 2) and into the group's staging slot (GEMM 1, freed one step later).
 //
-// Structure (persistent CTAs, one per SM, 17 warps):
-//   warps 0-3   epilogue: tcgen05.ld of dH_prev, row stores, ReLU mask of the previous layer from
-//               Z_prev and the butterfly column sums for its BN adjoint; at the end dW TMEM -> HBM
+// Structure (persistent CTAs, one per SM, 21 warps):
+//   warps 0-3   epilogue: tcgen05.ld of dH_prev + row stores; at the end dW / statistics read-out
 //   warp  4     one elected thread issues every tcgen05.mma (kind::tf32) and commit
-//   warps 5-16  three loader groups of 128 threads taking the tile's slabs round-robin: 16-byte
-//               LDGs (dH and Z, or Z_prev) -> registers -> BN adjoint / fold + ReLU -> TF32 ->
-//               swizzled st.shared -> fence.proxy.async -> mbarrier arrive; W^T tiles by 1-D TMA.
+//   warps 5-20  two loader groups of 256 threads taking the tile's slabs alternately, 4 float4 of a
+//               slab per thread: 16-byte LDGs -> registers -> BN adjoint / fold + ReLU (packed fp32)
+//               -> swizzled st.shared -> fence.proxy.async -> mbarrier arrive; W^T tiles by 1-D TMA.
+//               One group's load latency overlaps the other's arithmetic.  (A single group with a
+//               register prefetch of its next slab does not work: fence.proxy.async compiles to
+//               MEMBAR.ALL.CTA, which waits for the prefetch loads -- measured 1.5 us per slab.)
 //
 // Precision: TF32 operands (round-to-nearest), fp32 accumulation -- the arithmetic class of the
 // reference's own convolutions (torch.backends.cudnn.allow_tf32 defaults to True).
+#include <math.h>
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace pn2 {
@@ -43,15 +57,17 @@ using namespace tc;
 constexpr int BM = 128;                 // rows per tile
 constexpr int BK = 32;                  // channels per slab = one 128-byte swizzle row
 constexpr int SLAB = BM * BK * 4;       // 16 KB
-constexpr int kEpiWarps = 4, kGroups = 3, kGroupWarps = 4;
+constexpr int kEpiWarps = 4, kGroups = 2, kGroupWarps = 8;
+constexpr int kGroupThreads = 32 * kGroupWarps;  // 256: 4 float4 of a slab per thread
 constexpr int kMmaWarp = kEpiWarps;     // warp 4
 constexpr int kFirstLoadWarp = kEpiWarps + 1;
-constexpr int kThreads = 32 * (kEpiWarps + 1 + kGroups * kGroupWarps);  // 544
+constexpr int kThreads = 32 * (kEpiWarps + 1 + kGroups * kGroupWarps);  // 672
 constexpr int kMaxNB = 4;               // N <= 128
-constexpr int kMaxKB = 5;               // K <= 160
-// Every loader group owns ONE H_prev slab and ONE W^T tile slot: a slot then has a single, in-order
-// producer, so its phase-parity waits can never alias (with a shared ring a group running two uses
-// ahead of a lagging group would see the parity it expects and overwrite a live slab).
+constexpr int kMaxKB = 5;               // lda <= 160 (<= 128 when statistics are wanted)
+// Every loader group owns its H_prev slab(s), its dZ staging slab and its W^T tile slot: a slot then
+// has a single, in-order producer, so its phase-parity waits can never alias (with a shared ring a
+// group running two uses ahead of a lagging group would see the parity it expects and overwrite a
+// live slab).
 
 struct Params {
   // this layer, N output channels
@@ -61,6 +77,7 @@ struct Params {
   const float *Z;        // [P, N] pre-BN output of this layer
   const float *a, *b, *mean, *invstd;  // [N] BN fold and statistics of this layer
   const float *c1c2;     // [2][N] dbeta / P, dgamma / P (0 in eval mode)
+  const float *W;        // [N, K] this layer's weight, fp32 (statistics read-out)
   // the layer below, K channels
   const float *Aprev;    // [P, lda]: Z of the previous layer (a_in != nullptr) or the block's input rows
   const float *a_in, *b_in, *mean_in, *invstd_in;  // [K] fold / statistics of the previous layer
@@ -69,18 +86,31 @@ struct Params {
   float *dWpart;         // [gridDim.x][nb * 32][kb * 32]
   float *stats_part;     // [gridDim.x][2][kb * 32]  (nullptr: no BN below)
   int P, N, nb, K, lda, kb, kpad16;
-  int ns, relu, relu_in;
-  int groups, sets, w_slot_bytes, tmem_cols;  // loader groups in use; dZ sets (2, or 1 when N > 64)
+  int ns, ns_shift, relu, relu_in;       // ns_shift >= 0 when ns is a power of two
+  int sets, w_slot_bytes, tmem_cols;     // dZ sets (2, or 1 when N > 64)
+  int dbg;                               // PN2_BWD_DBG timing experiments (results invalid when != 0)
 };
 
+// PN2_BWD_DBG & 32: cycles each role spends in its waits, per CTA (read back with pn2_mlp_bwd_debug_read)
+__device__ unsigned long long g_wait_cycles[kNumSMs][16];
+__device__ __forceinline__ void timed_wait(uint64_t *bar, uint32_t parity, bool on, unsigned long long &acc) {
+  if (!on) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += static_cast<unsigned long long>(clock64() - t0);
+}
+
 struct __align__(8) Barriers {
-  uint64_t dz_full[2][kMaxNB];   // slab c of set s holds dZ           (128 arrivals: one loader group)
+  uint64_t dz_full[2][kMaxNB];   // slab c of set s holds dZ           (256 arrivals: one loader group)
   uint64_t dz_empty[4];          // both products of tile t retired: barrier t & 3 (1 commit).  Four
                                  // barriers for <= two sets keep a loader at most one phase behind.
   uint64_t w_full[kGroups];      // W^T tile landed in the group's slot (1 arrival + tx bytes)
-  uint64_t w_empty[kGroups];     // GEMM 1 step retired: W^T slot and K-major dZ staging slot free (1 commit)
-  uint64_t h_full[kGroups];      // H_prev slab ready                   (128 arrivals)
-  uint64_t h_empty[kGroups];     // GEMM 2 on the slab retired          (1 commit)
+  uint64_t w_empty[kGroups];     // GEMM 1 step retired: W^T slot and dZ staging slot free (1 commit)
+  uint64_t h_full[kGroups];      // H_prev slab(s) ready                (256 arrivals)
+  uint64_t h_empty[kGroups];     // GEMM 2 on them retired              (1 commit)
   uint64_t acc_full[2];          // dH_prev accumulator complete        (1 commit)
   uint64_t acc_empty[2];         // drained by the epilogue             (128 arrivals)
   uint64_t dw_full;              // every MMA of the CTA retired        (1 commit)
@@ -88,41 +118,62 @@ struct __align__(8) Barriers {
 };
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ float4 tf32x4(float4 v) {
   return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+}
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+// Blackwell packed fp32: two fused multiply-adds / multiplies per instruction (FFMA2 / FMUL2)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; "
+      "mov.b64 {%0,%1}, rd;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int nb = p.nb, kb = p.kb, G = p.groups;
+  const int nb = p.nb, kb = p.kb;
   const int nb32 = nb * 32, kb32 = kb * 32;
-  unsigned char *s_dz = smem;                                   // [sets][nb] slabs, MN-major image (GEMM 2)
-  unsigned char *s_h = s_dz + p.sets * nb * SLAB;               // [G] H_prev slabs, one per loader group
-  unsigned char *s_a1 = s_h + G * SLAB;                         // [G] K-major dZ staging slabs (GEMM 1)
-  unsigned char *s_w = s_a1 + G * SLAB;                         // [G] W^T tiles
-  float *s_tab = reinterpret_cast<float *>(s_w + G * p.w_slot_bytes);
-  float *t_a = s_tab, *t_b = t_a + nb32, *t_mu = t_b + nb32, *t_is = t_mu + nb32, *t_c1 = t_is + nb32,
-        *t_c2 = t_c1 + nb32;
-  float *u_a = t_c2 + nb32, *u_b = u_a + kb32, *u_mu = u_b + kb32, *u_is = u_mu + kb32;
-  float *s_stats = u_is + kb32;                                 // [kEpiWarps][2][kb32]
+  const bool dgrad = p.WTp != nullptr;
+  const bool stats = p.stats_part != nullptr;
+  const int hslabs = stats ? 2 : 1;                              // per group: H_prev, or M and M .* zhat
+  unsigned char *s_dz = smem;                                    // [sets][nb] slabs, MN-major image (GEMM 2)
+  unsigned char *s_h = s_dz + p.sets * nb * SLAB;                // [G][hslabs] slabs
+  unsigned char *s_a1 = s_h + kGroups * hslabs * SLAB;           // [G] K-major dZ staging slabs (GEMM 1)
+  unsigned char *s_w = s_a1 + kGroups * SLAB;                    // [G] W^T tiles
+  float *s_tab = reinterpret_cast<float *>(s_w + kGroups * p.w_slot_bytes);
+  // dZ = a * dY + C * z + D  with  C = -a * invstd * c2,  D = -a * c1 - C * mean   (one FMA each)
+  float *t_a = s_tab, *t_b = t_a + nb32, *t_C = t_b + nb32, *t_D = t_C + nb32, *t_x0 = t_D + nb32,
+        *t_x1 = t_x0 + nb32;  // (t_x0 / t_x1 unused: keeps the table block's size)
+  float *u_a = t_x1 + nb32, *u_b = u_a + kb32, *u_mu = u_b + kb32, *u_is = u_mu + kb32;
+  float *s_stats = u_is + kb32;                                  // [kEpiWarps][2][kb32]
   Barriers *bars = reinterpret_cast<Barriers *>(s_stats + kEpiWarps * 2 * kb32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m_tiles = (p.P + BM - 1) / BM;
   const int my_tiles = blockIdx.x < m_tiles ? (m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const bool dgrad = p.WTp != nullptr;
-  const bool stats = p.stats_part != nullptr;
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      for (int c = 0; c < kMaxNB; ++c) mbar_init(&bars->dz_full[s][c], 32 * kGroupWarps);
+      for (int c = 0; c < kMaxNB; ++c) mbar_init(&bars->dz_full[s][c], kGroupThreads);
       mbar_init(&bars->acc_full[s], 1);
       mbar_init(&bars->acc_empty[s], 32 * kEpiWarps);
     }
     for (int s = 0; s < 4; ++s) mbar_init(&bars->dz_empty[s], 1);
     for (int s = 0; s < kGroups; ++s) {
       mbar_init(&bars->w_full[s], 1), mbar_init(&bars->w_empty[s], 1);
-      mbar_init(&bars->h_full[s], 32 * kGroupWarps), mbar_init(&bars->h_empty[s], 1);
+      mbar_init(&bars->h_full[s], kGroupThreads), mbar_init(&bars->h_empty[s], 1);
     }
     mbar_init(&bars->dw_full, 1);
     mbar_fence_init();
@@ -135,10 +186,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = tid; i < nb32; i += kThreads) {
-    const bool ok = i < p.N;
-    t_a[i] = ok ? p.a[i] : 0.f, t_b[i] = ok ? p.b[i] : 0.f;
-    t_mu[i] = ok ? p.mean[i] : 0.f, t_is[i] = ok ? p.invstd[i] : 0.f;
-    t_c1[i] = ok ? p.c1c2[i] : 0.f, t_c2[i] = ok ? p.c1c2[p.N + i] : 0.f;
+    const bool ok = i < p.N;  // channels past N: all-zero constants give dZ = 0
+    const float a = ok ? p.a[i] : 0.f;
+    const float C = ok ? -a * p.invstd[i] * p.c1c2[p.N + i] : 0.f;
+    t_a[i] = a, t_b[i] = ok ? p.b[i] : 0.f;
+    t_C[i] = C, t_D[i] = ok ? -a * p.c1c2[i] - C * p.mean[i] : 0.f;
   }
   for (int i = tid; i < kb32; i += kThreads) {
     const bool ok = p.a_in != nullptr && i < p.K;
@@ -146,197 +198,288 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
     u_mu[i] = ok && p.mean_in != nullptr ? p.mean_in[i] : 0.f;
     u_is[i] = ok && p.invstd_in != nullptr ? p.invstd_in[i] : 0.f;
   }
+  // (zhat_prev = invstd_in * z + e with e = -mean_in * invstd_in is formed from u_mu / u_is by the loaders)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  // tensor memory: [acc 0 | acc 1] (kb32 columns each, only when dgrad) then dW (kb32 columns)
+  // tensor memory: [acc 0 | acc 1] (kb32 columns each, only when dgrad), then dW [kb32] -- or,
+  // with statistics, [S_h | Q_h] pairs of 32 columns per slab h of the layer below
   const uint32_t tm_acc = tmem_base, tm_dw = tmem_base + (dgrad ? 2 * kb32 : 0);
 
   if (warp >= kFirstLoadWarp) {
     // ======================================= loaders =======================================
     const int lw = warp - kFirstLoadWarp, grp = lw / kGroupWarps;
-    const int gt = (lw % kGroupWarps) * 32 + lane;  // 0..127 within the group
-    const int chunk = gt & 7, row0 = gt >> 3;       // 16-byte chunk of the slab row; rows row0 + 16 i
-    const int ipt = nb + kb;                         // items (slabs) per tile: dZ slabs, then H slabs
-    int tl = grp < G ? 0 : my_tiles, j = grp;  // groups beyond G idle
-    while (j >= ipt) j -= ipt, ++tl;
-    int w_use = 0, h_use = 0;                  // uses of this group's own W^T / H_prev slot so far
-    while (tl < my_tiles) {
+    const int gt = (lw % kGroupWarps) * 32 + lane;  // 0..255 within the group
+    const int chunk = gt & 7, row0 = (gt >> 3) * 4;  // 16-byte chunk of the slab row; rows row0 .. row0 + 3
+    const int ipt = nb + kb;                          // items (slabs) per tile: dZ slabs, then H slabs
+    uint32_t off16[4], off32[4];                      // byte offsets of the thread's 4 chunks in a slab
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      off16[i] = static_cast<uint32_t>((row0 + i) * 128 + ((chunk ^ ((row0 + i) & 7)) << 4));  // SWIZZLE_128B
+      off32[i] = swz_base32(row0 + i, chunk);                                                    // .._BASE32B
+    }
+    int w_use = 0, h_use = 0;                        // uses of this group's own slots so far
+    const bool tm = (p.dbg & 32) != 0;
+    unsigned long long c_w = 0, c_dz = 0, c_h = 0, c_ld = 0, c_tot = clock64();
+
+    // global loads of item (tl, j) into a register buffer: b[0..3] = dH (or dOut) / Z_prev rows,
+    // b[4..7] = Z rows (dZ items only).  Rows past P load as zeros.
+    auto issue = [&](int tl, int j, float4 (&b)[8]) {
       const int tile = blockIdx.x + tl * gridDim.x;
+      const int r0 = tile * BM + row0;
+      const bool full = (tile + 1) * BM <= p.P;
+      if (j < nb) {
+        const int col = j * BK + chunk * 4;
+        const bool colok = col < p.N;
+        const float *zp = p.Z + static_cast<size_t>(r0) * p.N + col;
+        if (p.dH != nullptr) {
+          const float *dp = p.dH + static_cast<size_t>(r0) * p.N + col;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool ok = colok && (full || r0 + i < p.P);
+            b[4 + i] = ok ? ldg4(zp + static_cast<size_t>(i) * p.N) : zero4();
+            b[i] = ok ? ldg4(dp + static_cast<size_t>(i) * p.N) : zero4();
+          }
+        } else {  // pooled: the thread's 4 consecutive rows lie in ONE group (ns % 4 == 0)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            b[4 + i] = (colok && (full || r0 + i < p.P)) ? ldg4(zp + static_cast<size_t>(i) * p.N) : zero4();
+          const int g = p.ns_shift >= 0 ? (r0 >> p.ns_shift) : r0 / p.ns;
+          const bool ok = colok && r0 < p.P;
+          b[0] = ok ? ldg4(p.dout + static_cast<size_t>(g) * p.N + col) : zero4();
+          b[1] = ok ? ldg4(reinterpret_cast<const float *>(p.argmax) + static_cast<size_t>(g) * p.N + col) : zero4();
+        }
+      } else {
+        const int col = (j - nb) * BK + chunk * 4;
+        const bool colok = col < p.lda;
+        const float *ap = p.Aprev + static_cast<size_t>(r0) * p.lda + col;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          b[i] = (colok && (full || r0 + i < p.P)) ? ldg4(ap + static_cast<size_t>(i) * p.lda) : zero4();
+      }
+    };
+
+    // Operands go to shared memory as plain fp32: kind::tf32 reads the upper 19 bits of each word
+    // (truncation), as the library TF32 GEMMs do with fp32 inputs.  The arithmetic is Blackwell's
+    // packed fp32 (FFMA2): the loaders' issue slots, not HBM, bound this kernel otherwise.
+    auto process = [&](int tl, int j, float4 (&b)[8]) {
+      const int tile = blockIdx.x + tl * gridDim.x;
+      const int r0 = tile * BM + row0;
+      const bool full = (tile + 1) * BM <= p.P;
       if (j < nb) {
         // ---------------- dZ slab c: columns [32c, 32c+32) of this layer ----------------
         const int c = j, col = c * BK + chunk * 4;
-        const bool colok = col < p.N;
-        float4 d[8], z[8];
+        if (p.dH == nullptr) {  // pooled layer: the gradient lives on the arg-max row of every (group, channel)
+          const int g = p.ns_shift >= 0 ? (r0 >> p.ns_shift) : r0 / p.ns;
+          const int s0 = r0 - g * p.ns;
+          const float4 dd = b[0];
+          const int4 am = make_int4(__float_as_int(b[1].x), __float_as_int(b[1].y), __float_as_int(b[1].z),
+                                    __float_as_int(b[1].w));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int grow = tile * BM + row0 + 16 * i;
-          const bool ok = colok && grow < p.P;
-          d[i] = z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok) {
-            z[i] = ldg4(p.Z + static_cast<size_t>(grow) * p.N + col);
-            if (p.dH != nullptr) {
-              d[i] = ldg4(p.dH + static_cast<size_t>(grow) * p.N + col);
-            } else {  // pooled layer: the gradient lives on the arg-max row of every (group, channel)
-              const int g = grow / p.ns, s = grow - g * p.ns;
-              const float4 dd = ldg4(p.dout + static_cast<size_t>(g) * p.N + col);
-              const int4 am = __ldg(reinterpret_cast<const int4 *>(p.argmax + static_cast<size_t>(g) * p.N + col));
-              d[i] = make_float4(am.x == s ? dd.x : 0.f, am.y == s ? dd.y : 0.f, am.z == s ? dd.z : 0.f,
-                                 am.w == s ? dd.w : 0.f);
-            }
-          }
+          for (int i = 0; i < 4; ++i)
+            b[i] = make_float4(am.x == s0 + i ? dd.x : 0.f, am.y == s0 + i ? dd.y : 0.f, am.z == s0 + i ? dd.z : 0.f,
+                               am.w == s0 + i ? dd.w : 0.f);
         }
-        const float4 fa = *reinterpret_cast<const float4 *>(t_a + col), fb = *reinterpret_cast<const float4 *>(t_b + col);
-        const float4 mu = *reinterpret_cast<const float4 *>(t_mu + col), is = *reinterpret_cast<const float4 *>(t_is + col);
-        const float4 k1 = *reinterpret_cast<const float4 *>(t_c1 + col), k2 = *reinterpret_cast<const float4 *>(t_c2 + col);
         const int set = p.sets == 2 ? (tl & 1) : 0;
-        if (dgrad) mbar_wait(&bars->w_empty[grp], (w_use & 1) ^ 1);  // W^T slot + staging slot free
-        if (dgrad && gt == 0) {  // this step's W^T tile: one contiguous pre-swizzled image
-          const uint32_t bytes = static_cast<uint32_t>(p.kpad16) * BK * 4;
-          mbar_expect_tx(&bars->w_full[grp], bytes);
-          tma_load_1d(s_w + grp * p.w_slot_bytes, p.WTp + static_cast<size_t>(c) * p.kpad16 * BK, bytes,
-                      &bars->w_full[grp]);
+        if (dgrad) {
+          timed_wait(&bars->w_empty[grp], (w_use & 1) ^ 1, tm, c_w);  // W^T slot + staging slot free
+          if (gt == 0) {  // this step's W^T tile: one contiguous pre-swizzled image
+            const uint32_t bytes = static_cast<uint32_t>(p.kpad16) * BK * 4;
+            mbar_expect_tx(&bars->w_full[grp], bytes);
+            tma_load_1d(s_w + grp * p.w_slot_bytes, p.WTp + static_cast<size_t>(c) * p.kpad16 * BK, bytes,
+                        &bars->w_full[grp]);
+          }
         }
         ++w_use;
         if (tl >= p.sets)  // the set's previous tile has retired
-          mbar_wait(&bars->dz_empty[(tl - p.sets) & 3], ((tl - p.sets) >> 2) & 1);
+          timed_wait(&bars->dz_empty[(tl - p.sets) & 3], ((tl - p.sets) >> 2) & 1, tm, c_dz);
+        if (tm) {  // time until the item's global loads have landed
+          const long long t0 = clock64();
+          asm volatile("" ::"f"(b[0].x), "f"(b[4].x), "f"(b[3].w), "f"(b[7].w));
+          c_ld += static_cast<unsigned long long>(clock64() - t0);
+        }
         unsigned char *slab = s_dz + (set * nb + c) * SLAB;
         unsigned char *stage = s_a1 + grp * SLAB;
-        const bool relu = p.relu != 0;
+        const float4 fa = lds4(t_a + col), fb = lds4(t_b + col), fC = lds4(t_C + col), fD = lds4(t_D + col);
+        const float2 a01 = make_float2(fa.x, fa.y), a23 = make_float2(fa.z, fa.w);
+        const float2 b01 = make_float2(fb.x, fb.y), b23 = make_float2(fb.z, fb.w);
+        const float2 C01 = make_float2(fC.x, fC.y), C23 = make_float2(fC.z, fC.w);
+        const float2 D01 = make_float2(fD.x, fD.y), D23 = make_float2(fD.z, fD.w);
+        const float thr = p.relu ? 0.f : -INFINITY;  // no ReLU: every gradient passes
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = row0 + 16 * i;
-          const float4 v = z[i];
-          float4 o;
-          o.x = fa.x * (((!relu || fmaf(fa.x, v.x, fb.x) > 0.f) ? d[i].x : 0.f) - k1.x - (v.x - mu.x) * is.x * k2.x);
-          o.y = fa.y * (((!relu || fmaf(fa.y, v.y, fb.y) > 0.f) ? d[i].y : 0.f) - k1.y - (v.y - mu.y) * is.y * k2.y);
-          o.z = fa.z * (((!relu || fmaf(fa.z, v.z, fb.z) > 0.f) ? d[i].z : 0.f) - k1.z - (v.z - mu.z) * is.z * k2.z);
-          o.w = fa.w * (((!relu || fmaf(fa.w, v.w, fb.w) > 0.f) ? d[i].w : 0.f) - k1.w - (v.w - mu.w) * is.w * k2.w);
-          if (!colok || tile * BM + r >= p.P) o = make_float4(0.f, 0.f, 0.f, 0.f);  // rows / channels past the end
-          o = tf32x4(o);
-          *reinterpret_cast<float4 *>(slab + swz_base32(r, chunk)) = o;
-          if (dgrad) *reinterpret_cast<float4 *>(stage + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = b[4 + i], d = b[i];
+          const float2 v01 = make_float2(v.x, v.y), v23 = make_float2(v.z, v.w);
+          const float2 y01 = fma2(a01, v01, b01), y23 = fma2(a23, v23, b23);
+          const float2 t01 = fma2(C01, v01, D01), t23 = fma2(C23, v23, D23);
+          const float2 e01 = make_float2(y01.x > thr ? d.x : 0.f, y01.y > thr ? d.y : 0.f);
+          const float2 e23 = make_float2(y23.x > thr ? d.z : 0.f, y23.y > thr ? d.w : 0.f);
+          const float2 o01 = fma2(a01, e01, t01), o23 = fma2(a23, e23, t23);
+          float4 o = make_float4(o01.x, o01.y, o23.x, o23.y);
+          if (!full && r0 + i >= p.P) o = zero4();  // rows past the end (channels past N: zero constants)
+          *reinterpret_cast<float4 *>(slab + off32[i]) = o;
+          if (dgrad) *reinterpret_cast<float4 *>(stage + off16[i]) = o;
         }
         fence_proxy_async();
         mbar_arrive(&bars->dz_full[set][c]);
       } else {
-        // ---------------- H_prev slab h: columns [32h, 32h+32) of the layer below ----------------
-        const int h = j - nb, col = h * BK + chunk * 4;
-        const bool colok = col < p.lda;
-        float4 v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int grow = tile * BM + row0 + 16 * i;
-          v[i] = (colok && grow < p.P) ? ldg4(p.Aprev + static_cast<size_t>(grow) * p.lda + col)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        // ---------------- slab h of the layer below: columns [32h, 32h+32) ----------------
+        const int col = (j - nb) * BK + chunk * 4;
         const bool fold = p.a_in != nullptr && col < p.K;
-        const float4 fa = *reinterpret_cast<const float4 *>(u_a + col), fb = *reinterpret_cast<const float4 *>(u_b + col);
-        mbar_wait(&bars->h_empty[grp], (h_use & 1) ^ 1);
+        const float4 fa = lds4(u_a + col), fb = lds4(u_b + col);
+        const float2 a01 = make_float2(fa.x, fa.y), a23 = make_float2(fa.z, fa.w);
+        const float2 b01 = make_float2(fb.x, fb.y), b23 = make_float2(fb.z, fb.w);
+        timed_wait(&bars->h_empty[grp], (h_use & 1) ^ 1, tm, c_h);
         ++h_use;
-        unsigned char *slab = s_h + grp * SLAB;
+        if (tm) {
+          const long long t0 = clock64();
+          asm volatile("" ::"f"(b[0].x), "f"(b[3].w));
+          c_ld += static_cast<unsigned long long>(clock64() - t0);
+        }
+        unsigned char *slab = s_h + grp * hslabs * SLAB;
+        if (!stats) {  // H_prev = relu(a_in * Z_prev + b_in), or the block's input rows as they are
+          const float lo = p.relu_in ? 0.f : -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = row0 + 16 * i;
-          float4 y = v[i];
-          if (fold) {
-            y.x = fmaf(fa.x, y.x, fb.x), y.y = fmaf(fa.y, y.y, fb.y), y.z = fmaf(fa.z, y.z, fb.z), y.w = fmaf(fa.w, y.w, fb.w);
-            if (p.relu_in) y.x = fmaxf(y.x, 0.f), y.y = fmaxf(y.y, 0.f), y.z = fmaxf(y.z, 0.f), y.w = fmaxf(y.w, 0.f);
-            if (tile * BM + r >= p.P) y = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < 4; ++i) {
+            float4 y = b[i];
+            if (fold) {
+              const float2 y01 = fma2(a01, make_float2(y.x, y.y), b01), y23 = fma2(a23, make_float2(y.z, y.w), b23);
+              y = make_float4(fmaxf(y01.x, lo), fmaxf(y01.y, lo), fmaxf(y23.x, lo), fmaxf(y23.y, lo));
+              if (!full && r0 + i >= p.P) y = zero4();
+            }
+            *reinterpret_cast<float4 *>(slab + off32[i]) = y;
           }
-          *reinterpret_cast<float4 *>(slab + swz_base32(r, chunk)) = tf32x4(y);
+        } else {       // M = ReLU mask of the layer below, and M .* zhat_prev
+          const float4 mu = lds4(u_mu + col), is = lds4(u_is + col);
+          const float2 s01 = make_float2(is.x, is.y), s23 = make_float2(is.z, is.w);
+          const float2 e01 = make_float2(-mu.x * is.x, -mu.y * is.y), e23 = make_float2(-mu.z * is.z, -mu.w * is.w);
+          const float thr = p.relu_in ? 0.f : -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 z = b[i];
+            const float2 z01 = make_float2(z.x, z.y), z23 = make_float2(z.z, z.w);
+            const float2 y01 = fma2(a01, z01, b01), y23 = fma2(a23, z23, b23);
+            const float2 h01 = fma2(s01, z01, e01), h23 = fma2(s23, z23, e23);   // zhat
+            float4 m = make_float4(y01.x > thr ? 1.f : 0.f, y01.y > thr ? 1.f : 0.f, y23.x > thr ? 1.f : 0.f,
+                                   y23.y > thr ? 1.f : 0.f);
+            if (!fold || (!full && r0 + i >= p.P)) m = zero4();
+            const float2 q01 = mul2(make_float2(m.x, m.y), h01), q23 = mul2(make_float2(m.z, m.w), h23);
+            *reinterpret_cast<float4 *>(slab + off32[i]) = m;
+            *reinterpret_cast<float4 *>(slab + SLAB + off32[i]) = make_float4(q01.x, q01.y, q23.x, q23.y);
+          }
         }
         fence_proxy_async();
         mbar_arrive(&bars->h_full[grp]);
       }
-      j += G;
+    };
+
+    // this group's items: every kGroups-th slab of the CTA's tile sequence
+    float4 buf[8];
+    int tl = 0, j = grp;
+    while (j >= ipt) j -= ipt, ++tl;
+    while (tl < my_tiles) {
+      issue(tl, j, buf);
+      process(tl, j, buf);
+      j += kGroups;
       while (j >= ipt) j -= ipt, ++tl;
+    }
+    if (tm && gt == 0) {
+      unsigned long long *o = g_wait_cycles[blockIdx.x] + grp * 5;
+      o[0] = clock64() - c_tot, o[1] = c_w, o[2] = c_dz, o[3] = c_h, o[4] = c_ld;
     }
   } else if (warp == kMmaWarp) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
-      const uint32_t idesc1 = make_idesc(BM, p.kpad16);                                   // dH_prev = dZ * W
-      const uint32_t idesc2 = make_idesc(BM, BK) | kIdescAMajorMN | kIdescBMajorMN;       // dW += dZ^T * H
-      int w_use[kGroups] = {0, 0, 0}, h_use[kGroups] = {0, 0, 0};
+    {
+      // One lane issues ~100 MMAs per tile, but the WHOLE warp runs this loop: with warp-uniform control
+      // flow the descriptors live in uniform registers and each MMA costs a couple of uniform adds.
+      // (Under `if (lane == 0)` every operand is re-materialised into uniform registers per
+      // instruction -- ~30 SASS instructions per MMA, which made this thread the kernel's bottleneck.)
+      const bool leader = lane == 0;
+      const uint32_t idesc1 = make_idesc(BM, p.kpad16);                                          // dH_prev = dZ * W
+      const uint32_t idesc2 = make_idesc(BM, hslabs * BK) | kIdescAMajorMN | kIdescBMajorMN;   // dW (S|Q) += dZ^T * H
+      const uint64_t mn_hi = make_desc_mn32(0, SLAB, 512);   // MN-major template: LBO = slab stride
+      const uint64_t k_hi = make_desc(0);                    // K-major template
+      auto addr = [](uint32_t a) { return static_cast<uint64_t>((a & 0x3ffff) >> 4); };
+      uint32_t w_par = 0, h_par = 0;  // bit g: phase parity of group g's W^T / H_prev slot
+      const bool tm = (p.dbg & 32) != 0;
+      unsigned long long c_acc = 0, c_dzf = 0, c_wf = 0, c_hf = 0;
       int g = 0;  // loader group of the next item (items are dealt round-robin)
       for (int tl = 0; tl < my_tiles; ++tl) {
         const int acc = tl & 1, acc_use = tl >> 1;
         const int set = p.sets == 2 ? (tl & 1) : 0, use = p.sets == 2 ? (tl >> 1) : tl;
-        const uint32_t dz_base = smem_u32(s_dz + set * nb * SLAB);
+        const uint64_t dz_desc = mn_hi | addr(smem_u32(s_dz + set * nb * SLAB));
         if (dgrad) {
-          mbar_wait(&bars->acc_empty[acc], (acc_use & 1) ^ 1);
+          timed_wait(&bars->acc_empty[acc], (acc_use & 1) ^ 1, tm, c_acc);
           tc_fence_after();
         }
         for (int c = 0; c < nb; ++c) {
-          mbar_wait(&bars->dz_full[set][c], use & 1);
+          timed_wait(&bars->dz_full[set][c], use & 1, tm, c_dzf);
           if (dgrad) {
-            mbar_wait(&bars->w_full[g], w_use[g] & 1);
-            ++w_use[g];
+            timed_wait(&bars->w_full[g], (w_par >> g) & 1, tm, c_wf);
+            w_par ^= 1u << g;
             tc_fence_after();
-            const uint64_t da = make_desc(smem_u32(s_a1 + g * SLAB));
-            const uint64_t db = make_desc(smem_u32(s_w + g * p.w_slot_bytes));
+            const uint64_t da = k_hi | addr(smem_u32(s_a1 + g * SLAB));
+            const uint64_t db = k_hi | addr(smem_u32(s_w + g * p.w_slot_bytes));
+            const uint32_t d = tm_acc + acc * kb32;
+            if (leader) {
+              tc_mma_tf32(d, da, db, idesc1, c != 0);
 #pragma unroll
-            for (int k = 0; k < BK / 8; ++k)
-              tc_mma_tf32(tm_acc + acc * kb32, da + 2 * k, db + 2 * k, idesc1, (c | k) != 0);
-            tc_commit(&bars->w_empty[g]);
+              for (int k = 1; k < BK / 8; ++k) tc_mma_tf32(d, da + 2 * k, db + 2 * k, idesc1, 1);
+              tc_commit(&bars->w_empty[g]);
+            }
+            __syncwarp();
           }
-          if (++g == G) g = 0;
+          g ^= 1;
         }
         tc_fence_after();
-        if (dgrad) tc_commit(&bars->acc_full[acc]);
+        if (dgrad && leader) tc_commit(&bars->acc_full[acc]);
         for (int h = 0; h < kb; ++h) {
-          mbar_wait(&bars->h_full[g], h_use[g] & 1);
-          ++h_use[g];
+          timed_wait(&bars->h_full[g], (h_par >> g) & 1, tm, c_hf);
+          h_par ^= 1u << g;
           tc_fence_after();
-          const uint32_t hb = smem_u32(s_h + g * SLAB);
-#pragma unroll 4
-          for (int ks = 0; ks < BM / 8; ++ks)  // 8 rows (one 1024-byte swizzle atom) per instruction
-            tc_mma_tf32(tm_dw + h * BK, make_desc_mn32(dz_base + ks * 1024, SLAB, 512),
-                        make_desc_mn32(hb + ks * 1024, SLAB, 512), idesc2, (tl | ks) != 0);
-          tc_commit(&bars->h_empty[g]);
-          if (++g == G) g = 0;
+          // stats mode: the group's [M | M .* zhat] slabs are adjacent, one N = 64 instruction covers both
+          const uint64_t hb = mn_hi | addr(smem_u32(s_h + g * hslabs * SLAB));
+          const uint32_t d = tm_dw + h * hslabs * BK;
+          if (leader) {
+            tc_mma_tf32(d, dz_desc, hb, idesc2, tl != 0);
+#pragma unroll
+            for (int ks = 1; ks < BM / 8; ++ks)  // 8 rows (two 4-row swizzle atoms, 1024 bytes) per instruction
+              tc_mma_tf32(d, dz_desc + 64 * ks, hb + 64 * ks, idesc2, 1);
+            tc_commit(&bars->h_empty[g]);
+          }
+          __syncwarp();
+          g ^= 1;
         }
-        tc_commit(&bars->dz_empty[tl & 3]);
+        if (leader) tc_commit(&bars->dz_empty[tl & 3]);
       }
-      tc_commit(&bars->dw_full);
+      if (leader) tc_commit(&bars->dw_full);
+      if (tm && leader) {
+        unsigned long long *o = g_wait_cycles[blockIdx.x] + 10;
+        o[0] = c_acc, o[1] = c_dzf, o[2] = c_wf, o[3] = c_hf;
+      }
     }
   } else {
     // ====================================== epilogue ======================================
     const int wq = warp;  // TMEM lane quarter
-    float csum[kMaxKB], cq[kMaxKB];
-#pragma unroll
-    for (int h = 0; h < kMaxKB; ++h) csum[h] = 0.f, cq[h] = 0.f;
     if (dgrad) {
       for (int tl = 0; tl < my_tiles; ++tl) {
-        const int tile = blockIdx.x + tl * gridDim.x, set = tl & 1, use = tl >> 1;
+        const int tile = blockIdx.x + tl * gridDim.x, acc = tl & 1, use = tl >> 1;
         const int grow = tile * BM + wq * 32 + lane;
         const bool rowok = grow < p.P;
-        mbar_wait(&bars->acc_full[set], use & 1);
+        {
+          unsigned long long c_e = 0;
+          timed_wait(&bars->acc_full[acc], use & 1, (p.dbg & 32) != 0, c_e);
+          if ((p.dbg & 32) && tid == 0) g_wait_cycles[blockIdx.x][14] = (tl == 0 ? 0 : g_wait_cycles[blockIdx.x][14]) + c_e;
+        }
         tc_fence_after();
 #pragma unroll
         for (int h = 0; h < kMaxKB; ++h) {
           if (h < kb) {
             const int n0 = h * BK;
-            float zh[32];          // zhat of the layer below where its ReLU passes the gradient
-            uint32_t on = 0;       // bit jj: dY_prev[row, n0 + jj] = dH_prev (else 0)
-            if (stats) {  // the previous layer's pre-BN output for this row (L2 hit: the loaders just read it)
-#pragma unroll
-              for (int jj = 0; jj < 32; jj += 4) {
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rowok && n0 + jj < p.lda) t = ldg4(p.Aprev + static_cast<size_t>(grow) * p.lda + n0 + jj);
-                zh[jj] = t.x, zh[jj + 1] = t.y, zh[jj + 2] = t.z, zh[jj + 3] = t.w;
-              }
-#pragma unroll
-              for (int jj = 0; jj < 32; ++jj) {
-                const float y = fmaf(u_a[n0 + jj], zh[jj], u_b[n0 + jj]);
-                if (rowok && n0 + jj < p.K && (!p.relu_in || y > 0.f)) on |= 1u << jj;
-                zh[jj] = (zh[jj] - u_mu[n0 + jj]) * u_is[n0 + jj];
-              }
-            }
             float v[32];
-            tc_ld32(tm_acc + (static_cast<uint32_t>(wq * 32) << 16) + set * kb32 + n0, v);
-            if (rowok) {
+            tc_ld32(tm_acc + (static_cast<uint32_t>(wq * 32) << 16) + acc * kb32 + n0, v);
+            if (rowok && !(p.dbg & 4)) {
               float *dst = p.dHprev + static_cast<size_t>(grow) * p.lda + n0;
               if (n0 + 32 <= p.lda && (p.lda & 7) == 0) {
 #pragma unroll
@@ -347,47 +490,50 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
                   if (n0 + jj < p.lda) *reinterpret_cast<float4 *>(dst + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
               }
             }
-            if (stats) {
-#pragma unroll
-              for (int jj = 0; jj < 32; ++jj) {
-                v[jj] = (on >> jj) & 1u ? v[jj] : 0.f;
-                zh[jj] *= v[jj];
-              }
-              csum[h] += warp_colsum32(v, lane);
-              cq[h] += warp_colsum32(zh, lane);
-            }
           }
         }
         tc_fence_before();
-        mbar_arrive(&bars->acc_empty[set]);
+        mbar_arrive(&bars->acc_empty[acc]);
       }
     }
-    if (stats) {
-#pragma unroll
-      for (int h = 0; h < kMaxKB; ++h)
-        if (h < kb) {
-          s_stats[(wq * 2 + 0) * kb32 + h * 32 + lane] = csum[h];
-          s_stats[(wq * 2 + 1) * kb32 + h * 32 + lane] = cq[h];
-        }
-    }
-    // dW: TMEM lanes = output channels of this layer, columns = channels of the layer below
+    // read-out.  TMEM lanes = output channels n of this layer, columns = channels c of the layer below.
     mbar_wait(&bars->dw_full, 0);
     tc_fence_after();
-    if (wq * 32 < nb32) {
-      float *dst = p.dWpart + (static_cast<size_t>(blockIdx.x) * nb32 + wq * 32 + lane) * kb32;
+    const int n = wq * 32 + lane;
+    const bool active = wq * 32 < nb32 && my_tiles > 0;
+    float *dst = p.dWpart + (static_cast<size_t>(blockIdx.x) * nb32 + n) * kb32;
 #pragma unroll
-      for (int h = 0; h < kMaxKB; ++h)
-        if (h < kb) {
-          float v[32];
-          if (my_tiles > 0) {
-            tc_ld32(tm_dw + (static_cast<uint32_t>(wq * 32) << 16) + h * BK, v);
-          } else {
+    for (int h = 0; h < kMaxKB; ++h) {
+      if (h < kb) {
+        float v[32];
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) v[jj] = 0.f;
+        for (int jj = 0; jj < 32; ++jj) v[jj] = 0.f;
+        if (active) tc_ld32(tm_dw + (static_cast<uint32_t>(wq * 32) << 16) + h * hslabs * BK, v);
+        if (!stats) {
+          if (wq * 32 < nb32)
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 8) st_global_v8(dst + h * 32 + jj, v + jj);
+        } else {
+          float q[32];
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) q[jj] = 0.f;
+          if (active) tc_ld32(tm_dw + (static_cast<uint32_t>(wq * 32) << 16) + h * hslabs * BK + BK, q);
+          // dW = g1 .* Q + g0 .* S with H_prev = M .* (g1 * zhat + g0): g1 = a_in / invstd_in, g0 = a_in * mean_in + b_in
+          float o[8];
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int c = h * 32 + jj;
+            const float g1 = u_is[c] > 0.f ? u_a[c] / u_is[c] : 0.f, g0 = fmaf(u_a[c], u_mu[c], u_b[c]);
+            o[jj & 7] = fmaf(g1, q[jj], g0 * v[jj]);
+            if ((jj & 7) == 7 && wq * 32 < nb32) st_global_v8(dst + h * 32 + jj - 7, o);
+            const float w = (n < p.N && c < p.K) ? __ldg(p.W + static_cast<size_t>(n) * p.K + c) : 0.f;
+            v[jj] *= w, q[jj] *= w;
           }
-#pragma unroll
-          for (int jj = 0; jj < 32; jj += 8) st_global_v8(dst + h * 32 + jj, v + jj);
+          const float cs = warp_colsum32(v, lane), cq = warp_colsum32(q, lane);
+          s_stats[(wq * 2 + 0) * kb32 + h * 32 + lane] = cs;
+          s_stats[(wq * 2 + 1) * kb32 + h * 32 + lane] = cq;
         }
+      }
     }
   }
 
@@ -395,8 +541,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
   __syncthreads();
   if (stats && tid < kb32) {  // combine the four epilogue warps, fixed order
     float s = 0.f, q = 0.f;
-    if (my_tiles > 0 && dgrad)
-      for (int w = 0; w < kEpiWarps; ++w) s += s_stats[(w * 2) * kb32 + tid], q += s_stats[(w * 2 + 1) * kb32 + tid];
+    for (int w = 0; w < kEpiWarps; ++w) s += s_stats[(w * 2) * kb32 + tid], q += s_stats[(w * 2 + 1) * kb32 + tid];
     float *dst = p.stats_part + static_cast<size_t>(blockIdx.x) * 2 * kb32;
     dst[tid] = s;
     dst[kb32 + tid] = q;
@@ -430,17 +575,17 @@ __global__ void pack_weights_t_kernel(const float *__restrict__ W, int N, int K,
 }
 
 struct Geom {
-  int nb, kb, kpad16, groups, sets, w_slot_bytes, tmem_cols, grid;
+  int nb, kb, kpad16, sets, w_slot_bytes, tmem_cols, grid;
   size_t smem;
 };
 
-inline bool geom(int p, int n, int k, int lda, bool dgrad, Geom *g) {
+inline bool geom(int p, int n, int k, int lda, bool dgrad, bool stats, Geom *g) {
   if (n <= 0 || k <= 0 || n > kMaxNB * BK || lda > kMaxKB * BK || n % 4 != 0 || lda % 4 != 0 || lda < k) return false;
   g->nb = (n + BK - 1) / BK;
   g->kb = (lda + BK - 1) / BK;
   g->kpad16 = (lda + 15) / 16 * 16;
   g->w_slot_bytes = (g->kpad16 * BK * 4 + 1023) / 1024 * 1024;
-  const int cols = (dgrad ? 3 : 1) * g->kb * BK;
+  const int cols = ((dgrad ? 2 : 0) + (stats ? 2 : 1)) * g->kb * BK;
   g->tmem_cols = 32;
   while (g->tmem_cols < cols) g->tmem_cols *= 2;
   if (g->tmem_cols > 512) return false;
@@ -448,10 +593,8 @@ inline bool geom(int p, int n, int k, int lda, bool dgrad, Geom *g) {
   const size_t fixed = static_cast<size_t>(g->sets) * g->nb * SLAB +
                        sizeof(float) * (6 * g->nb * 32 + 4 * g->kb * 32 + kEpiWarps * 2 * g->kb * 32) +
                        sizeof(Barriers) + 1024;
-  const size_t per_group = 2 * static_cast<size_t>(SLAB) + g->w_slot_bytes;
-  g->groups = kGroups;
-  while (g->groups > 1 && fixed + g->groups * per_group > 227 * 1024) --g->groups;
-  g->smem = fixed + g->groups * per_group;
+  const size_t per_group = (stats ? 3 : 2) * static_cast<size_t>(SLAB) + g->w_slot_bytes;
+  g->smem = fixed + kGroups * per_group;
   // GEMM 2 addresses four 32-channel slabs from the start of a dZ set whatever nb is: the slabs
   // past nb are other live shared memory (their rows of dW are never read) but must be mapped
   const size_t reach = static_cast<size_t>((g->sets - 1) * g->nb + kMaxNB) * SLAB;
@@ -467,10 +610,14 @@ inline bool geom(int p, int n, int k, int lda, bool dgrad, Geom *g) {
 
 using namespace pn2;
 
-// 1 when pn2_mlp_bwd_layer supports the shape (N <= 128 output channels, lda <= 160 input columns)
-extern "C" int pn2_mlp_bwd_supported(int p, int n, int k, int lda) {
+// 1 when pn2_mlp_bwd_layer supports the shape: N <= 128 output channels; lda <= 160 input columns,
+// <= 128 when the statistics of a BatchNorm below are wanted (with_stats)
+extern "C" int pn2_mlp_bwd_supported(int p, int n, int k, int lda, int with_stats) {
   bwd::Geom g;
-  return p > 0 && bwd::geom(p, n, k, lda, true, &g) ? 1 : 0;
+  return p > 0 && bwd::geom(p, n, k, lda, true, with_stats != 0, &g) ? 1 : 0;
+}
+extern "C" __attribute__((visibility("default"))) int pn2_mlp_bwd_debug_read(unsigned long long *out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out, bwd::g_wait_cycles, sizeof(unsigned long long) * kNumSMs * 16));
 }
 extern "C" int pn2_mlp_bwd_grid(int p) {
   const int m_tiles = (p + bwd::BM - 1) / bwd::BM;
@@ -495,30 +642,36 @@ extern "C" int pn2_mlp_pack_weights_t(int n, int k, int lda, int ldw, const floa
 extern "C" int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu, int relu_in, const float *dh,
                                  const float *dout, const int *argmax, const float *z, const float *a,
                                  const float *b, const float *mean, const float *invstd, const float *c1c2,
-                                 const float *a_prev, const float *a_in, const float *b_in,
+                                 const float *w, const float *a_prev, const float *a_in, const float *b_in,
                                  const float *mean_in, const float *invstd_in, const float *wt_packed,
                                  float *dh_prev, float *dw_part, float *stats_part, void *stream) {
   if (p <= 0) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(z, a, b, mean, invstd, c1c2, a_prev, dw_part);
   if (dh == nullptr && (dout == nullptr || argmax == nullptr || ns <= 0 || p % ns != 0)) return PN2_ERR_INVALID_ARG;
+  if (dh == nullptr && ns % 4 != 0) return PN2_ERR_UNSUPPORTED;  // a thread's 4 consecutive rows share one group
   if ((wt_packed == nullptr) != (dh_prev == nullptr)) return PN2_ERR_INVALID_ARG;
-  if (stats_part != nullptr && (wt_packed == nullptr || a_in == nullptr || mean_in == nullptr || invstd_in == nullptr))
+  if (stats_part != nullptr && (wt_packed == nullptr || a_in == nullptr || mean_in == nullptr ||
+                                invstd_in == nullptr || w == nullptr))
     return PN2_ERR_INVALID_ARG;
   if (a_in != nullptr && b_in == nullptr) return PN2_ERR_INVALID_ARG;
   bwd::Geom g;
-  if (!bwd::geom(p, n, k, lda, wt_packed != nullptr, &g)) return PN2_ERR_UNSUPPORTED;
+  if (!bwd::geom(p, n, k, lda, wt_packed != nullptr, stats_part != nullptr, &g)) return PN2_ERR_UNSUPPORTED;
   if (!aligned16(z) || !aligned16(a_prev) || !aligned16(dw_part) || (dh != nullptr && !aligned16(dh)) ||
       (dout != nullptr && (!aligned16(dout) || !aligned16(argmax))) || (dh_prev != nullptr && !aligned16(dh_prev)) ||
       (wt_packed != nullptr && !aligned16(wt_packed)))
     return PN2_ERR_UNSUPPORTED;
   bwd::Params prm;
   prm.dH = dh, prm.dout = dout, prm.argmax = argmax, prm.Z = z;
-  prm.a = a, prm.b = b, prm.mean = mean, prm.invstd = invstd, prm.c1c2 = c1c2;
+  prm.a = a, prm.b = b, prm.mean = mean, prm.invstd = invstd, prm.c1c2 = c1c2, prm.W = w;
   prm.Aprev = a_prev, prm.a_in = a_in, prm.b_in = b_in, prm.mean_in = mean_in, prm.invstd_in = invstd_in;
   prm.WTp = wt_packed, prm.dHprev = dh_prev, prm.dWpart = dw_part, prm.stats_part = stats_part;
   prm.P = p, prm.N = n, prm.nb = g.nb, prm.K = k, prm.lda = lda, prm.kb = g.kb, prm.kpad16 = g.kpad16;
   prm.ns = ns > 0 ? ns : 1, prm.relu = relu, prm.relu_in = relu_in;
-  prm.groups = g.groups, prm.sets = g.sets, prm.w_slot_bytes = g.w_slot_bytes, prm.tmem_cols = g.tmem_cols;
+  prm.dbg = getenv("PN2_BWD_DBG") != nullptr ? atoi(getenv("PN2_BWD_DBG")) : 0;
+  prm.ns_shift = -1;
+  for (int sh = 0; sh < 31; ++sh)
+    if ((1 << sh) == prm.ns) prm.ns_shift = sh;
+  prm.sets = g.sets, prm.w_slot_bytes = g.w_slot_bytes, prm.tmem_cols = g.tmem_cols;
   cudaError_t e = cudaFuncSetAttribute(bwd::mlp_bwd_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(g.smem));
   if (e != cudaSuccess) return static_cast<int>(e);

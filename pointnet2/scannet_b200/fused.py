@@ -22,7 +22,7 @@ from . import lib as _lib
 
 GEMM_TF32 = True   # tensor-core TF32 GEMMs, like the reference's cuDNN convs on Ampere+
 ENABLED = True     # module forward()s take the fused path when eligible
-TC_BWD = False     # backward layers on the fused tcgen05 kernel (csrc/mlp_bwd.cu: BN adjoint + dH + dW +
+TC_BWD = True      # backward layers on the fused tcgen05 kernel (csrc/mlp_bwd.cu: BN adjoint + dH + dW +
                    # next statistics in one pass) where the shape is supported and TC_GEMM is on
 TC_GEMM = True     # forward layers on the hand-written tcgen05 kernel (csrc/mlp_gemm.cu) when
                    # GEMM_TF32: BN fold + ReLU of the previous layer in its prologue, BN batch
@@ -161,7 +161,8 @@ class SharedMLPRows(Function):
                 W2 = W.reshape(W.shape[0], -1)
                 lda = x0.shape[1] if l == 0 else layers[l - 1].cout
                 bwd_fused[l] = bool(use_tc and TC_BWD and want_grad and
-                                    L.pn2_mlp_bwd_supported(P, W2.shape[0], W2.shape[1], lda))
+                                    L.pn2_mlp_bwd_supported(P, W2.shape[0], W2.shape[1], lda, int(l > 0)) and
+                                    not (l == nl - 1 and ns > 0 and ns % 4 != 0))
                 want_h = want_grad and not bwd_fused[l]   # the fused adjoint recomputes H_{l-1} from Z_{l-1}
                 st = _BNLayer()
                 st.cout = W2.shape[0]
@@ -276,7 +277,7 @@ class SharedMLPRows(Function):
                         None if pooled else dh.data_ptr(), dh.data_ptr() if pooled else None,
                         ctx.argmax.data_ptr() if pooled else None, st.z.data_ptr(), st.a.data_ptr(),
                         st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), c1c2.data_ptr(),
-                        a_prev.data_ptr(), prev.a.data_ptr() if prev is not None else None,
+                        W2c.data_ptr() if sp is not None else None, a_prev.data_ptr(), prev.a.data_ptr() if prev is not None else None,
                         prev.b.data_ptr() if prev is not None else None,
                         prev.mean.data_ptr() if prev is not None else None,
                         prev.invstd.data_ptr() if prev is not None else None,

@@ -152,6 +152,16 @@ def _lib_bytes(name, a):
         return 4 * b * m + 4 * b * c * min(n, m) + 4 * b * c * m, 0
     if name == "pn2_adam_flat":
         return 28 * a[0], 0
+    if name == "pn2_mlp_bwd_layer":
+        # read dh (or dout + arg-max), z, a_prev; write dh_prev when wanted; two products of 2*p*n*k flops
+        p, n, k, lda, ns = a[0], a[1], a[2], a[3], a[4]
+        dh, dh_prev = a[7], a[23]
+        up = 4 * p * n if dh else 8 * (p // max(ns, 1)) * n
+        return up + 4 * p * n + 4 * p * lda + (4 * p * lda if dh_prev else 0), (4 if dh_prev else 2) * p * n * k
+    if name == "pn2_relu_bn_bwd_stats":
+        return 8 * a[0] * a[1], 0
+    if name == "pn2_pool_bn_bwd_stats":
+        return 12 * a[0] * a[2], 0
     return None
 
 
@@ -167,8 +177,8 @@ class LibTimer(object):
 
     def __enter__(self):
         from . import lib
-        names = [n for n in lib.SIGNATURES if not n.endswith(("_bn", "_n_tiles", "_k_blocks", "_grid",
-                                                              "_workspace_floats"))]
+        names = [n for n in lib.SIGNATURES if not n.endswith(("_bn", "_n_tiles", "_k_blocks", "_grid", "_nb", "_kb",
+                                                              "_kpad", "_supported", "_workspace_floats"))]
         for name in names:
             fn = getattr(self.lib, name)
             self._saved[name] = fn

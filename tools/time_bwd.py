@@ -21,7 +21,11 @@ CASES = [  # name, P, N, K, lda, ns (pooled), fold, dgrad
     ("SA3 l2", 1 << 16, 128, 128, 128, 0, True, True),
 ]
 s = torch.cuda.current_stream().cuda_stream
+print("PN2_BWD_DBG =", os.environ.get("PN2_BWD_DBG"))
+ONLY = os.environ.get("ONLY")
 for name, P, N, K, lda, ns, fold, dgrad in CASES:
+    if ONLY and ONLY not in name:
+        continue
     g = torch.Generator(device=DEV).manual_seed(0)
     r = lambda *sh: torch.randn(*sh, device=DEV, generator=g)
     z, aprev = r(P, N), r(P, lda)
@@ -41,7 +45,7 @@ for name, P, N, K, lda, ns, fold, dgrad in CASES:
     p = lambda t: t.data_ptr() if t is not None else None
     def call():
         lib.check(L.pn2_mlp_bwd_layer(P, N, K, lda, ns, 1, 1, p(dh), p(dout), p(am), p(z), p(a), p(b), p(mean),
-                                      p(invstd), p(c1c2), p(aprev), p(a_in), p(b_in), p(mean_in), p(invstd_in),
+                                      p(invstd), p(c1c2), p(W), p(aprev), p(a_in), p(b_in), p(mean_in), p(invstd_in),
                                       p(wtp), p(dhp), p(dwp), p(sp), s), "bwd")
     for _ in range(3):
         call()
@@ -54,5 +58,13 @@ for name, P, N, K, lda, ns, fold, dgrad in CASES:
     torch.cuda.synchronize()
     us = 1e3 * e0.elapsed_time(e1) / 10
     byt = 4 * P * (N + lda + (lda if dgrad else 0) + (N if not ns else 0)) + (8 * (P // ns) * N if ns else 0)
+    if os.environ.get("PN2_BWD_DBG") and int(os.environ["PN2_BWD_DBG"]) & 32:
+        import ctypes, numpy as np
+        buf = np.zeros((148, 16), np.uint64)
+        L.pn2_mlp_bwd_debug_read.argtypes = [ctypes.c_void_p]
+        L.pn2_mlp_bwd_debug_read(buf.ctypes.data)
+        m = buf.astype(np.float64).mean(0) / 1.9e3   # us at ~1.9 GHz
+        print("   us/CTA: G0 total %.0f w_empty %.0f dz_empty %.0f h_empty %.0f loads %.0f | G1 total %.0f w %.0f dz %.0f h %.0f ld %.0f"
+              " | MMA acc_empty %.0f dz_full %.0f w_full %.0f h_full %.0f | EPI acc_full %.0f" % tuple(m[:15]))
     print("%-18s P=%7d N=%3d K=%3d  %7.1f us  %6.1f MB  %6.0f GB/s (%.0f%% of HBM peak)" % (
         name, P, N, K, us, byt / 1e6, byt / us / 1e3, 100 * byt / us / 1e3 / PEAK))
