@@ -227,17 +227,20 @@ PN2_API int pn2_fp_interp_rows_grad(int b, int n, int m, int c2, int c1, const f
  *   - partials (optional): per-CTA column sums / sums of squares of z,
  *     [pn2_mlp_gemm_grid(p, n)][2][n_tiles * bn] floats, to be finalised with
  *     pn2_bn_finalize (ld = n_tiles * bn).
+ * bn = pn2_mlp_gemm_bn(p, n) is the N tile per CTA (narrower when p is small, so that the grid
+ * still covers the machine).
  * w_packed comes from pn2_mlp_pack_weights (n_tiles*k_blocks*bn*32 floats: tile
  * images in the UMMA 128-byte-swizzled K-major layout).  a: [p, lda], lda % 4 == 0,
  * columns [k, lda) are read as part of the product (keep them zero); z: [p, ldz].
  * This replaces the cuDNN/cuBLAS 1x1 convolution the reference's SharedMLP calls
  * (pytorch_utils.py:87-95) plus the statistics pass of its BatchNorm2d (:100-104).
  * ========================================================================== */
-PN2_API int pn2_mlp_gemm_bn(int n);
-PN2_API int pn2_mlp_gemm_n_tiles(int n);
+PN2_API int pn2_mlp_gemm_bn(int p, int n);
+PN2_API int pn2_mlp_gemm_n_tiles(int p, int n);
 PN2_API int pn2_mlp_gemm_k_blocks(int k);
 PN2_API int pn2_mlp_gemm_grid(int p, int n);
-PN2_API int pn2_mlp_pack_weights(int n, int k, int ldw, const float *w, float *packed, void *stream);
+PN2_API int pn2_mlp_pack_weights(int p, int n, int k, int ldw, const float *w, float *packed,
+                                 void *stream);
 PN2_API int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const float *a,
                              const float *a_in, const float *b_in, int relu_in, float *h_out,
                              const float *w_packed, float *z, float *partials, void *stream);

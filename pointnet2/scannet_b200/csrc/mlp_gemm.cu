@@ -181,8 +181,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p) {
     }
   } else if (warp == kLoadWarps + kEpiWarps) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    {  // the whole warp runs the loop (warp-uniform control flow keeps the descriptors in uniform
+       // registers); lane 0 issues
+      const bool leader = lane == 0;
       const uint32_t idesc = make_idesc(BM, p.BN);
+      const uint64_t k_hi = make_desc(0);
       int s = 0, par = 0, t = 0, kb = 0;
       for (int it = 0; it < total_kb; ++it) {
         const int acc = t & 1;
@@ -192,13 +195,17 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p) {
         }
         mbar_wait(&bars->full[s], par);
         tc_fence_after();
-        const uint64_t da = make_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
-        const uint64_t db = make_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
+        const uint64_t da = k_hi | static_cast<uint64_t>((smem_u32(smem_a + s * A_STAGE_BYTES) & 0x3ffff) >> 4);
+        const uint64_t db = k_hi | static_cast<uint64_t>((smem_u32(smem_b + s * B_STAGE_BYTES) & 0x3ffff) >> 4);
+        if (leader) {
+          tc_mma_tf32(tmem_base + acc * acc_cols, da, db, idesc, kb != 0);
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k)  // 32 bytes (8 x tf32) further along K per instruction
-          tc_mma_tf32(tmem_base + acc * acc_cols, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-        tc_commit(&bars->empty[s]);                       // stage reusable once these MMAs retire
-        if (kb == p.k_blocks - 1) tc_commit(&bars->acc_full[acc]);
+          for (int k = 1; k < BK / 8; ++k)  // 32 bytes (8 x tf32) further along K per instruction
+            tc_mma_tf32(tmem_base + acc * acc_cols, da + 2 * k, db + 2 * k, idesc, 1);
+          tc_commit(&bars->empty[s]);                       // stage reusable once these MMAs retire
+          if (kb == p.k_blocks - 1) tc_commit(&bars->acc_full[acc]);
+        }
+        __syncwarp();
         if (++s == STAGES) s = 0, par ^= 1;
         if (++kb == p.k_blocks) kb = 0, ++t;
       }
@@ -301,9 +308,14 @@ __global__ void pack_weights_kernel(const float *__restrict__ W, int N, int K, i
   }
 }
 
-inline int pick_bn(int n) {  // UMMA N: multiple of 16 in [16, 256]
-  if (n > kMaxBN) return kMaxBN;
-  return (n + 15) / 16 * 16;
+// UMMA N per CTA: a multiple of 16 in [16, 256].  Few row tiles (the coarse levels: P = 2048 ... 65536)
+// would leave most SMs idle with one wide N tile per row tile, so N is split further until the grid
+// covers the machine (the A tile is then re-read from L2 by each N tile's CTA).
+inline int pick_bn(int p, int n) {
+  int bn = n > kMaxBN ? kMaxBN : (n + 15) / 16 * 16;
+  const int m_tiles = (p + BM - 1) / BM;
+  while (bn >= 64 && bn % 32 == 0 && m_tiles * ((n + bn - 1) / bn) < kNumSMs) bn /= 2;
+  return bn;
 }
 
 }  // namespace gemm
@@ -312,20 +324,20 @@ inline int pick_bn(int n) {  // UMMA N: multiple of 16 in [16, 256]
 using namespace pn2;
 
 // geometry helpers for the caller (sizes of the packed weights / the partials buffer)
-extern "C" int pn2_mlp_gemm_bn(int n) { return gemm::pick_bn(n); }
-extern "C" int pn2_mlp_gemm_n_tiles(int n) { return (n + gemm::pick_bn(n) - 1) / gemm::pick_bn(n); }
+extern "C" int pn2_mlp_gemm_bn(int p, int n) { return gemm::pick_bn(p, n); }
+extern "C" int pn2_mlp_gemm_n_tiles(int p, int n) { return (n + gemm::pick_bn(p, n) - 1) / gemm::pick_bn(p, n); }
 extern "C" int pn2_mlp_gemm_k_blocks(int k) { return (k + gemm::BK - 1) / gemm::BK; }
 extern "C" int pn2_mlp_gemm_grid(int p, int n) {
   const int m_tiles = (p + gemm::BM - 1) / gemm::BM;
-  const int ctas_per_sm = gemm::pick_bn(n) <= 128 ? 2 : 1;
-  const int per = ctas_per_sm * kNumSMs / pn2_mlp_gemm_n_tiles(n);
+  const int ctas_per_sm = gemm::pick_bn(p, n) <= 128 ? 2 : 1;
+  const int per = ctas_per_sm * kNumSMs / pn2_mlp_gemm_n_tiles(p, n);
   return m_tiles < per ? m_tiles : (per < 1 ? 1 : per);
 }
 
-extern "C" int pn2_mlp_pack_weights(int n, int k, int ldw, const float *w, float *packed, void *stream) {
-  if (n <= 0 || k <= 0 || ldw < k) return PN2_ERR_INVALID_ARG;
+extern "C" int pn2_mlp_pack_weights(int p, int n, int k, int ldw, const float *w, float *packed, void *stream) {
+  if (p <= 0 || n <= 0 || k <= 0 || ldw < k) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(w, packed);
-  const int bn = gemm::pick_bn(n), nt = pn2_mlp_gemm_n_tiles(n), kb = pn2_mlp_gemm_k_blocks(k);
+  const int bn = gemm::pick_bn(p, n), nt = pn2_mlp_gemm_n_tiles(p, n), kb = pn2_mlp_gemm_k_blocks(k);
   const size_t total = static_cast<size_t>(nt) * kb * bn * gemm::BK;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
@@ -347,7 +359,7 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   prm.A = a, prm.a_in = a_in, prm.b_in = b_in, prm.H_out = h_out, prm.Wp = w_packed, prm.Z = z;
   prm.partials = partials;
   prm.P = p, prm.lda = lda, prm.K = k, prm.k_blocks = pn2_mlp_gemm_k_blocks(k);
-  prm.N = n, prm.ldz = ldz, prm.BN = gemm::pick_bn(n), prm.n_tiles = pn2_mlp_gemm_n_tiles(n);
+  prm.N = n, prm.ldz = ldz, prm.BN = gemm::pick_bn(p, n), prm.n_tiles = pn2_mlp_gemm_n_tiles(p, n);
   prm.relu_in = relu_in;
   // as many stages as fit: the narrow layers (BN = 32..64) are pure streaming and need >100 KB of
   // loads in flight per SM to cover HBM latency; the wide ones get 4 x 48 KB

@@ -106,11 +106,11 @@ def _tc_layer(A, k, W2, fold, relu_in, want_h, want_stats):
     P, lda = A.shape
     N = W2.shape[0]
     s = _stream(dev)
-    bn, nt, kb = L.pn2_mlp_gemm_bn(N), L.pn2_mlp_gemm_n_tiles(N), L.pn2_mlp_gemm_k_blocks(k)
+    bn, nt, kb = L.pn2_mlp_gemm_bn(P, N), L.pn2_mlp_gemm_n_tiles(P, N), L.pn2_mlp_gemm_k_blocks(k)
     grid = L.pn2_mlp_gemm_grid(P, N)
     W2 = W2.contiguous()
     Wp = torch.empty(nt * kb * bn * 32, dtype=torch.float32, device=dev)
-    _lib.check(L.pn2_mlp_pack_weights(N, k, W2.shape[1], W2.data_ptr(), Wp.data_ptr(), s), "mlp_pack_weights")
+    _lib.check(L.pn2_mlp_pack_weights(P, N, k, W2.shape[1], W2.data_ptr(), Wp.data_ptr(), s), "mlp_pack_weights")
     z = torch.empty(P, N, dtype=torch.float32, device=dev)
     h = torch.empty_like(A) if (want_h and fold is not None) else None
     part = torch.empty(grid, 2, nt * bn, dtype=torch.float32, device=dev) if want_stats else None
@@ -405,10 +405,20 @@ def rows_of(t):
     return t.transpose(1, 2).contiguous()
 
 
+LAZY_CHANNEL_MAJOR = False  # set by the semseg models around their forward (see channel_major)
+
+
 def channel_major(rows3):
     """(B, N, C) rows -> the (B, C, N) contiguous tensor the op surface promises, remembering the
-    rows it came from so that the next fused block can skip the transpose back."""
-    out = rows3.transpose(1, 2).contiguous()
+    rows it came from so that the next fused block can skip the transpose back.
+
+    Inside the semseg models every consumer of a module output is another fused block, which takes
+    the rows alias: there (``LAZY_CHANNEL_MAJOR``) the channel-major tensor is returned as a
+    transposed VIEW of the rows -- same shape and values, no copy (and no copy of its gradient on
+    the way back); ``.contiguous()`` materialises it if some other consumer needs that."""
+    out = rows3.transpose(1, 2)
+    if not LAZY_CHANNEL_MAJOR:
+        out = out.contiguous()
     out._pn2_rows = rows3
     return out
 

@@ -41,11 +41,11 @@ SIGNATURES = {
     "pn2_fp_interp_rows": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_fp_interp_rows_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     # shared-MLP layer on the tensor cores
-    "pn2_mlp_gemm_bn": [_i],
-    "pn2_mlp_gemm_n_tiles": [_i],
+    "pn2_mlp_gemm_bn": [_i, _i],
+    "pn2_mlp_gemm_n_tiles": [_i, _i],
     "pn2_mlp_gemm_k_blocks": [_i],
     "pn2_mlp_gemm_grid": [_i, _i],
-    "pn2_mlp_pack_weights": [_i, _i, _i, _vp, _vp, _vp],
+    "pn2_mlp_pack_weights": [_i, _i, _i, _i, _vp, _vp, _vp],
     "pn2_mlp_gemm_fwd": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_bn_finalize": [_i, _i, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     # fused backward layer on the tensor cores

@@ -12,6 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import fused
+from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 from .pointnet2_modules import PointnetFPModule, PointnetSAModule, PointnetSAModuleMSG
 
@@ -87,6 +88,28 @@ class _Pointnet2SemSeg(nn.Module):
         """``plan`` (optional): a geometry.GeometryPlan built from this pointcloud's xyz; the
         sampling / grouping / neighbour indices are then taken from it instead of being
         recomputed inline (identical values, see geometry.py)."""
+        prev_lazy = fused.LAZY_CHANNEL_MAJOR
+        fused.LAZY_CHANNEL_MAJOR = fused.ENABLED and pointcloud.is_cuda and self._all_fused(pointcloud)
+        try:
+            return self._forward(pointcloud, plan)
+        finally:
+            fused.LAZY_CHANNEL_MAJOR = prev_lazy
+
+    def _all_fused(self, pointcloud):
+        """True when every SA / FP block takes the fused rows path, i.e. no module output is consumed
+        as a channel-major tensor (then those tensors need not be materialised)."""
+        like = pointcloud
+        if not all(fused.mlp_eligible(mlp, like) for sa in self.SA_modules for mlp in sa.mlps):
+            return False
+        if not all(fused.mlp_eligible(fp.mlp, like) for fp in self.FP_modules):
+            return False
+        widths = [sum(mlp[-1].conv.out_channels for mlp in sa.mlps) for sa in self.SA_modules]
+        return all(w % 4 == 0 for w in widths) and all(
+            isinstance(g, pointnet2_utils.QueryAndGroup) and g.use_xyz and not g.normalize_xyz
+            and not g.sample_uniformly and not g.ret_grouped_xyz and not g.ret_unique_cnt
+            for sa in self.SA_modules for g in sa.groupers)
+
+    def _forward(self, pointcloud, plan=None):
         xyz, features = self._break_up_pc(pointcloud)
         l_xyz, l_features = [xyz], [features]
         for k, sa in enumerate(self.SA_modules):

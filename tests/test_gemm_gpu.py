@@ -25,12 +25,12 @@ def run_gemm(A, W, k, a_in=None, b_in=None, relu=False, want_h=False):
     P, lda = A.shape
     N = W.shape[0]
     s = torch.cuda.current_stream().cuda_stream
-    bn, nt, kb = L.pn2_mlp_gemm_bn(N), L.pn2_mlp_gemm_n_tiles(N), L.pn2_mlp_gemm_k_blocks(k)
+    bn, nt, kb = L.pn2_mlp_gemm_bn(P, N), L.pn2_mlp_gemm_n_tiles(P, N), L.pn2_mlp_gemm_k_blocks(k)
     grid = L.pn2_mlp_gemm_grid(P, N)
     assert A.dtype == np.float32 and W.dtype == np.float32
     Wd = torch.from_numpy(W).to(DEV)
     Wp = torch.empty(nt * kb * bn * 32, dtype=torch.float32, device=DEV)
-    lib.check(L.pn2_mlp_pack_weights(N, k, W.shape[1], Wd.data_ptr(), Wp.data_ptr(), s), "pack")
+    lib.check(L.pn2_mlp_pack_weights(P, N, k, W.shape[1], Wd.data_ptr(), Wp.data_ptr(), s), "pack")
     Ad = torch.from_numpy(A).to(DEV)
     Z = torch.full((P, N), float("nan"), dtype=torch.float32, device=DEV)
     part = torch.zeros(grid, 2, nt * bn, dtype=torch.float32, device=DEV)
