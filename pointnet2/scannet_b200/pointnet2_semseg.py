@@ -125,8 +125,9 @@ class _Pointnet2SemSeg(nn.Module):
         if self._head_rows_ok(l_features[1]):
             # finest FP level and the classifier head stay in [points, channels] rows: the head's
             # output rows ARE the (B, N, num_classes) result, no transpose anywhere
-            rows = fp0.forward_rows(l_xyz[0], l_xyz[1], l_features[0], l_features[1], geo(0))
-            return self._head_rows(rows)
+            lead = self._head_lead(fp0)
+            rows = fp0.forward_rows(l_xyz[0], l_xyz[1], l_features[0], l_features[1], geo(0), tail=lead)
+            return self._head_rows(rows, skip=len(lead))
         l_features[0] = fp0(l_xyz[0], l_xyz[1], l_features[0], l_features[1], geo(0))
         return self.cls_layer(l_features[0]).transpose(1, 2).contiguous()
 
@@ -135,12 +136,27 @@ class _Pointnet2SemSeg(nn.Module):
         return (fused.mlp_eligible(units, known_feats) and fused.mlp_eligible(self.FP_modules[0].mlp, known_feats)
                 and known_feats.size(1) % 4 == 0)
 
-    def _head_rows(self, rows):
-        """cls_layer (Conv1d+BN+ReLU, Dropout, Conv1d+BN -- ref :152-159) on (B, N, C) rows."""
+    def _head_lead(self, fp0):
+        """The classifier units in front of its Dropout (ref :152-156) continue the finest FP block's
+        chain when their BatchNorms share its eps / momentum: one fused chain, no activation
+        materialised between the block and the head."""
+        lead = []
+        for m in self.cls_layer:
+            if isinstance(m, nn.Dropout):
+                break
+            lead.append(m)
+        ref = fp0.mlp[0].bn.bn
+        same = all(u.bn.bn.eps == ref.eps and u.bn.bn.momentum == ref.momentum and u.training == fp0.mlp[0].training
+                   for u in lead)
+        return lead if same else []
+
+    def _head_rows(self, rows, skip=0):
+        """cls_layer (Conv1d+BN+ReLU, Dropout, Conv1d+BN -- ref :152-159) on (B, N, C) rows; the first
+        ``skip`` units were already applied."""
         B, N, C = rows.shape
         x = rows.reshape(B * N, C)
         run = []
-        for m in self.cls_layer:
+        for m in list(self.cls_layer)[skip:]:
             if isinstance(m, nn.Dropout):
                 if run:
                     x = fused.run_mlp_rows(run, x, 0)
