@@ -123,24 +123,6 @@ __device__ __forceinline__ float4 tf32x4(float4 v) {
   return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
 }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-// Blackwell packed fp32: two fused multiply-adds / multiplies per instruction (FFMA2 / FMUL2)
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-  float2 r;
-  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
-      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
-      : "=f"(r.x), "=f"(r.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return r;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-  float2 r;
-  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; "
-      "mov.b64 {%0,%1}, rd;}"
-      : "=f"(r.x), "=f"(r.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return r;
-}
-
 __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int nb = p.nb, kb = p.kb;

@@ -28,6 +28,8 @@
 //
 // Precision: TF32 operands (round-to-nearest), fp32 accumulation -- the arithmetic class of
 // the reference's own convolutions (torch.backends.cudnn.allow_tf32 defaults to True).
+#include <math.h>
+
 #include "tc_common.cuh"
 
 namespace pn2 {
@@ -60,7 +62,7 @@ struct Params {
 
 using namespace tc;
 
-struct __align__(8) Barriers {
+struct __align__(16) Barriers {
   uint64_t raw[kMaxStages];    // cp.async chunks of A landed            (128 arrivals)
   uint64_t full[kMaxStages];   // A transformed + weight tile landed     (128 arrivals + 1 expect_tx)
   uint64_t empty[kMaxStages];  // MMAs that read the stage have retired  (1 commit)
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p) {
   unsigned char *smem_b = smem + STAGES * A_STAGE_BYTES;         // STAGES x b_stage_bytes
   Barriers *bars = reinterpret_cast<Barriers *>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
   float *s_stats = reinterpret_cast<float *>(bars + 1);          // [kEpiWarps][2][kMaxBN]
+  float *s_fold = s_stats + kEpiWarps * 2 * kMaxBN;              // [2][k_blocks * BK]: a_in, b_in of the fold
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tile = blockIdx.y;
@@ -101,6 +104,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p) {
                  "r"(static_cast<uint32_t>(p.tmem_cols))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < p.k_blocks * BK; i += kThreads) {
+    const bool ok = p.a_in != nullptr && i < p.K;
+    s_fold[i] = ok ? p.a_in[i] : 1.f;
+    s_fold[p.k_blocks * BK + i] = ok ? p.b_in[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -151,28 +159,33 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p) {
       if (issued < total_kb) issue(), ++issued;
       const int col = kb * BK + chunk * 4;
       mbar_wait(&bars->raw[s], par);
-      float4 fa = make_float4(1.f, 1.f, 1.f, 1.f), fb = make_float4(0.f, 0.f, 0.f, 0.f);
+      // fold constants from shared memory (staged once per CTA: as per-stage __ldg they were this
+      // loop's top stall, a global-load latency in front of every transform)
       const bool fold = p.a_in != nullptr && col < p.K;
-      if (fold) {
-        fa = __ldg(reinterpret_cast<const float4 *>(p.a_in + col));
-        fb = __ldg(reinterpret_cast<const float4 *>(p.b_in + col));
-      }
+      const float4 fa = *reinterpret_cast<const float4 *>(s_fold + col);
+      const float4 fb = *reinterpret_cast<const float4 *>(s_fold + p.k_blocks * BK + col);
       unsigned char *base = smem_a + s * A_STAGE_BYTES;
+      // The operand stays plain fp32 in shared memory: kind::tf32 reads the upper 19 bits of each
+      // word (truncation, what the library TF32 GEMMs do with fp32 inputs).  Without a fold (a block's
+      // first layer) the landed tile is therefore used as it is -- no pass over it at all; rows past
+      // P were zero-filled by cp.async.
+      if (fold) {
+        const float2 a01 = make_float2(fa.x, fa.y), a23 = make_float2(fa.z, fa.w);
+        const float2 b01 = make_float2(fb.x, fb.y), b23 = make_float2(fb.z, fb.w);
+        const float lo = p.relu_in ? 0.f : -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = row0 + 16 * i;
-        float4 *q = reinterpret_cast<float4 *>(base + r * 128 + ((chunk ^ (r & 7)) << 4));
-        float4 v = *q;
-        if (fold) {
-          v.x = fmaf(fa.x, v.x, fb.x), v.y = fmaf(fa.y, v.y, fb.y);
-          v.z = fmaf(fa.z, v.z, fb.z), v.w = fmaf(fa.w, v.w, fb.w);
-          if (p.relu_in) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+        for (int i = 0; i < 8; ++i) {
+          const int r = row0 + 16 * i;
+          float4 *q = reinterpret_cast<float4 *>(base + r * 128 + ((chunk ^ (r & 7)) << 4));
+          float4 v = *q;
+          const float2 y01 = fma2(a01, make_float2(v.x, v.y), b01), y23 = fma2(a23, make_float2(v.z, v.w), b23);
+          v = make_float4(fmaxf(y01.x, lo), fmaxf(y01.y, lo), fmaxf(y23.x, lo), fmaxf(y23.y, lo));
           const int grow = tile * BM + r;
           if (grow >= p.P) v = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past the end stay zero: the
           else if (p.H_out != nullptr && n_tile == 0)             // epilogue statistics rely on it
             *reinterpret_cast<float4 *>(p.H_out + static_cast<size_t>(grow) * p.lda + col) = v;
+          *q = v;
         }
-        *q = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
       }
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
       mbar_arrive(&bars->full[s]);
@@ -372,7 +385,8 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   if (prm.stages > gemm::kMaxStages) prm.stages = gemm::kMaxStages;
   if (prm.stages < 2) return PN2_ERR_UNSUPPORTED;
   const size_t smem = static_cast<size_t>(prm.stages) * (gemm::A_STAGE_BYTES + prm.b_stage_bytes) +
-                      sizeof(gemm::Barriers) + sizeof(float) * gemm::kEpiWarps * 2 * gemm::kMaxBN;
+                      sizeof(gemm::Barriers) + sizeof(float) * gemm::kEpiWarps * 2 * gemm::kMaxBN +
+                      sizeof(float) * 2 * prm.k_blocks * gemm::BK;
   cudaError_t e = cudaFuncSetAttribute(gemm::gemm_tf32_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);

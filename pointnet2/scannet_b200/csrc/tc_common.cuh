@@ -121,6 +121,24 @@ __device__ __forceinline__ uint64_t make_desc_mn32(uint32_t smem_addr, uint32_t 
 __device__ __forceinline__ uint32_t swz_base32(int r, int chunk) {
   return static_cast<uint32_t>(r * 128 + ((((chunk >> 1) ^ (r & 3)) << 5) | ((chunk & 1) << 4)));
 }
+// Blackwell packed fp32: two fused multiply-adds / multiplies per instruction (FFMA2 / FMUL2)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; "
+      "mov.b64 {%0,%1}, rd;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+
 constexpr uint32_t kIdescAMajorMN = 1u << 15, kIdescBMajorMN = 1u << 16;
 
 }  // namespace tc

@@ -1,7 +1,9 @@
 """GPU parity of the tcgen05 shared-MLP layer (csrc/mlp_gemm.cu) through the C ABI.
 
-Reference: the same product in fp64 on operands rounded to TF32 exactly as the kernel rounds
-them (cvt.rna: nearest, ties away from zero).  What remains is fp32 accumulation order, so the
+Reference: the same product in fp64 on operands reduced to TF32 exactly as the kernel's are: the
+activation tile stays plain fp32 in shared memory and the tensor core reads the upper 19 bits of
+each word (truncation); the packed weights are rounded (cvt.rna: nearest, ties away from zero).
+What remains is fp32 accumulation order, so the
 tolerance is 2e-5 of the output's max magnitude; the fused BatchNorm statistics (column sums and
 sums of squares) within 1e-4 relative; the side-output act(A) within 1e-6.
 """
@@ -18,6 +20,11 @@ DEV = "cuda:0"
 def tf32_rna(x):
     u = x.astype(np.float32).view(np.uint32)
     return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def tf32_trunc(x):
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return (u & np.uint32(0xFFFFE000)).view(np.float32)
 
 
 def run_gemm(A, W, k, a_in=None, b_in=None, relu=False, want_h=False):
@@ -56,7 +63,7 @@ def test_gemm_plain(P, K, lda, N):
     A[:, :K] = rng.standard_normal((P, K)).astype(np.float32)
     W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
     Z, stats, _ = run_gemm(A, W, K)
-    ref = tf32_rna(A[:, :K]).astype(np.float64) @ tf32_rna(W).astype(np.float64).T
+    ref = tf32_trunc(A[:, :K]).astype(np.float64) @ tf32_rna(W).astype(np.float64).T
     assert np.isfinite(Z).all()
     assert np.abs(Z - ref).max() <= 2e-5 * np.abs(ref).max()
     np.testing.assert_allclose(stats[0], ref.sum(0), rtol=1e-4, atol=1e-4 * np.abs(ref).sum(0).max())
@@ -75,6 +82,6 @@ def test_gemm_fused_bn_relu_prologue(P, K, N, relu):
     if relu:
         act = np.maximum(act, 0)
     np.testing.assert_allclose(H, act, rtol=1e-6, atol=1e-6)
-    ref = tf32_rna(H).astype(np.float64) @ tf32_rna(W).astype(np.float64).T
+    ref = tf32_trunc(H).astype(np.float64) @ tf32_rna(W).astype(np.float64).T
     assert np.abs(Z - ref).max() <= 2e-5 * np.abs(ref).max()
     np.testing.assert_allclose(stats[1], (ref * ref).sum(0), rtol=1e-4)
