@@ -125,19 +125,24 @@ bn_stats_finalize_kernel(int P, int C, int ld, int nblk, const float *__restrict
   double s, q;
   warp_sum_partials(ld, c, nblk, partials, s, q);
   if ((threadIdx.x & 31) != 0) return;
-  const double mean = s / P;
-  double var = q / P - mean * mean;  // biased, as BatchNorm normalises with
+  // fp64 only where cancellation needs it (q/P - mean^2), and no fp64 division or square root:
+  // Blackwell's fp64 rate makes a handful of DP divides the cost of this whole kernel.
+  const double inv_p = static_cast<double>(1.0f / static_cast<float>(P)) ;
+  const double ip = inv_p * (2.0 - static_cast<double>(P) * inv_p);  // one Newton step: 1/P to fp64 accuracy
+  const double mean = s * ip;
+  double var = q * ip - mean * mean;  // biased, as BatchNorm normalises with
   if (var < 0.0) var = 0.0;
-  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float varf = static_cast<float>(var);
+  const float invstd = 1.0f / sqrtf(varf + eps);
   const float ga = gamma[c] * invstd;
   a[c] = ga;
   b[c] = beta[c] - static_cast<float>(mean) * ga;
   mean_out[c] = static_cast<float>(mean);
   invstd_out[c] = invstd;
   if (running_mean != nullptr) {  // torch: running = (1-m)*running + m*stat, unbiased variance
-    const double unbiased = P > 1 ? var * P / (P - 1.0) : var;
+    const float unbiased = P > 1 ? varf * (static_cast<float>(P) / static_cast<float>(P - 1)) : varf;
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
   }
 }
 
@@ -235,8 +240,9 @@ bwd_stats_finalize_kernel(int P, int C, int ld, int nblk, int training, const fl
   if ((threadIdx.x & 31) != 0) return;
   dbeta[c] = static_cast<float>(s);
   dgamma[c] = static_cast<float>(q);
-  c1[c] = training ? static_cast<float>(s / P) : 0.f;
-  c2[c] = training ? static_cast<float>(q / P) : 0.f;
+  const float inv_p = 1.0f / static_cast<float>(P);  // no fp64 division (see bn_stats_finalize_kernel)
+  c1[c] = training ? static_cast<float>(s) * inv_p : 0.f;
+  c2[c] = training ? static_cast<float>(q) * inv_p : 0.f;
 }
 
 // dense dZ of the pooled layer: dZ[p,c] = a*(dY - c1 - zhat*c2), dY nonzero at the arg-max row
