@@ -16,6 +16,9 @@
 // into shared memory with a 1-D TMA bulk copy (cp.async.bulk + mbarrier) and
 // scanned from there; larger clouds (whole scenes) are scanned straight from
 // L2 with coalesced loads.
+#include <limits.h>
+#include <stdlib.h>
+
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -137,6 +140,114 @@ ball_query_kernel(BqParams p, const float *__restrict__ new_xyz,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Grid variant (512 <= n <= 8192 points per cloud, the training chunks): the cloud is counting-
+// sorted into a spatial hash of cell size 1.001 * radius in shared memory, and a centre only
+// tests the points of its 27 neighbouring cells (tens of candidates instead of all n: the balls
+// of the SSG levels hold ~5-15 points).  A warp owns a centre: lane l < 27 walks cell l's bucket,
+// hits are appended to a per-warp list, and the nsample SMALLEST indices are extracted in
+// ascending order with warp minima -- the reference's "first nsample hits in index order".  The
+// distance is the same un-contracted fp32 expression, evaluated on a subset of the same pairs, so
+// the result is bit-identical to the full scan (a list overflow falls back to the full scan).
+// ---------------------------------------------------------------------------------------------
+constexpr int kGridThreads = 1024, kGridWarps = kGridThreads / 32;
+constexpr int kGridBuckets = 4096, kGridHitCap = 128;
+
+__global__ void __launch_bounds__(kGridThreads, 1)
+ball_query_grid_kernel(BqParams p, float inv, const float *__restrict__ new_xyz,
+                       const float *__restrict__ xyz, int *__restrict__ idx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 *s_pts = reinterpret_cast<float4 *>(smem_raw);                       // [n]
+  int *s_start = reinterpret_cast<int *>(s_pts + p.n);                       // [T + 1]
+  int *s_cnt = s_start + kGridBuckets + 1;                                    // [T]
+  int *s_hits = s_cnt + kGridBuckets;                                         // [warps][cap]
+  int *s_rows = s_hits + kGridWarps * kGridHitCap;                            // [warps][nsample]
+  int *s_hitcnt = s_rows + kGridWarps * p.nsample;                            // [warps]
+  int *s_scratch = s_hitcnt + kGridWarps;                                     // [32]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cloud = blockIdx.y;
+  const float *pts = xyz + static_cast<size_t>(cloud) * p.n * 3;
+  const float *ctr = new_xyz + static_cast<size_t>(cloud) * p.m * 3;
+  int *out = idx + static_cast<size_t>(cloud) * p.m * p.nsample;
+  // inv = 1 / (1.001 * radius): cell size just above the radius (computed on the host)
+
+  for (int i = tid; i < kGridBuckets; i += kGridThreads) s_cnt[i] = 0;
+  __syncthreads();
+  grid_build<kGridThreads>(pts, p.n, inv, kGridBuckets, s_cnt, s_start, s_pts, s_scratch);
+
+  const int j0 = blockIdx.x * p.centres_per_cta;
+  const int j1 = min(j0 + p.centres_per_cta, p.m);
+  int *hits = s_hits + warp * kGridHitCap;
+  int *row = s_rows + warp * p.nsample;
+  for (int j = j0 + warp; j < j1; j += kGridWarps) {
+    const float cx = __ldg(ctr + 3 * j), cy = __ldg(ctr + 3 * j + 1), cz = __ldg(ctr + 3 * j + 2);
+    int tx = grid_cell(cx, inv), ty = grid_cell(cy, inv), tz = grid_cell(cz, inv);
+    int s = 0, e = 0;
+    if (lane < 27) {
+      tx += lane % 3 - 1, ty += (lane / 3) % 3 - 1, tz += lane / 9 - 1;
+      const unsigned b = grid_hash(tx, ty, tz, kGridBuckets - 1);
+      s = s_start[b], e = s_start[b + 1];
+    }
+    if (lane == 0) s_hitcnt[warp] = 0;
+    __syncwarp();
+    const int steps = __reduce_max_sync(0xffffffffu, e - s);
+    for (int t = 0; t < steps; ++t) {
+      if (s + t < e) {
+        const float4 q = s_pts[s + t];
+        // the bucket may also hold points of other cells (hash collisions): only this cell's count
+        if (grid_cell(q.x, inv) == tx && grid_cell(q.y, inv) == ty && grid_cell(q.z, inv) == tz &&
+            sqdist_rn(cx, cy, cz, q.x, q.y, q.z) < p.radius2) {
+          const int pos = atomicAdd(&s_hitcnt[warp], 1);
+          if (pos < kGridHitCap) hits[pos] = __float_as_int(q.w);
+        }
+      }
+    }
+    __syncwarp();
+    const int H = s_hitcnt[warp];
+    int *dst = out + static_cast<size_t>(j) * p.nsample;
+    if (H > kGridHitCap) {
+      // more hits than the list holds: the reference's scan over all points, in index order
+      int cnt = 0, first = 0;
+      const unsigned lt = (1u << lane) - 1u;
+      for (int base = 0; base < p.n && cnt < p.nsample; base += 32) {
+        const int k = base + lane;
+        bool hit = false;
+        if (k < p.n)
+          hit = sqdist_rn(cx, cy, cz, __ldg(pts + 3 * k), __ldg(pts + 3 * k + 1), __ldg(pts + 3 * k + 2)) < p.radius2;
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask == 0u) continue;
+        if (cnt == 0) first = base + __ffs(mask) - 1;
+        const int slot = cnt + __popc(mask & lt);
+        if (hit && slot < p.nsample) row[slot] = k;
+        cnt += __popc(mask);
+      }
+      __syncwarp();
+      const int filled = min(cnt, p.nsample);
+      for (int l = lane; l < p.nsample; l += 32) dst[l] = l < filled ? row[l] : first;
+    } else {
+      int v[kGridHitCap / 32];
+#pragma unroll
+      for (int i = 0; i < kGridHitCap / 32; ++i) v[i] = lane + 32 * i < H ? hits[lane + 32 * i] : INT_MAX;
+      const int filled = min(H, p.nsample);
+      for (int l = 0; l < filled; ++l) {
+        int mine = v[0];
+#pragma unroll
+        for (int i = 1; i < kGridHitCap / 32; ++i) mine = min(mine, v[i]);
+        const int best = __reduce_min_sync(0xffffffffu, mine);
+#pragma unroll
+        for (int i = 0; i < kGridHitCap / 32; ++i)
+          if (v[i] == best) v[i] = INT_MAX;  // indices are unique: exactly one lane holds it
+        if (lane == 0) row[l] = best;
+      }
+      __syncwarp();
+      const int first = filled > 0 ? row[0] : 0;  // empty ball: zeros (ball_query.cpp:19-21)
+      for (int l = lane; l < p.nsample; l += 32) dst[l] = l < filled ? row[l] : first;
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace pn2
 
 extern "C" int pn2_query_ball_point(int b, int n, int m, float radius,
@@ -160,6 +271,25 @@ extern "C" int pn2_query_ball_point(int b, int n, int m, float radius,
   p.centres_per_cta = (m + ctas_per_cloud - 1) / ctas_per_cloud;
   ctas_per_cloud = (m + p.centres_per_cta - 1) / p.centres_per_cta;
 
+  // training-chunk sizes: spatial hash in shared memory, 27 cells per centre instead of all n points
+  if (n >= 512 && n <= 8192 && nsample <= 128 && radius >= 1e-3f && radius <= 1e3f &&
+      getenv("PN2_BQ_NO_GRID") == nullptr) {
+    int splits = kNumSMs / b;  // CTAs per cloud (each rebuilds the grid: ~n/1024 steps)
+    if (splits < 1) splits = 1;
+    if (splits > (m + 4 * kGridWarps - 1) / (4 * kGridWarps)) splits = (m + 4 * kGridWarps - 1) / (4 * kGridWarps);
+    p.centres_per_cta = (m + splits - 1) / splits;
+    splits = (m + p.centres_per_cta - 1) / p.centres_per_cta;
+    p.stage_floats = 0;
+    const size_t gsmem = sizeof(float4) * n + sizeof(int) * (2 * kGridBuckets + 1 + kGridWarps * kGridHitCap +
+                                                             kGridWarps * nsample + kGridWarps + 32);
+    cudaError_t ge = cudaFuncSetAttribute(ball_query_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(gsmem));
+    if (ge != cudaSuccess) return static_cast<int>(ge);
+    ball_query_grid_kernel<<<dim3(splits, b), kGridThreads, gsmem, static_cast<cudaStream_t>(stream)>>>(
+        p, 1.0f / (radius * 1.001f), new_xyz, xyz, idx);
+    count_launch();
+    PN2_RETURN_LAUNCH_STATUS();
+  }
   const bool staged = n <= kBqStagePts;
   p.stage_floats = staged ? (3 * n + 3) / 4 * 4 : 0;  // keeps the row buffers 16-byte aligned
   const size_t smem = sizeof(float) * p.stage_floats + sizeof(int) * kBqWarps * kBqQ * nsample;

@@ -67,6 +67,76 @@ __device__ __forceinline__ float sqnorm_rn(float x, float y, float z) {
                    __fmul_rn(z, z));
 }
 
+// ---- spatial hash shared by the grid-based ball query and 3-NN ------------------------------
+// Cell of a coordinate for cell size 1 / inv: floor(x * inv), a monotone function of x, clamped so
+// that the integer arithmetic of the hash cannot overflow.  Two coordinates closer than the cell
+// size land in the same or in adjacent cells (the callers keep a 1e-3 relative margin for the fp32
+// rounding of x * inv).
+__device__ __forceinline__ int grid_cell(float x, float inv) {
+  return max(-(1 << 20), min(1 << 20, __float2int_rd(x * inv)));
+}
+__device__ __forceinline__ unsigned grid_hash(int ix, int iy, int iz, unsigned mask) {
+  return ((static_cast<unsigned>(ix) * 73856093u) ^ (static_cast<unsigned>(iy) * 19349663u) ^
+          (static_cast<unsigned>(iz) * 83492791u)) & mask;
+}
+// Counting sort of a cloud's points into hash buckets, in shared memory (order inside a bucket is
+// arbitrary).  cnt[T] must be zero on entry and is used as the fill cursor; start[T + 1] receives
+// the bucket offsets; sorted[n] the points as (x, y, z, bits(index)).  All threads of the CTA call.
+template <int kThreads>
+__device__ __forceinline__ void grid_build(const float *__restrict__ pts, int n, float inv, int T, int *cnt,
+                                           int *start, float4 *sorted, int *scratch) {
+  const int tid = threadIdx.x;
+  for (int k = tid; k < n; k += kThreads) {
+    const float x = __ldg(pts + 3 * k), y = __ldg(pts + 3 * k + 1), z = __ldg(pts + 3 * k + 2);
+    atomicAdd(&cnt[grid_hash(grid_cell(x, inv), grid_cell(y, inv), grid_cell(z, inv), T - 1)], 1);
+  }
+  __syncthreads();
+  // exclusive scan of cnt[0..T): each thread owns T / kThreads consecutive buckets
+  const int per = (T + kThreads - 1) / kThreads;
+  int local = 0;
+  for (int i = 0; i < per; ++i) {
+    const int b = tid * per + i;
+    if (b < T) local += cnt[b];
+  }
+  int incl = local;
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) scratch[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < kThreads / 32 ? scratch[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    scratch[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  int run = incl - local + (warp > 0 ? scratch[warp - 1] : 0);
+  for (int i = 0; i < per; ++i) {
+    const int b = tid * per + i;
+    if (b < T) {
+      const int c = cnt[b];
+      start[b] = run;
+      cnt[b] = 0;
+      run += c;
+    }
+  }
+  if (tid == kThreads - 1) start[T] = n;
+  __syncthreads();
+  for (int k = tid; k < n; k += kThreads) {
+    const float x = __ldg(pts + 3 * k), y = __ldg(pts + 3 * k + 1), z = __ldg(pts + 3 * k + 2);
+    const unsigned b = grid_hash(grid_cell(x, inv), grid_cell(y, inv), grid_cell(z, inv), T - 1);
+    sorted[start[b] + atomicAdd(&cnt[b], 1)] = make_float4(x, y, z, __int_as_float(k));
+  }
+  __syncthreads();
+}
+
 // ---- mbarrier + 1-D TMA bulk copy (global -> shared::cta) -----------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
