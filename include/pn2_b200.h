@@ -270,6 +270,9 @@ PN2_API int pn2_bn_finalize(int p, int c, int ld, int nblk, const float *partial
  * pn2_bwd_stats_finalize.  Supported: n <= 128, n % 4 == 0, lda <= 160 (128 with
  * statistics), lda % 4 == 0 (pn2_mlp_bwd_supported); wt_packed from pn2_mlp_pack_weights_t (nb * kpad * 32 floats,
  * kpad = pn2_mlp_bwd_kpad(lda)).  TF32 operands, fp32 accumulation.
+ * sched: two ints, zero before the first launch (the kernel re-arms them): the tile counter of the
+ * dynamic scheduler -- row tiles are handed out by an atomic counter so that the kernel keeps its
+ * speed when other streams hold part of the SMs.  One buffer per stream that launches the kernel.
  * ========================================================================== */
 PN2_API int pn2_mlp_bwd_supported(int p, int n, int k, int lda, int with_stats);
 PN2_API int pn2_mlp_bwd_grid(int p);
@@ -284,7 +287,7 @@ PN2_API int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu, in
                               const float *c1c2, const float *w, const float *a_prev, const float *a_in,
                               const float *b_in, const float *mean_in, const float *invstd_in,
                               const float *wt_packed, float *dh_prev, float *dw_part,
-                              float *stats_part, void *stream);
+                              float *stats_part, int *sched, void *stream);
 PN2_API int pn2_pool_bn_bwd_stats(int g, int ns, int c, int training, const float *dout,
                                   const int *argmax, const float *z, const float *a, const float *b,
                                   const float *mean, const float *invstd, float *dgamma,

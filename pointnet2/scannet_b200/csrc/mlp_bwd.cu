@@ -89,6 +89,7 @@ struct Params {
   int ns, ns_shift, relu, relu_in;       // ns_shift >= 0 when ns is a power of two
   int sets, w_slot_bytes, tmem_cols;     // dZ sets (2, or 1 when N > 64)
   int dbg;                               // PN2_BWD_DBG timing experiments (results invalid when != 0)
+  int *sched;                            // [2] {next tile, CTAs finished}, zero between launches (self-resetting)
 };
 
 // PN2_BWD_DBG & 32: cycles each role spends in its waits, per CTA (read back with pn2_mlp_bwd_debug_read)
@@ -114,6 +115,9 @@ struct __align__(8) Barriers {
   uint64_t acc_full[2];          // dH_prev accumulator complete        (1 commit)
   uint64_t acc_empty[2];         // drained by the epilogue             (128 arrivals)
   uint64_t dw_full;              // every MMA of the CTA retired        (1 commit)
+  uint64_t tile_full[8];         // tile queue slot published           (1 arrival)
+  int tile_id[8];                // row tile of the CTA's t-th tile, -1 = no more tiles
+  int tiles_done;                // number of tiles this CTA processed (written by the MMA warp)
   uint32_t tmem_base;
 };
 
@@ -144,7 +148,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m_tiles = (p.P + BM - 1) / BM;
-  const int my_tiles = blockIdx.x < m_tiles ? (m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // Row tiles are handed out DYNAMICALLY (one global atomic counter): the kernel usually shares the
+  // GPU with the next batch's geometry kernels on another stream (FPS holds 32 SMs for ~0.7 ms), and
+  // with a static round-robin the CTAs that cannot become resident delay their share of the tiles
+  // until the first wave has finished -- up to 2x the kernel time.  The MMA warp fetches tile ids two
+  // tiles ahead and publishes them in a shared-memory queue that the other roles read.
+  auto tile_of = [&](int tl) -> int {
+    mbar_wait(&bars->tile_full[tl & 7], (tl >> 3) & 1);
+    return bars->tile_id[tl & 7];
+  };
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -158,6 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
       mbar_init(&bars->h_full[s], kGroupThreads), mbar_init(&bars->h_empty[s], 1);
     }
     mbar_init(&bars->dw_full, 1);
+    for (int s = 0; s < 8; ++s) mbar_init(&bars->tile_full[s], 1);
     mbar_fence_init();
   }
   if (warp == kMmaWarp) {
@@ -207,8 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
 
     // global loads of item (tl, j) into a register buffer: b[0..3] = dH (or dOut) / Z_prev rows,
     // b[4..7] = Z rows (dZ items only).  Rows past P load as zeros.
-    auto issue = [&](int tl, int j, float4 (&b)[8]) {
-      const int tile = blockIdx.x + tl * gridDim.x;
+    auto issue = [&](int tile, int j, float4 (&b)[8]) {
       const int r0 = tile * BM + row0;
       const bool full = (tile + 1) * BM <= p.P;
       if (j < nb) {
@@ -245,8 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
     // Operands go to shared memory as plain fp32: kind::tf32 reads the upper 19 bits of each word
     // (truncation), as the library TF32 GEMMs do with fp32 inputs.  The arithmetic is Blackwell's
     // packed fp32 (FFMA2): the loaders' issue slots, not HBM, bound this kernel otherwise.
-    auto process = [&](int tl, int j, float4 (&b)[8]) {
-      const int tile = blockIdx.x + tl * gridDim.x;
+    auto process = [&](int tl, int tile, int j, float4 (&b)[8]) {
       const int r0 = tile * BM + row0;
       const bool full = (tile + 1) * BM <= p.P;
       if (j < nb) {
@@ -360,9 +371,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
     float4 buf[8];
     int tl = 0, j = grp;
     while (j >= ipt) j -= ipt, ++tl;
-    while (tl < my_tiles) {
-      issue(tl, j, buf);
-      process(tl, j, buf);
+    int cur_tl = -1, tile = -1;
+    while (true) {
+      if (tl != cur_tl) cur_tl = tl, tile = tile_of(tl);
+      if (tile < 0) break;
+      issue(tile, j, buf);
+      process(tl, tile, j, buf);
       j += kGroups;
       while (j >= ipt) j -= ipt, ++tl;
     }
@@ -387,7 +401,26 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
       const bool tm = (p.dbg & 32) != 0;
       unsigned long long c_acc = 0, c_dzf = 0, c_wf = 0, c_hf = 0;
       int g = 0;  // loader group of the next item (items are dealt round-robin)
-      for (int tl = 0; tl < my_tiles; ++tl) {
+      // tile scheduler: ids of the tiles tl and tl + 1 are known; tl + 2 is fetched while tile tl's MMAs are issued
+      auto fetch = [&](bool want) -> int {  // one lane asks, every lane gets the answer (uniform control flow)
+        int id = -1;
+        if (want && leader) {
+          id = p.sched != nullptr ? atomicAdd(p.sched, 1) : -1;
+          if (id >= m_tiles) id = -1;
+        }
+        return __shfl_sync(0xffffffffu, id, 0);
+      };
+      auto publish = [&](int tl, int id) {
+        if (leader) {
+          bars->tile_id[tl & 7] = id;
+          mbar_arrive(&bars->tile_full[tl & 7]);
+        }
+      };
+      int id_cur = fetch(true), id_next = fetch(id_cur >= 0);
+      publish(0, id_cur), publish(1, id_next);
+      int tl = 0;
+      for (; id_cur >= 0; ++tl) {
+        const int id_after = fetch(id_next >= 0);   // lands while this tile's MMAs are issued
         const int acc = tl & 1, acc_use = tl >> 1;
         const int set = p.sets == 2 ? (tl & 1) : 0, use = p.sets == 2 ? (tl >> 1) : tl;
         const uint64_t dz_desc = mn_hi | addr(smem_u32(s_dz + set * nb * SLAB));
@@ -434,8 +467,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
           g ^= 1;
         }
         if (leader) tc_commit(&bars->dz_empty[tl & 3]);
+        publish(tl + 2, id_after);
+        id_cur = id_next, id_next = id_after;
       }
-      if (leader) tc_commit(&bars->dw_full);
+      if (leader) {
+        bars->tiles_done = tl;
+        tc_commit(&bars->dw_full);
+        // every CTA draws exactly one id past the end; the last one to do so re-arms the counters
+        if (p.sched != nullptr && atomicAdd(p.sched + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+          p.sched[0] = 0, p.sched[1] = 0;
+          __threadfence();
+        }
+      }
       if (tm && leader) {
         unsigned long long *o = g_wait_cycles[blockIdx.x] + 10;
         o[0] = c_acc, o[1] = c_dzf, o[2] = c_wf, o[3] = c_hf;
@@ -445,8 +488,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
     // ====================================== epilogue ======================================
     const int wq = warp;  // TMEM lane quarter
     if (dgrad) {
-      for (int tl = 0; tl < my_tiles; ++tl) {
-        const int tile = blockIdx.x + tl * gridDim.x, acc = tl & 1, use = tl >> 1;
+      for (int tl = 0;; ++tl) {
+        const int tile = tile_of(tl), acc = tl & 1, use = tl >> 1;
+        if (tile < 0) break;
         const int grow = tile * BM + wq * 32 + lane;
         const bool rowok = grow < p.P;
         {
@@ -482,7 +526,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
     mbar_wait(&bars->dw_full, 0);
     tc_fence_after();
     const int n = wq * 32 + lane;
-    const bool active = wq * 32 < nb32 && my_tiles > 0;
+    const bool active = wq * 32 < nb32 && bars->tiles_done > 0;  // written before the dw_full commit
     float *dst = p.dWpart + (static_cast<size_t>(blockIdx.x) * nb32 + n) * kb32;
 #pragma unroll
     for (int h = 0; h < kMaxKB; ++h) {
@@ -521,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
 
   tc_fence_before();
   __syncthreads();
-  if (stats && tid < kb32) {  // combine the four epilogue warps, fixed order
+  if (stats && tid < kb32) {  // combine the four epilogue warps, fixed order (all zero if the CTA got no tile)
     float s = 0.f, q = 0.f;
     for (int w = 0; w < kEpiWarps; ++w) s += s_stats[(w * 2) * kb32 + tid], q += s_stats[(w * 2 + 1) * kb32 + tid];
     float *dst = p.stats_part + static_cast<size_t>(blockIdx.x) * 2 * kb32;
@@ -626,9 +670,9 @@ extern "C" int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu,
                                  const float *b, const float *mean, const float *invstd, const float *c1c2,
                                  const float *w, const float *a_prev, const float *a_in, const float *b_in,
                                  const float *mean_in, const float *invstd_in, const float *wt_packed,
-                                 float *dh_prev, float *dw_part, float *stats_part, void *stream) {
+                                 float *dh_prev, float *dw_part, float *stats_part, int *sched, void *stream) {
   if (p <= 0) return PN2_ERR_INVALID_ARG;
-  PN2_CHECK_PTRS(z, a, b, mean, invstd, c1c2, a_prev, dw_part);
+  PN2_CHECK_PTRS(z, a, b, mean, invstd, c1c2, a_prev, dw_part, sched);
   if (dh == nullptr && (dout == nullptr || argmax == nullptr || ns <= 0 || p % ns != 0)) return PN2_ERR_INVALID_ARG;
   if (dh == nullptr && ns % 4 != 0) return PN2_ERR_UNSUPPORTED;  // a thread's 4 consecutive rows share one group
   if ((wt_packed == nullptr) != (dh_prev == nullptr)) return PN2_ERR_INVALID_ARG;
@@ -649,6 +693,7 @@ extern "C" int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu,
   prm.WTp = wt_packed, prm.dHprev = dh_prev, prm.dWpart = dw_part, prm.stats_part = stats_part;
   prm.P = p, prm.N = n, prm.nb = g.nb, prm.K = k, prm.lda = lda, prm.kb = g.kb, prm.kpad16 = g.kpad16;
   prm.ns = ns > 0 ? ns : 1, prm.relu = relu, prm.relu_in = relu_in;
+  prm.sched = sched;
   prm.dbg = getenv("PN2_BWD_DBG") != nullptr ? atoi(getenv("PN2_BWD_DBG")) : 0;
   prm.ns_shift = -1;
   for (int sh = 0; sh < 31; ++sh)

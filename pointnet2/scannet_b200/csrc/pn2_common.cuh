@@ -167,6 +167,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
       "r"(phase)
       : "memory");
 }
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t phase) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+  return ok != 0;
+}
 // bytes must be a multiple of 16; src and dst 16-byte aligned.
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem,
                                             uint32_t bytes, uint64_t *bar) {

@@ -68,6 +68,19 @@ def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+_sched = {}
+
+
+def _sched_counters(dev):
+    """Two zeroed ints per (device, stream): the tile counter of the persistent kernels' dynamic
+    scheduler (the kernels re-arm it themselves; kernels of one stream run one after another)."""
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _sched.get(key)
+    if buf is None:
+        buf = _sched[key] = torch.zeros(64, dtype=torch.int32, device=dev)
+    return buf
+
+
 def _ws(c, dev):
     n = _lib.load().pn2_bn_stats_workspace_floats(c) + 2 * c
     return torch.empty(n, dtype=torch.float32, device=dev)
@@ -283,7 +296,8 @@ class SharedMLPRows(Function):
                         prev.invstd.data_ptr() if prev is not None else None,
                         wtp.data_ptr() if wtp is not None else None,
                         dh_prev.data_ptr() if dh_prev is not None else None, dwp.data_ptr(),
-                        sp.data_ptr() if sp is not None else None, s), "mlp_bwd_layer")
+                        sp.data_ptr() if sp is not None else None, _sched_counters(dev).data_ptr(), s),
+                        "mlp_bwd_layer")
                     dW = f32(nb * 32, kb * 32)
                     _lib.check(L.pn2_sum_partials(grid, nb * 32 * kb * 32, dwp.data_ptr(), dW.data_ptr(), s),
                                "sum_partials")

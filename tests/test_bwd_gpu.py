@@ -36,6 +36,15 @@ def ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+_sched = []
+
+
+def SCHED():
+    if not _sched:
+        _sched.append(torch.zeros(2, dtype=torch.int32, device=DEV))
+    return _sched[0]
+
+
 def make_case(rng, P, N, K, lda, ns, relu, fold, relu_in):
     f32 = np.float32
     z = rng.standard_normal((P, N)).astype(f32)
@@ -124,7 +133,7 @@ def run_layer(c, dgrad=True, stats=True):
                                   ptr(t["dout"]), ptr(t["argmax"]), ptr(t["z"]), ptr(t["a"]), ptr(t["b"]),
                                   ptr(t["mean"]), ptr(t["invstd"]), ptr(t["c1c2"]), ptr(t["W"]), ptr(t["aprev"]), ptr(t["a_in"]),
                                   ptr(t["b_in"]), ptr(t["mean_in"]), ptr(t["invstd_in"]), ptr(wtp), ptr(dh_prev),
-                                  ptr(dwp), ptr(sp), s), "mlp_bwd_layer")
+                                  ptr(dwp), ptr(sp), ptr(SCHED()), s), "mlp_bwd_layer")
     torch.cuda.synchronize()
     out = {"dw": dwp.double().sum(0).cpu().numpy()[:N, :K]}
     if dgrad:

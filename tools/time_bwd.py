@@ -21,6 +21,7 @@ CASES = [  # name, P, N, K, lda, ns (pooled), fold, dgrad
     ("SA3 l2", 1 << 16, 128, 128, 128, 0, True, True),
 ]
 s = torch.cuda.current_stream().cuda_stream
+sched = torch.zeros(2, dtype=torch.int32, device=DEV)
 print("PN2_BWD_DBG =", os.environ.get("PN2_BWD_DBG"))
 ONLY = os.environ.get("ONLY")
 for name, P, N, K, lda, ns, fold, dgrad in CASES:
@@ -46,7 +47,7 @@ for name, P, N, K, lda, ns, fold, dgrad in CASES:
     def call():
         lib.check(L.pn2_mlp_bwd_layer(P, N, K, lda, ns, 1, 1, p(dh), p(dout), p(am), p(z), p(a), p(b), p(mean),
                                       p(invstd), p(c1c2), p(W), p(aprev), p(a_in), p(b_in), p(mean_in), p(invstd_in),
-                                      p(wtp), p(dhp), p(dwp), p(sp), s), "bwd")
+                                      p(wtp), p(dhp), p(dwp), p(sp), sched.data_ptr(), s), "bwd")
     for _ in range(3):
         call()
     torch.cuda.synchronize()
