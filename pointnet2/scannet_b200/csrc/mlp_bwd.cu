@@ -221,6 +221,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
     // global loads of item (tl, j) into a register buffer: b[0..3] = dH (or dOut) / Z_prev rows,
     // b[4..7] = Z rows (dZ items only).  Rows past P load as zeros.
     auto issue = [&](int tile, int j, float4 (&b)[8]) {
+      if (p.dbg & 16) {  // timing experiment: no global loads
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = zero4();
+        return;
+      }
       const int r0 = tile * BM + row0;
       const bool full = (tile + 1) * BM <= p.P;
       if (j < nb) {
