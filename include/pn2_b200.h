@@ -243,7 +243,11 @@ PN2_API int pn2_mlp_pack_weights(int p, int n, int k, int ldw, const float *w, f
                                  void *stream);
 PN2_API int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const float *a,
                              const float *a_in, const float *b_in, int relu_in, float *h_out,
-                             const float *w_packed, float *z, float *partials, void *stream);
+                             const float *w_packed, float *z, float *partials,
+                             const unsigned char *drop, float drop_scale, void *stream);
+/* drop (optional, [p, k] bytes; needs a_in, excludes h_out): keep mask of an nn.Dropout sitting between
+ * the previous layer's activation and this layer (pointnet2_semseg.py:156): act(a) is multiplied by
+ * drop ? drop_scale : 0 on the tile, so the dropped activation is never materialised. */
 PN2_API int pn2_bn_finalize(int p, int c, int ld, int nblk, const float *partials,
                             const float *gamma, const float *beta, float eps, float momentum,
                             float *running_mean, float *running_var, long long *num_batches_tracked,
@@ -287,7 +291,12 @@ PN2_API int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu, in
                               const float *c1c2, const float *w, const float *a_prev, const float *a_in,
                               const float *b_in, const float *mean_in, const float *invstd_in,
                               const float *wt_packed, float *dh_prev, float *dw_part,
-                              float *stats_part, int *sched, void *stream);
+                              float *stats_part, int *sched, const unsigned char *drop_out,
+                              float drop_out_scale, const unsigned char *drop_in, float drop_in_scale,
+                              void *stream);
+/* drop_out [p, n] / drop_in [p, k] (optional byte keep masks): dropout applied to this layer's
+ * activated output (its adjoint multiplies dh first) / to the activation of the layer below (H_prev
+ * and the ReLU mask of the statistics products carry it). */
 PN2_API int pn2_pool_bn_bwd_stats(int g, int ns, int c, int training, const float *dout,
                                   const int *argmax, const float *z, const float *a, const float *b,
                                   const float *mean, const float *invstd, float *dgamma,

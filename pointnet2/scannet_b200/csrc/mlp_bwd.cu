@@ -90,6 +90,8 @@ struct Params {
   int sets, w_slot_bytes, tmem_cols;     // dZ sets (2, or 1 when N > 64)
   int dbg;                               // PN2_BWD_DBG timing experiments (results invalid when != 0)
   int *sched;                            // [2] {next tile, CTAs finished}, zero between launches (self-resetting)
+  const unsigned char *drop_out, *drop_in;  // [P, N] / [P, K] dropout keep masks (nullptr: none)
+  float drop_out_scale, drop_in_scale;
 };
 
 // PN2_BWD_DBG & 32: cycles each role spends in its waits, per CTA (read back with pn2_mlp_bwd_debug_read)
@@ -127,6 +129,9 @@ __device__ __forceinline__ float4 tf32x4(float4 v) {
   return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
 }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+// kDrop: dropout keep masks present (the classifier head's chain); compiled out otherwise -- the loader
+// chain bounds this kernel and every instruction in it counts.
+template <bool kDrop>
 __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int nb = p.nb, kb = p.kb;
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
 
     // global loads of item (tl, j) into a register buffer: b[0..3] = dH (or dOut) / Z_prev rows,
     // b[4..7] = Z rows (dZ items only).  Rows past P load as zeros.
-    auto issue = [&](int tile, int j, float4 (&b)[8]) {
+    auto issue = [&](int tile, int j, float4 (&b)[8], uint32_t (&mk)[4]) {
       if (p.dbg & 16) {  // timing experiment: no global loads
 #pragma unroll
         for (int i = 0; i < 8; ++i) b[i] = zero4();
@@ -228,6 +233,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
       }
       const int r0 = tile * BM + row0;
       const bool full = (tile + 1) * BM <= p.P;
+      if (kDrop) {  // dropout keep-mask bytes of this thread's 4 columns (all-ones where there is no dropout)
+        const unsigned char *dm = j < nb ? p.drop_out : p.drop_in;
+        const int ld = j < nb ? p.N : p.K;
+        const int col = (j < nb ? j : j - nb) * BK + chunk * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          mk[i] = (kDrop && dm != nullptr && col < ld && r0 + i < p.P)
+                      ? __ldg(reinterpret_cast<const uint32_t *>(dm + static_cast<size_t>(r0 + i) * ld + col))
+                      : 0x01010101u;
+      }
       if (j < nb) {
         const int col = j * BK + chunk * 4;
         const bool colok = col < p.N;
@@ -262,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
     // Operands go to shared memory as plain fp32: kind::tf32 reads the upper 19 bits of each word
     // (truncation), as the library TF32 GEMMs do with fp32 inputs.  The arithmetic is Blackwell's
     // packed fp32 (FFMA2): the loaders' issue slots, not HBM, bound this kernel otherwise.
-    auto process = [&](int tl, int tile, int j, float4 (&b)[8]) {
+    auto process = [&](int tl, int tile, int j, float4 (&b)[8], const uint32_t (&mk)[4]) {
       const int r0 = tile * BM + row0;
       const bool full = (tile + 1) * BM <= p.P;
       if (j < nb) {
@@ -305,6 +320,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
         const float2 C01 = make_float2(fC.x, fC.y), C23 = make_float2(fC.z, fC.w);
         const float2 D01 = make_float2(fD.x, fD.y), D23 = make_float2(fD.z, fD.w);
         const float thr = p.relu ? 0.f : -INFINITY;  // no ReLU: every gradient passes
+        if (kDrop && p.drop_out != nullptr) {  // adjoint of the dropout on this layer's output
+          const float sc = p.drop_out_scale;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            b[i] = make_float4((mk[i] & 0xffu) ? b[i].x * sc : 0.f, (mk[i] & 0xff00u) ? b[i].y * sc : 0.f,
+                               (mk[i] & 0xff0000u) ? b[i].z * sc : 0.f, (mk[i] & 0xff000000u) ? b[i].w * sc : 0.f);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 v = b[4 + i], d = b[i];
@@ -344,6 +366,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
             if (fold) {
               const float2 y01 = fma2(a01, make_float2(y.x, y.y), b01), y23 = fma2(a23, make_float2(y.z, y.w), b23);
               y = make_float4(fmaxf(y01.x, lo), fmaxf(y01.y, lo), fmaxf(y23.x, lo), fmaxf(y23.y, lo));
+              if (kDrop && p.drop_in != nullptr) {
+                const float sc = p.drop_in_scale;
+                y = make_float4((mk[i] & 0xffu) ? y.x * sc : 0.f, (mk[i] & 0xff00u) ? y.y * sc : 0.f,
+                                (mk[i] & 0xff0000u) ? y.z * sc : 0.f, (mk[i] & 0xff000000u) ? y.w * sc : 0.f);
+              }
               if (!full && r0 + i >= p.P) y = zero4();
             }
             *reinterpret_cast<float4 *>(slab + off32[i]) = y;
@@ -361,6 +388,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
             const float2 h01 = fma2(s01, z01, e01), h23 = fma2(s23, z23, e23);   // zhat
             float4 m = make_float4(y01.x > thr ? 1.f : 0.f, y01.y > thr ? 1.f : 0.f, y23.x > thr ? 1.f : 0.f,
                                    y23.y > thr ? 1.f : 0.f);
+            if (kDrop && p.drop_in != nullptr) {  // M carries the dropout of the layer below
+              const float keep = p.drop_in_scale;
+              m = make_float4((mk[i] & 0xffu) ? m.x * keep : 0.f, (mk[i] & 0xff00u) ? m.y * keep : 0.f,
+                              (mk[i] & 0xff0000u) ? m.z * keep : 0.f, (mk[i] & 0xff000000u) ? m.w * keep : 0.f);
+            }
             if (!fold || (!full && r0 + i >= p.P)) m = zero4();
             const float2 q01 = mul2(make_float2(m.x, m.y), h01), q23 = mul2(make_float2(m.z, m.w), h23);
             *reinterpret_cast<float4 *>(slab + off32[i]) = m;
@@ -374,14 +406,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
 
     // this group's items: every kGroups-th slab of the CTA's tile sequence
     float4 buf[8];
+    uint32_t mk[4];
     int tl = 0, j = grp;
     while (j >= ipt) j -= ipt, ++tl;
     int cur_tl = -1, tile = -1;
     while (true) {
       if (tl != cur_tl) cur_tl = tl, tile = tile_of(tl);
       if (tile < 0) break;
-      issue(tile, j, buf);
-      process(tl, tile, j, buf);
+      issue(tile, j, buf, mk);
+      process(tl, tile, j, buf, mk);
       j += kGroups;
       while (j >= ipt) j -= ipt, ++tl;
     }
@@ -675,7 +708,9 @@ extern "C" int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu,
                                  const float *b, const float *mean, const float *invstd, const float *c1c2,
                                  const float *w, const float *a_prev, const float *a_in, const float *b_in,
                                  const float *mean_in, const float *invstd_in, const float *wt_packed,
-                                 float *dh_prev, float *dw_part, float *stats_part, int *sched, void *stream) {
+                                 float *dh_prev, float *dw_part, float *stats_part, int *sched,
+                                 const unsigned char *drop_out, float drop_out_scale, const unsigned char *drop_in,
+                                 float drop_in_scale, void *stream) {
   if (p <= 0) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(z, a, b, mean, invstd, c1c2, a_prev, dw_part, sched);
   if (dh == nullptr && (dout == nullptr || argmax == nullptr || ns <= 0 || p % ns != 0)) return PN2_ERR_INVALID_ARG;
@@ -699,15 +734,17 @@ extern "C" int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu,
   prm.P = p, prm.N = n, prm.nb = g.nb, prm.K = k, prm.lda = lda, prm.kb = g.kb, prm.kpad16 = g.kpad16;
   prm.ns = ns > 0 ? ns : 1, prm.relu = relu, prm.relu_in = relu_in;
   prm.sched = sched;
+  if ((drop_out != nullptr && dh == nullptr) || (drop_in != nullptr && a_in == nullptr)) return PN2_ERR_INVALID_ARG;
+  prm.drop_out = drop_out, prm.drop_in = drop_in, prm.drop_out_scale = drop_out_scale, prm.drop_in_scale = drop_in_scale;
   prm.dbg = getenv("PN2_BWD_DBG") != nullptr ? atoi(getenv("PN2_BWD_DBG")) : 0;
   prm.ns_shift = -1;
   for (int sh = 0; sh < 31; ++sh)
     if ((1 << sh) == prm.ns) prm.ns_shift = sh;
   prm.sets = g.sets, prm.w_slot_bytes = g.w_slot_bytes, prm.tmem_cols = g.tmem_cols;
-  cudaError_t e = cudaFuncSetAttribute(bwd::mlp_bwd_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(g.smem));
+  auto kern = (drop_out != nullptr || drop_in != nullptr) ? bwd::mlp_bwd_layer_kernel<true> : bwd::mlp_bwd_layer_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  bwd::mlp_bwd_layer_kernel<<<g.grid, bwd::kThreads, g.smem, static_cast<cudaStream_t>(stream)>>>(prm);
+  kern<<<g.grid, bwd::kThreads, g.smem, static_cast<cudaStream_t>(stream)>>>(prm);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

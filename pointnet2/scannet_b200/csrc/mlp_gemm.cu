@@ -58,6 +58,11 @@ struct Params {
   int relu_in;
   int stages, b_stage_bytes;  // pipeline depth; bytes reserved per weight stage (multiple of 1024)
   int tmem_cols;              // 512 (one CTA per SM) or 256 (two): two accumulators of tmem_cols / 2
+  // dropout between the previous layer's activation and this layer (nn.Dropout in the classifier,
+  // pointnet2_semseg.py:156): act(x) is multiplied by drop[p, k] ? drop_scale : 0 on the A tile
+  const unsigned char *drop;  // [P, K] keep mask (nullptr: none); requires a_in
+  float drop_scale;
+  int mask_off;               // offset of the stage's mask tile inside its weight stage
 };
 
 using namespace tc;
@@ -71,6 +76,7 @@ struct __align__(16) Barriers {
   uint32_t tmem_base;
 };
 
+template <bool kDrop>  // dropout keep mask on the A tile (compiled out otherwise)
 __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int STAGES = p.stages, B_STAGE_BYTES = p.b_stage_bytes;
@@ -143,6 +149,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p) {
         const bool ok = grow < p.P && col < p.lda;
         const float *src = ok ? p.A + static_cast<size_t>(grow) * p.lda + col : p.A;
         cp_async16(dst0 + r * 128 + ((chunk ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+        if (kDrop) {  // this thread's 4 mask bytes of the row ([128 rows][32 bytes] per stage)
+          const bool mok = grow < p.P && col < p.K;
+          cp_async4(smem_u32(smem_b + s * B_STAGE_BYTES + p.mask_off) + r * 32 + chunk * 4,
+                    mok ? p.drop + static_cast<size_t>(grow) * p.K + col : p.drop, mok ? 4u : 0u);
+        }
       }
       cp_async_arrive(&bars->raw[s]);
       if (++is_s == STAGES) is_s = 0, is_par ^= 1;
@@ -180,6 +191,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p) {
           float4 v = *q;
           const float2 y01 = fma2(a01, make_float2(v.x, v.y), b01), y23 = fma2(a23, make_float2(v.z, v.w), b23);
           v = make_float4(fmaxf(y01.x, lo), fmaxf(y01.y, lo), fmaxf(y23.x, lo), fmaxf(y23.y, lo));
+          if (kDrop) {
+            const uint32_t m = *reinterpret_cast<const uint32_t *>(smem_b + s * B_STAGE_BYTES + p.mask_off + r * 32 + chunk * 4);
+            v.x = (m & 0xffu) ? v.x * p.drop_scale : 0.f, v.y = (m & 0xff00u) ? v.y * p.drop_scale : 0.f;
+            v.z = (m & 0xff0000u) ? v.z * p.drop_scale : 0.f, v.w = (m & 0xff000000u) ? v.w * p.drop_scale : 0.f;
+          }
           const int grow = tile * BM + r;
           if (grow >= p.P) v = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past the end stay zero: the
           else if (p.H_out != nullptr && n_tile == 0)             // epilogue statistics rely on it
@@ -361,7 +377,8 @@ extern "C" int pn2_mlp_pack_weights(int p, int n, int k, int ldw, const float *w
 
 extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const float *a, const float *a_in,
                                 const float *b_in, int relu_in, float *h_out, const float *w_packed,
-                                float *z, float *partials, void *stream) {
+                                float *z, float *partials, const unsigned char *drop, float drop_scale,
+                                void *stream) {
   if (p <= 0 || k <= 0 || n <= 0 || lda < 4 || lda % 4 != 0) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(a, w_packed);
   if (!aligned16(a) || !aligned16(w_packed)) return PN2_ERR_UNSUPPORTED;
@@ -377,6 +394,9 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   // as many stages as fit: the narrow layers (BN = 32..64) are pure streaming and need >100 KB of
   // loads in flight per SM to cover HBM latency; the wide ones get 4 x 48 KB
   prm.b_stage_bytes = (prm.BN * gemm::BK * 4 + 1023) / 1024 * 1024;
+  if (drop != nullptr && (a_in == nullptr || h_out != nullptr || k % 4 != 0)) return PN2_ERR_INVALID_ARG;
+  prm.drop = drop, prm.drop_scale = drop_scale, prm.mask_off = prm.b_stage_bytes;
+  if (drop != nullptr) prm.b_stage_bytes += gemm::BM * gemm::BK;  // + [128 rows][32 mask bytes]
   // Narrow layers (BN <= 128) are pure streaming: two CTAs per SM (256 TMEM columns and <= 96 KB of
   // stages each) double the loads in flight and the warps available to hide latency.
   const bool two_per_sm = prm.BN <= 128;
@@ -387,11 +407,11 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   const size_t smem = static_cast<size_t>(prm.stages) * (gemm::A_STAGE_BYTES + prm.b_stage_bytes) +
                       sizeof(gemm::Barriers) + sizeof(float) * gemm::kEpiWarps * 2 * gemm::kMaxBN +
                       sizeof(float) * 2 * prm.k_blocks * gemm::BK;
-  cudaError_t e = cudaFuncSetAttribute(gemm::gemm_tf32_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
+  auto kern = drop != nullptr ? gemm::gemm_tf32_fwd_kernel<true> : gemm::gemm_tf32_fwd_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid(pn2_mlp_gemm_grid(p, n), prm.n_tiles);  // the partials buffer is sized by the same function
-  gemm::gemm_tf32_fwd_kernel<<<grid, gemm::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(prm);
+  kern<<<grid, gemm::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(prm);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

@@ -111,8 +111,9 @@ def _bn_forward(z, gamma, beta, rm, rv, eps, momentum, training, nbt=None):
     return a, b, mean, invstd
 
 
-def _tc_layer(A, k, W2, fold, relu_in, want_h, want_stats):
-    """One layer on the tcgen05 kernel: z = act(A)[:, :k] @ W2^T.  fold = (a_in, b_in) or None.
+def _tc_layer(A, k, W2, fold, relu_in, want_h, want_stats, drop=None):
+    """One layer on the tcgen05 kernel: z = act(A)[:, :k] @ W2^T.  fold = (a_in, b_in) or None;
+    drop = (keep mask uint8 [P, k], scale) of a dropout between act(A) and this layer, or None.
     -> (z, h_out or None, partials or None, (ld, nblk))"""
     L = _lib.load()
     dev = A.device
@@ -132,7 +133,9 @@ def _tc_layer(A, k, W2, fold, relu_in, want_h, want_stats):
         fold[0].data_ptr() if fold is not None else None,
         fold[1].data_ptr() if fold is not None else None, int(relu_in),
         h.data_ptr() if h is not None else None, Wp.data_ptr(), z.data_ptr(),
-        part.data_ptr() if part is not None else None, s), "mlp_gemm_fwd")
+        part.data_ptr() if part is not None else None,
+        drop[0].data_ptr() if drop is not None else None, float(drop[1]) if drop is not None else 1.0, s),
+        "mlp_gemm_fwd")
     return z, h, part, (nt * bn, grid)
 
 
@@ -151,14 +154,16 @@ def _bn_finalize(P, C, part, ld, nblk, gamma, beta, rm, rv, eps, momentum, nbt=N
 class SharedMLPRows(Function):
     """x0 [P, Cin] -> out [P/ns, C_L] (max over each run of ns rows) or [P, C_L] (ns == 0).
 
-    args: x0, ns, training, eps, momentum, buffers, relus, then (W, gamma, beta) per layer.
+    args: x0, ns, training, eps, momentum, buffers, relus, drops, then (W, gamma, beta) per layer.
+    ``drops``: per layer None or (keep mask uint8 [P, C_l], scale): dropout on that layer's activated
+    output, applied inside the NEXT layer's kernels (tensor-core path with fused backward only).
     ``buffers`` is a list of (running_mean, running_var, num_batches_tracked) per layer (updated
     in place, as torch.nn.BatchNorm does in train mode);
     ``relus`` one flag per layer (the pooled last layer always has its ReLU).
     """
 
     @staticmethod
-    def forward(ctx, x0, ns, training, eps, momentum, buffers, relus, *params):
+    def forward(ctx, x0, ns, training, eps, momentum, buffers, relus, drops, *params):
         L = _lib.load()
         dev = x0.device
         nl = len(params) // 3
@@ -187,8 +192,10 @@ class SharedMLPRows(Function):
                     prev = layers[l - 1] if l > 0 else None
                     A = prev.z if prev is not None else x0
                     fold = (prev.a, prev.b) if prev is not None else None
+                    drop = drops[l - 1] if l > 0 else None
+                    assert drop is None or (bwd_fused[l] and bwd_fused[l - 1]), "dropout needs the fused backward layers"
                     st.z, h, part, (ld, nblk) = _tc_layer(A, W2.shape[1], W2, fold,
-                                                          relus[l - 1] if l > 0 else False, want_h, training)
+                                                          relus[l - 1] if l > 0 else False, want_h, training, drop)
                     if l > 0:
                         hs.append(h)          # None when the fused backward layer will recompute it
                     if training:
@@ -224,7 +231,8 @@ class SharedMLPRows(Function):
                                                       st.b.data_ptr(), out.data_ptr(), argmax.data_ptr(),
                                                       _stream(dev)), "bn_relu_groupmax")
         ctx.layers, ctx.hs, ctx.argmax, ctx.bwd_fused = layers, hs, argmax, bwd_fused
-        ctx.ns, ctx.training, ctx.nl, ctx.relus = ns, training, nl, relus
+        assert use_tc or not any(d is not None for d in drops), "dropout inside the chain needs the tensor-core path"
+        ctx.ns, ctx.training, ctx.nl, ctx.relus, ctx.drops = ns, training, nl, relus, drops
         ctx.weights = [params[3 * l] for l in range(nl)]
         return out
 
@@ -284,6 +292,7 @@ class SharedMLPRows(Function):
                         if prev is not None:
                             sp = f32(grid, 2, kb * 32)
                     dwp = f32(grid, nb * 32 * kb * 32)
+                    d_out, d_in = ctx.drops[l], (ctx.drops[l - 1] if l > 0 else None)
                     _lib.check(L.pn2_mlp_bwd_layer(
                         P, C, K, lda, ns if pooled else 0, 1 if pooled else int(ctx.relus[l]),
                         int(ctx.relus[l - 1]) if prev is not None else 0,
@@ -296,7 +305,9 @@ class SharedMLPRows(Function):
                         prev.invstd.data_ptr() if prev is not None else None,
                         wtp.data_ptr() if wtp is not None else None,
                         dh_prev.data_ptr() if dh_prev is not None else None, dwp.data_ptr(),
-                        sp.data_ptr() if sp is not None else None, _sched_counters(dev).data_ptr(), s),
+                        sp.data_ptr() if sp is not None else None, _sched_counters(dev).data_ptr(),
+                        d_out[0].data_ptr() if d_out is not None else None, float(d_out[1]) if d_out is not None else 1.0,
+                        d_in[0].data_ptr() if d_in is not None else None, float(d_in[1]) if d_in is not None else 1.0, s),
                         "mlp_bwd_layer")
                     dW = f32(nb * 32, kb * 32)
                     _lib.check(L.pn2_sum_partials(grid, nb * 32 * kb * 32, dwp.data_ptr(), dW.data_ptr(), s),
@@ -341,7 +352,7 @@ class SharedMLPRows(Function):
                     dh = _mm(dz, W2)                           # [P, Cin]
                 else:
                     dh = None
-        return (dh if ctx.needs_input_grad[0] else None, None, None, None, None, None, None) + tuple(grads)
+        return (dh if ctx.needs_input_grad[0] else None, None, None, None, None, None, None, None) + tuple(grads)
 
 
 class SAGroupRows(Function):
@@ -459,9 +470,11 @@ def mlp_eligible(mlp, x_like):
     return True
 
 
-def run_mlp_rows(mlp, x0, ns):
+def run_mlp_rows(mlp, x0, ns, dropouts=None):
     """Apply a SharedMLP (or any sequence of conv+BN[+ReLU] units) to rows ``x0`` [P, Cin(_pad)];
-    ns > 0 pools every run of ns rows after the last layer."""
+    ns > 0 pools every run of ns rows after the last layer.  ``dropouts``: {unit index: p} (or
+    {unit index: (p, keep mask)}) -- nn.Dropout(p) on that unit's output, applied inside the next
+    unit's kernels (see ``chain_supports_dropout``); ignored in eval mode."""
     params, buffers, relus = [], [], []
     layers = list(mlp)
     training = layers[0].training
@@ -470,9 +483,36 @@ def run_mlp_rows(mlp, x0, ns):
         params += [layer.conv.weight, norm.weight, norm.bias]
         buffers.append((norm.running_mean, norm.running_var, norm.num_batches_tracked))
         relus.append(getattr(layer, "activation", None) is not None)
+    drops = [None] * len(layers)
+    if dropouts and training:
+        for i, spec in dropouts.items():
+            p, mask = spec if isinstance(spec, tuple) else (spec, None)
+            if p <= 0.0:
+                continue
+            if mask is None:  # keep mask, one byte per element
+                mask = torch.empty(x0.shape[0], layers[i].conv.weight.shape[0], dtype=torch.uint8,
+                                   device=x0.device).bernoulli_(1.0 - p)
+            drops[i] = (mask, 1.0 / (1.0 - p))
     # running statistics AND num_batches_tracked are updated inside the finalise kernels
     return SharedMLPRows.apply(x0, ns, training, float(norms[0].eps), float(norms[0].momentum), buffers,
-                               tuple(relus), *params)
+                               tuple(relus), tuple(drops), *params)
+
+
+def chain_supports_dropout(units, x0, i):
+    """Can nn.Dropout after unit ``i`` of the chain be applied inside the kernels of unit i + 1?  Needs the
+    tensor-core forward layer and the fused backward layers for units i and i + 1."""
+    if not (TC_GEMM and GEMM_TF32 and TC_BWD and ENABLED) or i + 1 >= len(units):
+        return False
+    L = _lib.load()
+    shape = tuple(x0.shape) if hasattr(x0, "shape") else tuple(x0)   # rows [P, width] or just their shape
+    P = shape[0]
+    for l in (i, i + 1):
+        W = units[l].conv.weight
+        cout, cin = W.shape[0], W.reshape(W.shape[0], -1).shape[1]
+        lda = shape[1] if l == 0 else units[l - 1].conv.weight.shape[0]
+        if not L.pn2_mlp_bwd_supported(P, cout, cin, lda, int(l > 0)):
+            return False
+    return units[i].conv.weight.shape[0] % 4 == 0 and any(p.requires_grad for p in units[0].parameters())
 
 
 def pad4(c):

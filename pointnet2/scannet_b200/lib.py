@@ -46,7 +46,7 @@ SIGNATURES = {
     "pn2_mlp_gemm_k_blocks": [_i],
     "pn2_mlp_gemm_grid": [_i, _i],
     "pn2_mlp_pack_weights": [_i, _i, _i, _i, _vp, _vp, _vp],
-    "pn2_mlp_gemm_fwd": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],
+    "pn2_mlp_gemm_fwd": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp],
     "pn2_bn_finalize": [_i, _i, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     # fused backward layer on the tensor cores
     "pn2_mlp_bwd_supported": [_i, _i, _i, _i, _i],
@@ -55,7 +55,7 @@ SIGNATURES = {
     "pn2_mlp_bwd_kb": [_i],
     "pn2_mlp_bwd_kpad": [_i],
     "pn2_mlp_pack_weights_t": [_i, _i, _i, _i, _vp, _vp, _vp],
-    "pn2_mlp_bwd_layer": [_i] * 7 + [_vp] * 21,
+    "pn2_mlp_bwd_layer": [_i] * 7 + [_vp] * 20 + [_vp, _f, _vp, _f, _vp],
     "pn2_pool_bn_bwd_stats": [_i, _i, _i, _i] + [_vp] * 12,
     "pn2_relu_bn_bwd_stats": [_i, _i, _i, _i] + [_vp] * 11,
     "pn2_bwd_stats_finalize": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],

@@ -143,11 +143,12 @@ class PointnetFPModule(nn.Module):
             [interpolated, unknow_feats], dim=1)             # (B, C2 + C1, n)
         return self.mlp(feats.unsqueeze(-1)).squeeze(-1)
 
-    def forward_rows(self, unknown, known, unknow_feats, known_feats, geometry=None, tail=()):
+    def forward_rows(self, unknown, known, unknow_feats, known_feats, geometry=None, tail=(), tail_dropouts=None):
         """Fused path, point-major result (B, n, mlp[-1]): interpolation + concat written straight
         into [positions, channels] rows, then the shared MLP on rows (fused.py).  ``tail``: further
         conv + BN (+ ReLU) units applied to the result in the same chain (the classifier's first unit:
-        this block's last activation is then never written out or re-read)."""
+        this block's last activation is then never written out or re-read); ``tail_dropouts``:
+        {index into tail: p} -- nn.Dropout(p) after that tail unit, applied inside the next unit."""
         B, n, _ = unknown.shape
         if geometry is not None:
             idx, weight = geometry
@@ -157,4 +158,5 @@ class PointnetFPModule(nn.Module):
             weight = recip / torch.sum(recip, dim=2, keepdim=True)
         skip = fused.rows_of(unknow_feats) if unknow_feats is not None else None
         rows = fused.FPInterpRows.apply(fused.rows_of(known_feats), skip, idx, weight)
-        return fused.run_mlp_rows(list(self.mlp) + list(tail), rows, 0).view(B, n, -1)
+        drops = {len(self.mlp) + i: p for i, p in (tail_dropouts or {}).items()}
+        return fused.run_mlp_rows(list(self.mlp) + list(tail), rows, 0, drops).view(B, n, -1)

@@ -125,9 +125,10 @@ class _Pointnet2SemSeg(nn.Module):
         if self._head_rows_ok(l_features[1]):
             # finest FP level and the classifier head stay in [points, channels] rows: the head's
             # output rows ARE the (B, N, num_classes) result, no transpose anywhere
-            lead = self._head_lead(fp0)
-            rows = fp0.forward_rows(l_xyz[0], l_xyz[1], l_features[0], l_features[1], geo(0), tail=lead)
-            return self._head_rows(rows, skip=len(lead))
+            lead, drops, used = self._head_lead(fp0, l_features[0], l_features[1])
+            rows = fp0.forward_rows(l_xyz[0], l_xyz[1], l_features[0], l_features[1], geo(0), tail=lead,
+                                    tail_dropouts=drops)
+            return self._head_rows(rows, skip=used)
         l_features[0] = fp0(l_xyz[0], l_xyz[1], l_features[0], l_features[1], geo(0))
         return self.cls_layer(l_features[0]).transpose(1, 2).contiguous()
 
@@ -136,36 +137,66 @@ class _Pointnet2SemSeg(nn.Module):
         return (fused.mlp_eligible(units, known_feats) and fused.mlp_eligible(self.FP_modules[0].mlp, known_feats)
                 and known_feats.size(1) % 4 == 0)
 
-    def _head_lead(self, fp0):
-        """The classifier units in front of its Dropout (ref :152-156) continue the finest FP block's
-        chain when their BatchNorms share its eps / momentum: one fused chain, no activation
-        materialised between the block and the head."""
-        lead = []
-        for m in self.cls_layer:
-            if isinstance(m, nn.Dropout):
-                break
-            lead.append(m)
+    def _head_lead(self, fp0, skip_feats, known_feats):
+        """The classifier (Conv1d+BN+ReLU, Dropout, Conv1d+BN -- ref :152-159) continues the finest FP
+        block's chain as far as the kernels allow: units whose BatchNorms share the block's eps /
+        momentum, and a Dropout between two units where both have fused backward layers (it is then a
+        keep mask inside the second unit's kernels; in eval mode it is the identity).
+        -> (units, {index in units: p of the Dropout after that unit}, modules of cls_layer consumed)"""
         ref = fp0.mlp[0].bn.bn
-        same = all(u.bn.bn.eps == ref.eps and u.bn.bn.momentum == ref.momentum and u.training == fp0.mlp[0].training
-                   for u in lead)
-        return lead if same else []
+        mods = list(self.cls_layer)
+        rows_shape = (known_feats.size(0) * skip_feats.size(2),
+                      fused.pad4(known_feats.size(1) + skip_feats.size(1))) if skip_feats is not None else None
+        units, drops, used, pending = [], {}, 0, None
+        for i, m in enumerate(mods):
+            if isinstance(m, nn.Dropout):
+                nxt = mods[i + 1] if i + 1 < len(mods) else None
+                if not units or nxt is None or isinstance(nxt, nn.Dropout) or pending is not None:
+                    break
+                if self.training and m.p > 0.0:
+                    chain = list(fp0.mlp) + units + [nxt]
+                    if rows_shape is None or not fused.chain_supports_dropout(chain, rows_shape, len(chain) - 2):
+                        break
+                    pending = m.p
+                else:
+                    pending = 0.0
+                continue
+            bn = m.bn.bn
+            if not (bn.eps == ref.eps and bn.momentum == ref.momentum and m.training == fp0.mlp[0].training):
+                break
+            if pending:
+                drops[len(units) - 1] = pending
+            pending = None
+            units.append(m)
+            used = i + 1
+        return units, drops, used
 
     def _head_rows(self, rows, skip=0):
         """cls_layer (Conv1d+BN+ReLU, Dropout, Conv1d+BN -- ref :152-159) on (B, N, C) rows; the first
-        ``skip`` units were already applied."""
+        ``skip`` units were already applied.  A Dropout between two units is applied inside the second
+        unit's kernels where they support it (the dropped activation is then never materialised)."""
         B, N, C = rows.shape
         x = rows.reshape(B * N, C)
-        run = []
-        for m in list(self.cls_layer)[skip:]:
-            if isinstance(m, nn.Dropout):
-                if run:
-                    x = fused.run_mlp_rows(run, x, 0)
-                    run = []
-                x = F.dropout(x, m.p, self.training)
-            else:
-                run.append(m)
-        if run:
-            x = fused.run_mlp_rows(run, x, 0)
+        mods = list(self.cls_layer)[skip:]
+        i = 0
+        while i < len(mods):
+            if isinstance(mods[i], nn.Dropout):
+                x = F.dropout(x, mods[i].p, self.training)
+                i += 1
+                continue
+            run, drops = [], {}
+            while i < len(mods):
+                m = mods[i]
+                if isinstance(m, nn.Dropout):
+                    nxt = mods[i + 1] if i + 1 < len(mods) and not isinstance(mods[i + 1], nn.Dropout) else None
+                    if not (run and nxt is not None and self.training and x.is_cuda and
+                            fused.chain_supports_dropout(run + [nxt], x, len(run) - 1)):
+                        break
+                    drops[len(run) - 1] = m.p
+                else:
+                    run.append(m)
+                i += 1
+            x = fused.run_mlp_rows(run, x, 0, drops)
         return x.view(B, N, -1)
 
 

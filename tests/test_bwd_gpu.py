@@ -133,7 +133,7 @@ def run_layer(c, dgrad=True, stats=True):
                                   ptr(t["dout"]), ptr(t["argmax"]), ptr(t["z"]), ptr(t["a"]), ptr(t["b"]),
                                   ptr(t["mean"]), ptr(t["invstd"]), ptr(t["c1c2"]), ptr(t["W"]), ptr(t["aprev"]), ptr(t["a_in"]),
                                   ptr(t["b_in"]), ptr(t["mean_in"]), ptr(t["invstd_in"]), ptr(wtp), ptr(dh_prev),
-                                  ptr(dwp), ptr(sp), ptr(SCHED()), s), "mlp_bwd_layer")
+                                  ptr(dwp), ptr(sp), ptr(SCHED()), None, 1.0, None, 1.0, s), "mlp_bwd_layer")
     torch.cuda.synchronize()
     out = {"dw": dwp.double().sum(0).cpu().numpy()[:N, :K]}
     if dgrad:

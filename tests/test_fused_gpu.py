@@ -282,3 +282,42 @@ def test_pipelined_step_equals_eager_step():
         for a, b in zip(piped.plan.tensors(), fresh.tensors()):
             assert torch.equal(a, b), "step %d trained with a plan that is not its batch's" % i
     assert np.allclose(got, want, rtol=1e-2), (got, want)
+
+
+def test_dropout_inside_the_chain_matches_materialised_dropout():
+    """nn.Dropout between two units (the classifier head, pointnet2_semseg.py:152-159) applied inside the
+    second unit's kernels, against the same units run one by one with the dropped activation
+    materialised in between -- same keep mask, same kernels otherwise."""
+    from pointnet2.scannet_b200 import pytorch_utils as pt_utils
+    torch.manual_seed(0)
+    P, p_drop = 5000, 0.5
+    u0 = pt_utils.Conv1d(64, 128, bn=True).to(DEV).train()
+    u1 = pt_utils.Conv1d(128, 128, bn=True).to(DEV).train()
+    u2 = pt_utils.Conv1d(128, 20, activation=None, bn=True).to(DEV).train()
+    x = torch.randn(P, 64, device=DEV)
+    mask = torch.empty(P, 128, dtype=torch.uint8, device=DEV).bernoulli_(1.0 - p_drop)
+    w = torch.randn(P, 20, device=DEV)
+    assert fused.chain_supports_dropout([u0, u1, u2], x, 1)
+
+    def run_chain(chained):
+        units = [copy.deepcopy(u) for u in (u0, u1, u2)]
+        xi = x.clone().requires_grad_(True)
+        if chained:
+            y = fused.run_mlp_rows(units, xi, 0, {1: (p_drop, mask)})
+        else:
+            h = fused.run_mlp_rows(units[:2], xi, 0)
+            h = h * mask.float() * (1.0 / (1.0 - p_drop))
+            y = fused.run_mlp_rows(units[2:], h, 0)
+        (y * w).sum().backward()
+        grads = [q.grad for u in units for q in u.parameters()]
+        bufs = [b.clone() for u in units for b in u.buffers() if b.dtype != torch.long]
+        return y.detach(), xi.grad, grads, bufs
+
+    y1, gx1, g1, b1 = run_chain(True)
+    y2, gx2, g2, b2 = run_chain(False)
+    assert rel_err(y1, y2) < 1e-3, rel_err(y1, y2)
+    assert l2_err(gx1, gx2) < 5e-3, l2_err(gx1, gx2)
+    for a, b in zip(g1, g2):
+        assert l2_err(a, b) < 5e-3, l2_err(a, b)
+    for a, b in zip(b1, b2):
+        assert rel_err(a, b) < 1e-3

@@ -48,7 +48,7 @@ def run_gemm(A, W, k, a_in=None, b_in=None, relu=False, want_h=False):
                                  ad.data_ptr() if ad is not None else None,
                                  bd.data_ptr() if bd is not None else None, int(relu),
                                  H.data_ptr() if H is not None else None, Wp.data_ptr(), Z.data_ptr(),
-                                 part.data_ptr(), s), "gemm")
+                                 part.data_ptr(), None, 1.0, s), "gemm")
     torch.cuda.synchronize()
     return Z.cpu().numpy(), part.cpu().numpy().sum(0)[:, :N], (H.cpu().numpy() if want_h else None)
 

@@ -47,7 +47,7 @@ for name, P, N, K, lda, ns, fold, dgrad in CASES:
     def call():
         lib.check(L.pn2_mlp_bwd_layer(P, N, K, lda, ns, 1, 1, p(dh), p(dout), p(am), p(z), p(a), p(b), p(mean),
                                       p(invstd), p(c1c2), p(W), p(aprev), p(a_in), p(b_in), p(mean_in), p(invstd_in),
-                                      p(wtp), p(dhp), p(dwp), p(sp), sched.data_ptr(), s), "bwd")
+                                      p(wtp), p(dhp), p(dwp), p(sp), sched.data_ptr(), None, 1.0, None, 1.0, s), "bwd")
     for _ in range(3):
         call()
     torch.cuda.synchronize()
