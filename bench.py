@@ -376,10 +376,17 @@ def run_reference(args, world, rank, local):
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
     ref = build_ref.load_ref("stock")
-    saved = pointnet2_utils._ext
+    from pointnet2.scannet_b200 import fused, pointnet2_semseg, train
+    saved = pointnet2_utils._ext, fused.ENABLED
     pointnet2_utils._ext = ref  # the reference's own seam (pointnet2_utils.py:25-33)
+    # NONE of this repository's kernels on this arm: the modules run the reference's formulation
+    # (QueryAndGroup -> torch.nn Conv2d + BatchNorm2d + ReLU -> max_pool2d; tests/test_host_cpu.py shows
+    # the mirror modules equal the reference's bit for bit in that mode), torch.optim.Adam, eager launches
+    fused.ENABLED = False
     try:
-        step = build_step(args, in_ch, "cuda")
+        torch.manual_seed(0)
+        model = pointnet2_semseg.get_model(NUM_CLASSES, is_msg=args.msg, input_channels=in_ch).to("cuda").train()
+        step = train.TrainStep(model, lr=1e-3, fused_adam=False)
         dev = [tuple(t.cuda() for t in b) for b in batches]
         for i in range(args.warmup):
             step(*dev[i % len(dev)])
@@ -390,7 +397,7 @@ def run_reference(args, world, rank, local):
         clocks = sampler.stop()
         ms_e2e, _ = time_steps(step, batches, args.steps, 1, e2e=True)
     finally:
-        pointnet2_utils._ext = saved
+        pointnet2_utils._ext, fused.ENABLED = saved
     chunks = args.batch * args.steps
     v, ve = round(chunks / (ms * 1e-3), 2), round(chunks / (ms_e2e * 1e-3), 2)
     sample = ("the reference's own CUDA kernels (pointnet2/_ext_src compiled unmodified, -O3, sm_100a) on the "
