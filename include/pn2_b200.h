@@ -319,9 +319,39 @@ PN2_API int pn2_bwd_stats_finalize(int p, int c, int ld, int nblk, int training,
  * launch is CUDA-graph replayable; the gradient is multiplied by grad_scale first.
  * ========================================================================== */
 PN2_API int pn2_sum_partials(int s, int m, const float *in, float *out, void *stream);
+/* pn2_sum_partials(s, m, dw_partials, dw) and pn2_bwd_stats_finalize(p, c, ld, nblk, training,
+ * stat_partials, dgamma, dbeta, c1c2) -- the two reductions behind one fused backward layer --
+ * as ONE launch (same arithmetic, same order). */
+PN2_API int pn2_mlp_bwd_finalize(int s, int m, const float *dw_partials, float *dw, int p, int c, int ld,
+                                 int nblk, int training, const float *stat_partials, float *dgamma,
+                                 float *dbeta, float *c1c2, void *stream);
 PN2_API int pn2_adam_flat(long long n, float *param, const float *grad, float *exp_avg,
                           float *exp_avg_sq, long long *step, float lr, float beta1, float beta2,
                           float eps, float weight_decay, float grad_scale, void *stream);
+
+/* ==========================================================================
+ * Weighted cross-entropy of the training step.
+ * Replaces F.cross_entropy(reduction="none", ignore_index) -> mean(loss * weights)
+ * of lib/loss.py:10-18 (log_softmax, nll_loss, mul, mean and their adjoints: six
+ * torch kernels) on the classifier's logit rows.
+ *
+ * logits [p, c] fp32 rows (c % 4 == 0, 16-byte aligned), targets [p] int64,
+ * weights [p] fp32 or NULL.
+ * pn2_weighted_ce_fwd: loss[0] = 1/p * sum_i w_i * (lse_i - logits[i, t_i]); rows whose
+ *   target equals ignore_index contribute 0 (and still count in 1/p, like the reference's
+ *   mean over a reduction="none" loss); lse [p] is kept for the adjoint; `partials`
+ *   holds pn2_weighted_ce_partials(p) floats; `counter` is ONE zero-initialised
+ *   unsigned that the kernel re-arms itself (last-CTA final sum, fixed order, fp64).
+ * pn2_weighted_ce_bwd: dlogits[i, c] = grad_loss[0]/p * w_i * (softmax(logits[i])[c] - [c == t_i]);
+ *   grad_loss is a DEVICE scalar (the upstream gradient of the loss).
+ * ========================================================================== */
+PN2_API int pn2_weighted_ce_partials(int p);
+PN2_API int pn2_weighted_ce_fwd(int p, int c, long long ignore_index, const float *logits,
+                                const long long *targets, const float *weights, float *lse,
+                                float *partials, unsigned *counter, float *loss, void *stream);
+PN2_API int pn2_weighted_ce_bwd(int p, int c, long long ignore_index, const float *logits,
+                                const long long *targets, const float *weights, const float *lse,
+                                const float *grad_loss, float *dlogits, void *stream);
 
 #ifdef __cplusplus
 }

@@ -23,12 +23,20 @@
 //   warp  8    one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) into a
 //              double-buffered TMEM accumulator and commits to the stage / accumulator
 //              mbarriers;
-//   warps 4-7  epilogue: tcgen05.ld 32 lanes x 32 columns, coalesced 128-byte row stores of
-//              Z, butterfly transpose-reduction of the column sums.
+//   warps 4-7  epilogue: tcgen05.ld 32 lanes x 32 columns; the warp's 32 x 32 block of Z is staged in
+//              shared memory (128-byte rows, 16-byte chunks XOR-swizzled: conflict-free STS.128) and
+//              written by ONE TMA tensor store (cp.async.bulk.tensor.2d, SWIZZLE_128B; rows past P and
+//              columns past N are clipped by the tensor map) -- a thread storing its own row straight
+//              to global memory costs the LSU ~48 wavefronts per STG.256, which made the stores 58 % of
+//              this kernel's L1 data-pipe traffic (ncu: l1tex data-pipe 75 % of peak, its limiter);
+//              butterfly transpose-reduction of the column sums.
 //
 // Precision: TF32 operands (round-to-nearest), fp32 accumulation -- the arithmetic class of
 // the reference's own convolutions (torch.backends.cudnn.allow_tf32 defaults to True).
+#include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "tc_common.cuh"
 
@@ -44,6 +52,8 @@ constexpr int kMaxBN = 256;
 constexpr int A_STAGE_BYTES = BM * BK * 4;        // 16 KB
 constexpr int kSmemBudget = 200 * 1024;           // A + B stages, one CTA per SM (BN > 128)
 constexpr int kSmemBudgetHalf = 96 * 1024;        // two CTAs per SM (BN <= 128: 256 TMEM columns each)
+constexpr int kOutStageBytes = 32 * 128;          // one epilogue warp's 32 rows x 32 fp32 block of Z
+constexpr int kOutBytes = kEpiWarps * kOutStageBytes;
 
 struct Params {
   const float *A;        // [P, lda]
@@ -56,6 +66,7 @@ struct Params {
   int P, lda, K, k_blocks;
   int N, ldz, BN, n_tiles;
   int relu_in;
+  int tma_store;              // Z leaves through the tensor map (else per-thread row stores)
   int stages, b_stage_bytes;  // pipeline depth; bytes reserved per weight stage (multiple of 1024)
   int tmem_cols;              // 512 (one CTA per SM) or 256 (two): two accumulators of tmem_cols / 2
   // dropout between the previous layer's activation and this layer (nn.Dropout in the classifier,
@@ -77,12 +88,13 @@ struct __align__(16) Barriers {
 };
 
 template <bool kDrop>  // dropout keep mask on the A tile (compiled out otherwise)
-__global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p) {
+__global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, const __grid_constant__ CUtensorMap tm_z) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int STAGES = p.stages, B_STAGE_BYTES = p.b_stage_bytes;
   unsigned char *smem_a = smem;                                  // STAGES x 16 KB
   unsigned char *smem_b = smem + STAGES * A_STAGE_BYTES;         // STAGES x b_stage_bytes
-  Barriers *bars = reinterpret_cast<Barriers *>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  unsigned char *smem_out = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);  // kEpiWarps x 4 KB, 1024-aligned
+  Barriers *bars = reinterpret_cast<Barriers *>(smem_out + kOutBytes);
   float *s_stats = reinterpret_cast<float *>(bars + 1);          // [kEpiWarps][2][kMaxBN]
   float *s_fold = s_stats + kEpiWarps * 2 * kMaxBN;              // [2][k_blocks * BK]: a_in, b_in of the fold
 
@@ -258,7 +270,25 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p) {
           float v[32];
           tc_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * acc_cols + c * 32, v);
           const int n0 = n_tile * p.BN + c * 32;
-          if (p.Z != nullptr && grow < p.P) {
+          if (p.Z != nullptr && p.tma_store) {
+            // stage the warp's 32 x 32 block (row = lane) and hand it to the TMA engine
+            unsigned char *stg = smem_out + wq * kOutStageBytes;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous block read out
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4 *>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tm_z)),
+                           "r"(smem_u32(stg)), "r"(n0), "r"(tile * BM + wq * 32)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          } else if (p.Z != nullptr && grow < p.P) {
             float *dst = p.Z + static_cast<size_t>(grow) * p.ldz + n0;
             if (n0 + 32 <= p.N && (p.ldz & 7) == 0) {  // the thread's 128-byte row segment: 4 x STG.256
 #pragma unroll
@@ -286,6 +316,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p) {
       tc_fence_before();
       mbar_arrive(&bars->acc_empty[acc]);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // tensor stores complete
     if (p.partials != nullptr) {
 #pragma unroll
       for (int c = 0; c < kMaxBN / 32; ++c)
@@ -340,6 +371,33 @@ __global__ void pack_weights_kernel(const float *__restrict__ W, int N, int K, i
 // UMMA N per CTA: a multiple of 16 in [16, 256].  Few row tiles (the coarse levels: P = 2048 ... 65536)
 // would leave most SMs idle with one wide N tile per row tile, so N is split further until the grid
 // covers the machine (the A tile is then re-read from L2 by each N tile's CTA).
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links only libcudart)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// fp32 row-major [rows, cols] with `ld` floats between rows, boxes of 32 x 32, SWIZZLE_128B
+static bool make_tmap_rows32(CUtensorMap *tm, const float *base, int rows, int cols, int ld) {
+  EncodeTiledFn enc = encode_tiled();
+  if (enc == nullptr) return false;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 inline int pick_bn(int p, int n) {
   int bn = n > kMaxBN ? kMaxBN : (n + 15) / 16 * 16;
   const int m_tiles = (p + BM - 1) / BM;
@@ -401,17 +459,23 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   // stages each) double the loads in flight and the warps available to hide latency.
   const bool two_per_sm = prm.BN <= 128;
   prm.tmem_cols = two_per_sm ? 256 : 512;
-  prm.stages = (two_per_sm ? gemm::kSmemBudgetHalf : gemm::kSmemBudget) / (gemm::A_STAGE_BYTES + prm.b_stage_bytes);
+  // the epilogue's staging blocks come out of the same budget (two CTAs of <= 113 KB share an SM)
+  prm.stages = ((two_per_sm ? gemm::kSmemBudgetHalf : gemm::kSmemBudget) - gemm::kOutBytes) /
+               (gemm::A_STAGE_BYTES + prm.b_stage_bytes);
   if (prm.stages > gemm::kMaxStages) prm.stages = gemm::kMaxStages;
   if (prm.stages < 2) return PN2_ERR_UNSUPPORTED;
-  const size_t smem = static_cast<size_t>(prm.stages) * (gemm::A_STAGE_BYTES + prm.b_stage_bytes) +
+  const size_t smem = static_cast<size_t>(prm.stages) * (gemm::A_STAGE_BYTES + prm.b_stage_bytes) + gemm::kOutBytes +
                       sizeof(gemm::Barriers) + sizeof(float) * gemm::kEpiWarps * 2 * gemm::kMaxBN +
                       sizeof(float) * 2 * prm.k_blocks * gemm::BK;
+  CUtensorMap tm_z;
+  memset(&tm_z, 0, sizeof(tm_z));
+  static const bool no_tma = getenv("PN2_GEMM_NO_TMA_STORE") != nullptr;   // timing experiments only
+  prm.tma_store = (z != nullptr && !no_tma && gemm::make_tmap_rows32(&tm_z, z, p, n, ldz)) ? 1 : 0;
   auto kern = drop != nullptr ? gemm::gemm_tf32_fwd_kernel<true> : gemm::gemm_tf32_fwd_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid(pn2_mlp_gemm_grid(p, n), prm.n_tiles);  // the partials buffer is sized by the same function
-  kern<<<grid, gemm::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(prm);
+  kern<<<grid, gemm::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(prm, tm_z);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

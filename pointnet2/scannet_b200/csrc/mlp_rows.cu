@@ -22,6 +22,8 @@
 //
 // Train-mode BN adjoint per channel (P rows, zhat = (z-mean)*invstd, a = gamma*invstd):
 //   dbeta = sum dY,  dgamma = sum dY*zhat,  dZ = a * (dY - dbeta/P - zhat*dgamma/P)
+#include <cstdlib>
+
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -430,6 +432,200 @@ fp_interp_rows_grad_kernel(size_t total4, int n, int m, int c2, int c1, int ct4,
   }
 }
 
+// ---- the four gather / scatter kernels above, U float4 elements per thread -----------------
+// One element per thread leaves a single dependent chain (index -> gathered row -> store) in
+// flight per thread and spends most of its issue slots on 64-bit divisions.  Here a thread owns
+// U elements kRowThreads apart (every access of a warp stays coalesced), all index loads are
+// issued first, then all gathers, then the stores; the flat element id is split with
+// multiply-shift divisions (FastDiv, exact below 2^31 elements -- larger launches take the
+// one-element kernels).
+struct FastDiv {
+  unsigned d, mul, shr;
+};
+static FastDiv fast_div(unsigned d) {
+  FastDiv f{d, 0u, 0u};
+  if (d <= 1) return f;
+  unsigned l = 0;
+  while ((1ull << l) < d) ++l;
+  f.mul = static_cast<unsigned>(((1ull << (31 + l)) + d - 1) / d);
+  f.shr = l - 1;
+  return f;
+}
+__device__ __forceinline__ unsigned fdiv(unsigned x, const FastDiv &f) {
+  return f.d <= 1 ? x : (__umulhi(x, f.mul) >> f.shr);
+}
+
+template <int U>
+__global__ void __launch_bounds__(kRowThreads)
+sa_group_rows_kernel_u(unsigned total4, FastDiv ct4, FastDiv np_ns, FastDiv ns, int n,
+                       const float *__restrict__ table, const float *__restrict__ new_xyz,
+                       const int *__restrict__ idx, float *__restrict__ rows) {
+  const unsigned base = blockIdx.x * (kRowThreads * U) + threadIdx.x;
+  unsigned p[U], c4[U];
+  int k[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned e = min(base + u * kRowThreads, total4 - 1);
+    p[u] = fdiv(e, ct4);
+    c4[u] = e - p[u] * ct4.d;
+    k[u] = __ldg(idx + p[u]);
+  }
+  float4 v[U];
+  float cx[U], cy[U], cz[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned cloud = fdiv(p[u], np_ns);
+    v[u] = ld4(table, (static_cast<size_t>(cloud) * n + k[u]) * ct4.d + c4[u]);
+    cx[u] = cy[u] = cz[u] = 0.f;
+    if (c4[u] == 0) {
+      const float *ctr = new_xyz + static_cast<size_t>(fdiv(p[u], ns)) * 3;
+      cx[u] = __ldg(ctr), cy[u] = __ldg(ctr + 1), cz[u] = __ldg(ctr + 2);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned e = base + u * kRowThreads;
+    v[u].x -= cx[u], v[u].y -= cy[u], v[u].z -= cz[u];
+    if (e < total4) reinterpret_cast<float4 *>(rows)[e] = v[u];
+  }
+}
+
+template <int U>
+__global__ void __launch_bounds__(kRowThreads)
+sa_group_rows_grad_kernel_u(unsigned total4, FastDiv ct4, FastDiv np_ns, int n,
+                            const float *__restrict__ grad_rows, const int *__restrict__ idx,
+                            float *__restrict__ grad_table) {
+  const unsigned base = blockIdx.x * (kRowThreads * U) + threadIdx.x;
+  unsigned p[U], c4[U];
+  int k[U];
+  float4 g[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned e = min(base + u * kRowThreads, total4 - 1);
+    p[u] = fdiv(e, ct4);
+    c4[u] = e - p[u] * ct4.d;
+    k[u] = __ldg(idx + p[u]);
+    g[u] = ld4(grad_rows, e);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned cloud = fdiv(p[u], np_ns);
+    if (base + u * kRowThreads < total4)
+      red_add_v4(grad_table + ((static_cast<size_t>(cloud) * n + k[u]) * ct4.d + c4[u]) * 4, g[u]);
+  }
+}
+
+template <int U>
+__global__ void __launch_bounds__(kRowThreads)
+fp_interp_rows_kernel_u(unsigned total4, FastDiv ct4, FastDiv nn, int m, int c2, int c1,
+                        const float *__restrict__ known, const float *__restrict__ skip,
+                        const int *__restrict__ idx, const float *__restrict__ weight,
+                        float *__restrict__ rows) {
+  const unsigned base = blockIdx.x * (kRowThreads * U) + threadIdx.x;
+  const unsigned k4 = c2 >> 2;
+  unsigned p[U], c4[U];
+  int i1[U], i2[U], i3[U];
+  float w1[U], w2[U], w3[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned e = min(base + u * kRowThreads, total4 - 1);
+    p[u] = fdiv(e, ct4);
+    c4[u] = e - p[u] * ct4.d;
+    if (c4[u] < k4) {
+      const size_t q = static_cast<size_t>(p[u]) * 3;
+      i1[u] = __ldg(idx + q), i2[u] = __ldg(idx + q + 1), i3[u] = __ldg(idx + q + 2);
+      w1[u] = __ldg(weight + q), w2[u] = __ldg(weight + q + 1), w3[u] = __ldg(weight + q + 2);
+    }
+  }
+  float4 a[U], b[U], c[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (c4[u] < k4) {
+      const size_t row0 = static_cast<size_t>(fdiv(p[u], nn)) * m;
+      a[u] = ld4(known, (row0 + i1[u]) * k4 + c4[u]);
+      b[u] = ld4(known, (row0 + i2[u]) * k4 + c4[u]);
+      c[u] = ld4(known, (row0 + i3[u]) * k4 + c4[u]);
+    } else {
+      const int ch = static_cast<int>(c4[u] * 4) - c2;
+      const float *sr = skip + static_cast<size_t>(p[u]) * c1;
+      a[u].x = ch + 0 < c1 ? __ldg(sr + ch + 0) : 0.f;
+      a[u].y = ch + 1 < c1 ? __ldg(sr + ch + 1) : 0.f;
+      a[u].z = ch + 2 < c1 ? __ldg(sr + ch + 2) : 0.f;
+      a[u].w = ch + 3 < c1 ? __ldg(sr + ch + 3) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    float4 v = a[u];
+    if (c4[u] < k4) {  // ((k1*w1) + (k2*w2)) + (k3*w3), one rounding per operation (interpolate_gpu.cu:95-98)
+      v.x = __fadd_rn(__fadd_rn(__fmul_rn(a[u].x, w1[u]), __fmul_rn(b[u].x, w2[u])), __fmul_rn(c[u].x, w3[u]));
+      v.y = __fadd_rn(__fadd_rn(__fmul_rn(a[u].y, w1[u]), __fmul_rn(b[u].y, w2[u])), __fmul_rn(c[u].y, w3[u]));
+      v.z = __fadd_rn(__fadd_rn(__fmul_rn(a[u].z, w1[u]), __fmul_rn(b[u].z, w2[u])), __fmul_rn(c[u].z, w3[u]));
+      v.w = __fadd_rn(__fadd_rn(__fmul_rn(a[u].w, w1[u]), __fmul_rn(b[u].w, w2[u])), __fmul_rn(c[u].w, w3[u]));
+    }
+    const unsigned e = base + u * kRowThreads;
+    if (e < total4) reinterpret_cast<float4 *>(rows)[e] = v;
+  }
+}
+
+template <int U>
+__global__ void __launch_bounds__(kRowThreads)
+fp_interp_rows_grad_kernel_u(unsigned total4, FastDiv ct4, FastDiv nn, int m, int c2, int c1,
+                             const float *__restrict__ grad_rows, const int *__restrict__ idx,
+                             const float *__restrict__ weight, float *__restrict__ grad_known,
+                             float *__restrict__ grad_skip) {
+  const unsigned base = blockIdx.x * (kRowThreads * U) + threadIdx.x;
+  const unsigned k4 = c2 >> 2;
+  unsigned p[U], c4[U];
+  int it[U][3];
+  float w[U][3];
+  float4 g[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned e = min(base + u * kRowThreads, total4 - 1);
+    p[u] = fdiv(e, ct4);
+    c4[u] = e - p[u] * ct4.d;
+    g[u] = ld4(grad_rows, e);
+    if (c4[u] < k4) {
+      const size_t q = static_cast<size_t>(p[u]) * 3;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) it[u][t] = __ldg(idx + q + t), w[u][t] = __ldg(weight + q + t);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (base + u * kRowThreads >= total4) continue;
+    if (c4[u] < k4) {
+      const size_t row0 = static_cast<size_t>(fdiv(p[u], nn)) * m;
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+        red_add_v4(grad_known + ((row0 + it[u][t]) * k4 + c4[u]) * 4,
+                   make_float4(__fmul_rn(g[u].x, w[u][t]), __fmul_rn(g[u].y, w[u][t]),
+                               __fmul_rn(g[u].z, w[u][t]), __fmul_rn(g[u].w, w[u][t])));
+    } else if (grad_skip != nullptr) {
+      const int ch = static_cast<int>(c4[u] * 4) - c2;
+      float *sr = grad_skip + static_cast<size_t>(p[u]) * c1;
+      if (ch + 0 < c1) sr[ch + 0] = g[u].x;
+      if (ch + 1 < c1) sr[ch + 1] = g[u].y;
+      if (ch + 2 < c1) sr[ch + 2] = g[u].z;
+      if (ch + 3 < c1) sr[ch + 3] = g[u].w;
+    }
+  }
+}
+
+// elements per thread of the kernels above: 4 unless PN2_ROWS_U says 1 (the one-element kernels), 2 or 4
+static int rows_unroll(size_t total4) {
+  static const int env = [] {
+    const char *e = getenv("PN2_ROWS_U");
+    const int v = e != nullptr ? atoi(e) : 4;
+    return (v == 1 || v == 2 || v == 4) ? v : 4;
+  }();
+  return total4 < (1ull << 31) ? env : 1;
+}
+static inline unsigned blocks_u(size_t total4, int u) {
+  return static_cast<unsigned>((total4 + static_cast<size_t>(kRowThreads) * u - 1) / (static_cast<size_t>(kRowThreads) * u));
+}
+
 static inline int blocks_for(size_t total, int cap = 0) {
   size_t nb = (total + kRowThreads - 1) / kRowThreads;
   if (cap > 0 && nb > static_cast<size_t>(cap)) nb = cap;
@@ -598,8 +794,18 @@ extern "C" int pn2_sa_group_rows(int b, int n, int npoint, int nsample, int ct, 
   PN2_CHECK_PTRS(table, new_xyz, idx, rows);
   if (!rows_ok(ct, table) || !aligned16(rows)) return PN2_ERR_UNSUPPORTED;
   const size_t total4 = static_cast<size_t>(b) * npoint * nsample * (ct / 4);
-  sa_group_rows_kernel<<<blocks_for(total4), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      total4, n, npoint * nsample, nsample, ct / 4, table, new_xyz, idx, rows);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int u = rows_unroll(total4);
+  const FastDiv dct = fast_div(ct / 4), dcl = fast_div(npoint * nsample), dns = fast_div(nsample);
+  if (u == 4)
+    sa_group_rows_kernel_u<4><<<blocks_u(total4, 4), kRowThreads, 0, s>>>(
+        static_cast<unsigned>(total4), dct, dcl, dns, n, table, new_xyz, idx, rows);
+  else if (u == 2)
+    sa_group_rows_kernel_u<2><<<blocks_u(total4, 2), kRowThreads, 0, s>>>(
+        static_cast<unsigned>(total4), dct, dcl, dns, n, table, new_xyz, idx, rows);
+  else
+    sa_group_rows_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(
+        total4, n, npoint * nsample, nsample, ct / 4, table, new_xyz, idx, rows);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -613,8 +819,17 @@ extern "C" int pn2_sa_group_rows_grad(int b, int n, int npoint, int nsample, int
   cudaError_t e = cudaMemsetAsync(grad_table, 0, sizeof(float) * static_cast<size_t>(b) * n * ct, s);
   if (e != cudaSuccess) return static_cast<int>(e);
   const size_t total4 = static_cast<size_t>(b) * npoint * nsample * (ct / 4);
-  sa_group_rows_grad_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(total4, n, npoint * nsample, ct / 4,
-                                                                      grad_rows, idx, grad_table);
+  const int u = rows_unroll(total4);
+  const FastDiv dct = fast_div(ct / 4), dcl = fast_div(npoint * nsample);
+  if (u == 4)
+    sa_group_rows_grad_kernel_u<4><<<blocks_u(total4, 4), kRowThreads, 0, s>>>(
+        static_cast<unsigned>(total4), dct, dcl, n, grad_rows, idx, grad_table);
+  else if (u == 2)
+    sa_group_rows_grad_kernel_u<2><<<blocks_u(total4, 2), kRowThreads, 0, s>>>(
+        static_cast<unsigned>(total4), dct, dcl, n, grad_rows, idx, grad_table);
+  else
+    sa_group_rows_grad_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(total4, n, npoint * nsample, ct / 4,
+                                                                        grad_rows, idx, grad_table);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -627,8 +842,18 @@ extern "C" int pn2_fp_interp_rows(int b, int n, int m, int c2, int c1, const flo
   const int ct = (c2 + c1 + 3) / 4 * 4;
   if (!aligned16(known) || !aligned16(rows) || ct > 4096) return PN2_ERR_UNSUPPORTED;
   const size_t total4 = static_cast<size_t>(b) * n * (ct / 4);
-  fp_interp_rows_kernel<<<blocks_for(total4), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      total4, n, m, c2, c1, ct / 4, known, skip, idx, weight, rows);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int u = rows_unroll(total4);
+  const FastDiv dct = fast_div(ct / 4), dn = fast_div(n);
+  if (u == 4)
+    fp_interp_rows_kernel_u<4><<<blocks_u(total4, 4), kRowThreads, 0, s>>>(
+        static_cast<unsigned>(total4), dct, dn, m, c2, c1, known, skip, idx, weight, rows);
+  else if (u == 2)
+    fp_interp_rows_kernel_u<2><<<blocks_u(total4, 2), kRowThreads, 0, s>>>(
+        static_cast<unsigned>(total4), dct, dn, m, c2, c1, known, skip, idx, weight, rows);
+  else
+    fp_interp_rows_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(
+        total4, n, m, c2, c1, ct / 4, known, skip, idx, weight, rows);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -645,8 +870,17 @@ extern "C" int pn2_fp_interp_rows_grad(int b, int n, int m, int c2, int c1, cons
   cudaError_t e = cudaMemsetAsync(grad_known, 0, sizeof(float) * static_cast<size_t>(b) * m * c2, s);
   if (e != cudaSuccess) return static_cast<int>(e);
   const size_t total4 = static_cast<size_t>(b) * n * (ct / 4);
-  fp_interp_rows_grad_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(total4, n, m, c2, c1, ct / 4, grad_rows,
-                                                                       idx, weight, grad_known, grad_skip);
+  const int u = rows_unroll(total4);
+  const FastDiv dct = fast_div(ct / 4), dn = fast_div(n);
+  if (u == 4)
+    fp_interp_rows_grad_kernel_u<4><<<blocks_u(total4, 4), kRowThreads, 0, s>>>(
+        static_cast<unsigned>(total4), dct, dn, m, c2, c1, grad_rows, idx, weight, grad_known, grad_skip);
+  else if (u == 2)
+    fp_interp_rows_grad_kernel_u<2><<<blocks_u(total4, 2), kRowThreads, 0, s>>>(
+        static_cast<unsigned>(total4), dct, dn, m, c2, c1, grad_rows, idx, weight, grad_known, grad_skip);
+  else
+    fp_interp_rows_grad_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(total4, n, m, c2, c1, ct / 4, grad_rows,
+                                                                         idx, weight, grad_known, grad_skip);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -697,6 +931,57 @@ extern "C" int pn2_sum_partials(int s, int m, const float *in, float *out, void 
   const int warps_per_cta = kRowThreads / 32;
   sum_partials_kernel<<<(m / 4 + warps_per_cta - 1) / warps_per_cta, kRowThreads, 0,
                         static_cast<cudaStream_t>(stream)>>>(s, m / 4, in, out);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+// The two reductions that follow a fused backward layer (csrc/mlp_bwd.cu) in ONE launch: CTAs
+// [0, dw_blocks) sum the per-CTA weight-gradient partials (sum_partials_kernel's arithmetic and
+// order), the rest finalise the statistics of the layer below (bwd_stats_finalize_kernel's).
+__global__ void __launch_bounds__(kRowThreads)
+bwd_layer_finalize_kernel(int dw_blocks, int S, int M4, const float *__restrict__ dwp, float *__restrict__ dw,
+                          int P, int C, int ld, int nblk, int training, const float *__restrict__ partials,
+                          float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ c1,
+                          float *__restrict__ c2) {
+  const int lane = threadIdx.x & 31;
+  if (static_cast<int>(blockIdx.x) < dw_blocks) {
+    const int j = blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (j >= M4) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = lane; s < S; s += 32) {
+      const float4 v = ld4(dwp, static_cast<size_t>(s) * M4 + j);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o), acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o), acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (lane == 0) reinterpret_cast<float4 *>(dw)[j] = acc;
+    return;
+  }
+  const int c = (blockIdx.x - dw_blocks) * (kRowThreads / 32) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s, q;
+  warp_sum_partials(ld, c, nblk, partials, s, q);
+  if (lane != 0) return;
+  dbeta[c] = static_cast<float>(s);
+  dgamma[c] = static_cast<float>(q);
+  const float inv_p = 1.0f / static_cast<float>(P);
+  c1[c] = training ? static_cast<float>(s) * inv_p : 0.f;
+  c2[c] = training ? static_cast<float>(q) * inv_p : 0.f;
+}
+
+extern "C" int pn2_mlp_bwd_finalize(int s, int m, const float *dw_partials, float *dw, int p, int c, int ld,
+                                    int nblk, int training, const float *stat_partials, float *dgamma,
+                                    float *dbeta, float *c1c2, void *stream) {
+  if (s <= 0 || m <= 0 || m % 4 != 0 || p <= 0 || c <= 0 || ld < c || nblk <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(dw_partials, dw, stat_partials, dgamma, dbeta, c1c2);
+  if (!aligned16(dw_partials) || !aligned16(dw)) return PN2_ERR_UNSUPPORTED;
+  const int warps = kRowThreads / 32;
+  const int dw_blocks = (m / 4 + warps - 1) / warps, st_blocks = (c + warps - 1) / warps;
+  bwd_layer_finalize_kernel<<<dw_blocks + st_blocks, kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      dw_blocks, s, m / 4, dw_partials, dw, p, c, ld, nblk, training, stat_partials, dgamma, dbeta, c1c2,
+      c1c2 + c);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

@@ -310,18 +310,20 @@ class SharedMLPRows(Function):
                         d_in[0].data_ptr() if d_in is not None else None, float(d_in[1]) if d_in is not None else 1.0, s),
                         "mlp_bwd_layer")
                     dW = f32(nb * 32, kb * 32)
-                    _lib.check(L.pn2_sum_partials(grid, nb * 32 * kb * 32, dwp.data_ptr(), dW.data_ptr(), s),
-                               "sum_partials")
-                    grads[3 * l] = dW[:C, :K].reshape(W.shape)
-                    grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
                     pending = None
-                    if sp is not None:
+                    if sp is not None:   # weight-gradient partials + the statistics of the layer below: one launch
                         Kc = prev.cout
                         pg, pb, pc = f32(Kc), f32(Kc), f32(2 * Kc)
-                        _lib.check(L.pn2_bwd_stats_finalize(P, Kc, kb * 32, grid, training, sp.data_ptr(),
-                                                            pg.data_ptr(), pb.data_ptr(), pc.data_ptr(), s),
-                                   "bwd_stats_finalize")
+                        _lib.check(L.pn2_mlp_bwd_finalize(grid, nb * 32 * kb * 32, dwp.data_ptr(), dW.data_ptr(),
+                                                          P, Kc, kb * 32, grid, training, sp.data_ptr(),
+                                                          pg.data_ptr(), pb.data_ptr(), pc.data_ptr(), s),
+                                   "mlp_bwd_finalize")
                         pending = (pg, pb, pc)
+                    else:
+                        _lib.check(L.pn2_sum_partials(grid, nb * 32 * kb * 32, dwp.data_ptr(), dW.data_ptr(), s),
+                                   "sum_partials")
+                    grads[3 * l] = dW[:C, :K].reshape(W.shape)
+                    grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
                     dh = dh_prev
                     continue
                 # ---- streaming adjoint kernels + cuBLAS GEMMs ----

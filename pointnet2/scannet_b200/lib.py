@@ -61,7 +61,12 @@ SIGNATURES = {
     "pn2_bwd_stats_finalize": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     # flat-buffer training-step utilities
     "pn2_sum_partials": [_i, _i, _vp, _vp, _vp],
+    "pn2_mlp_bwd_finalize": [_i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_adam_flat": [ctypes.c_longlong, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp],
+    # weighted cross-entropy of the training step
+    "pn2_weighted_ce_partials": [_i],
+    "pn2_weighted_ce_fwd": [_i, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pn2_weighted_ce_bwd": [_i, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
 }
 LIBRARY_SYMBOLS = ("pn2_abi_version", "pn2_launch_count", "pn2_reset_launch_count",
                    "pn2_status_string")

@@ -81,7 +81,13 @@ class _Pointnet2SemSeg(nn.Module):
     @staticmethod
     def _break_up_pc(pc):
         xyz = pc[..., 0:3].contiguous()
-        features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+        if pc.size(-1) <= 3:
+            return xyz, None
+        if fused.LAZY_CHANNEL_MAJOR:
+            # every consumer is a fused block reading point-major rows: one copy of the feature columns,
+            # handed on as a channel-major VIEW that remembers its rows (no transpose there and back)
+            return xyz, fused.channel_major(pc[..., 3:].contiguous())
+        features = pc[..., 3:].transpose(1, 2).contiguous()
         return xyz, features
 
     def forward(self, pointcloud, plan=None):

@@ -162,6 +162,10 @@ def _lib_bytes(name, a):
         return 8 * a[0] * a[1], 0
     if name == "pn2_pool_bn_bwd_stats":
         return 12 * a[0] * a[2], 0
+    if name == "pn2_weighted_ce_fwd":                          # logits, targets (int64), weights; lse out
+        return 4 * a[0] * a[1] + 16 * a[0], 0
+    if name == "pn2_weighted_ce_bwd":                          # logits in, d logits out, targets, weights, lse
+        return 8 * a[0] * a[1] + 16 * a[0], 0
     return None
 
 

@@ -24,9 +24,9 @@ if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
 
 
 def weighted_cross_entropy(logits, targets, weights=None):
-    """logits (P, classes), targets (P,), weights (P,) -> scalar  (lib/loss.py:10-18)."""
-    loss = F.cross_entropy(logits, targets, reduction="none")
-    return torch.mean(loss * weights) if weights is not None else torch.mean(loss)
+    """logits (P, classes), targets (P,), weights (P,) -> scalar  (lib/loss.py:10-18; loss.py)."""
+    from . import loss as _loss
+    return _loss.weighted_cross_entropy(logits, targets, weights)
 
 
 class GradBucket(object):

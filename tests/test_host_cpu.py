@@ -227,3 +227,24 @@ def test_grad_bucket_all_reduce_gloo_world2(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert "rank %d ok" % r in o
+
+
+# ------------------------------------------------------------------ loss mirror
+def test_weighted_ce_mirror_equals_reference_on_cpu():
+    """CPU tensors take the reference's torch formulation: same values as lib/loss.py, bit for bit."""
+    from pointnet2.scannet_b200 import loss as L
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(500, 20, generator=g)
+    targets = torch.randint(0, 20, (500,), generator=g)
+    targets[::9] = -100
+    weights = torch.rand(500, generator=g)
+    assert not L.kernel_eligible(logits, targets, weights)
+    mine = L.WeightedCrossEntropyLoss()(logits, targets, weights)
+    per = torch.nn.functional.cross_entropy(logits, targets, reduction="none", ignore_index=-100)
+    assert torch.equal(mine, torch.mean(per * weights))
+    if os.path.isfile("/root/reference/lib/loss.py"):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_ref_loss", "/root/reference/lib/loss.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        assert torch.equal(mine, mod.WeightedCrossEntropyLoss()(logits, targets, weights))
