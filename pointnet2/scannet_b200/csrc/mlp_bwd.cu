@@ -46,6 +46,7 @@
 // reference's own convolutions (torch.backends.cudnn.allow_tf32 defaults to True).
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "tc_common.cuh"
 
@@ -88,6 +89,7 @@ struct Params {
   int P, N, nb, K, lda, kb, kpad16;
   int ns, ns_shift, relu, relu_in;       // ns_shift >= 0 when ns is a power of two
   int sets, w_slot_bytes, tmem_cols;     // dZ sets (2, or 1 when N > 64)
+  int out_bytes;                         // 16 KB of staging blocks when dH_prev leaves through the tensor map, else 0
   int dbg;                               // PN2_BWD_DBG timing experiments (results invalid when != 0)
   int *sched;                            // [2] {next tile, CTAs finished}, zero between launches (self-resetting)
   const unsigned char *drop_out, *drop_in;  // [P, N] / [P, K] dropout keep masks (nullptr: none)
@@ -132,7 +134,7 @@ __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.
 // kDrop: dropout keep masks present (the classifier head's chain); compiled out otherwise -- the loader
 // chain bounds this kernel and every instruction in it counts.
 template <bool kDrop>
-__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
+__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, const __grid_constant__ CUtensorMap tm_dh) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int nb = p.nb, kb = p.kb;
   const int nb32 = nb * 32, kb32 = kb * 32;
@@ -143,7 +145,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
   unsigned char *s_h = s_dz + p.sets * nb * SLAB;                // [G][hslabs] slabs
   unsigned char *s_a1 = s_h + kGroups * hslabs * SLAB;           // [G] K-major dZ staging slabs (GEMM 1)
   unsigned char *s_w = s_a1 + kGroups * SLAB;                    // [G] W^T tiles
-  float *s_tab = reinterpret_cast<float *>(s_w + kGroups * p.w_slot_bytes);
+  unsigned char *s_out = s_w + kGroups * p.w_slot_bytes;         // [kEpiWarps] 4 KB blocks of dH_prev (TMA store)
+  float *s_tab = reinterpret_cast<float *>(s_out + p.out_bytes);
   // dZ = a * dY + C * z + D  with  C = -a * invstd * c2,  D = -a * c1 - C * mean   (one FMA each)
   float *t_a = s_tab, *t_b = t_a + nb32, *t_C = t_b + nb32, *t_D = t_C + nb32, *t_x0 = t_D + nb32,
         *t_x1 = t_x0 + nb32;  // (t_x0 / t_x1 unused: keeps the table block's size)
@@ -543,7 +546,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
             const int n0 = h * BK;
             float v[32];
             tc_ld32(tm_acc + (static_cast<uint32_t>(wq * 32) << 16) + acc * kb32 + n0, v);
-            if (rowok && !(p.dbg & 4)) {
+            if (p.out_bytes && !(p.dbg & 4)) {  // staged block -> one TMA tensor store (see tc_common.cuh)
+              tma_store_block32(&tm_dh, s_out + wq * 4096, v, lane, n0, tile * BM + wq * 32);
+            } else if (rowok && !(p.dbg & 4)) {
               float *dst = p.dHprev + static_cast<size_t>(grow) * p.lda + n0;
               if (n0 + 32 <= p.lda && (p.lda & 7) == 0) {
 #pragma unroll
@@ -559,6 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p) {
         tc_fence_before();
         mbar_arrive(&bars->acc_empty[acc]);
       }
+      tma_store_drain(lane);
     }
     // read-out.  TMEM lanes = output channels n of this layer, columns = channels c of the layer below.
     mbar_wait(&bars->dw_full, 0);
@@ -639,7 +645,7 @@ __global__ void pack_weights_t_kernel(const float *__restrict__ W, int N, int K,
 }
 
 struct Geom {
-  int nb, kb, kpad16, sets, w_slot_bytes, tmem_cols, grid;
+  int nb, kb, kpad16, sets, w_slot_bytes, tmem_cols, grid, out_bytes;
   size_t smem;
 };
 
@@ -659,6 +665,8 @@ inline bool geom(int p, int n, int k, int lda, bool dgrad, bool stats, Geom *g) 
                        sizeof(Barriers) + 1024;
   const size_t per_group = (stats ? 3 : 2) * static_cast<size_t>(SLAB) + g->w_slot_bytes;
   g->smem = fixed + kGroups * per_group;
+  g->out_bytes = 0;
+  if (dgrad && g->smem + kEpiWarps * 4096 <= 227 * 1024) g->out_bytes = kEpiWarps * 4096, g->smem += g->out_bytes;
   // GEMM 2 addresses four 32-channel slabs from the start of a dZ set whatever nb is: the slabs
   // past nb are other live shared memory (their rows of dW are never read) but must be mapped
   const size_t reach = static_cast<size_t>((g->sets - 1) * g->nb + kMaxNB) * SLAB;
@@ -741,10 +749,15 @@ extern "C" int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu,
   for (int sh = 0; sh < 31; ++sh)
     if ((1 << sh) == prm.ns) prm.ns_shift = sh;
   prm.sets = g.sets, prm.w_slot_bytes = g.w_slot_bytes, prm.tmem_cols = g.tmem_cols;
+  CUtensorMap tm_dh;
+  memset(&tm_dh, 0, sizeof(tm_dh));
+  static const bool no_tma = getenv("PN2_BWD_NO_TMA_STORE") != nullptr;   // timing experiments only
+  prm.out_bytes = (g.out_bytes != 0 && !no_tma && tc::make_tmap_rows32(&tm_dh, dh_prev, p, lda, lda)) ? g.out_bytes : 0;
+  if (prm.out_bytes == 0) g.smem -= g.out_bytes;
   auto kern = (drop_out != nullptr || drop_in != nullptr) ? bwd::mlp_bwd_layer_kernel<true> : bwd::mlp_bwd_layer_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  kern<<<g.grid, bwd::kThreads, g.smem, static_cast<cudaStream_t>(stream)>>>(prm);
+  kern<<<g.grid, bwd::kThreads, g.smem, static_cast<cudaStream_t>(stream)>>>(prm, tm_dh);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

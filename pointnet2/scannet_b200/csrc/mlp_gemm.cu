@@ -33,7 +33,6 @@
 //
 // Precision: TF32 operands (round-to-nearest), fp32 accumulation -- the arithmetic class of
 // the reference's own convolutions (torch.backends.cudnn.allow_tf32 defaults to True).
-#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -271,23 +270,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
           tc_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * acc_cols + c * 32, v);
           const int n0 = n_tile * p.BN + c * 32;
           if (p.Z != nullptr && p.tma_store) {
-            // stage the warp's 32 x 32 block (row = lane) and hand it to the TMA engine
-            unsigned char *stg = smem_out + wq * kOutStageBytes;
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous block read out
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4 *>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                               reinterpret_cast<uint64_t>(&tm_z)),
-                           "r"(smem_u32(stg)), "r"(n0), "r"(tile * BM + wq * 32)
-                           : "memory");
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
+            tma_store_block32(&tm_z, smem_out + wq * kOutStageBytes, v, lane, n0, tile * BM + wq * 32);
           } else if (p.Z != nullptr && grow < p.P) {
             float *dst = p.Z + static_cast<size_t>(grow) * p.ldz + n0;
             if (n0 + 32 <= p.N && (p.ldz & 7) == 0) {  // the thread's 128-byte row segment: 4 x STG.256
@@ -316,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
       tc_fence_before();
       mbar_arrive(&bars->acc_empty[acc]);
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // tensor stores complete
+    tma_store_drain(lane);
     if (p.partials != nullptr) {
 #pragma unroll
       for (int c = 0; c < kMaxBN / 32; ++c)
@@ -371,33 +354,6 @@ __global__ void pack_weights_kernel(const float *__restrict__ W, int N, int K, i
 // UMMA N per CTA: a multiple of 16 in [16, 256].  Few row tiles (the coarse levels: P = 2048 ... 65536)
 // would leave most SMs idle with one wide N tile per row tile, so N is split further until the grid
 // covers the machine (the A tile is then re-read from L2 by each N tile's CTA).
-// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links only libcudart)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled() {
-  static EncodeTiledFn fn = [] {
-    void *f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      f = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(f);
-  }();
-  return fn;
-}
-// fp32 row-major [rows, cols] with `ld` floats between rows, boxes of 32 x 32, SWIZZLE_128B
-static bool make_tmap_rows32(CUtensorMap *tm, const float *base, int rows, int cols, int ld) {
-  EncodeTiledFn enc = encode_tiled();
-  if (enc == nullptr) return false;
-  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
-  const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
-  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 inline int pick_bn(int p, int n) {
   int bn = n > kMaxBN ? kMaxBN : (n + 15) / 16 * 16;
   const int m_tiles = (p + BM - 1) / BM;
@@ -470,7 +426,7 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   CUtensorMap tm_z;
   memset(&tm_z, 0, sizeof(tm_z));
   static const bool no_tma = getenv("PN2_GEMM_NO_TMA_STORE") != nullptr;   // timing experiments only
-  prm.tma_store = (z != nullptr && !no_tma && gemm::make_tmap_rows32(&tm_z, z, p, n, ldz)) ? 1 : 0;
+  prm.tma_store = (z != nullptr && !no_tma && tc::make_tmap_rows32(&tm_z, z, p, n, ldz)) ? 1 : 0;
   auto kern = drop != nullptr ? gemm::gemm_tf32_fwd_kernel<true> : gemm::gemm_tf32_fwd_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);

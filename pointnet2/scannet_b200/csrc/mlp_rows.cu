@@ -613,12 +613,13 @@ fp_interp_rows_grad_kernel_u(unsigned total4, FastDiv ct4, FastDiv nn, int m, in
   }
 }
 
-// elements per thread of the kernels above: 4 unless PN2_ROWS_U says 1 (the one-element kernels), 2 or 4
+// elements per thread of the kernels above: 2 (measured best at the SSG shapes: tools/time_rows.py; 4 costs
+// occupancy) unless PN2_ROWS_U says 1 (the one-element kernels) or 4
 static int rows_unroll(size_t total4) {
   static const int env = [] {
     const char *e = getenv("PN2_ROWS_U");
-    const int v = e != nullptr ? atoi(e) : 4;
-    return (v == 1 || v == 2 || v == 4) ? v : 4;
+    const int v = e != nullptr ? atoi(e) : 2;
+    return (v == 1 || v == 2 || v == 4) ? v : 2;
   }();
   return total4 < (1ull << 31) ? env : 1;
 }

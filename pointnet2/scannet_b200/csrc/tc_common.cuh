@@ -1,6 +1,8 @@
 // tcgen05 / TMEM / mbarrier PTX wrappers and UMMA descriptor builders shared by the tensor-core
 // kernels (mlp_gemm.cu: forward layer, mlp_bwd.cu: fused backward layer).  sm_100a only.
 #pragma once
+#include <cuda.h>
+
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -68,6 +70,62 @@ __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links only libcudart)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// fp32 row-major [rows, cols] with `ld` floats between rows, boxes of 32 x 32, SWIZZLE_128B
+inline bool make_tmap_rows32(CUtensorMap *tm, const float *base, int rows, int cols, int ld) {
+  EncodeTiledFn enc = encode_tiled();
+  if (enc == nullptr) return false;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// ---- TMA tensor store of one warp's 32 x 32 fp32 block (row = lane) ---------------------------------
+// A thread that stores its own 128-byte row segment straight to global memory costs the LSU ~48
+// wavefronts per STG.256 (32 lanes, 32 different lines); staged in shared memory with the 16-byte
+// chunks XOR-swizzled by (row & 7) the same block is 8 conflict-free STS.128 per thread and ONE
+// cp.async.bulk.tensor.2d (SWIZZLE_128B tensor map, box 32 x 32) that clips rows / columns past the
+// tensor's extent.  `stg`: the warp's own 4 KB, 1024-byte aligned block.  All 32 lanes call.
+__device__ __forceinline__ void tma_store_block32(const CUtensorMap *tm, unsigned char *stg, const float (&v)[32],
+                                                  int lane, int col0, int row0) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous block read out
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4 *>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_u32(stg)), "r"(col0), "r"(row0)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+// before the CTA exits (its shared memory is released) / before the data is consumed
+__device__ __forceinline__ void tma_store_drain(int lane) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of
