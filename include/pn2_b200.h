@@ -261,12 +261,15 @@ PN2_API int pn2_bn_finalize(int p, int c, int ld, int nblk, const float *partial
  *     dZ      = a * (dY - c1 - zhat * c2)   dY = relu-masked dh, or (dh == NULL) the
  *                                           arg-max scatter of dout over groups of ns rows
  *     dh_prev = dZ * W                      [p, lda]   (wt_packed / dh_prev NULL: skipped)
- *     dW      = dZ^T * H_prev               per-CTA partials [pn2_mlp_bwd_grid(p)][nb*32][kb*32],
+ *     dW      = dZ^T * H_prev               per-CTA partials dw_part [pn2_mlp_bwd_grid(p)][nb*32][kb*32],
  *                                           nb = pn2_mlp_bwd_nb(n), kb = pn2_mlp_bwd_kb(lda)
- *     stats   = column sums of dY_prev and dY_prev * zhat_prev, per-CTA partials
- *               [grid][2][kb*32] for pn2_bwd_stats_finalize (stats_part NULL: skipped);
- *               they are obtained as sum_n w[n,c] * (dZ^T M)[n,c] from two tensor-core
- *               products with the ReLU mask M of the layer below (w [n, k] fp32)
+ *                                           (stats_part NULL; sum them with pn2_sum_partials)
+ *     stats   (stats_part != NULL: there is a BatchNorm below)  instead of dW the kernel leaves the two
+ *               tensor-core products with the ReLU mask M of the layer below,
+ *               S = dZ^T M in dw_part and Q = dZ^T (M .* zhat_prev) in stats_part (same shape):
+ *               dW = g1 .* Q + g0 .* S and the column sums of dY_prev, dY_prev * zhat_prev
+ *               (= sum_n w .* S, sum_n w .* Q) are linear in them, so pn2_mlp_bwd_finalize forms
+ *               them once from the sums over all CTAs (w [n, k] fp32 is not read by the layer kernel)
  * with H_prev = relu_in ? max(a_in * a_prev + b_in, 0) : ... recomputed from the previous
  * layer's pre-BN output a_prev [p, lda] (a_in NULL: a_prev is used as it is, e.g. the
  * block's grouped input rows).  z [p, n], a/b/mean/invstd [n] are this layer's saved
@@ -294,6 +297,16 @@ PN2_API int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu, in
                               float *stats_part, int *sched, const unsigned char *drop_out,
                               float drop_out_scale, const unsigned char *drop_in, float drop_in_scale,
                               void *stream);
+/* after pn2_mlp_bwd_layer with stats_part: sums the `parts` = pn2_mlp_bwd_grid(p) images (fixed order) ->
+ * dw [nb*32][kb*32] (rows >= n / columns >= k are padding), dgamma / dbeta [k] of the layer below and
+ * c1c2 = [dbeta / p | dgamma / p] ([k | k]; zeros in eval mode) for that layer's own pn2_mlp_bwd_layer. */
+PN2_API int pn2_mlp_bwd_finalize_scratch_floats(int n, int lda);
+PN2_API int pn2_mlp_bwd_finalize(int parts, int n, int k, int lda, const float *s_part, const float *q_part,
+                                 const float *w, const float *a_in, const float *b_in, const float *mean_in,
+                                 const float *invstd_in, int p, int training, float *dw, float *dgamma,
+                                 float *dbeta, float *c1c2, float *scratch, unsigned *counter, void *stream);
+/* scratch: pn2_mlp_bwd_finalize_scratch_floats(n, lda) floats; counter: ONE zero-initialised unsigned per
+ * launching stream, re-armed by the kernel (its last CTA adds the row groups' column sums, fixed order). */
 /* drop_out [p, n] / drop_in [p, k] (optional byte keep masks): dropout applied to this layer's
  * activated output (its adjoint multiplies dh first) / to the activation of the layer below (H_prev
  * and the ReLU mask of the statistics products carry it). */
@@ -319,12 +332,6 @@ PN2_API int pn2_bwd_stats_finalize(int p, int c, int ld, int nblk, int training,
  * launch is CUDA-graph replayable; the gradient is multiplied by grad_scale first.
  * ========================================================================== */
 PN2_API int pn2_sum_partials(int s, int m, const float *in, float *out, void *stream);
-/* pn2_sum_partials(s, m, dw_partials, dw) and pn2_bwd_stats_finalize(p, c, ld, nblk, training,
- * stat_partials, dgamma, dbeta, c1c2) -- the two reductions behind one fused backward layer --
- * as ONE launch (same arithmetic, same order). */
-PN2_API int pn2_mlp_bwd_finalize(int s, int m, const float *dw_partials, float *dw, int p, int c, int ld,
-                                 int nblk, int training, const float *stat_partials, float *dgamma,
-                                 float *dbeta, float *c1c2, void *stream);
 PN2_API int pn2_adam_flat(long long n, float *param, const float *grad, float *exp_avg,
                           float *exp_avg_sq, long long *step, float lr, float beta1, float beta2,
                           float eps, float weight_decay, float grad_scale, void *stream);

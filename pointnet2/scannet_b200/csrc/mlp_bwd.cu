@@ -84,8 +84,8 @@ struct Params {
   const float *a_in, *b_in, *mean_in, *invstd_in;  // [K] fold / statistics of the previous layer
   const float *WTp;      // packed W^T tiles [nb][kpad16][32] (nullptr: dH_prev not wanted)
   float *dHprev;         // [P, lda]
-  float *dWpart;         // [gridDim.x][nb * 32][kb * 32]
-  float *stats_part;     // [gridDim.x][2][kb * 32]  (nullptr: no BN below)
+  float *dWpart;         // [gridDim.x][nb * 32][kb * 32]: dW per CTA -- or, with a BN below, S = dZ^T M
+  float *stats_part;     // [gridDim.x][nb * 32][kb * 32]: Q = dZ^T (M .* zhat_prev)  (nullptr: no BN below)
   int P, N, nb, K, lda, kb, kpad16;
   int ns, ns_shift, relu, relu_in;       // ns_shift >= 0 when ns is a power of two
   int sets, w_slot_bytes, tmem_cols;     // dZ sets (2, or 1 when N > 64)
@@ -97,7 +97,7 @@ struct Params {
 };
 
 // PN2_BWD_DBG & 32: cycles each role spends in its waits, per CTA (read back with pn2_mlp_bwd_debug_read)
-__device__ unsigned long long g_wait_cycles[kNumSMs][16];
+__device__ unsigned long long g_wait_cycles[kNumSMs][20];
 __device__ __forceinline__ void timed_wait(uint64_t *bar, uint32_t parity, bool on, unsigned long long &acc) {
   if (!on) {
     mbar_wait(bar, parity);
@@ -134,8 +134,11 @@ __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.
 // kDrop: dropout keep masks present (the classifier head's chain); compiled out otherwise -- the loader
 // chain bounds this kernel and every instruction in it counts.
 template <bool kDrop>
-__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, const __grid_constant__ CUtensorMap tm_dh) {
+__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, const __grid_constant__ CUtensorMap tm_dh,
+                                                                    const __grid_constant__ CUtensorMap tm_dw,
+                                                                    const __grid_constant__ CUtensorMap tm_q) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  const long long t_entry = (p.dbg & 32) ? clock64() : 0;
   const int nb = p.nb, kb = p.kb;
   const int nb32 = nb * 32, kb32 = kb * 32;
   const bool dgrad = p.WTp != nullptr;
@@ -206,9 +209,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  if ((p.dbg & 32) && tid == 0) g_wait_cycles[blockIdx.x][16] = clock64() - t_entry;  // set-up
   // tensor memory: [acc 0 | acc 1] (kb32 columns each, only when dgrad), then dW [kb32] -- or,
   // with statistics, [S_h | Q_h] pairs of 32 columns per slab h of the layer below
-  const uint32_t tm_acc = tmem_base, tm_dw = tmem_base + (dgrad ? 2 * kb32 : 0);
+  const uint32_t tm_acc = tmem_base, tm_dw_addr = tmem_base + (dgrad ? 2 * kb32 : 0);
 
   if (warp >= kFirstLoadWarp) {
     // ======================================= loaders =======================================
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
           tc_fence_after();
           // stats mode: the group's [M | M .* zhat] slabs are adjacent, one N = 64 instruction covers both
           const uint64_t hb = mn_hi | addr(smem_u32(s_h + g * hslabs * SLAB));
-          const uint32_t d = tm_dw + h * hslabs * BK;
+          const uint32_t d = tm_dw_addr + h * hslabs * BK;
           if (leader) {
             tc_mma_tf32(d, dz_desc, hb, idesc2, tl != 0);
 #pragma unroll
@@ -569,53 +573,49 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
     // read-out.  TMEM lanes = output channels n of this layer, columns = channels c of the layer below.
     mbar_wait(&bars->dw_full, 0);
     tc_fence_after();
+    const long long t_ro = (p.dbg & 32) ? clock64() : 0;
+    if ((p.dbg & 32) && tid == 0) g_wait_cycles[blockIdx.x][17] = t_ro - t_entry;  // entry -> all MMAs retired
+    // With a BatchNorm below, the two accumulators S = dZ^T M and Q = dZ^T (M .* zhat) are written out
+    // as they are: dW = g1 .* Q + g0 .* S and the statistics sum_n W .* S, sum_n W .* Q are linear in
+    // them, so pn2_mlp_bwd_finalize forms them ONCE from the sums over all CTAs (done per CTA here,
+    // with W re-read from L2 by every CTA at the same moment, this tail took 47 us at N = K = 128).
     const int n = wq * 32 + lane;
-    const bool active = wq * 32 < nb32 && bars->tiles_done > 0;  // written before the dw_full commit
-    float *dst = p.dWpart + (static_cast<size_t>(blockIdx.x) * nb32 + n) * kb32;
+    const bool mine = wq * 32 < nb32;
+    const bool active = mine && bars->tiles_done > 0;  // written before the dw_full commit
+    const int row0 = blockIdx.x * nb32 + wq * 32;
+    auto put = [&](float *base, const CUtensorMap *tm, const float (&v)[32], int h) {
+      if (!mine) return;
+      if (p.out_bytes) {
+        tma_store_block32(tm, s_out + wq * 4096, v, lane, h * 32, row0);
+      } else {
+        float *dst = base + (static_cast<size_t>(row0) + lane) * kb32 + h * 32;
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 8) st_global_v8(dst + jj, v + jj);
+      }
+    };
 #pragma unroll
     for (int h = 0; h < kMaxKB; ++h) {
       if (h < kb) {
         float v[32];
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) v[jj] = 0.f;
-        if (active) tc_ld32(tm_dw + (static_cast<uint32_t>(wq * 32) << 16) + h * hslabs * BK, v);
-        if (!stats) {
-          if (wq * 32 < nb32)
+        if (active) tc_ld32(tm_dw_addr + (static_cast<uint32_t>(wq * 32) << 16) + h * hslabs * BK, v);
+        put(p.dWpart, &tm_dw, v, h);
+        if (stats) {
 #pragma unroll
-            for (int jj = 0; jj < 32; jj += 8) st_global_v8(dst + h * 32 + jj, v + jj);
-        } else {
-          float q[32];
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) q[jj] = 0.f;
-          if (active) tc_ld32(tm_dw + (static_cast<uint32_t>(wq * 32) << 16) + h * hslabs * BK + BK, q);
-          // dW = g1 .* Q + g0 .* S with H_prev = M .* (g1 * zhat + g0): g1 = a_in / invstd_in, g0 = a_in * mean_in + b_in
-          float o[8];
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const int c = h * 32 + jj;
-            const float g1 = u_is[c] > 0.f ? u_a[c] / u_is[c] : 0.f, g0 = fmaf(u_a[c], u_mu[c], u_b[c]);
-            o[jj & 7] = fmaf(g1, q[jj], g0 * v[jj]);
-            if ((jj & 7) == 7 && wq * 32 < nb32) st_global_v8(dst + h * 32 + jj - 7, o);
-            const float w = (n < p.N && c < p.K) ? __ldg(p.W + static_cast<size_t>(n) * p.K + c) : 0.f;
-            v[jj] *= w, q[jj] *= w;
-          }
-          const float cs = warp_colsum32(v, lane), cq = warp_colsum32(q, lane);
-          s_stats[(wq * 2 + 0) * kb32 + h * 32 + lane] = cs;
-          s_stats[(wq * 2 + 1) * kb32 + h * 32 + lane] = cq;
+          for (int jj = 0; jj < 32; ++jj) v[jj] = 0.f;
+          if (active) tc_ld32(tm_dw_addr + (static_cast<uint32_t>(wq * 32) << 16) + h * hslabs * BK + BK, v);
+          put(p.stats_part, &tm_q, v, h);
         }
       }
     }
+    tma_store_drain(lane);
+    (void)n;
+    if ((p.dbg & 32) && tid == 0) g_wait_cycles[blockIdx.x][15] = clock64() - t_ro;  // read-out
   }
 
   tc_fence_before();
   __syncthreads();
-  if (stats && tid < kb32) {  // combine the four epilogue warps, fixed order (all zero if the CTA got no tile)
-    float s = 0.f, q = 0.f;
-    for (int w = 0; w < kEpiWarps; ++w) s += s_stats[(w * 2) * kb32 + tid], q += s_stats[(w * 2 + 1) * kb32 + tid];
-    float *dst = p.stats_part + static_cast<size_t>(blockIdx.x) * 2 * kb32;
-    dst[tid] = s;
-    dst[kb32 + tid] = q;
-  }
   if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -642,6 +642,93 @@ __global__ void pack_weights_t_kernel(const float *__restrict__ W, int N, int K,
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
     Wp[i] = __uint_as_float(t);
   }
+}
+
+// Everything that follows a fused backward layer with a BatchNorm below, in ONE launch: the per-CTA
+// images S_p = dZ^T M and Q_p = dZ^T (M .* zhat_prev) are summed over the CTAs (fixed order), then
+//   dW[n, c]   = g1[c] * Q[n, c] + g0[c] * S[n, c]      g1 = a_in / invstd_in, g0 = a_in * mean_in + b_in
+//   dbeta[c]   = sum_n W[n, c] * S[n, c]                 (gradient wrt the layer below's BN output, summed)
+//   dgamma[c]  = sum_n W[n, c] * Q[n, c]
+//   c1 = dbeta / P, c2 = dgamma / P                      (0 in eval mode)
+// Grid (column slab of 32, group of 8 rows n), 512 threads = 8 image slices x 8 rows x 8 float4 column
+// groups: a thread adds the images i = slice, slice + 8, ... of its (n, c4) -- independent 16-byte loads,
+// a warp covers four 128-byte row segments -- the slices are combined through shared memory in fixed
+// order, then the CTA's 8 rows; the CTA that finishes last adds the row groups' partial column sums (fixed
+// order, fp64) into dbeta / dgamma / c1 / c2.
+constexpr int kFinRows = 8, kFinSlices = 8, kFinThreads = 64 * kFinSlices;
+__global__ void __launch_bounds__(kFinThreads)
+bwd_layer_finalize_sq_kernel(int parts, int N, int K, int nb32, int kb32, const float *__restrict__ s_part,
+                             const float *__restrict__ q_part, const float *__restrict__ W,
+                             const float *__restrict__ a_in, const float *__restrict__ b_in,
+                             const float *__restrict__ mean_in, const float *__restrict__ invstd_in, int P,
+                             int training, float *__restrict__ dW, float *__restrict__ dgamma,
+                             float *__restrict__ dbeta, float *__restrict__ c1, float *__restrict__ c2,
+                             float *__restrict__ scratch, unsigned *__restrict__ counter) {
+  __shared__ float4 s_red[kFinSlices][64][2];
+  __shared__ float s_col[kFinRows][2][32];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, c4l = tid & 7, r = (tid >> 3) & 7, slice = tid >> 6;
+  const int n = blockIdx.y * kFinRows + r, c0 = blockIdx.x * 32 + c4l * 4;
+  const size_t image = static_cast<size_t>(nb32) * kb32, off = static_cast<size_t>(n) * kb32 + c0;
+  float4 s = zero4(), q = zero4();
+#pragma unroll 4
+  for (int i = slice; i < parts; i += kFinSlices) {
+    const float4 a = ldg4(s_part + i * image + off), b = ldg4(q_part + i * image + off);
+    s.x += a.x, s.y += a.y, s.z += a.z, s.w += a.w;
+    q.x += b.x, q.y += b.y, q.z += b.z, q.w += b.w;
+  }
+  s_red[slice][tid & 63][0] = s, s_red[slice][tid & 63][1] = q;
+  __syncthreads();
+  if (slice == 0) {
+#pragma unroll
+    for (int k = 1; k < kFinSlices; ++k) {
+      const float4 a = s_red[k][tid][0], b = s_red[k][tid][1];
+      s.x += a.x, s.y += a.y, s.z += a.z, s.w += a.w;
+      q.x += b.x, q.y += b.y, q.z += b.z, q.w += b.w;
+    }
+    const float sv[4] = {s.x, s.y, s.z, s.w}, qv[4] = {q.x, q.y, q.z, q.w};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = c0 + e;
+      const bool ok = c < K;
+      const float is = ok ? __ldg(invstd_in + c) : 0.f, a = ok ? __ldg(a_in + c) : 0.f;
+      const float g1 = is > 0.f ? a / is : 0.f;
+      const float g0 = ok ? fmaf(a, __ldg(mean_in + c), __ldg(b_in + c)) : 0.f;
+      o[e] = fmaf(g1, qv[e], g0 * sv[e]);
+      const float w = (ok && n < N) ? __ldg(W + static_cast<size_t>(n) * K + c) : 0.f;
+      s_col[r][0][c4l * 4 + e] = w * sv[e];
+      s_col[r][1][c4l * 4 + e] = w * qv[e];
+    }
+    *reinterpret_cast<float4 *>(dW + off) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  __syncthreads();
+  if (tid < 64) {  // the CTA's 8 rows, fixed order -> scratch [gridDim.y][2][kb32]
+    const int which = tid >> 5, cl = tid & 31;
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kFinRows; ++k) t += s_col[k][which][cl];
+    scratch[(static_cast<size_t>(blockIdx.y) * 2 + which) * kb32 + blockIdx.x * 32 + cl] = t;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(counter, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int c = tid; c < K; c += kFinThreads) {
+    double sb = 0.0, sg = 0.0;
+    for (unsigned g = 0; g < gridDim.y; ++g) {
+      sb += static_cast<double>(__ldcg(scratch + (static_cast<size_t>(g) * 2 + 0) * kb32 + c));
+      sg += static_cast<double>(__ldcg(scratch + (static_cast<size_t>(g) * 2 + 1) * kb32 + c));
+    }
+    dbeta[c] = static_cast<float>(sb);
+    dgamma[c] = static_cast<float>(sg);
+    const float inv_p = 1.0f / static_cast<float>(P);
+    c1[c] = training ? static_cast<float>(sb) * inv_p : 0.f;
+    c2[c] = training ? static_cast<float>(sg) * inv_p : 0.f;
+  }
+  if (tid == 0) *counter = 0u;  // re-armed for the next launch on this stream
 }
 
 struct Geom {
@@ -689,7 +776,7 @@ extern "C" int pn2_mlp_bwd_supported(int p, int n, int k, int lda, int with_stat
   return p > 0 && bwd::geom(p, n, k, lda, true, with_stats != 0, &g) ? 1 : 0;
 }
 extern "C" __attribute__((visibility("default"))) int pn2_mlp_bwd_debug_read(unsigned long long *out) {
-  return static_cast<int>(cudaMemcpyFromSymbol(out, bwd::g_wait_cycles, sizeof(unsigned long long) * kNumSMs * 16));
+  return static_cast<int>(cudaMemcpyFromSymbol(out, bwd::g_wait_cycles, sizeof(unsigned long long) * kNumSMs * 20));
 }
 extern "C" int pn2_mlp_bwd_grid(int p) {
   const int m_tiles = (p + bwd::BM - 1) / bwd::BM;
@@ -730,7 +817,7 @@ extern "C" int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu,
   if (a_in != nullptr && b_in == nullptr) return PN2_ERR_INVALID_ARG;
   bwd::Geom g;
   if (!bwd::geom(p, n, k, lda, wt_packed != nullptr, stats_part != nullptr, &g)) return PN2_ERR_UNSUPPORTED;
-  if (!aligned16(z) || !aligned16(a_prev) || !aligned16(dw_part) || (dh != nullptr && !aligned16(dh)) ||
+  if (!aligned16(z) || !aligned16(a_prev) || !aligned16(dw_part) || (stats_part != nullptr && !aligned16(stats_part)) || (dh != nullptr && !aligned16(dh)) ||
       (dout != nullptr && (!aligned16(dout) || !aligned16(argmax))) || (dh_prev != nullptr && !aligned16(dh_prev)) ||
       (wt_packed != nullptr && !aligned16(wt_packed)))
     return PN2_ERR_UNSUPPORTED;
@@ -752,12 +839,38 @@ extern "C" int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu,
   CUtensorMap tm_dh;
   memset(&tm_dh, 0, sizeof(tm_dh));
   static const bool no_tma = getenv("PN2_BWD_NO_TMA_STORE") != nullptr;   // timing experiments only
-  prm.out_bytes = (g.out_bytes != 0 && !no_tma && tc::make_tmap_rows32(&tm_dh, dh_prev, p, lda, lda)) ? g.out_bytes : 0;
+  CUtensorMap tm_dw, tm_q;
+  memset(&tm_dw, 0, sizeof(tm_dw)), memset(&tm_q, 0, sizeof(tm_q));
+  const int part_rows = g.grid * g.nb * 32, part_cols = g.kb * 32;  // per-CTA images of dW (or S and Q)
+  prm.out_bytes = (g.out_bytes != 0 && !no_tma && tc::make_tmap_rows32(&tm_dh, dh_prev, p, lda, lda) &&
+                   tc::make_tmap_rows32(&tm_dw, dw_part, part_rows, part_cols, part_cols) &&
+                   (stats_part == nullptr || tc::make_tmap_rows32(&tm_q, stats_part, part_rows, part_cols, part_cols)))
+                      ? g.out_bytes : 0;
   if (prm.out_bytes == 0) g.smem -= g.out_bytes;
   auto kern = (drop_out != nullptr || drop_in != nullptr) ? bwd::mlp_bwd_layer_kernel<true> : bwd::mlp_bwd_layer_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  kern<<<g.grid, bwd::kThreads, g.smem, static_cast<cudaStream_t>(stream)>>>(prm, tm_dh);
+  kern<<<g.grid, bwd::kThreads, g.smem, static_cast<cudaStream_t>(stream)>>>(prm, tm_dh, tm_dw, tm_q);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_mlp_bwd_finalize_scratch_floats(int n, int lda) {
+  return pn2_mlp_bwd_nb(n) * (32 / bwd::kFinRows) * 2 * pn2_mlp_bwd_kb(lda) * 32;
+}
+
+extern "C" int pn2_mlp_bwd_finalize(int parts, int n, int k, int lda, const float *s_part, const float *q_part,
+                                    const float *w, const float *a_in, const float *b_in, const float *mean_in,
+                                    const float *invstd_in, int p, int training, float *dw, float *dgamma,
+                                    float *dbeta, float *c1c2, float *scratch, unsigned *counter, void *stream) {
+  if (parts <= 0 || n <= 0 || k <= 0 || lda < k || p <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(s_part, q_part, w, a_in, b_in, mean_in, invstd_in, dw, dgamma, dbeta, c1c2, scratch, counter);
+  if (!aligned16(s_part) || !aligned16(q_part) || !aligned16(dw)) return PN2_ERR_UNSUPPORTED;
+  const int nb32 = pn2_mlp_bwd_nb(n) * 32, kb32 = pn2_mlp_bwd_kb(lda) * 32;
+  dim3 grid(kb32 / 32, nb32 / bwd::kFinRows);
+  bwd::bwd_layer_finalize_sq_kernel<<<grid, bwd::kFinThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      parts, n, k, nb32, kb32, s_part, q_part, w, a_in, b_in, mean_in, invstd_in, p, training, dw, dgamma, dbeta,
+      c1c2, c1c2 + k, scratch, counter);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

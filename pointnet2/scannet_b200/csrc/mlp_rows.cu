@@ -936,57 +936,6 @@ extern "C" int pn2_sum_partials(int s, int m, const float *in, float *out, void 
   PN2_RETURN_LAUNCH_STATUS();
 }
 
-// The two reductions that follow a fused backward layer (csrc/mlp_bwd.cu) in ONE launch: CTAs
-// [0, dw_blocks) sum the per-CTA weight-gradient partials (sum_partials_kernel's arithmetic and
-// order), the rest finalise the statistics of the layer below (bwd_stats_finalize_kernel's).
-__global__ void __launch_bounds__(kRowThreads)
-bwd_layer_finalize_kernel(int dw_blocks, int S, int M4, const float *__restrict__ dwp, float *__restrict__ dw,
-                          int P, int C, int ld, int nblk, int training, const float *__restrict__ partials,
-                          float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ c1,
-                          float *__restrict__ c2) {
-  const int lane = threadIdx.x & 31;
-  if (static_cast<int>(blockIdx.x) < dw_blocks) {
-    const int j = blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
-    if (j >= M4) return;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = lane; s < S; s += 32) {
-      const float4 v = ld4(dwp, static_cast<size_t>(s) * M4 + j);
-      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o), acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o), acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-    }
-    if (lane == 0) reinterpret_cast<float4 *>(dw)[j] = acc;
-    return;
-  }
-  const int c = (blockIdx.x - dw_blocks) * (kRowThreads / 32) + (threadIdx.x >> 5);
-  if (c >= C) return;
-  double s, q;
-  warp_sum_partials(ld, c, nblk, partials, s, q);
-  if (lane != 0) return;
-  dbeta[c] = static_cast<float>(s);
-  dgamma[c] = static_cast<float>(q);
-  const float inv_p = 1.0f / static_cast<float>(P);
-  c1[c] = training ? static_cast<float>(s) * inv_p : 0.f;
-  c2[c] = training ? static_cast<float>(q) * inv_p : 0.f;
-}
-
-extern "C" int pn2_mlp_bwd_finalize(int s, int m, const float *dw_partials, float *dw, int p, int c, int ld,
-                                    int nblk, int training, const float *stat_partials, float *dgamma,
-                                    float *dbeta, float *c1c2, void *stream) {
-  if (s <= 0 || m <= 0 || m % 4 != 0 || p <= 0 || c <= 0 || ld < c || nblk <= 0) return PN2_ERR_INVALID_ARG;
-  PN2_CHECK_PTRS(dw_partials, dw, stat_partials, dgamma, dbeta, c1c2);
-  if (!aligned16(dw_partials) || !aligned16(dw)) return PN2_ERR_UNSUPPORTED;
-  const int warps = kRowThreads / 32;
-  const int dw_blocks = (m / 4 + warps - 1) / warps, st_blocks = (c + warps - 1) / warps;
-  bwd_layer_finalize_kernel<<<dw_blocks + st_blocks, kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      dw_blocks, s, m / 4, dw_partials, dw, p, c, ld, nblk, training, stat_partials, dgamma, dbeta, c1c2,
-      c1c2 + c);
-  count_launch();
-  PN2_RETURN_LAUNCH_STATUS();
-}
-
 // Adam (torch.optim.Adam semantics: L2 weight decay added to the gradient, bias correction,
 // eps outside the square root) over ONE flat parameter buffer; the step count lives on the
 // device so that the launch can be replayed from a CUDA graph.  grad_scale multiplies the

@@ -289,8 +289,8 @@ class SharedMLPRows(Function):
                         _lib.check(L.pn2_mlp_pack_weights_t(C, K, lda, W2c.shape[1], W2c.data_ptr(), wtp.data_ptr(), s),
                                    "mlp_pack_weights_t")
                         dh_prev = f32(P, lda)
-                        if prev is not None:
-                            sp = f32(grid, 2, kb * 32)
+                        if prev is not None:   # BatchNorm below: the kernel leaves S in dwp and Q in sp
+                            sp = f32(grid, nb * 32 * kb * 32)
                     dwp = f32(grid, nb * 32 * kb * 32)
                     d_out, d_in = ctx.drops[l], (ctx.drops[l - 1] if l > 0 else None)
                     _lib.check(L.pn2_mlp_bwd_layer(
@@ -314,9 +314,13 @@ class SharedMLPRows(Function):
                     if sp is not None:   # weight-gradient partials + the statistics of the layer below: one launch
                         Kc = prev.cout
                         pg, pb, pc = f32(Kc), f32(Kc), f32(2 * Kc)
-                        _lib.check(L.pn2_mlp_bwd_finalize(grid, nb * 32 * kb * 32, dwp.data_ptr(), dW.data_ptr(),
-                                                          P, Kc, kb * 32, grid, training, sp.data_ptr(),
-                                                          pg.data_ptr(), pb.data_ptr(), pc.data_ptr(), s),
+                        scratch = f32(L.pn2_mlp_bwd_finalize_scratch_floats(C, lda))
+                        _lib.check(L.pn2_mlp_bwd_finalize(grid, C, Kc, lda, dwp.data_ptr(), sp.data_ptr(),
+                                                          W2c.data_ptr(), prev.a.data_ptr(), prev.b.data_ptr(),
+                                                          prev.mean.data_ptr(), prev.invstd.data_ptr(), P, training,
+                                                          dW.data_ptr(), pg.data_ptr(), pb.data_ptr(), pc.data_ptr(),
+                                                          scratch.data_ptr(),
+                                                          _sched_counters(dev)[8:].data_ptr(), s),
                                    "mlp_bwd_finalize")
                         pending = (pg, pb, pc)
                     else:

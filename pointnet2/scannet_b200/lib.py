@@ -56,12 +56,13 @@ SIGNATURES = {
     "pn2_mlp_bwd_kpad": [_i],
     "pn2_mlp_pack_weights_t": [_i, _i, _i, _i, _vp, _vp, _vp],
     "pn2_mlp_bwd_layer": [_i] * 7 + [_vp] * 20 + [_vp, _f, _vp, _f, _vp],
+    "pn2_mlp_bwd_finalize_scratch_floats": [_i, _i],
+    "pn2_mlp_bwd_finalize": [_i, _i, _i, _i] + [_vp] * 7 + [_i, _i] + [_vp] * 7,
     "pn2_pool_bn_bwd_stats": [_i, _i, _i, _i] + [_vp] * 12,
     "pn2_relu_bn_bwd_stats": [_i, _i, _i, _i] + [_vp] * 11,
     "pn2_bwd_stats_finalize": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     # flat-buffer training-step utilities
     "pn2_sum_partials": [_i, _i, _vp, _vp, _vp],
-    "pn2_mlp_bwd_finalize": [_i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_adam_flat": [ctypes.c_longlong, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp],
     # weighted cross-entropy of the training step
     "pn2_weighted_ce_partials": [_i],

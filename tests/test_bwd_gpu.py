@@ -45,6 +45,15 @@ def SCHED():
     return _sched[0]
 
 
+_fin = []
+
+
+def FIN_COUNTER():
+    if not _fin:
+        _fin.append(torch.zeros(1, dtype=torch.int32, device=DEV))
+    return _fin[0]
+
+
 def make_case(rng, P, N, K, lda, ns, relu, fold, relu_in):
     f32 = np.float32
     z = rng.standard_normal((P, N)).astype(f32)
@@ -128,19 +137,36 @@ def run_layer(c, dgrad=True, stats=True):
     dh_prev = torch.full((P, lda), float("nan"), dtype=torch.float32, device=DEV) if dgrad else None
     dwp = torch.full((grid, nb * 32, kb * 32), float("nan"), dtype=torch.float32, device=DEV)
     stats = stats and dgrad and c["a_in"] is not None
-    sp = torch.full((grid, 2, kb * 32), float("nan"), dtype=torch.float32, device=DEV) if stats else None
+    # with a BatchNorm below the kernel leaves S = dZ^T M in dwp and Q = dZ^T (M .* zhat) in sp
+    sp = torch.full((grid, nb * 32, kb * 32), float("nan"), dtype=torch.float32, device=DEV) if stats else None
     lib.check(L.pn2_mlp_bwd_layer(P, N, K, lda, c["ns"], int(c["relu"]), int(c["relu_in"]), ptr(t["dh"]),
                                   ptr(t["dout"]), ptr(t["argmax"]), ptr(t["z"]), ptr(t["a"]), ptr(t["b"]),
                                   ptr(t["mean"]), ptr(t["invstd"]), ptr(t["c1c2"]), ptr(t["W"]), ptr(t["aprev"]), ptr(t["a_in"]),
                                   ptr(t["b_in"]), ptr(t["mean_in"]), ptr(t["invstd_in"]), ptr(wtp), ptr(dh_prev),
                                   ptr(dwp), ptr(sp), ptr(SCHED()), None, 1.0, None, 1.0, s), "mlp_bwd_layer")
     torch.cuda.synchronize()
-    out = {"dw": dwp.double().sum(0).cpu().numpy()[:N, :K]}
+    out = {}
     if dgrad:
         out["dh_prev"] = dh_prev.cpu().numpy()
-    if stats:
-        sq = sp.double().sum(0).cpu().numpy()
-        out["s"], out["q"] = sq[0, :K], sq[1, :K]
+    if stats:   # pn2_mlp_bwd_finalize: sums over the CTAs, dW = g1 Q + g0 S, s = sum_n W .* S, q likewise
+        dW = torch.full((nb * 32, kb * 32), float("nan"), dtype=torch.float32, device=DEV)
+        dgamma, dbeta, c1c2 = (torch.full((m,), float("nan"), dtype=torch.float32, device=DEV) for m in (K, K, 2 * K))
+        scratch = torch.empty(L.pn2_mlp_bwd_finalize_scratch_floats(N, lda), dtype=torch.float32, device=DEV)
+        lib.check(L.pn2_mlp_bwd_finalize(grid, N, K, lda, ptr(dwp), ptr(sp), ptr(t["W"]), ptr(t["a_in"]), ptr(t["b_in"]),
+                                         ptr(t["mean_in"]), ptr(t["invstd_in"]), P, 1, ptr(dW), ptr(dgamma), ptr(dbeta),
+                                         ptr(c1c2),
+                                         ptr(scratch), ptr(FIN_COUNTER()), s), "mlp_bwd_finalize")
+        torch.cuda.synchronize()
+        out["dw"] = dW.double().cpu().numpy()[:N, :K]
+        out["s"], out["q"] = dbeta.double().cpu().numpy(), dgamma.double().cpu().numpy()
+        assert np.allclose(c1c2.cpu().numpy(), np.concatenate([out["s"], out["q"]]) / P, rtol=1e-6, atol=1e-30)
+        # the same sums straight from the images (fp64 on the host)
+        S, Q = dwp.double().sum(0).cpu().numpy()[:N, :K], sp.double().sum(0).cpu().numpy()[:N, :K]
+        w64 = c["W"].astype(np.float64)
+        assert np.abs((w64 * S).sum(0) - out["s"]).max() <= 1e-5 * max(np.abs(out["s"]).max(), 1e-30)
+        assert np.abs((w64 * Q).sum(0) - out["q"]).max() <= 1e-5 * max(np.abs(out["q"]).max(), 1e-30)
+    else:
+        out["dw"] = dwp.double().sum(0).cpu().numpy()[:N, :K]
     return out
 
 

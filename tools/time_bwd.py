@@ -42,7 +42,7 @@ for name, P, N, K, lda, ns, fold, dgrad in CASES:
         lib.check(L.pn2_mlp_pack_weights_t(N, K, lda, K, W.data_ptr(), wtp.data_ptr(), s), "pack")
     dhp = torch.empty(P, lda, device=DEV) if dgrad else None
     dwp = torch.empty(grid, nb * 32 * kb * 32, device=DEV)
-    sp = torch.empty(grid, 2, kb * 32, device=DEV) if (dgrad and fold) else None
+    sp = torch.empty(grid, nb * 32 * kb * 32, device=DEV) if (dgrad and fold) else None
     p = lambda t: t.data_ptr() if t is not None else None
     def call():
         lib.check(L.pn2_mlp_bwd_layer(P, N, K, lda, ns, 1, 1, p(dh), p(dout), p(am), p(z), p(a), p(b), p(mean),
@@ -61,11 +61,11 @@ for name, P, N, K, lda, ns, fold, dgrad in CASES:
     byt = 4 * P * (N + lda + (lda if dgrad else 0) + (N if not ns else 0)) + (8 * (P // ns) * N if ns else 0)
     if os.environ.get("PN2_BWD_DBG") and int(os.environ["PN2_BWD_DBG"]) & 32:
         import ctypes, numpy as np
-        buf = np.zeros((148, 16), np.uint64)
+        buf = np.zeros((148, 20), np.uint64)
         L.pn2_mlp_bwd_debug_read.argtypes = [ctypes.c_void_p]
         L.pn2_mlp_bwd_debug_read(buf.ctypes.data)
         m = buf.astype(np.float64).mean(0) / 1.9e3   # us at ~1.9 GHz
         print("   us/CTA: G0 total %.0f w_empty %.0f dz_empty %.0f h_empty %.0f loads %.0f | G1 total %.0f w %.0f dz %.0f h %.0f ld %.0f"
-              " | MMA acc_empty %.0f dz_full %.0f w_full %.0f h_full %.0f | EPI acc_full %.0f" % tuple(m[:15]))
+              " | MMA acc_empty %.0f dz_full %.0f w_full %.0f h_full %.0f | EPI acc_full %.0f | read-out %.1f set-up %.1f entry->mma done %.1f" % tuple(m[:18]))
     print("%-18s P=%7d N=%3d K=%3d  %7.1f us  %6.1f MB  %6.0f GB/s (%.0f%% of HBM peak)" % (
         name, P, N, K, us, byt / 1e6, byt / us / 1e3, 100 * byt / us / 1e3 / PEAK))
