@@ -241,10 +241,21 @@ PN2_API int pn2_mlp_gemm_k_blocks(int k);
 PN2_API int pn2_mlp_gemm_grid(int p, int n);
 PN2_API int pn2_mlp_pack_weights(int p, int n, int k, int ldw, const float *w, float *packed,
                                  void *stream);
+PN2_API int pn2_mlp_gemm_pool_supported(int ns);
 PN2_API int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const float *a,
                              const float *a_in, const float *b_in, int relu_in, float *h_out,
                              const float *w_packed, float *z, float *partials,
-                             const unsigned char *drop, float drop_scale, void *stream);
+                             const unsigned char *drop, float drop_scale, int pool_ns, float *zmax,
+                             float *zmin, int *imax, int *imin, void *stream);
+/* pool_ns (0: none; else pn2_mlp_gemm_pool_supported(pool_ns), p % pool_ns == 0): the layer is the pooled
+ * last layer of an SA block (max_pool2d over nsample, pointnet2_modules.py:68-70): next to z the kernel
+ * leaves, per group of pool_ns rows and channel, the max and the min of z and the first row attaining
+ * each (zmax / zmin / imax / imin, [p / pool_ns, n]), read from its staged output blocks -- z is not
+ * re-read.  pn2_groupmax_from_extrema turns them into max_s relu(a*z+b) and its arg-max row once the
+ * BatchNorm fold (a, b) is known: the sign of a picks max or min. */
+PN2_API int pn2_groupmax_from_extrema(int g, int c, const float *zmax, const float *zmin, const int *imax,
+                                      const int *imin, const float *a, const float *b, float *out,
+                                      int *argmax, void *stream);
 /* drop (optional, [p, k] bytes; needs a_in, excludes h_out): keep mask of an nn.Dropout sitting between
  * the previous layer's activation and this layer (pointnet2_semseg.py:156): act(a) is multiplied by
  * drop ? drop_scale : 0 on the tile, so the dropped activation is never materialised. */

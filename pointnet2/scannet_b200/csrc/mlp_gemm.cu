@@ -66,6 +66,12 @@ struct Params {
   int N, ldz, BN, n_tiles;
   int relu_in;
   int tma_store;              // Z leaves through the tensor map (else per-thread row stores)
+  // group extrema for the pooled last layer of an SA block (pool_ns = 16 or 32 rows per group, 0 = none):
+  // max / min of Z over every group and the first row attaining them, [P / pool_ns, N] each; the sign of
+  // the BatchNorm scale (known only after this kernel) decides which one max-pooling needs
+  int pool_ns;
+  float *zmax, *zmin;
+  int *imax, *imin;
   int stages, b_stage_bytes;  // pipeline depth; bytes reserved per weight stage (multiple of 1024)
   int tmem_cols;              // 512 (one CTA per SM) or 256 (two): two accumulators of tmem_cols / 2
   // dropout between the previous layer's activation and this layer (nn.Dropout in the classifier,
@@ -287,7 +293,34 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
                   if (n0 + j + e < p.N) dst[j + e] = v[j + e];
               }
           }
-          if (p.partials != nullptr) {  // rows past P are zero (zero-filled A): they add nothing
+          if (p.pool_ns != 0) {
+            // pooled layer: column pass over the staged block (lane = column; the swizzle makes every row
+            // read conflict-free) for the group extrema and this layer's BatchNorm sums.  (For the other
+            // layers the shuffle butterfly below is cheaper than 32 more shared-memory wavefronts per
+            // block: measured +93 us per step with the column pass everywhere.)
+            const unsigned char *stg = smem_out + wq * kOutStageBytes + ((lane & 3) << 2);
+            const int cj = lane >> 2;
+            const int halves = 32 / p.pool_ns;  // 1 or 2 groups in the block
+            float s0 = 0.f, q0 = 0.f;
+            for (int hh = 0; hh < halves; ++hh) {
+              float mx = -INFINITY, mn = INFINITY;
+              int ix = 0, in = 0;
+#pragma unroll 8
+              for (int rr = 0; rr < p.pool_ns; ++rr) {
+                const int r = hh * p.pool_ns + rr;
+                const float x = *reinterpret_cast<const float *>(stg + r * 128 + ((cj ^ (r & 7)) << 4));
+                s0 += x, q0 = fmaf(x, x, q0);
+                if (x > mx) mx = x, ix = rr;
+                if (x < mn) mn = x, in = rr;
+              }
+              const long long grp = (static_cast<long long>(tile) * BM + wq * 32) / p.pool_ns + hh;
+              if (grp * p.pool_ns < p.P && n0 + lane < p.N) {
+                const size_t o = static_cast<size_t>(grp) * p.N + n0 + lane;
+                p.zmax[o] = mx, p.zmin[o] = mn, p.imax[o] = ix, p.imin[o] = in;
+              }
+            }
+            csum[c] += s0, csq[c] += q0;
+          } else if (p.partials != nullptr) {  // rows past P are zero (zero-filled A): they add nothing
             float sq[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
@@ -389,10 +422,12 @@ extern "C" int pn2_mlp_pack_weights(int p, int n, int k, int ldw, const float *w
   PN2_RETURN_LAUNCH_STATUS();
 }
 
+extern "C" int pn2_mlp_gemm_pool_supported(int ns) { return (ns == 16 || ns == 32) ? 1 : 0; }
+
 extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const float *a, const float *a_in,
                                 const float *b_in, int relu_in, float *h_out, const float *w_packed,
                                 float *z, float *partials, const unsigned char *drop, float drop_scale,
-                                void *stream) {
+                                int pool_ns, float *zmax, float *zmin, int *imax, int *imin, void *stream) {
   if (p <= 0 || k <= 0 || n <= 0 || lda < 4 || lda % 4 != 0) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(a, w_packed);
   if (!aligned16(a) || !aligned16(w_packed)) return PN2_ERR_UNSUPPORTED;
@@ -427,6 +462,12 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   memset(&tm_z, 0, sizeof(tm_z));
   static const bool no_tma = getenv("PN2_GEMM_NO_TMA_STORE") != nullptr;   // timing experiments only
   prm.tma_store = (z != nullptr && !no_tma && tc::make_tmap_rows32(&tm_z, z, p, n, ldz)) ? 1 : 0;
+  prm.pool_ns = pool_ns, prm.zmax = zmax, prm.zmin = zmin, prm.imax = imax, prm.imin = imin;
+  if (pool_ns != 0) {
+    if (!pn2_mlp_gemm_pool_supported(pool_ns) || p % pool_ns != 0) return PN2_ERR_UNSUPPORTED;
+    PN2_CHECK_PTRS(zmax, zmin, imax, imin);
+    if (!prm.tma_store) return PN2_ERR_UNSUPPORTED;  // the extrema are read from the staged output blocks
+  }
   auto kern = drop != nullptr ? gemm::gemm_tf32_fwd_kernel<true> : gemm::gemm_tf32_fwd_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);

@@ -203,6 +203,26 @@ bn_relu_groupmax_kernel(int G, int ns, int C4, const float *__restrict__ z, cons
   reinterpret_cast<int4 *>(argmax)[i] = arg;
 }
 
+// out[g, c] and its arg-max row from the group extrema of Z that the tensor-core layer left
+// (csrc/mlp_gemm.cu, pool_ns): max_s relu(a*z_s + b) = relu(a * (a > 0 ? max z : min z) + b), a
+// monotone map of z; the row is the first one attaining that extremum -- row 0 when the result
+// is not positive, as bn_relu_groupmax_kernel's strict comparison leaves it.
+__global__ void __launch_bounds__(kRowThreads)
+groupmax_from_extrema_kernel(size_t total, int C, const float *__restrict__ zmax, const float *__restrict__ zmin,
+                             const int *__restrict__ imax, const int *__restrict__ imin,
+                             const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out,
+                             int *__restrict__ argmax) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  const float aa = __ldg(a + c), bb = __ldg(b + c);
+  const bool up = aa > 0.f;
+  const float y = fmaf(aa, up ? __ldg(zmax + i) : __ldg(zmin + i), bb);
+  const bool pos = y > 0.f && aa != 0.f;
+  out[i] = fmaxf(y, 0.f);
+  argmax[i] = pos ? (up ? __ldg(imax + i) : __ldg(imin + i)) : 0;
+}
+
 // ------------------------------------------------------------- adjoint of the pooled layer
 // sparse statistics: only the arg-max row of every (group, channel) carries a gradient
 __global__ void __launch_bounds__(kRowThreads)
@@ -691,6 +711,18 @@ extern "C" int pn2_bn_relu_groupmax(int g, int ns, int c, const float *z, const 
   const size_t total4 = static_cast<size_t>(g) * (c / 4);
   bn_relu_groupmax_kernel<<<blocks_for(total4), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       g, ns, c / 4, z, a, b, out, argmax);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_groupmax_from_extrema(int g, int c, const float *zmax, const float *zmin, const int *imax,
+                                         const int *imin, const float *a, const float *b, float *out,
+                                         int *argmax, void *stream) {
+  if (g <= 0 || c <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(zmax, zmin, imax, imin, a, b, out, argmax);
+  const size_t total = static_cast<size_t>(g) * c;
+  groupmax_from_extrema_kernel<<<blocks_for(total), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      total, c, zmax, zmin, imax, imin, a, b, out, argmax);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

@@ -24,6 +24,7 @@ GEMM_TF32 = True   # tensor-core TF32 GEMMs, like the reference's cuDNN convs on
 ENABLED = True     # module forward()s take the fused path when eligible
 TC_BWD = True      # backward layers on the fused tcgen05 kernel (csrc/mlp_bwd.cu: BN adjoint + dH + dW +
                    # next statistics in one pass) where the shape is supported and TC_GEMM is on
+POOL_IN_GEMM = True  # pooled last layer: group extrema from the tensor-core layer's epilogue (no pass over Z)
 TC_GEMM = True     # forward layers on the hand-written tcgen05 kernel (csrc/mlp_gemm.cu) when
                    # GEMM_TF32: BN fold + ReLU of the previous layer in its prologue, BN batch
                    # statistics in its epilogue; off: cuBLAS GEMM + separate streaming kernels
@@ -111,10 +112,11 @@ def _bn_forward(z, gamma, beta, rm, rv, eps, momentum, training, nbt=None):
     return a, b, mean, invstd
 
 
-def _tc_layer(A, k, W2, fold, relu_in, want_h, want_stats, drop=None):
+def _tc_layer(A, k, W2, fold, relu_in, want_h, want_stats, drop=None, pool_ns=0):
     """One layer on the tcgen05 kernel: z = act(A)[:, :k] @ W2^T.  fold = (a_in, b_in) or None;
-    drop = (keep mask uint8 [P, k], scale) of a dropout between act(A) and this layer, or None.
-    -> (z, h_out or None, partials or None, (ld, nblk))"""
+    drop = (keep mask uint8 [P, k], scale) of a dropout between act(A) and this layer, or None;
+    pool_ns > 0: also the per-group extrema of z (zmax, zmin, imax, imin), see pn2_mlp_gemm_fwd.
+    -> (z, h_out or None, partials or None, (ld, nblk)[, extrema])"""
     L = _lib.load()
     dev = A.device
     P, lda = A.shape
@@ -128,14 +130,22 @@ def _tc_layer(A, k, W2, fold, relu_in, want_h, want_stats, drop=None):
     z = torch.empty(P, N, dtype=torch.float32, device=dev)
     h = torch.empty_like(A) if (want_h and fold is not None) else None
     part = torch.empty(grid, 2, nt * bn, dtype=torch.float32, device=dev) if want_stats else None
+    ext = None
+    if pool_ns:
+        G = P // pool_ns
+        ext = (torch.empty(G, N, dtype=torch.float32, device=dev), torch.empty(G, N, dtype=torch.float32, device=dev),
+               torch.empty(G, N, dtype=torch.int32, device=dev), torch.empty(G, N, dtype=torch.int32, device=dev))
     _lib.check(L.pn2_mlp_gemm_fwd(
         P, k, lda, N, N, A.data_ptr(),
         fold[0].data_ptr() if fold is not None else None,
         fold[1].data_ptr() if fold is not None else None, int(relu_in),
         h.data_ptr() if h is not None else None, Wp.data_ptr(), z.data_ptr(),
         part.data_ptr() if part is not None else None,
-        drop[0].data_ptr() if drop is not None else None, float(drop[1]) if drop is not None else 1.0, s),
+        drop[0].data_ptr() if drop is not None else None, float(drop[1]) if drop is not None else 1.0,
+        int(pool_ns), *((t.data_ptr() for t in ext) if ext is not None else (None, None, None, None)), s),
         "mlp_gemm_fwd")
+    if pool_ns:
+        return z, h, part, (nt * bn, grid), ext
     return z, h, part, (nt * bn, grid)
 
 
@@ -194,8 +204,15 @@ class SharedMLPRows(Function):
                     fold = (prev.a, prev.b) if prev is not None else None
                     drop = drops[l - 1] if l > 0 else None
                     assert drop is None or (bwd_fused[l] and bwd_fused[l - 1]), "dropout needs the fused backward layers"
-                    st.z, h, part, (ld, nblk) = _tc_layer(A, W2.shape[1], W2, fold,
-                                                          relus[l - 1] if l > 0 else False, want_h, training, drop)
+                    # pooled last layer: the group extrema of z come out of the same kernel
+                    ext = None
+                    pool_here = (l == nl - 1 and ns > 0 and POOL_IN_GEMM and P % ns == 0
+                                 and bool(L.pn2_mlp_gemm_pool_supported(ns)))
+                    res = _tc_layer(A, W2.shape[1], W2, fold, relus[l - 1] if l > 0 else False, want_h, training,
+                                    drop, ns if pool_here else 0)
+                    st.z, h, part, (ld, nblk) = res[:4]
+                    if pool_here:
+                        ext = res[4]
                     if l > 0:
                         hs.append(h)          # None when the fused backward layer will recompute it
                     if training:
@@ -223,6 +240,14 @@ class SharedMLPRows(Function):
                         hs.append(h)
                     else:
                         out = h
+                elif use_tc and ext is not None:
+                    G = P // ns
+                    out = torch.empty(G, C, dtype=torch.float32, device=dev)
+                    argmax = torch.empty(G, C, dtype=torch.int32, device=dev)
+                    _lib.check(L.pn2_groupmax_from_extrema(G, C, ext[0].data_ptr(), ext[1].data_ptr(),
+                                                           ext[2].data_ptr(), ext[3].data_ptr(), st.a.data_ptr(),
+                                                           st.b.data_ptr(), out.data_ptr(), argmax.data_ptr(),
+                                                           _stream(dev)), "groupmax_from_extrema")
                 else:
                     G = P // ns
                     out = torch.empty(G, C, dtype=torch.float32, device=dev)

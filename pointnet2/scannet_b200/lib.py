@@ -46,7 +46,10 @@ SIGNATURES = {
     "pn2_mlp_gemm_k_blocks": [_i],
     "pn2_mlp_gemm_grid": [_i, _i],
     "pn2_mlp_pack_weights": [_i, _i, _i, _i, _vp, _vp, _vp],
-    "pn2_mlp_gemm_fwd": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp],
+    "pn2_mlp_gemm_pool_supported": [_i],
+    "pn2_mlp_gemm_fwd": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f,
+                         _i, _vp, _vp, _vp, _vp, _vp],
+    "pn2_groupmax_from_extrema": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_bn_finalize": [_i, _i, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     # fused backward layer on the tensor cores
     "pn2_mlp_bwd_supported": [_i, _i, _i, _i, _i],

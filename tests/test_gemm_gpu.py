@@ -11,10 +11,14 @@ import numpy as np
 import pytest
 import torch
 
-from pointnet2.scannet_b200 import lib
+from pointnet2.scannet_b200 import fused, lib
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+
+
+def L_():
+    return lib.load()
 
 
 def tf32_rna(x):
@@ -48,7 +52,7 @@ def run_gemm(A, W, k, a_in=None, b_in=None, relu=False, want_h=False):
                                  ad.data_ptr() if ad is not None else None,
                                  bd.data_ptr() if bd is not None else None, int(relu),
                                  H.data_ptr() if H is not None else None, Wp.data_ptr(), Z.data_ptr(),
-                                 part.data_ptr(), None, 1.0, s), "gemm")
+                                 part.data_ptr(), None, 1.0, 0, None, None, None, None, s), "gemm")
     torch.cuda.synchronize()
     return Z.cpu().numpy(), part.cpu().numpy().sum(0)[:, :N], (H.cpu().numpy() if want_h else None)
 
@@ -85,3 +89,44 @@ def test_gemm_fused_bn_relu_prologue(P, K, N, relu):
     ref = tf32_trunc(H).astype(np.float64) @ tf32_rna(W).astype(np.float64).T
     assert np.abs(Z - ref).max() <= 2e-5 * np.abs(ref).max()
     np.testing.assert_allclose(stats[1], (ref * ref).sum(0), rtol=1e-4)
+
+
+@pytest.mark.parametrize("G,ns,K,N", [(64, 32, 32, 64), (100, 32, 64, 128), (37, 16, 32, 32), (300, 32, 128, 256),
+                                       (5, 16, 64, 20)])
+def test_pooled_layer_extrema_and_groupmax(G, ns, K, N):
+    """Pooled last layer of an SA block: the group extrema the layer leaves (read from its staged
+    output blocks) are exactly the max / min of the Z it wrote and the first rows attaining them, and
+    pn2_groupmax_from_extrema reproduces pn2_bn_relu_groupmax (the streaming kernel over Z) bit for
+    bit -- values and arg-max rows -- for positive, negative and zero BatchNorm scales."""
+    rng = np.random.default_rng(G * ns + N)
+    P = G * ns
+    A = torch.from_numpy(rng.standard_normal((P, K)).astype(np.float32)).to(DEV)
+    A[: P // 3] = A[0]                                            # ties: whole groups of identical rows
+    W = torch.from_numpy((rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)).to(DEV)
+    assert L_().pn2_mlp_gemm_pool_supported(ns) == 1
+    z, h, part, (ld, nblk), ext = fused._tc_layer(A, K, W, None, False, False, True, None, ns)
+    zmax, zmin, imax, imin = ext
+    torch.cuda.synchronize()
+    zg = z.view(G, ns, N)
+    assert torch.equal(zmax, zg.max(dim=1).values) and torch.equal(zmin, zg.min(dim=1).values)
+    first_max = (zg == zmax.unsqueeze(1)).float().argmax(dim=1).int()   # first row attaining the max
+    first_min = (zg == zmin.unsqueeze(1)).float().argmax(dim=1).int()
+    assert torch.equal(imax, first_max) and torch.equal(imin, first_min)
+    # statistics from the same column pass
+    ps = part.sum(0)
+    assert torch.allclose(ps[0, :N], z.sum(0), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(ps[1, :N], (z * z).sum(0), rtol=1e-4, atol=1e-3)
+    a = torch.from_numpy(rng.uniform(0.5, 1.5, N).astype(np.float32) * rng.choice([-1.0, 1.0, 0.0], N).astype(np.float32)).to(DEV)
+    b = torch.from_numpy((0.3 * rng.standard_normal(N)).astype(np.float32)).to(DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    out1, arg1 = torch.empty(G, N, device=DEV), torch.empty(G, N, dtype=torch.int32, device=DEV)
+    out2, arg2 = torch.empty(G, N, device=DEV), torch.empty(G, N, dtype=torch.int32, device=DEV)
+    lib.check(L_().pn2_bn_relu_groupmax(G, ns, N, z.data_ptr(), a.data_ptr(), b.data_ptr(), out1.data_ptr(),
+                                        arg1.data_ptr(), s), "groupmax")
+    lib.check(L_().pn2_groupmax_from_extrema(G, N, zmax.data_ptr(), zmin.data_ptr(), imax.data_ptr(), imin.data_ptr(),
+                                             a.data_ptr(), b.data_ptr(), out2.data_ptr(), arg2.data_ptr(), s), "from_extrema")
+    torch.cuda.synchronize()
+    assert torch.equal(out1, out2)
+    # the rows can only differ where two different z of a group round to the same a*z+b (then both rows carry
+    # the same value); on these inputs ties are exact duplicates, so the rows agree as well
+    assert torch.equal(arg1, arg2)
