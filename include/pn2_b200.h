@@ -343,6 +343,10 @@ PN2_API int pn2_bwd_stats_finalize(int p, int c, int ld, int nblk, int training,
  * launch is CUDA-graph replayable; the gradient is multiplied by grad_scale first.
  * ========================================================================== */
 PN2_API int pn2_sum_partials(int s, int m, const float *in, float *out, void *stream);
+/* pn2_dropout_mask: byte keep mask of n elements, P(keep) = keep (resolution 2^-16), counter-based:
+ * state = {seed, launch counter} (device int64[2]); the call bumps the counter, so replays of a captured
+ * launch draw fresh masks.  The fused chain applies the mask inside the next layer's kernels. */
+PN2_API int pn2_dropout_mask(long long n, float keep, long long *state, unsigned char *mask, void *stream);
 PN2_API int pn2_adam_flat(long long n, float *param, const float *grad, float *exp_avg,
                           float *exp_avg_sq, long long *step, float lr, float beta1, float beta2,
                           float eps, float weight_decay, float grad_scale, void *stream);

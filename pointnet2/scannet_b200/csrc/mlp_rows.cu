@@ -101,9 +101,22 @@ __device__ __forceinline__ void warp_sum_partials(int ld, int c, int nblk, const
                                                   double &s, double &q) {
   const int lane = threadIdx.x & 31;
   s = 0.0, q = 0.0;
-  for (int k = lane; k < nblk; k += 32) {  // partials: [nblk][2][ld]
-    s += __ldg(partials + static_cast<size_t>(k) * 2 * ld + c);
-    q += __ldg(partials + static_cast<size_t>(k) * 2 * ld + ld + c);
+  // partials: [nblk][2][ld].  All of the lane's loads are issued before the first add (same order of
+  // additions as a plain loop, hence the same bits): a dependent loop costs one L2 round trip per
+  // iteration, ~10 of them for the ~300 partials of a tensor-core layer.
+  constexpr int kBatch = 10;
+  for (int k0 = lane; k0 < nblk; k0 += 32 * kBatch) {
+    float vs[kBatch], vq[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int k = k0 + 32 * i;
+      const bool ok = k < nblk;
+      vs[i] = ok ? __ldg(partials + static_cast<size_t>(k) * 2 * ld + c) : 0.f;
+      vq[i] = ok ? __ldg(partials + static_cast<size_t>(k) * 2 * ld + ld + c) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i)
+      if (k0 + 32 * i < nblk) s += vs[i], q += vq[i];
   }
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -946,9 +959,15 @@ sum_partials_kernel(int S, int M4, const float *__restrict__ in, float *__restri
   const int lane = threadIdx.x & 31;
   if (j >= M4) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = lane; s < S; s += 32) {
-    const float4 v = ld4(in, static_cast<size_t>(s) * M4 + j);
-    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+  constexpr int kBatch = 5;  // loads of a batch are issued together; additions keep the plain loop's order
+  for (int s0 = lane; s0 < S; s0 += 32 * kBatch) {
+    float4 v[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i)
+      v[i] = s0 + 32 * i < S ? ld4(in, static_cast<size_t>(s0 + 32 * i) * M4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i)
+      if (s0 + 32 * i < S) acc.x += v[i].x, acc.y += v[i].y, acc.z += v[i].z, acc.w += v[i].w;
   }
   for (int o = 16; o > 0; o >>= 1) {
     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o), acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
@@ -965,6 +984,52 @@ extern "C" int pn2_sum_partials(int s, int m, const float *in, float *out, void 
   sum_partials_kernel<<<(m / 4 + warps_per_cta - 1) / warps_per_cta, kRowThreads, 0,
                         static_cast<cudaStream_t>(stream)>>>(s, m / 4, in, out);
   count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+// Dropout keep mask (one byte per element) for the classifier's nn.Dropout inside the fused chain
+// (pointnet2_semseg.py:156): counter-based -- element i of launch t keeps iff the i-th 16-bit lane of
+// splitmix64(seed, t, i / 4) is below keep * 65536 -- so the launch is CUDA-graph replayable (the launch
+// counter lives on the device and is bumped by the launch) and one pass at store bandwidth replaces
+// torch's Philox bernoulli_ over bytes (47 us for the head's [262144, 128] mask).
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(kRowThreads)
+dropout_mask_kernel(size_t n16, size_t n, unsigned threshold, const long long *__restrict__ state,
+                    unsigned char *__restrict__ mask) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;  // 16 mask bytes per thread
+  if (i >= n16) return;
+  const unsigned long long key = splitmix64(static_cast<unsigned long long>(state[0]) ^
+                                            (static_cast<unsigned long long>(state[1]) * 0xD1342543DE82EF95ull));
+  unsigned w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const unsigned long long h = splitmix64(key + (i * 4 + k));
+    w[k] = ((h & 0xffffull) < threshold ? 1u : 0u) | (((h >> 16) & 0xffffull) < threshold ? 0x100u : 0u) |
+           (((h >> 32) & 0xffffull) < threshold ? 0x10000u : 0u) | ((h >> 48) < threshold ? 0x1000000u : 0u);
+  }
+  if (i * 16 + 16 <= n) {
+    reinterpret_cast<uint4 *>(mask)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    for (size_t b = i * 16; b < n; ++b) mask[b] = static_cast<unsigned char>((w[(b >> 2) & 3] >> (8 * (b & 3))) & 1u);
+  }
+}
+__global__ void bump_counter_kernel(long long *state) { state[1] += 1; }
+
+extern "C" int pn2_dropout_mask(long long n, float keep, long long *state, unsigned char *mask, void *stream) {
+  if (n <= 0 || !(keep >= 0.f && keep <= 1.f)) return PN2_ERR_INVALID_ARG;
+  if (state == nullptr || mask == nullptr) return PN2_ERR_INVALID_ARG;
+  if (!aligned16(mask) || (reinterpret_cast<uintptr_t>(state) & 7u) != 0) return PN2_ERR_ALIGNMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n16 = (static_cast<size_t>(n) + 15) / 16;
+  const unsigned threshold = static_cast<unsigned>(static_cast<double>(keep) * 65536.0 + 0.5);
+  dropout_mask_kernel<<<blocks_for(n16), kRowThreads, 0, s>>>(n16, static_cast<size_t>(n), threshold, state, mask);
+  bump_counter_kernel<<<1, 1, 0, s>>>(state);
+  count_launch(2);
   PN2_RETURN_LAUNCH_STATUS();
 }
 

@@ -521,12 +521,29 @@ def run_mlp_rows(mlp, x0, ns, dropouts=None):
             if p <= 0.0:
                 continue
             if mask is None:  # keep mask, one byte per element
-                mask = torch.empty(x0.shape[0], layers[i].conv.weight.shape[0], dtype=torch.uint8,
-                                   device=x0.device).bernoulli_(1.0 - p)
+                mask = _dropout_mask(x0.shape[0], layers[i].conv.weight.shape[0], 1.0 - p, x0.device)
             drops[i] = (mask, 1.0 / (1.0 - p))
     # running statistics AND num_batches_tracked are updated inside the finalise kernels
     return SharedMLPRows.apply(x0, ns, training, float(norms[0].eps), float(norms[0].momentum), buffers,
                                tuple(relus), tuple(drops), *params)
+
+
+_drop_state = {}
+
+
+def _dropout_mask(rows, cols, keep, dev):
+    """uint8 keep mask [rows, cols] from the library's counter-based generator (pn2_dropout_mask): its
+    state (seed drawn once from torch's CPU generator, launch counter) lives on the device, so the launch
+    is CUDA-graph replayable and every replay draws a fresh mask."""
+    st = _drop_state.get(dev)
+    if st is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        st = _drop_state[dev] = torch.tensor([seed, 0], dtype=torch.int64, device=dev)
+    mask = torch.empty(rows, cols, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().pn2_dropout_mask(rows * cols, float(keep), st.data_ptr(), mask.data_ptr(), _stream(dev)),
+                   "dropout_mask")
+    return mask
 
 
 def chain_supports_dropout(units, x0, i):

@@ -17,10 +17,11 @@ class GeometryPlan(object):
     """sa[k] = (new_xyz (B, npoint, 3), [idx (B, npoint, nsample) per scale]);
     fp[k] = (idx (B, n, 3) int32, weight (B, n, 3)) for FP_modules[k]."""
 
-    __slots__ = ("sa", "fp")
+    __slots__ = ("sa", "fp", "_flat")
 
     def __init__(self, sa, fp):
         self.sa, self.fp = sa, fp
+        self._flat = None
 
     def tensors(self):
         out = []
@@ -32,8 +33,34 @@ class GeometryPlan(object):
         return out
 
     def copy_from(self, other):
+        """Device copy of another plan of the same shapes: ONE copy when both plans live in flat buffers
+        (``pack``), else one per tensor."""
+        a, b = getattr(self, "_flat", None), getattr(other, "_flat", None)
+        if a is not None and b is not None and a.numel() == b.numel():
+            a.copy_(b, non_blocking=True)
+            return
         for dst, src in zip(self.tensors(), other.tensors()):
             dst.copy_(src, non_blocking=True)
+
+    def pack(self):
+        """Re-home every tensor of the plan as a view into one flat byte buffer (values kept), so that a
+        trainer can hand a whole plan over with a single device copy.  -> self"""
+        ts = self.tensors()
+        offs, total = [], 0
+        for t in ts:
+            offs.append(total)
+            total += (t.numel() * t.element_size() + 255) // 256 * 256
+        flat = torch.empty(total, dtype=torch.uint8, device=ts[0].device)
+        views = []
+        for t, o in zip(ts, offs):
+            v = flat[o:o + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+            v.copy_(t)
+            views.append(v)
+        it = iter(views)
+        self.sa = [(next(it), [next(it) for _ in idxs]) for _, idxs in self.sa]
+        self.fp = [(next(it), next(it)) for _ in self.fp]
+        self._flat = flat
+        return self
 
 
 @torch.no_grad()

@@ -66,6 +66,7 @@ SIGNATURES = {
     "pn2_bwd_stats_finalize": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     # flat-buffer training-step utilities
     "pn2_sum_partials": [_i, _i, _vp, _vp, _vp],
+    "pn2_dropout_mask": [ctypes.c_longlong, _f, _vp, _vp, _vp],
     "pn2_adam_flat": [ctypes.c_longlong, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp],
     # weighted cross-entropy of the training step
     "pn2_weighted_ce_partials": [_i],

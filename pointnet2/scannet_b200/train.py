@@ -228,8 +228,9 @@ class PipelinedTrainStep(object):
         warm = torch.cuda.Stream()
         warm.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(warm):
-            self.plan = geometry.build_plan(model, self.static[0][..., 0:3].contiguous())
-            self.plan_next = geometry.build_plan(model, self.next[0][..., 0:3].contiguous())
+            # both plans live in flat buffers: handing the prefetched plan over is one device copy
+            self.plan = geometry.build_plan(model, self.static[0][..., 0:3].contiguous()).pack()
+            self.plan_next = geometry.build_plan(model, self.next[0][..., 0:3].contiguous()).pack()
             for _ in range(warmup):
                 self._body()
         torch.cuda.current_stream().wait_stream(warm)

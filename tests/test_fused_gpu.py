@@ -321,3 +321,34 @@ def test_dropout_inside_the_chain_matches_materialised_dropout():
         assert l2_err(a, b) < 5e-3, l2_err(a, b)
     for a, b in zip(b1, b2):
         assert rel_err(a, b) < 1e-3
+
+
+def test_dropout_mask_generator():
+    """pn2_dropout_mask: keep rate, byte values, a fresh mask per launch (device-side counter), tails that are
+    not a multiple of 16 bytes, reproducibility from (seed, counter)."""
+    from pointnet2.scannet_b200 import lib
+    L = lib.load()
+    s = torch.cuda.current_stream().cuda_stream
+    state = torch.tensor([1234, 0], dtype=torch.int64, device=DEV)
+    n = 1 << 20
+    m1 = torch.full((n + 16,), 7, dtype=torch.uint8, device=DEV)
+    m2 = torch.empty(n, dtype=torch.uint8, device=DEV)
+    lib.check(L.pn2_dropout_mask(n, 0.5, state.data_ptr(), m1.data_ptr(), s), "mask")
+    lib.check(L.pn2_dropout_mask(n, 0.5, state.data_ptr(), m2.data_ptr(), s), "mask")
+    torch.cuda.synchronize()
+    assert state.tolist() == [1234, 2]
+    assert int(m1[n:].min()) == 7 and int(m1[:n].max()) == 1           # nothing written past n; bytes are 0 / 1
+    for m in (m1[:n], m2):
+        assert abs(float(m.float().mean()) - 0.5) < 5e-3
+    assert float((m1[:n] != m2).float().mean()) > 0.4                   # a fresh draw per launch
+    state2 = torch.tensor([1234, 0], dtype=torch.int64, device=DEV)
+    m3 = torch.empty(n, dtype=torch.uint8, device=DEV)
+    lib.check(L.pn2_dropout_mask(n, 0.5, state2.data_ptr(), m3.data_ptr(), s), "mask")
+    assert torch.equal(m3, m1[:n])                                      # same (seed, counter) -> same mask
+    odd = torch.full((64,), 9, dtype=torch.uint8, device=DEV)
+    lib.check(L.pn2_dropout_mask(37, 0.8, state2.data_ptr(), odd.data_ptr(), s), "mask")
+    torch.cuda.synchronize()
+    assert int(odd[37:].min()) == 9 and int(odd[:37].max()) <= 1
+    big = torch.empty(1 << 22, dtype=torch.uint8, device=DEV)
+    lib.check(L.pn2_dropout_mask(big.numel(), 0.8, state2.data_ptr(), big.data_ptr(), s), "mask")
+    assert abs(float(big.float().mean()) - 0.8) < 2e-3

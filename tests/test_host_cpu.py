@@ -248,3 +248,28 @@ def test_weighted_ce_mirror_equals_reference_on_cpu():
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         assert torch.equal(mine, mod.WeightedCrossEntropyLoss()(logits, targets, weights))
+
+
+def test_geometry_plan_pack_and_single_copy():
+    """GeometryPlan.pack(): every tensor becomes a view into one flat buffer (values kept) and
+    copy_from between two packed plans is one copy; packed <-> unpacked falls back to per-tensor copies."""
+    from pointnet2.scannet_b200.geometry import GeometryPlan
+
+    def make(fill):
+        sa = [(fill(2, 4, 3), [fill(2, 4, 8).to(torch.int32), fill(2, 4, 5).to(torch.int32)]) for _ in range(2)]
+        fp = [(fill(2, 9, 3).to(torch.int32), fill(2, 9, 3)) for _ in range(3)]
+        return GeometryPlan(sa, fp)
+
+    g = torch.Generator().manual_seed(0)
+    src = make(lambda *s: torch.randint(0, 100, s, generator=g).float())
+    want = [t.clone() for t in src.tensors()]
+    packed = src.pack()
+    assert packed._flat is not None and all(torch.equal(a, b) for a, b in zip(packed.tensors(), want))
+    base = packed._flat.untyped_storage().data_ptr()
+    assert all(t.untyped_storage().data_ptr() == base for t in packed.tensors())
+    dst = make(lambda *s: torch.zeros(*s)).pack()
+    dst.copy_from(packed)
+    assert all(torch.equal(a, b) for a, b in zip(dst.tensors(), want))
+    loose = make(lambda *s: torch.zeros(*s))
+    loose.copy_from(packed)
+    assert all(torch.equal(a, b) for a, b in zip(loose.tensors(), want))
