@@ -66,6 +66,7 @@ struct Params {
   int N, ldz, BN, n_tiles;
   int relu_in;
   int tma_store;              // Z leaves through the tensor map (else per-thread row stores)
+  int tma_load;               // A tiles arrive by tensor loads (else cp.async chunks)
   // group extrema for the pooled last layer of an SA block (pool_ns = 16 or 32 rows per group, 0 = none):
   // max / min of Z over every group and the first row attaining them, [P / pool_ns, N] each; the sign of
   // the BatchNorm scale (known only after this kernel) decides which one max-pooling needs
@@ -93,7 +94,8 @@ struct __align__(16) Barriers {
 };
 
 template <bool kDrop>  // dropout keep mask on the A tile (compiled out otherwise)
-__global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, const __grid_constant__ CUtensorMap tm_z) {
+__global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, const __grid_constant__ CUtensorMap tm_z,
+                                                                     const __grid_constant__ CUtensorMap tm_a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int STAGES = p.stages, B_STAGE_BYTES = p.b_stage_bytes;
   unsigned char *smem_a = smem;                                  // STAGES x 16 KB
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&bars->raw[s], 32 * kLoadWarps);
+      mbar_init(&bars->raw[s], p.tma_load ? 1 : 32 * kLoadWarps);
       mbar_init(&bars->full[s], 32 * kLoadWarps + 1);
       mbar_init(&bars->empty[s], 1);
     }
@@ -156,6 +158,17 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
         tma_load_1d(smem_b + s * B_STAGE_BYTES,
                     p.Wp + (static_cast<size_t>(n_tile) * p.k_blocks + kb) * p.BN * BK, b_bytes,
                     &bars->full[s]);
+      }
+      if (!kDrop && p.tma_load) {
+        // the whole 128 x 32 K block by ONE tensor load: same swizzled image as the cp.async path writes,
+        // rows past P / columns past lda zero-filled by the TMA unit, no LSU wavefronts, no address math
+        if (tid == 0) {
+          mbar_expect_tx(&bars->raw[s], A_STAGE_BYTES);
+          tma_load_box(&tm_a, smem_a + s * A_STAGE_BYTES, kb * BK, tile * BM, &bars->raw[s]);
+        }
+        if (++is_s == STAGES) is_s = 0, is_par ^= 1;
+        if (++is_kb == p.k_blocks) is_kb = 0, is_tile += gridDim.x;
+        return;
       }
       const int col = kb * BK + chunk * 4;
       const uint32_t dst0 = smem_u32(smem_a + s * A_STAGE_BYTES);
@@ -462,6 +475,10 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   memset(&tm_z, 0, sizeof(tm_z));
   static const bool no_tma = getenv("PN2_GEMM_NO_TMA_STORE") != nullptr;   // timing experiments only
   prm.tma_store = (z != nullptr && !no_tma && tc::make_tmap_rows32(&tm_z, z, p, n, ldz)) ? 1 : 0;
+  CUtensorMap tm_a;
+  memset(&tm_a, 0, sizeof(tm_a));
+  static const bool no_tma_load = getenv("PN2_GEMM_NO_TMA_LOAD") != nullptr;  // timing experiments only
+  prm.tma_load = (drop == nullptr && !no_tma_load && tc::make_tmap_rows32(&tm_a, a, p, lda, lda, gemm::BM)) ? 1 : 0;
   prm.pool_ns = pool_ns, prm.zmax = zmax, prm.zmin = zmin, prm.imax = imax, prm.imin = imin;
   if (pool_ns != 0) {
     if (!pn2_mlp_gemm_pool_supported(pool_ns) || p % pool_ns != 0) return PN2_ERR_UNSUPPORTED;
@@ -472,7 +489,7 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid(pn2_mlp_gemm_grid(p, n), prm.n_tiles);  // the partials buffer is sized by the same function
-  kern<<<grid, gemm::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(prm, tm_z);
+  kern<<<grid, gemm::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(prm, tm_z, tm_a);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

@@ -87,16 +87,28 @@ inline EncodeTiledFn encode_tiled() {
   }();
   return fn;
 }
-// fp32 row-major [rows, cols] with `ld` floats between rows, boxes of 32 x 32, SWIZZLE_128B
-inline bool make_tmap_rows32(CUtensorMap *tm, const float *base, int rows, int cols, int ld) {
+// fp32 row-major [rows, cols] with `ld` floats between rows, boxes of box_rows x 32 columns (one
+// 128-byte swizzle row per box row), SWIZZLE_128B.  Reads outside [rows, cols] are zero-filled, writes
+// outside are dropped.
+inline bool make_tmap_rows32(CUtensorMap *tm, const float *base, int rows, int cols, int ld, int box_rows = 32) {
   EncodeTiledFn enc = encode_tiled();
   if (enc == nullptr) return false;
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
-  const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+  const cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)}, estr[2] = {1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// TMA tensor load of one box (its rows x 32 columns at (col0, row0)) into 1024-byte aligned shared
+// memory; completes `bytes` = box bytes on `bar` (zero-filled parts included).  One thread calls.
+__device__ __forceinline__ void tma_load_box(const CUtensorMap *tm, void *dst_smem, int col0, int row0, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(col0), "r"(row0)
+      : "memory");
 }
 
 // ---- TMA tensor store of one warp's 32 x 32 fp32 block (row = lane) ---------------------------------
