@@ -54,6 +54,8 @@ def parse():
     p.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of from a CUDA graph")
     p.add_argument("--no-prefetch", action="store_true",
                    help="compute each batch's sampling/grouping geometry inline instead of one batch ahead")
+    p.add_argument("--no-split", action="store_true",
+                   help="one CUDA graph for the whole step (the next batch's geometry then starts beside the forward pass)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-per-op", action="store_true")
     p.add_argument("--cpu-sample-chunks", type=int, default=2)
@@ -244,9 +246,11 @@ def run_product(args, world, rank, local):
     if not args.no_graph:
         try:  # single GPU: the whole step; DP: forward+backward in the graph, NCCL + Adam after it
             cls = train.GraphedTrainStep if args.no_prefetch else train.PipelinedTrainStep
-            step = cls(eager, dev[0], scope="step" if world == 1 else "fwd_bwd")
+            kw = {} if args.no_prefetch else {"split_fwd_bwd": not args.no_split}
+            step = cls(eager, dev[0], scope="step" if world == 1 else "fwd_bwd", **kw)
             launch_mode = "cuda-graph(%s)%s" % (step.scope, "" if args.no_prefetch else
-                                                 " + geometry of batch i+1 prefetched on a side stream")
+                                                 " + geometry of batch i+1 prefetched on a side stream"
+                                                 + ("" if args.no_split else ", released after the forward pass"))
         except Exception as e:  # noqa: BLE001
             sys.stderr.write("CUDA graph capture failed, running eagerly: %r\n" % (e,))
             torch.cuda.synchronize()

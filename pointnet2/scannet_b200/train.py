@@ -29,6 +29,12 @@ def weighted_cross_entropy(logits, targets, weights=None):
     return _loss.weighted_cross_entropy(logits, targets, weights)
 
 
+# timing experiment only (results invalid): skip the geometry graph, i.e. train every batch on the first
+# batch's sampling / grouping indices -- shows how much of the overlapped geometry work is NOT hidden
+import os as _os
+_STALE_GEOMETRY = _os.environ.get("PN2_STALE_GEOMETRY") == "1"
+
+
 class GradBucket(object):
     """All gradients of a module as views into one contiguous fp32 buffer."""
 
@@ -133,17 +139,23 @@ class TrainStep(object):
             return dist.get_world_size(self.group)
         return 1
 
-    def forward_backward(self, pointcloud, targets, weights, plan=None):
+    def forward_loss(self, pointcloud, targets, weights, plan=None):
         if self.flat_mode:
             self.opt.zero_grad()
         else:
             self.bucket.zero()
         logits = self.model(pointcloud, plan) if plan is not None else self.model(pointcloud)
-        loss = weighted_cross_entropy(logits.reshape(-1, logits.size(-1)),
+        return weighted_cross_entropy(logits.reshape(-1, logits.size(-1)),
                                       targets.reshape(-1), weights.reshape(-1))
+
+    def backward_pack(self, loss):
         loss.backward()
         if self.flat_mode:
             self.opt.pack_grads()
+
+    def forward_backward(self, pointcloud, targets, weights, plan=None):
+        loss = self.forward_loss(pointcloud, targets, weights, plan)
+        self.backward_pack(loss)
         return loss
 
     def reduce_and_update(self):
@@ -211,7 +223,7 @@ class PipelinedTrainStep(object):
     computed by the same kernels; only WHEN it is computed changes.  Call ``prefetch(batch)`` with
     the next batch before (or right after) calling the step on the current one."""
 
-    def __init__(self, step, example, scope="step", warmup=3):
+    def __init__(self, step, example, scope="step", warmup=3, split_fwd_bwd=True):
         from . import geometry
         assert scope in ("step", "fwd_bwd")
         self.step, self.scope = step, scope
@@ -240,11 +252,28 @@ class PipelinedTrainStep(object):
         with torch.cuda.graph(self.geo_graph, stream=self.side):
             fresh = geometry.build_plan(model, self.next[0][..., 0:3].contiguous())
             self.plan_next.copy_from(fresh)
-        # graph 2 (main stream): the training step on (static, plan)
+        # graphs 2a / 2b (main stream): the training step on (static, plan), split after the forward pass.
+        # The geometry graph of the NEXT batch is released by an event recorded between the two, so that it
+        # overlaps the backward pass -- whose tensor-core layers hand out their row tiles dynamically and
+        # keep their speed when FPS holds 32 SMs -- instead of the forward pass, whose statically tiled
+        # layers wait for the CTAs that cannot become resident (measured: 0.48 ms of the 1.0 ms of geometry
+        # work stayed exposed when it started together with the step).
+        self.split = split_fwd_bwd
+        self.fwd_done = torch.cuda.Event()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._body()
+        if self.split:
+            with torch.cuda.graph(self.graph):
+                self.loss = self.step.forward_loss(*self.static, plan=self.plan)
+            self.graph_bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_bwd, pool=self.graph.pool()):
+                self.step.backward_pack(self.loss)
+                if self.scope == "step":
+                    self.step.reduce_and_update()
+        else:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._body()
         self._have_next = False
+        self._fwd_recorded = False
         torch.cuda.synchronize()
 
     def _body(self):
@@ -260,7 +289,10 @@ class PipelinedTrainStep(object):
         with torch.cuda.stream(self.side):
             for s, t in zip(self.next, (pointcloud, targets, weights)):
                 s.copy_(t, non_blocking=True)
-            self.geo_graph.replay()
+            if self.split and self._fwd_recorded:
+                self.side.wait_event(self.fwd_done)   # start beside the backward pass of the running step
+            if not _STALE_GEOMETRY:
+                self.geo_graph.replay()
             self.ready.record(self.side)
         self._have_next = True
         del main
@@ -277,6 +309,10 @@ class PipelinedTrainStep(object):
         self.copied.record(main)
         self._have_next = False
         self.graph.replay()
+        if self.split:
+            self.fwd_done.record(main)
+            self._fwd_recorded = True
+            self.graph_bwd.replay()
         if self.scope == "fwd_bwd":
             self.step.reduce_and_update()
         return self.loss

@@ -352,3 +352,28 @@ def test_dropout_mask_generator():
     big = torch.empty(1 << 22, dtype=torch.uint8, device=DEV)
     lib.check(L.pn2_dropout_mask(big.numel(), 0.8, state2.data_ptr(), big.data_ptr(), s), "mask")
     assert abs(float(big.float().mean()) - 0.8) < 2e-3
+
+
+@pytest.mark.parametrize("B,n,m,c2,c1", [(3, 8192, 1024, 128, 6), (2, 1024, 256, 256, 64), (2, 256, 64, 256, 128),
+                                         (2, 64, 16, 512, 256), (1, 1000, 100, 64, 0), (2, 777, 50, 96, 3),
+                                         (1, 300, 40, 36, 5)])
+def test_fp_interp_rows_bit_exact(B, n, m, c2, c1):
+    """pn2_fp_interp_rows (both the shared-memory variant and the plain gather kernel, whichever the
+    launcher picks for the shape) against the reference's arithmetic evaluated by torch elementwise ops:
+    ((k1*w1) + (k2*w2)) + (k3*w3), one rounding per operation (interpolate_gpu.cu:95-98) -- bit-exact --
+    followed by the skip columns and zero padding (pointnet2_modules.py:407-412)."""
+    g = torch.Generator(device="cpu").manual_seed(n + m)
+    known = torch.randn(B, m, c2, generator=g).to(DEV)
+    skip = torch.randn(B, n, c1, generator=g).to(DEV) if c1 else None
+    idx = torch.randint(0, m, (B, n, 3), generator=g, dtype=torch.int32).to(DEV)
+    w = torch.rand(B, n, 3, generator=g).to(DEV)
+    rows = fused.FPInterpRows.apply(known, skip, idx, w)
+    ct = fused.pad4(c2 + c1)
+    assert rows.shape == (B * n, ct)
+    gath = [torch.gather(known, 1, idx[:, :, t].long().unsqueeze(-1).expand(-1, -1, c2)) for t in range(3)]
+    want = (gath[0] * w[:, :, 0:1] + gath[1] * w[:, :, 1:2]) + gath[2] * w[:, :, 2:3]
+    got = rows.view(B, n, ct)
+    assert torch.equal(got[:, :, :c2], want)
+    if c1:
+        assert torch.equal(got[:, :, c2:c2 + c1], skip)
+    assert float(got[:, :, c2 + c1:].abs().max()) == 0.0 if ct > c2 + c1 else True
