@@ -151,3 +151,24 @@ def adversarial_clouds(seed=7):
         .reshape(-1, 3).astype(np.float32) + 1.0
     out["n_300"] = rng.uniform(0.5, 2.0, (300, 3)).astype(np.float32)[rng.integers(0, 150, 300)]
     return out
+
+
+def make_prep_scene(seed, npoints=40000, size=(4.0, 3.5, 2.7), num_classes=21, multiview=0):
+    """A synthetic scene in the reference's PREPROCESSED file format
+    (/root/reference/preprocessing/collect_scannet_scenes.py:64-79): float64 (npoints, 11) rows
+    [x y z | r g b in 0..255 | nx ny nz | instance | semantic label], the point columns holding
+    float32-representable values (they come from a float32 .ply).  About 15 % of the points are
+    unannotated (label 0).  `multiview` > 0 also returns a float32 (npoints, multiview) feature
+    matrix (the h5py rows of lib/dataset.py:46-47)."""
+    rng = np.random.default_rng(seed)
+    s9 = make_scene(seed, npoints=npoints, size=size).astype(np.float64)
+    s9[:, 3:6] = np.floor(s9[:, 3:6] * 256.0).clip(0, 255)
+    label = rng.integers(1, num_classes, npoints).astype(np.float64)
+    label[rng.random(npoints) < 0.15] = 0.0
+    inst = rng.integers(0, 40, npoints).astype(np.float64)
+    scene = np.concatenate([s9, inst[:, None], label[:, None]], axis=1)
+    if multiview:
+        feat = np.maximum(rng.normal(0, 1, (npoints, multiview)), 0).astype(np.float32)
+        feat[rng.random(npoints) < 0.3] = 0.0
+        return scene, feat
+    return scene
