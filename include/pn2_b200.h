@@ -375,6 +375,43 @@ PN2_API int pn2_weighted_ce_bwd(int p, int c, long long ignore_index, const floa
                                 const long long *targets, const float *weights, const float *lse,
                                 const float *grad_loss, float *dlogits, void *stream);
 
+/* ==========================================================================
+ * Chunk generation with the scene resident in HBM (csrc/chunker.cu).
+ * Replaces the NumPy code of lib/dataset.py that cuts training chunks
+ * (ScannetDataset.generate_chunks :204-250, __getitem__ :61-94, _augment :99-200) and
+ * whole-scene tiles (ScannetDatasetWholeScene.__getitem__ :293-353) and collate_*'s casts
+ * (:379-381).  scene [n, ld] float32 rows in the reference's preprocessed layout
+ * (x y z | r g b 0..255 | nx ny nz | instance | label; collect_scannet_scenes.py:64-79 --
+ * float64 there, float32-representable values); comparisons and arithmetic run in double
+ * exactly as NumPy's; the random draws are made by the caller (np.random) and passed in.
+ *
+ * pn2_crop_try: one try of generate_chunks (:220-238) around scene row `centre_row`:
+ *   sel[0 .. count) = rows inside [curmin - 0.2, curmax + 0.2] in scene order;
+ *   stats[4] = {count, rows with label > 0, occupied voxels of the 31 x 31 x 62 grid among the rows
+ *   inside [curmin - 0.01, curmax + 0.01], rows whose voxel key is not finite (degenerate box)}.
+ * pn2_box_select: nbox boxes [lo, hi] (double [nbox, 3], device): sel [nbox, n], count [nbox] and
+ *   (optional) mask [nbox, n] bytes = the scene-length membership mask.
+ * pn2_chunk_centre: centre[3] (double, device) = mean of the xyz of rows sel[choice[i]]
+ *   (sel NULL: choice[i] are scene rows).
+ * pn2_chunk_assemble: out [npoints, ldo] float32 = [xyz | features(feat_first) | rgb / 255 | normal |
+ *   features(!feat_first)] of those rows, labels int64, weights = labelweights[label] (* wmask[choice[i]]
+ *   when wmask is given: the reference's `mask = mask[choice]`, :334).  aug_ops: bit 0 translate,
+ *   bit 1 rotate, bit 2 scale, applied in that order about `centre`; aug_host: 13 HOST doubles
+ *   t[3], R[9] row-major, f (read during the call).
+ * ========================================================================== */
+PN2_API int pn2_crop_try(int n, int ld, const float *scene, int label_col, int centre_row, double zmin,
+                         double zmax, int *sel, int *stats, void *stream);
+PN2_API int pn2_box_select(int n, int ld, const float *scene, int nbox, const double *lo, const double *hi,
+                           int *sel, int *count, unsigned char *mask, void *stream);
+PN2_API int pn2_chunk_centre(int npoints, int ld, const float *scene, const int *sel, const int *choice,
+                             double *centre, void *stream);
+PN2_API int pn2_chunk_assemble(int npoints, int ld, const float *scene, const int *sel, const int *choice,
+                               const float *feature, int nfeat, int feat_first, int use_color,
+                               int use_normal, int label_col, const float *labelweights, int num_classes,
+                               const unsigned char *wmask, const double *centre, int aug_ops,
+                               const double *aug_host, int ldo, float *out, long long *labels,
+                               float *weights, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

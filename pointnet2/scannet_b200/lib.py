@@ -72,6 +72,12 @@ SIGNATURES = {
     "pn2_weighted_ce_partials": [_i],
     "pn2_weighted_ce_fwd": [_i, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_weighted_ce_bwd": [_i, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    # chunk generation (scene resident in HBM)
+    "pn2_crop_try": [_i, _i, _vp, _i, _i, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp],
+    "pn2_box_select": [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pn2_chunk_centre": [_i, _i, _vp, _vp, _vp, _vp, _vp],
+    "pn2_chunk_assemble": [_i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i,
+                           _vp, _vp, _vp, _vp],
 }
 LIBRARY_SYMBOLS = ("pn2_abi_version", "pn2_launch_count", "pn2_reset_launch_count",
                    "pn2_status_string")
