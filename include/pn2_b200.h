@@ -398,7 +398,16 @@ PN2_API int pn2_weighted_ce_bwd(int p, int c, long long ignore_index, const floa
  *   when wmask is given: the reference's `mask = mask[choice]`, :334).  aug_ops: bit 0 translate,
  *   bit 1 rotate, bit 2 scale, applied in that order about `centre`; aug_host: 13 HOST doubles
  *   t[3], R[9] row-major, f (read during the call).
+ * pn2_chunk_batch: the same for `nchunk` chunks in two launches.  desc: DEVICE array of nchunk records of
+ * pn2_chunk_desc_bytes() bytes: { scene, feature, sel, choice, wmask pointers (8 bytes each); int ld, nfeat;
+ * int aug_ops, 4 bytes padding; double t[3], R[9], f; double centre[3] (scratch, written by the call) };
+ * out [nchunk, npoints, ldo], labels / weights [nchunk, npoints].  The row checks of
+ * pn2_chunk_assemble (ld, nfeat against ldo) are the caller's.
  * ========================================================================== */
+PN2_API int pn2_chunk_desc_bytes(void);
+PN2_API int pn2_chunk_batch(int nchunk, int npoints, void *desc, int feat_first, int use_color,
+                            int use_normal, int label_col, const float *labelweights, int num_classes,
+                            int ldo, float *out, long long *labels, float *weights, void *stream);
 PN2_API int pn2_crop_try(int n, int ld, const float *scene, int label_col, int centre_row, double zmin,
                          double zmax, int *sel, int *stats, void *stream);
 PN2_API int pn2_box_select(int n, int ld, const float *scene, int nbox, const double *lo, const double *hi,

@@ -33,6 +33,10 @@ import torch
 from . import lib as _lib
 
 LABEL_COL = 10  # lib/dataset.py:39, 71
+# one record per chunk of a batched launch: csrc/chunker.cu's ChunkDesc (size checked at first use)
+DESC = np.dtype([("scene", "u8"), ("feature", "u8"), ("sel", "u8"), ("choice", "u8"), ("wmask", "u8"),
+                 ("ld", "i4"), ("nfeat", "i4"), ("ops", "i4"), ("_pad", "i4"), ("t", "f8", 3), ("R", "f8", 9),
+                 ("f", "f8"), ("centre", "f8", 3)])
 
 
 def _stream(dev):
@@ -80,10 +84,18 @@ def _label_weights(scenes, num_classes, is_weighting):
     return 1 / np.log(1.2 + hist)
 
 
+# the populations of the reference's np.random.choice calls (lib/dataset.py:104, 148-150, 162-186, 200);
+# choice() on a cached array consumes the generator exactly like choice() on a fresh np.arange
+_POP_P = np.arange(0.01, 1.01, 0.01)
+_POP_T = np.arange(-0.5, 0.501, 0.001)
+_POP_R = np.arange(-5, 5.001, 0.001)
+_POP_S = np.arange(0.95, 1.051, 0.001)
+
+
 def _draw_augmentation():
     """The draws of _augment / _translate / _rotate / _scale (lib/dataset.py:104-137, 148-150, 162-186,
     200) from np.random, in the reference's order -> (ops bit mask, 13 doubles t | R | f)."""
-    p = np.random.choice(np.arange(0.01, 1.01, 0.01), size=1)[0]
+    p = np.random.choice(_POP_P, size=1)[0]
     eighth = int(p >= 1 / 8) + int(p >= 2 / 8) + int(p >= 3 / 8) + int(p >= 4 / 8) + int(p >= 5 / 8) \
         + int(p >= 6 / 8) + int(p >= 7 / 8)
     ops = ("t", "r", "s", "tr", "ts", "rs", "trs", "")[eighth]
@@ -95,17 +107,17 @@ def _draw_augmentation():
         if op == "t":
             mask |= 1
             for d in range(3):
-                params[d] = np.random.choice(np.arange(-0.5, 0.501, 0.001), size=1)[0]
+                params[d] = np.random.choice(_POP_T, size=1)[0]
         elif op == "r":
             mask |= 2
-            a, b, c = (np.random.choice(np.arange(-5, 5.001, 0.001), size=1)[0] * 3.14 / 180 for _ in range(3))
+            a, b, c = (np.random.choice(_POP_R, size=1)[0] * 3.14 / 180 for _ in range(3))
             Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
             Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
             Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
             params[3:12] = np.matmul(np.matmul(Rz, Ry), Rx).ravel()
         else:
             mask |= 4
-            params[12] = np.random.choice(np.arange(0.95, 1.051, 0.001), size=1)[0]
+            params[12] = np.random.choice(_POP_S, size=1)[0]
     return mask, params
 
 
@@ -127,6 +139,28 @@ class _Base(object):
     def channels(self):
         return 3 * int(self.use_color) + 3 * int(self.use_normal) + \
             (next(iter(self.stores.values())).nfeat if self.use_multiview else 0)
+
+    def _assemble_batch(self, entries, npoints, out, labels, weights, feat_first):
+        """entries: [(store, sel or None, choice, wmask or None, aug or None)] -> out [len, npoints, ldo] in
+        two launches (one descriptor table, one host->device copy)."""
+        L, dev = self._L, self.device
+        if L.pn2_chunk_desc_bytes() != DESC.itemsize:
+            raise RuntimeError("ChunkDesc layout mismatch: rebuild libpn2_b200.so")
+        desc = np.zeros(len(entries), DESC)
+        for d, (st, sel, choice, wmask, aug) in zip(desc, entries):
+            d["scene"], d["ld"], d["nfeat"] = st.rows.data_ptr(), st.ld, st.nfeat
+            d["feature"] = st.feature.data_ptr() if st.nfeat else 0
+            d["sel"] = sel.data_ptr() if sel is not None else 0
+            d["choice"] = choice.data_ptr()
+            d["wmask"] = wmask.data_ptr() if wmask is not None else 0
+            if aug is not None and aug[0]:
+                d["ops"], d["t"], d["R"], d["f"] = aug[0], aug[1][:3], aug[1][3:12], aug[1][12]
+        table = torch.from_numpy(desc.view(np.uint8).reshape(len(entries), DESC.itemsize)).to(dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.pn2_chunk_batch(len(entries), npoints, table.data_ptr(), int(feat_first),
+                                         int(self.use_color), int(self.use_normal), LABEL_COL, self._lw.data_ptr(),
+                                         self.num_classes, out.shape[-1], out.data_ptr(), labels.data_ptr(),
+                                         weights.data_ptr(), _stream(dev)), "chunk_batch")
 
     def _assemble(self, st, sel, choice, out, labels, weights, feat_first, wmask=None, aug=None):
         L, dev = self._L, self.device
@@ -218,8 +252,12 @@ class ScannetDataset(_Base):
         out = torch.empty(B, self.npoints, c, dtype=torch.float32, device=dev)
         labels = torch.empty(B, self.npoints, dtype=torch.int64, device=dev)
         weights = torch.empty(B, self.npoints, dtype=torch.float32, device=dev)
-        for b, i in enumerate(indices):
-            self._item_into(i, out[b], labels[b], weights[b])
+        entries = []
+        for i in indices:   # the augmentation draws, item by item in the reference's order
+            scene_id = self.scene_list[i]
+            entries.append((self.stores[scene_id], None, self.chunk_data[scene_id], None,
+                            _draw_augmentation() if self.phase == "train" else None))
+        self._assemble_batch(entries, self.npoints, out, labels, weights, feat_first=True)
         return out[:, :, :3], out[:, :, 3:], labels, weights, time.time() - start
 
 
@@ -269,8 +307,8 @@ class ScannetDatasetWholeScene(_Base):
         out = torch.empty(K, self.npoints, c, dtype=torch.float32, device=dev)
         labels = torch.empty(K, self.npoints, dtype=torch.int64, device=dev)
         weights = torch.empty(K, self.npoints, dtype=torch.float32, device=dev)
-        for t, b in enumerate(keep):
-            self._assemble(st, sel[b], choice[t], out[t], labels[t], weights[t], feat_first=False, wmask=mask[b])
+        self._assemble_batch([(st, sel[b], choice[t], mask[b], None) for t, b in enumerate(keep)], self.npoints,
+                             out, labels, weights, feat_first=False)
         return out, labels, weights, time.time() - start
 
 

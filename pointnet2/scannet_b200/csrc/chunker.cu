@@ -165,9 +165,9 @@ __device__ __forceinline__ int source_row(const int *__restrict__ sel, const int
 }
 
 // centre[d] = mean over the chunk's rows of the d-th coordinate, in double (fixed summation tree).
-__global__ void __launch_bounds__(kSelThreads)
-chunk_centre_kernel(int npoints, int ld, const float *__restrict__ scene, const int *__restrict__ sel,
-                    const int *__restrict__ choice, double *__restrict__ centre) {
+__device__ __forceinline__ void chunk_centre(int npoints, int ld, const float *__restrict__ scene,
+                                             const int *__restrict__ sel, const int *__restrict__ choice,
+                                             double *__restrict__ centre) {
   __shared__ double s_sum[kSelThreads / 32][3];
   double acc[3] = {0.0, 0.0, 0.0};
   for (int i = threadIdx.x; i < npoints; i += kSelThreads) {
@@ -188,6 +188,12 @@ chunk_centre_kernel(int npoints, int ld, const float *__restrict__ scene, const 
   }
 }
 
+__global__ void __launch_bounds__(kSelThreads)
+chunk_centre_kernel(int npoints, int ld, const float *__restrict__ scene, const int *__restrict__ sel,
+                    const int *__restrict__ choice, double *__restrict__ centre) {
+  chunk_centre(npoints, ld, scene, sel, choice, centre);
+}
+
 struct Augment {   // _augment's draws (lib/dataset.py:104-137): ops applied in the order t, r, s
   int ops;         // bit 0 translate, bit 1 rotate, bit 2 scale
   double t[3], R[9], f;
@@ -198,14 +204,14 @@ constexpr int kAsmRows = 256;  // rows per CTA
 
 // out[i, :] = [xyz' | (features) | rgb / 255 | normal | (features)] of scene row sel[choice[i]] as float32,
 // labels[i] = (int) label column, weights[i] = labelweights[label] * (wmask ? wmask[choice[i]] : 1).
-__global__ void __launch_bounds__(kAsmThreads)
-chunk_assemble_kernel(int npoints, int ld, const float *__restrict__ scene, const int *__restrict__ sel,
-                      const int *__restrict__ choice, const float *__restrict__ feature, int nfeat,
-                      int feat_first, int use_color, int use_normal, int label_col,
-                      const float *__restrict__ labelweights, int num_classes,
-                      const unsigned char *__restrict__ wmask, const double *__restrict__ centre, Augment aug,
-                      int ldo, float *__restrict__ out, long long *__restrict__ labels,
-                      float *__restrict__ weights) {
+__device__ __forceinline__ void
+chunk_assemble(int npoints, int ld, const float *__restrict__ scene, const int *__restrict__ sel,
+               const int *__restrict__ choice, const float *__restrict__ feature, int nfeat,
+               int feat_first, int use_color, int use_normal, int label_col,
+               const float *__restrict__ labelweights, int num_classes,
+               const unsigned char *__restrict__ wmask, const double *__restrict__ centre, const Augment &aug,
+               int ldo, float *__restrict__ out, long long *__restrict__ labels,
+               float *__restrict__ weights) {
   __shared__ int s_src[kAsmRows];
   const int row0 = blockIdx.x * kAsmRows;
   const int rows = min(kAsmRows, npoints - row0);
@@ -268,6 +274,49 @@ chunk_assemble_kernel(int npoints, int ld, const float *__restrict__ scene, cons
     out[static_cast<size_t>(row0 + rr) * ldo + col0 + cc] =
         __ldg(feature + static_cast<size_t>(s_src[rr]) * nfeat + cc);
   }
+}
+
+__global__ void __launch_bounds__(kAsmThreads)
+chunk_assemble_kernel(int npoints, int ld, const float *__restrict__ scene, const int *__restrict__ sel,
+                      const int *__restrict__ choice, const float *__restrict__ feature, int nfeat,
+                      int feat_first, int use_color, int use_normal, int label_col,
+                      const float *__restrict__ labelweights, int num_classes,
+                      const unsigned char *__restrict__ wmask, const double *__restrict__ centre, Augment aug,
+                      int ldo, float *__restrict__ out, long long *__restrict__ labels,
+                      float *__restrict__ weights) {
+  chunk_assemble(npoints, ld, scene, sel, choice, feature, nfeat, feat_first, use_color, use_normal, label_col,
+                 labelweights, num_classes, wmask, centre, aug, ldo, out, labels, weights);
+}
+
+// ---- a whole batch in two launches: one descriptor per chunk (scenes differ per chunk) ----------------
+struct ChunkDesc {              // mirrored by chunker.py's DESC dtype (pn2_chunk_desc_bytes checks the size)
+  const float *scene;
+  const float *feature;
+  const int *sel;
+  const int *choice;
+  const unsigned char *wmask;
+  int ld, nfeat;
+  Augment aug;                  // ops (+ 4 bytes padding), t[3], R[9], f
+  double centre[3];             // written by chunk_centre_batch_kernel
+};
+
+__global__ void __launch_bounds__(kSelThreads)
+chunk_centre_batch_kernel(int npoints, ChunkDesc *__restrict__ desc) {
+  ChunkDesc *d = desc + blockIdx.x;
+  if (d->aug.ops == 0) return;
+  chunk_centre(npoints, d->ld, d->scene, d->sel, d->choice, d->centre);
+}
+
+__global__ void __launch_bounds__(kAsmThreads)
+chunk_assemble_batch_kernel(int npoints, const ChunkDesc *__restrict__ desc, int feat_first, int use_color,
+                            int use_normal, int label_col, const float *__restrict__ labelweights,
+                            int num_classes, int ldo, float *__restrict__ out, long long *__restrict__ labels,
+                            float *__restrict__ weights) {
+  const ChunkDesc *d = desc + blockIdx.y;
+  const size_t off = static_cast<size_t>(blockIdx.y) * npoints;
+  chunk_assemble(npoints, d->ld, d->scene, d->sel, d->choice, d->feature, d->nfeat, feat_first, use_color,
+                 use_normal, label_col, labelweights, num_classes, d->wmask, d->centre, d->aug, ldo,
+                 out + off * ldo, labels + off, weights + off);
 }
 
 }  // namespace pn2
@@ -336,5 +385,24 @@ extern "C" int pn2_chunk_assemble(int npoints, int ld, const float *scene, const
       npoints, ld, scene, sel, choice, feature, nfeat, feat_first != 0, use_color != 0, use_normal != 0,
       label_col, labelweights, num_classes, wmask, centre, aug, ldo, out, labels, weights);
   count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_chunk_desc_bytes(void) { return static_cast<int>(sizeof(ChunkDesc)); }
+
+extern "C" int pn2_chunk_batch(int nchunk, int npoints, void *desc, int feat_first, int use_color,
+                               int use_normal, int label_col, const float *labelweights, int num_classes,
+                               int ldo, float *out, long long *labels, float *weights, void *stream) {
+  if (nchunk <= 0 || nchunk > 65535 || npoints <= 0 || num_classes <= 0 || label_col < 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(desc, labelweights, out, labels, weights);
+  if ((reinterpret_cast<uintptr_t>(desc) & 7u) != 0 || (reinterpret_cast<uintptr_t>(labels) & 7u) != 0)
+    return PN2_ERR_ALIGNMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  chunk_centre_batch_kernel<<<nchunk, kSelThreads, 0, s>>>(npoints, static_cast<ChunkDesc *>(desc));
+  const dim3 grid((npoints + kAsmRows - 1) / kAsmRows, nchunk);
+  chunk_assemble_batch_kernel<<<grid, kAsmThreads, 0, s>>>(
+      npoints, static_cast<const ChunkDesc *>(desc), feat_first != 0, use_color != 0, use_normal != 0, label_col,
+      labelweights, num_classes, ldo, out, labels, weights);
+  count_launch(2);
   PN2_RETURN_LAUNCH_STATUS();
 }

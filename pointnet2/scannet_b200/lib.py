@@ -75,6 +75,8 @@ SIGNATURES = {
     # chunk generation (scene resident in HBM)
     "pn2_crop_try": [_i, _i, _vp, _i, _i, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp],
     "pn2_box_select": [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pn2_chunk_desc_bytes": [],
+    "pn2_chunk_batch": [_i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_chunk_centre": [_i, _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_chunk_assemble": [_i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i,
                            _vp, _vp, _vp, _vp],
