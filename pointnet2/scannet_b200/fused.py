@@ -13,6 +13,8 @@ Numerics: BatchNorm statistics fp32 partials + fp64 finalise; GEMMs in TF32 when
 ``GEMM_TF32`` (the arithmetic class of the reference's own cuDNN convs, whose
 ``cudnn.allow_tf32`` defaults to True) or in fp32 otherwise.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -82,6 +84,65 @@ def _sched_counters(dev):
     return buf
 
 
+# ---- weight-tile packing beside the step ------------------------------------------------------------
+# The tensor-core layers read their weights as pre-packed UMMA tile images (pn2_mlp_pack_weights[_t]):
+# ~33 tiny launches per SSG step that depend on nothing but the weights.  Inside ``pack_branch`` they
+# run on a forked side stream (a parallel branch of the captured step graph) into PERSISTENT tile
+# buffers -- persistent because a buffer from the per-step allocator could be a block whose previous
+# tenant is still in flight on the main stream -- and the consuming layer waits for its own pack event.
+PACK_BRANCH = os.environ.get("PN2_PACK_BRANCH", "1") != "0"
+_pack_state = {"stream": None, "active": False, "bufs": {}}
+
+
+class pack_branch(object):
+    """with pack_branch(dev): forward pass -- fork at entry, join at exit (capture-legal)."""
+
+    def __init__(self, dev):
+        self.dev = torch.device(dev)
+
+    def __enter__(self):
+        self.on = PACK_BRANCH and ENABLED and self.dev.type == "cuda" and not _pack_state["active"]
+        if self.on:
+            if _pack_state["stream"] is None:
+                _pack_state["stream"] = torch.cuda.Stream(self.dev)
+            _pack_state["stream"].wait_stream(torch.cuda.current_stream(self.dev))
+            _pack_state["active"] = True
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            _pack_state["active"] = False
+            torch.cuda.current_stream(self.dev).wait_stream(_pack_state["stream"])
+        return False
+
+
+def _packed(kind, W2, dims, floats, launch):
+    """Tile image of W2 for this step: launch(ptr, stream) packs it.  Inside a pack_branch the launch
+    goes to the branch stream and the current stream waits for it; outside, it is an ordinary launch
+    into a per-step buffer."""
+    dev = W2.device
+    if not _pack_state["active"]:
+        buf = torch.empty(floats, dtype=torch.float32, device=dev)
+        launch(buf.data_ptr(), _stream(dev))
+        return buf
+    key = (kind, W2.data_ptr(), dims, floats)
+    buf = _pack_state["bufs"].get(key)
+    if buf is None:
+        if torch.cuda.is_current_stream_capturing():
+            # never allocate a persistent buffer from a graph's private pool: this layer packs in line
+            # (callers that want the branch inside a graph run one eager step first, as the trainers do)
+            buf = torch.empty(floats, dtype=torch.float32, device=dev)
+            launch(buf.data_ptr(), _stream(dev))
+            return buf
+        buf = _pack_state["bufs"][key] = torch.empty(floats, dtype=torch.float32, device=dev)
+    side = _pack_state["stream"]
+    launch(buf.data_ptr(), side.cuda_stream)
+    ev = torch.cuda.Event()
+    ev.record(side)
+    torch.cuda.current_stream(dev).wait_event(ev)
+    return buf
+
+
 def _ws(c, dev):
     n = _lib.load().pn2_bn_stats_workspace_floats(c) + 2 * c
     return torch.empty(n, dtype=torch.float32, device=dev)
@@ -125,8 +186,8 @@ def _tc_layer(A, k, W2, fold, relu_in, want_h, want_stats, drop=None, pool_ns=0)
     bn, nt, kb = L.pn2_mlp_gemm_bn(P, N), L.pn2_mlp_gemm_n_tiles(P, N), L.pn2_mlp_gemm_k_blocks(k)
     grid = L.pn2_mlp_gemm_grid(P, N)
     W2 = W2.contiguous()
-    Wp = torch.empty(nt * kb * bn * 32, dtype=torch.float32, device=dev)
-    _lib.check(L.pn2_mlp_pack_weights(P, N, k, W2.shape[1], W2.data_ptr(), Wp.data_ptr(), s), "mlp_pack_weights")
+    Wp = _packed("fwd", W2, (P, N, k), nt * kb * bn * 32, lambda ptr, st: _lib.check(
+        L.pn2_mlp_pack_weights(P, N, k, W2.shape[1], W2.data_ptr(), ptr, st), "mlp_pack_weights"))
     z = torch.empty(P, N, dtype=torch.float32, device=dev)
     h = torch.empty_like(A) if (want_h and fold is not None) else None
     part = torch.empty(grid, 2, nt * bn, dtype=torch.float32, device=dev) if want_stats else None
@@ -183,6 +244,7 @@ class SharedMLPRows(Function):
         use_tc = TC_GEMM and GEMM_TF32
         want_grad = any(ctx.needs_input_grad)
         bwd_fused = [False] * nl
+        wt_packed = [None] * nl   # transposed tile images for the fused backward layers, packed beside the forward pass
         with torch.cuda.device(dev):
             for l in range(nl):
                 W, gamma, beta = params[3 * l:3 * l + 3]
@@ -213,6 +275,12 @@ class SharedMLPRows(Function):
                     st.z, h, part, (ld, nblk) = res[:4]
                     if pool_here:
                         ext = res[4]
+                    if bwd_fused[l] and _pack_state["active"] and (l > 0 or ctx.needs_input_grad[0]):
+                        W2c, Cn, Kk = W2.contiguous(), W2.shape[0], W2.shape[1]
+                        wt_packed[l] = _packed(
+                            "bwd", W2c, (Cn, Kk, lda), L.pn2_mlp_bwd_nb(Cn) * L.pn2_mlp_bwd_kpad(lda) * 32,
+                            lambda ptr, strm: _lib.check(L.pn2_mlp_pack_weights_t(
+                                Cn, Kk, lda, W2c.shape[1], W2c.data_ptr(), ptr, strm), "mlp_pack_weights_t"))
                     if l > 0:
                         hs.append(h)          # None when the fused backward layer will recompute it
                     if training:
@@ -255,7 +323,7 @@ class SharedMLPRows(Function):
                     _lib.check(L.pn2_bn_relu_groupmax(G, ns, C, st.z.data_ptr(), st.a.data_ptr(),
                                                       st.b.data_ptr(), out.data_ptr(), argmax.data_ptr(),
                                                       _stream(dev)), "bn_relu_groupmax")
-        ctx.layers, ctx.hs, ctx.argmax, ctx.bwd_fused = layers, hs, argmax, bwd_fused
+        ctx.layers, ctx.hs, ctx.argmax, ctx.bwd_fused, ctx.wt_packed = layers, hs, argmax, bwd_fused, wt_packed
         assert use_tc or not any(d is not None for d in drops), "dropout inside the chain needs the tensor-core path"
         ctx.ns, ctx.training, ctx.nl, ctx.relus, ctx.drops = ns, training, nl, relus, drops
         ctx.weights = [params[3 * l] for l in range(nl)]
@@ -310,9 +378,11 @@ class SharedMLPRows(Function):
                     wtp = dh_prev = sp = None
                     if need_dh:
                         W2c = W2.contiguous()
-                        wtp = f32(nb * kpad * 32)
-                        _lib.check(L.pn2_mlp_pack_weights_t(C, K, lda, W2c.shape[1], W2c.data_ptr(), wtp.data_ptr(), s),
-                                   "mlp_pack_weights_t")
+                        wtp = ctx.wt_packed[l]
+                        if wtp is None:
+                            wtp = f32(nb * kpad * 32)
+                            _lib.check(L.pn2_mlp_pack_weights_t(C, K, lda, W2c.shape[1], W2c.data_ptr(),
+                                                                wtp.data_ptr(), s), "mlp_pack_weights_t")
                         dh_prev = f32(P, lda)
                         if prev is not None:   # BatchNorm below: the kernel leaves S in dwp and Q in sp
                             sp = f32(grid, nb * 32 * kb * 32)

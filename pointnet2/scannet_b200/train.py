@@ -144,7 +144,9 @@ class TrainStep(object):
             self.opt.zero_grad()
         else:
             self.bucket.zero()
-        logits = self.model(pointcloud, plan) if plan is not None else self.model(pointcloud)
+        from . import fused
+        with fused.pack_branch(pointcloud.device):   # weight-tile packing on a forked branch (CUDA only)
+            logits = self.model(pointcloud, plan) if plan is not None else self.model(pointcloud)
         return weighted_cross_entropy(logits.reshape(-1, logits.size(-1)),
                                       targets.reshape(-1), weights.reshape(-1))
 

@@ -250,7 +250,8 @@ def test_flat_adam_matches_torch_adam():
     assert set(mine.state_dict()) == set(ref.state_dict())
 
 
-def test_pipelined_step_equals_eager_step():
+@pytest.mark.parametrize("warmup", [0, 1])
+def test_pipelined_step_equals_eager_step(warmup):
     """CUDA-graph replay with the geometry of the next batch prefetched on a side stream: (1) the plan
     a step trains with is, bit for bit, the plan of ITS batch (not a stale one); (2) losses follow the
     eager step's (1e-2: Adam's first steps amplify the summation-order noise of the backward pass --
@@ -268,8 +269,12 @@ def test_pipelined_step_equals_eager_step():
         return train.TrainStep(m, lr=1e-3)
 
     eager = make()
+    for _ in range(warmup):          # the pipelined step's warm-up is a real optimisation step on its example batch
+        eager(*batches[2])
     want = [float(eager(*batches[i % 3]).item()) for i in range(5)]
-    piped = train.PipelinedTrainStep(make(), batches[2], warmup=0)
+    # warmup = 1: the weight-tile packing runs as a forked branch of the captured graph (fused.pack_branch);
+    # warmup = 0: no eager step allocated its persistent buffers, so the graph packs in line
+    piped = train.PipelinedTrainStep(make(), batches[2], warmup=warmup)
     piped.prefetch(*batches[0])
     got = []
     for i in range(5):
