@@ -143,6 +143,52 @@ def _packed(kind, W2, dims, floats, launch):
     return buf
 
 
+# ---- weight gradients beside the backward pass -------------------------------------------------------
+# dW of a layer is needed by nobody before the optimiser, while dH_prev is needed by the next kernel.  Inside
+# ``dw_branch`` (the trainers wrap loss.backward() in it) the dW work of the layers that do not run on the
+# fused backward kernel -- the split-K cuBLAS product dZ^T H and its partial sum -- and the dW-only partial
+# sums of the fused layers go to a forked side stream and are joined once, before the gradients are
+# packed.  Their operands are kept referenced until the join (no allocator reuse under the branch's feet).
+DW_BRANCH = os.environ.get("PN2_DW_BRANCH", "1") != "0"
+_dw_state = {"stream": None, "active": False, "keep": [], "warmed": False}
+
+
+class dw_branch(object):
+    def __init__(self, dev):
+        self.dev = torch.device(dev)
+
+    def __enter__(self):
+        self.on = DW_BRANCH and ENABLED and self.dev.type == "cuda" and not _dw_state["active"]
+        if self.on and torch.cuda.is_current_stream_capturing() and not _dw_state["warmed"]:
+            self.on = False   # first use must be eager (cuBLAS handle / workspace of the branch stream)
+        if self.on:
+            if _dw_state["stream"] is None:
+                _dw_state["stream"] = torch.cuda.Stream(self.dev)
+            _dw_state["active"] = True
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            _dw_state["active"] = False
+            torch.cuda.current_stream(self.dev).wait_stream(_dw_state["stream"])
+            _dw_state["keep"].clear()
+            if not torch.cuda.is_current_stream_capturing():
+                _dw_state["warmed"] = True
+        return False
+
+
+def _on_dw_branch(dev, operands, fn):
+    """fn() on the dW branch stream, after everything queued on the current stream so far."""
+    if not _dw_state["active"]:
+        return fn()
+    side = _dw_state["stream"]
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        out = fn()
+    _dw_state["keep"].append((operands, out))
+    return out
+
+
 def _ws(c, dev):
     n = _lib.load().pn2_bn_stats_workspace_floats(c) + 2 * c
     return torch.empty(n, dtype=torch.float32, device=dev)
@@ -419,8 +465,8 @@ class SharedMLPRows(Function):
                                    "mlp_bwd_finalize")
                         pending = (pg, pb, pc)
                     else:
-                        _lib.check(L.pn2_sum_partials(grid, nb * 32 * kb * 32, dwp.data_ptr(), dW.data_ptr(), s),
-                                   "sum_partials")
+                        _on_dw_branch(dev, (dwp, dW), lambda: _lib.check(L.pn2_sum_partials(
+                            grid, nb * 32 * kb * 32, dwp.data_ptr(), dW.data_ptr(), _stream(dev)), "sum_partials"))
                     grads[3 * l] = dW[:C, :K].reshape(W.shape)
                     grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
                     dh = dh_prev
@@ -442,7 +488,7 @@ class SharedMLPRows(Function):
                                                  st.invstd.data_ptr(), dz.data_ptr(), dgamma.data_ptr(),
                                                  dbeta.data_ptr(), ws.data_ptr(), s), "relu_bn_bwd")
                 h_prev = hs[l]
-                dW = _mm_tn_splitk(dz, h_prev)                 # [Cout, Cin(_pad)]
+                dW = _on_dw_branch(dev, (dz, h_prev), lambda: _mm_tn_splitk(dz, h_prev))   # [Cout, Cin(_pad)]
                 if dW.shape[1] != W2.shape[1]:
                     dW = dW[:, :W2.shape[1]]
                 grads[3 * l] = dW.reshape(W.shape)

@@ -151,7 +151,9 @@ class TrainStep(object):
                                       targets.reshape(-1), weights.reshape(-1))
 
     def backward_pack(self, loss):
-        loss.backward()
+        from . import fused
+        with fused.dw_branch(loss.device):   # weight-gradient GEMMs of the wide layers on a forked branch
+            loss.backward()
         if self.flat_mode:
             self.opt.pack_grads()
 
