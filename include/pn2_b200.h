@@ -252,10 +252,11 @@ PN2_API int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const float 
  * leaves, per group of pool_ns rows and channel, the max and the min of z and the first row attaining
  * each (zmax / zmin / imax / imin, [p / pool_ns, n]), read from its staged output blocks -- z is not
  * re-read.  pn2_groupmax_from_extrema turns them into max_s relu(a*z+b) and its arg-max row once the
- * BatchNorm fold (a, b) is known: the sign of a picks max or min. */
+ * BatchNorm fold (a, b) is known: the sign of a picks max or min.  zsel (optional, [g, c]) receives the
+ * picked extremum = z at the arg-max row; pn2_pool_bn_bwd_stats reads it instead of gathering over z. */
 PN2_API int pn2_groupmax_from_extrema(int g, int c, const float *zmax, const float *zmin, const int *imax,
                                       const int *imin, const float *a, const float *b, float *out,
-                                      int *argmax, void *stream);
+                                      int *argmax, float *zsel, void *stream);
 /* drop (optional, [p, k] bytes; needs a_in, excludes h_out): keep mask of an nn.Dropout sitting between
  * the previous layer's activation and this layer (pointnet2_semseg.py:156): act(a) is multiplied by
  * drop ? drop_scale : 0 on the tile, so the dropped activation is never materialised. */
@@ -322,7 +323,8 @@ PN2_API int pn2_mlp_bwd_finalize(int parts, int n, int k, int lda, const float *
  * activated output (its adjoint multiplies dh first) / to the activation of the layer below (H_prev
  * and the ReLU mask of the statistics products carry it). */
 PN2_API int pn2_pool_bn_bwd_stats(int g, int ns, int c, int training, const float *dout,
-                                  const int *argmax, const float *z, const float *a, const float *b,
+                                  const int *argmax, const float *z, const float *zsel /* optional */,
+                                  const float *a, const float *b,
                                   const float *mean, const float *invstd, float *dgamma,
                                   float *dbeta, float *c1c2, float *workspace, void *stream);
 PN2_API int pn2_relu_bn_bwd_stats(int p, int c, int training, int relu, const float *dh,

@@ -224,14 +224,16 @@ __global__ void __launch_bounds__(kRowThreads)
 groupmax_from_extrema_kernel(size_t total, int C, const float *__restrict__ zmax, const float *__restrict__ zmin,
                              const int *__restrict__ imax, const int *__restrict__ imin,
                              const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out,
-                             int *__restrict__ argmax) {
+                             int *__restrict__ argmax, float *__restrict__ zsel) {
   const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
   if (i >= total) return;
   const int c = static_cast<int>(i % C);
   const float aa = __ldg(a + c), bb = __ldg(b + c);
   const bool up = aa > 0.f;
-  const float y = fmaf(aa, up ? __ldg(zmax + i) : __ldg(zmin + i), bb);
+  const float zs = up ? __ldg(zmax + i) : __ldg(zmin + i);
+  const float y = fmaf(aa, zs, bb);
   const bool pos = y > 0.f && aa != 0.f;
+  if (zsel != nullptr) zsel[i] = zs;   // = z at the arg-max row whenever that row carries a gradient (a != 0)
   out[i] = fmaxf(y, 0.f);
   argmax[i] = pos ? (up ? __ldg(imax + i) : __ldg(imin + i)) : 0;
 }
@@ -240,20 +242,28 @@ groupmax_from_extrema_kernel(size_t total, int C, const float *__restrict__ zmax
 // sparse statistics: only the arg-max row of every (group, channel) carries a gradient
 __global__ void __launch_bounds__(kRowThreads)
 pool_bwd_stats_kernel(ColGeom g, int ns, const float *__restrict__ dout, const int *__restrict__ argmax,
-                      const float *__restrict__ z, const float *__restrict__ a, const float *__restrict__ b,
-                      const float *__restrict__ mean, const float *__restrict__ invstd,
-                      float *__restrict__ partials) {
+                      const float *__restrict__ z, const float *__restrict__ zsel, const float *__restrict__ a,
+                      const float *__restrict__ b, const float *__restrict__ mean,
+                      const float *__restrict__ invstd, float *__restrict__ partials) {
   // rows here are GROUPS (g.P = G)
   col_reduce2(g, partials, [&](int grp, int c4, float4 &s, float4 &q) {
     const size_t i = static_cast<size_t>(grp) * g.C4 + c4;
     const float4 d = ld4(dout, i);
     const int4 am = __ldg(reinterpret_cast<const int4 *>(argmax) + i);
     const float4 aa = ld4(a, c4), bb = ld4(b, c4), mu = ld4(mean, c4), is = ld4(invstd, c4);
-    const size_t base = static_cast<size_t>(grp) * ns;
-    const float z0 = __ldg(z + (base + am.x) * g.C + 4 * c4 + 0);
-    const float z1 = __ldg(z + (base + am.y) * g.C + 4 * c4 + 1);
-    const float z2 = __ldg(z + (base + am.z) * g.C + 4 * c4 + 2);
-    const float z3 = __ldg(z + (base + am.w) * g.C + 4 * c4 + 3);
+    float z0, z1, z2, z3;
+    if (zsel != nullptr && aa.x != 0.f && aa.y != 0.f && aa.z != 0.f && aa.w != 0.f) {
+      // the forward pass kept z at the arg-max row (pn2_groupmax_from_extrema): no gather over z.  Where the
+      // group's maximum is not positive the kept value differs from z at row 0, but that entry is masked.
+      const float4 zs = ld4(zsel, i);
+      z0 = zs.x, z1 = zs.y, z2 = zs.z, z3 = zs.w;
+    } else {
+      const size_t base = static_cast<size_t>(grp) * ns;
+      z0 = __ldg(z + (base + am.x) * g.C + 4 * c4 + 0);
+      z1 = __ldg(z + (base + am.y) * g.C + 4 * c4 + 1);
+      z2 = __ldg(z + (base + am.z) * g.C + 4 * c4 + 2);
+      z3 = __ldg(z + (base + am.w) * g.C + 4 * c4 + 3);
+    }
     const float d0 = fmaf(aa.x, z0, bb.x) > 0.f ? d.x : 0.f, d1 = fmaf(aa.y, z1, bb.y) > 0.f ? d.y : 0.f;
     const float d2 = fmaf(aa.z, z2, bb.z) > 0.f ? d.z : 0.f, d3 = fmaf(aa.w, z3, bb.w) > 0.f ? d.w : 0.f;
     s.x += d0, s.y += d1, s.z += d2, s.w += d3;
@@ -730,12 +740,12 @@ extern "C" int pn2_bn_relu_groupmax(int g, int ns, int c, const float *z, const 
 
 extern "C" int pn2_groupmax_from_extrema(int g, int c, const float *zmax, const float *zmin, const int *imax,
                                          const int *imin, const float *a, const float *b, float *out,
-                                         int *argmax, void *stream) {
+                                         int *argmax, float *zsel, void *stream) {
   if (g <= 0 || c <= 0) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(zmax, zmin, imax, imin, a, b, out, argmax);
   const size_t total = static_cast<size_t>(g) * c;
   groupmax_from_extrema_kernel<<<blocks_for(total), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      total, c, zmax, zmin, imax, imin, a, b, out, argmax);
+      total, c, zmax, zmin, imax, imin, a, b, out, argmax, zsel);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -753,7 +763,7 @@ extern "C" int pn2_pool_bn_bwd(int g, int ns, int c, int training, const float *
   const ColGeom geom = col_geom(g, c, &nblk);
   float *c1 = workspace + static_cast<size_t>(kMaxPartials) * 2 * c, *c2 = c1 + c;
   const size_t smem = sizeof(float4) * 2 * geom.row_lanes * geom.C4;
-  pool_bwd_stats_kernel<<<nblk, kRowThreads, smem, s>>>(geom, ns, dout, argmax, z, a, b, mean, invstd, workspace);
+  pool_bwd_stats_kernel<<<nblk, kRowThreads, smem, s>>>(geom, ns, dout, argmax, z, nullptr, a, b, mean, invstd, workspace);
   bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(g * ns, c, c, nblk, training, workspace, dgamma,
                                                             dbeta, c1, c2);
   const size_t total4 = static_cast<size_t>(g) * (c / 4);
@@ -787,7 +797,7 @@ extern "C" int pn2_relu_bn_bwd(int p, int c, int training, int relu, const float
 // Statistics halves of the two adjoints above, for the fused tensor-core backward layer
 // (mlp_bwd.cu), which forms dZ on chip: dgamma, dbeta and c1c2 = [dbeta / P | dgamma / P].
 extern "C" int pn2_pool_bn_bwd_stats(int g, int ns, int c, int training, const float *dout, const int *argmax,
-                                     const float *z, const float *a, const float *b, const float *mean,
+                                     const float *z, const float *zsel, const float *a, const float *b, const float *mean,
                                      const float *invstd, float *dgamma, float *dbeta, float *c1c2,
                                      float *workspace, void *stream) {
   if (g <= 0 || ns <= 0 || c <= 0) return PN2_ERR_INVALID_ARG;
@@ -797,7 +807,8 @@ extern "C" int pn2_pool_bn_bwd_stats(int g, int ns, int c, int training, const f
   int nblk;
   const ColGeom geom = col_geom(g, c, &nblk);
   const size_t smem = sizeof(float4) * 2 * geom.row_lanes * geom.C4;
-  pool_bwd_stats_kernel<<<nblk, kRowThreads, smem, s>>>(geom, ns, dout, argmax, z, a, b, mean, invstd, workspace);
+  if (zsel != nullptr && !aligned16(zsel)) return PN2_ERR_UNSUPPORTED;
+  pool_bwd_stats_kernel<<<nblk, kRowThreads, smem, s>>>(geom, ns, dout, argmax, z, zsel, a, b, mean, invstd, workspace);
   bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(
       g * ns, c, c, nblk, training, workspace, dgamma, dbeta, c1c2, c1c2 + c);
   count_launch(2);

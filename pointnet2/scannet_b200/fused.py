@@ -286,7 +286,7 @@ class SharedMLPRows(Function):
         nl = len(params) // 3
         P = x0.shape[0]
         layers, hs = [], [x0]
-        out = argmax = None
+        out = argmax = zsel = None
         use_tc = TC_GEMM and GEMM_TF32
         want_grad = any(ctx.needs_input_grad)
         bwd_fused = [False] * nl
@@ -358,9 +358,12 @@ class SharedMLPRows(Function):
                     G = P // ns
                     out = torch.empty(G, C, dtype=torch.float32, device=dev)
                     argmax = torch.empty(G, C, dtype=torch.int32, device=dev)
+                    if want_grad and bwd_fused[l] and C % 4 == 0:   # z at the arg-max rows, for the adjoint's statistics
+                        zsel = torch.empty(G, C, dtype=torch.float32, device=dev)
                     _lib.check(L.pn2_groupmax_from_extrema(G, C, ext[0].data_ptr(), ext[1].data_ptr(),
                                                            ext[2].data_ptr(), ext[3].data_ptr(), st.a.data_ptr(),
                                                            st.b.data_ptr(), out.data_ptr(), argmax.data_ptr(),
+                                                           zsel.data_ptr() if zsel is not None else None,
                                                            _stream(dev)), "groupmax_from_extrema")
                 else:
                     G = P // ns
@@ -370,6 +373,7 @@ class SharedMLPRows(Function):
                                                       st.b.data_ptr(), out.data_ptr(), argmax.data_ptr(),
                                                       _stream(dev)), "bn_relu_groupmax")
         ctx.layers, ctx.hs, ctx.argmax, ctx.bwd_fused, ctx.wt_packed = layers, hs, argmax, bwd_fused, wt_packed
+        ctx.zsel = zsel
         assert use_tc or not any(d is not None for d in drops), "dropout inside the chain needs the tensor-core path"
         ctx.ns, ctx.training, ctx.nl, ctx.relus, ctx.drops = ns, training, nl, relus, drops
         ctx.weights = [params[3 * l] for l in range(nl)]
@@ -406,6 +410,7 @@ class SharedMLPRows(Function):
                         if pooled:
                             _lib.check(L.pn2_pool_bn_bwd_stats(
                                 P // ns, ns, C, training, dh.data_ptr(), ctx.argmax.data_ptr(), st.z.data_ptr(),
+                                ctx.zsel.data_ptr() if ctx.zsel is not None else None,
                                 st.a.data_ptr(), st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
                                 dgamma.data_ptr(), dbeta.data_ptr(), c1c2.data_ptr(), _ws(C, dev).data_ptr(), s),
                                 "pool_bn_bwd_stats")

@@ -49,7 +49,7 @@ SIGNATURES = {
     "pn2_mlp_gemm_pool_supported": [_i],
     "pn2_mlp_gemm_fwd": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f,
                          _i, _vp, _vp, _vp, _vp, _vp],
-    "pn2_groupmax_from_extrema": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pn2_groupmax_from_extrema": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_bn_finalize": [_i, _i, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     # fused backward layer on the tensor cores
     "pn2_mlp_bwd_supported": [_i, _i, _i, _i, _i],
@@ -61,7 +61,7 @@ SIGNATURES = {
     "pn2_mlp_bwd_layer": [_i] * 7 + [_vp] * 20 + [_vp, _f, _vp, _f, _vp],
     "pn2_mlp_bwd_finalize_scratch_floats": [_i, _i],
     "pn2_mlp_bwd_finalize": [_i, _i, _i, _i] + [_vp] * 7 + [_i, _i] + [_vp] * 7,
-    "pn2_pool_bn_bwd_stats": [_i, _i, _i, _i] + [_vp] * 12,
+    "pn2_pool_bn_bwd_stats": [_i, _i, _i, _i] + [_vp] * 13,
     "pn2_relu_bn_bwd_stats": [_i, _i, _i, _i] + [_vp] * 11,
     "pn2_bwd_stats_finalize": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     # flat-buffer training-step utilities

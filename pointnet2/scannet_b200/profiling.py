@@ -160,7 +160,7 @@ def _lib_bytes(name, a):
         return up + 4 * p * n + 4 * p * lda + (4 * p * lda if dh_prev else 0), (4 if dh_prev else 2) * p * n * k
     if name == "pn2_relu_bn_bwd_stats":
         return 8 * a[0] * a[1], 0
-    if name == "pn2_pool_bn_bwd_stats":
+    if name == "pn2_pool_bn_bwd_stats":   # dout, arg-max and z at the arg-max rows (gathered, or kept by the forward pass)
         return 12 * a[0] * a[2], 0
     if name == "pn2_weighted_ce_fwd":                          # logits, targets (int64), weights; lse out
         return 4 * a[0] * a[1] + 16 * a[0], 0

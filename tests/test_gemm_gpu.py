@@ -123,10 +123,31 @@ def test_pooled_layer_extrema_and_groupmax(G, ns, K, N):
     out2, arg2 = torch.empty(G, N, device=DEV), torch.empty(G, N, dtype=torch.int32, device=DEV)
     lib.check(L_().pn2_bn_relu_groupmax(G, ns, N, z.data_ptr(), a.data_ptr(), b.data_ptr(), out1.data_ptr(),
                                         arg1.data_ptr(), s), "groupmax")
+    zsel = torch.empty(G, N, device=DEV)
     lib.check(L_().pn2_groupmax_from_extrema(G, N, zmax.data_ptr(), zmin.data_ptr(), imax.data_ptr(), imin.data_ptr(),
-                                             a.data_ptr(), b.data_ptr(), out2.data_ptr(), arg2.data_ptr(), s), "from_extrema")
+                                             a.data_ptr(), b.data_ptr(), out2.data_ptr(), arg2.data_ptr(),
+                                             zsel.data_ptr(), s), "from_extrema")
     torch.cuda.synchronize()
     assert torch.equal(out1, out2)
+    # zsel = z at the arg-max row wherever the pooled value is positive, and the adjoint's statistics read
+    # from it are bit-identical to the ones gathered over z
+    zg = z.view(G, ns, N).gather(1, arg2.long().unsqueeze(1)).squeeze(1)
+    live = (out2 > 0) & (a != 0).unsqueeze(0)     # a == 0: the value is b for every row, the kernels gather z instead
+    assert torch.equal(zsel[live], zg[live])
+    mean, invstd = torch.randn(N, device=DEV), torch.rand(N, device=DEV) + 0.5
+    dout = torch.randn(G, N, device=DEV)
+    res = []
+    for zs in (None, zsel):
+        dg, db, c12 = torch.empty(N, device=DEV), torch.empty(N, device=DEV), torch.empty(2 * N, device=DEV)
+        ws = torch.empty(L_().pn2_bn_stats_workspace_floats(N) + 2 * N, device=DEV)
+        lib.check(L_().pn2_pool_bn_bwd_stats(G, ns, N, 1, dout.data_ptr(), arg2.data_ptr(), z.data_ptr(),
+                                             zs.data_ptr() if zs is not None else None, a.data_ptr(), b.data_ptr(),
+                                             mean.data_ptr(), invstd.data_ptr(), dg.data_ptr(), db.data_ptr(),
+                                             c12.data_ptr(), ws.data_ptr(), s), "pool_bn_bwd_stats")
+        res.append((dg, db, c12))
+    torch.cuda.synchronize()
+    for x, y in zip(*res):
+        assert torch.equal(x, y)
     # the rows can only differ where two different z of a group round to the same a*z+b (then both rows carry
     # the same value); on these inputs ties are exact duplicates, so the rows agree as well
     assert torch.equal(arg1, arg2)

@@ -40,7 +40,7 @@ for name, P, K, N in [("SA1.l2", 1 << 20, 32, 64), ("SA2.l2", 1 << 18, 64, 128),
         z, h, part, geo, ext = fused._tc_layer(A, K, W, (a_in, b_in), True, False, True, None, ns)
         lib.check(L.pn2_groupmax_from_extrema(G, N, ext[0].data_ptr(), ext[1].data_ptr(), ext[2].data_ptr(),
                                               ext[3].data_ptr(), a.data_ptr(), b.data_ptr(), out.data_ptr(),
-                                              arg.data_ptr(), s), "x")
+                                              arg.data_ptr(), None, s), "x")
 
     def twopass():
         z, h, part, geo = fused._tc_layer(A, K, W, (a_in, b_in), True, False, True)
