@@ -424,6 +424,11 @@ def run_reference(args, world, rank, local):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE line, the JSON: libraries that chat on fd 1 (NCCL prints its version there
+    # when NCCL_DEBUG is set) are sent to stderr, the result goes to a private copy of the original stdout
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl != "product":
         rank = int(os.environ.get("RANK", "0"))
         if rank != 0:
@@ -438,7 +443,8 @@ def main():
             dist.barrier()
             dist.destroy_process_group()
     if res is not None:
-        print(json.dumps(res))
+        out.write(json.dumps(res) + "\n")
+        out.flush()
     return 0
 
 

@@ -273,3 +273,29 @@ def test_geometry_plan_pack_and_single_copy():
     loose = make(lambda *s: torch.zeros(*s))
     loose.copy_from(packed)
     assert all(torch.equal(a, b) for a, b in zip(loose.tensors(), want))
+
+
+def test_chunker_augmentation_draws_follow_the_reference_order():
+    """The product's host-side draws (chunker._draw_augmentation) consume np.random exactly like the
+    oracle's restatement of _augment / _translate / _rotate / _scale (pinned against the reference's own
+    classes in test_chunker_cpu.py) and yield the same parameters, for every branch of _augment."""
+    import numpy as np
+    from oracle import chunker_np as O
+    from pointnet2.scannet_b200 import chunker
+    seen = set()
+    for seed in range(60):
+        np.random.seed(seed)
+        ops, t, R, f = O.draw_augmentation(np.random)
+        after_oracle = np.random.random()
+        np.random.seed(seed)
+        mask, params = chunker._draw_augmentation()
+        assert np.random.random() == after_oracle          # same number of draws
+        assert mask == sum({"t": 1, "r": 2, "s": 4}[o] for o in ops)
+        assert np.array_equal(params[:3], t) and np.array_equal(params[3:12], R.ravel()) and params[12] == f
+        seen.add(ops)
+    assert seen == {"t", "r", "s", "tr", "ts", "rs", "trs", ""}
+
+
+def test_chunker_descriptor_matches_the_library():
+    from pointnet2.scannet_b200 import chunker, lib
+    assert lib.load().pn2_chunk_desc_bytes() == chunker.DESC.itemsize
