@@ -423,6 +423,27 @@ PN2_API int pn2_chunk_assemble(int npoints, int ld, const float *scene, const in
                                const double *aug_host, int ldo, float *out, long long *labels,
                                float *weights, void *stream);
 
+/* ==========================================================================
+ * Per-iteration evaluation metrics on the device (csrc/metrics.cu).
+ * Replace the host path of compute_acc / compute_miou (scripts/eval.py:39-129, called by
+ * lib/solver.py:327-347 every iteration): filter_points' Python loop over all points (:42-43),
+ * point_cloud_label_to_surface_voxel_label_fast (lib/pc_util.py:39-51) and the per-class passes.
+ * coords [p, 3] float32, preds / targets [p] int64.
+ * pn2_first_occurrence_xyz: rep[i] = lowest index with the same (bitwise) coordinates -- the points
+ *   filter_points keeps are those with rep[i] == i.  table: pn2_metrics_table_ints(p) ints of scratch.
+ * pn2_first_occurrence_voxel: vrep[i] = lowest kept index in i's voxel of edge `res` (the voxel key is
+ *   evaluated in float32 exactly as NumPy evaluates it there); -1 for filtered points.  bounds: 6 unsigned,
+ *   vkey: p unsigned, table as above (all scratch).
+ * pn2_confusion: conf[t * nc + q] += 1 over the points with rep[i] == i (caller zero-fills conf [nc, nc] and
+ *   bad [1]; bad counts labels outside [0, nc)); nc <= 64.
+ * ========================================================================== */
+PN2_API int pn2_metrics_table_ints(int p);
+PN2_API int pn2_first_occurrence_xyz(int p, const float *coords, int *table, int *rep, void *stream);
+PN2_API int pn2_first_occurrence_voxel(int p, const float *coords, const int *rep, float res, unsigned *bounds,
+                                       unsigned *vkey, int *table, int *vrep, void *stream);
+PN2_API int pn2_confusion(int p, const int *rep, const long long *preds, const long long *targets, int nc,
+                          int *conf, int *bad, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,6 +107,7 @@ class pack_branch(object):
                 _pack_state["stream"] = torch.cuda.Stream(self.dev)
             _pack_state["stream"].wait_stream(torch.cuda.current_stream(self.dev))
             _pack_state["active"] = True
+            _pack_state["n_drop"] = 0
         return self
 
     def __exit__(self, *exc):
@@ -660,10 +661,27 @@ def _dropout_mask(rows, cols, keep, dev):
     if st is None:
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         st = _drop_state[dev] = torch.tensor([seed, 0], dtype=torch.int64, device=dev)
+    def launch(ptr, strm):
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().pn2_dropout_mask(rows * cols, float(keep), st.data_ptr(), ptr, strm), "dropout_mask")
+
+    if _pack_state["active"]:
+        # the mask depends on nothing: drawn on the packing branch, into a persistent buffer (kept for the
+        # backward pass; the next step's branch forks after it).  One buffer per dropout site of the step.
+        n = _pack_state["n_drop"] = _pack_state.get("n_drop", 0) + 1
+        key = ("drop", n, rows, cols, dev)
+        buf = _pack_state["bufs"].get(key)
+        if buf is None and not torch.cuda.is_current_stream_capturing():
+            buf = _pack_state["bufs"][key] = torch.empty(rows, cols, dtype=torch.uint8, device=dev)
+        if buf is not None:
+            side = _pack_state["stream"]
+            launch(buf.data_ptr(), side.cuda_stream)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            torch.cuda.current_stream(dev).wait_event(ev)
+            return buf
     mask = torch.empty(rows, cols, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(_lib.load().pn2_dropout_mask(rows * cols, float(keep), st.data_ptr(), mask.data_ptr(), _stream(dev)),
-                   "dropout_mask")
+    launch(mask.data_ptr(), _stream(dev))
     return mask
 
 

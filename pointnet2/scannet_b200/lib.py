@@ -72,6 +72,11 @@ SIGNATURES = {
     "pn2_weighted_ce_partials": [_i],
     "pn2_weighted_ce_fwd": [_i, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_weighted_ce_bwd": [_i, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    # per-iteration metrics on the device
+    "pn2_metrics_table_ints": [_i],
+    "pn2_first_occurrence_xyz": [_i, _vp, _vp, _vp, _vp],
+    "pn2_first_occurrence_voxel": [_i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp],
+    "pn2_confusion": [_i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
     # chunk generation (scene resident in HBM)
     "pn2_crop_try": [_i, _i, _vp, _i, _i, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp],
     "pn2_box_select": [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp],
