@@ -313,9 +313,19 @@ def run_product(args, world, rank, local):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         nprof = min(args.steps, 5)
+        def local_step(*batch):
+            # the step WITHOUT its collective: only rank 0 runs this pass (the other ranks are already waiting
+            # at the final barrier), so the gradient all-reduce of TrainStep.__call__ would never be matched
+            loss = eager.forward_backward(*batch)
+            if eager.flat_mode:
+                eager.opt.step(grad_scale=1.0)
+            else:
+                eager.optimizer.step()
+            return loss
+
         with profiling.LibTimer() as timer:
             for i in range(nprof):
-                eager(*dev[i % len(dev)])
+                local_step(*dev[i % len(dev)])
         rows = timer.summary(nprof)
         for r in rows:
             if r.get("gbs"):
@@ -353,7 +363,7 @@ def run_product(args, world, rank, local):
             res["fps"] = {"call": f["call"], "us_per_call": f["us_per_call"],
                           "ns_per_iteration": round(1e3 * f["us_per_call"] / max(m - 1, 1), 1),
                           "note": "latency-bound (m-1 dependent iterations), not a bandwidth roofline"}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # reported at N = 1 only
         try:
             res["cpu_baseline"] = cpu_baseline(args, in_ch)
         except Exception as e:  # noqa: BLE001
