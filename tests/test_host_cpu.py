@@ -299,3 +299,23 @@ def test_chunker_augmentation_draws_follow_the_reference_order():
 def test_chunker_descriptor_matches_the_library():
     from pointnet2.scannet_b200 import chunker, lib
     assert lib.load().pn2_chunk_desc_bytes() == chunker.DESC.itemsize
+
+
+def test_bench_prints_exactly_one_json_line():
+    """The driver parses bench.py's stdout: ONE JSON line, whatever the libraries print.  Exercised on the arm
+    that runs without a GPU (the reference arm's CPU-port fallback, bounded sample)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference-cpu", "--steps", "1",
+                        "--warmup", "0", "--cpu-sample-chunks", "1", "--npoints", "512"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = p.stdout.strip().splitlines()
+    assert len(lines) == 1, p.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
