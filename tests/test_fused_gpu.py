@@ -363,8 +363,8 @@ def test_dropout_mask_generator():
                                          (2, 64, 16, 512, 256), (1, 1000, 100, 64, 0), (2, 777, 50, 96, 3),
                                          (1, 300, 40, 36, 5)])
 def test_fp_interp_rows_bit_exact(B, n, m, c2, c1):
-    """pn2_fp_interp_rows (both the shared-memory variant and the plain gather kernel, whichever the
-    launcher picks for the shape) against the reference's arithmetic evaluated by torch elementwise ops:
+    """pn2_fp_interp_rows (whichever of the gather kernels -- 1, 2 or 4 elements per thread -- the launcher
+    picks for the shape) against the reference's arithmetic evaluated by torch elementwise ops:
     ((k1*w1) + (k2*w2)) + (k3*w3), one rounding per operation (interpolate_gpu.cu:95-98) -- bit-exact --
     followed by the skip columns and zero padding (pointnet2_modules.py:407-412)."""
     g = torch.Generator(device="cpu").manual_seed(n + m)

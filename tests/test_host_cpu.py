@@ -319,3 +319,14 @@ def test_bench_prints_exactly_one_json_line():
               "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+
+
+def test_bench_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun the reference arm runs on rank 0 alone; every other rank exits 0 without output."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert p.returncode == 0 and p.stdout.strip() == ""
