@@ -1,3 +1,5 @@
+"""Known-pattern probes of the tcgen05 forward layer (all-ones, identity and column-selecting weights) through
+tests/test_gemm_gpu.run_gemm: prints what lands where when an operand layout or descriptor is suspected."""
 import sys, os
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
