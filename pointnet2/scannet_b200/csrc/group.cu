@@ -19,6 +19,8 @@
 // first (warp-aggregated scatter-add) and only the row's head lane issues the
 // atomic.  Outputs too large for shared memory fall back to memset + global
 // reductions.
+#include <stdlib.h>
+
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -56,11 +58,82 @@ group_fwd_kernel(int c, int n, int E, int ch_per_cta, const float *__restrict__ 
   }
 }
 
+// ---- EXPERIMENT, off unless PN2_GROUP_SMEM=1 (written after round 1's GPU budget was spent: parity
+// and speed NOT measured yet; tests/test_experimental_gpu.py compare it with the kernel
+// above bit for bit when PN2_EXPERIMENTAL=1).  The kernel above is bound by L1 gathers (a warp's 32
+// indices touch up to 32 sectors per load instruction).  Here a CTA owns (cloud, channel tile),
+// copies its [channels][n] rows -- contiguous in memory, each element read from HBM exactly once --
+// into shared memory with 128-bit loads, and gathers from there: a 32-way scattered LDS costs a few
+// bank-conflict replays instead of 32 sector lookups.  Same thread mapping and stores as above.
+constexpr int kGsThreads = 512;
+constexpr int kGsSmemBytes = 56 * 1024;  // four CTAs per SM
+
+template <bool kVec>
+__global__ void __launch_bounds__(kGsThreads)
+group_fwd_smem_kernel(int c, int n, int E, int ch_per_cta, const float *__restrict__ points,
+                      const int *__restrict__ idx, float *__restrict__ out) {
+  extern __shared__ __align__(16) float s_src[];  // [channels of this CTA][n]
+  const int cloud = blockIdx.y, tid = threadIdx.x;
+  const int c0 = blockIdx.x * ch_per_cta;
+  const int nc = min(ch_per_cta, c - c0);
+  const float *src = points + (static_cast<size_t>(cloud) * c + c0) * n;
+  const int total = nc * n;
+  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(points) & 15u) == 0) {
+    for (int i = tid * 4; i < total; i += kGsThreads * 4)
+      *reinterpret_cast<float4 *>(s_src + i) = __ldg(reinterpret_cast<const float4 *>(src + i));
+  } else {
+    for (int i = tid; i < total; i += kGsThreads) s_src[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int *ix = idx + static_cast<size_t>(cloud) * E;
+  float *dst = out + (static_cast<size_t>(cloud) * c + c0) * E;
+  if (kVec) {
+    for (int e = tid * 4; e < E; e += kGsThreads * 4) {
+      const int4 i = ld_nc_i4(ix + e);
+#pragma unroll 4
+      for (int l = 0; l < nc; ++l) {
+        const float *row = s_src + l * n;
+        st_cs_f4(dst + static_cast<size_t>(l) * E + e, make_float4(row[i.x], row[i.y], row[i.z], row[i.w]));
+      }
+    }
+  } else {
+    for (int e = tid; e < E; e += kGsThreads) {
+      const int i = __ldg(ix + e);
+      for (int l = 0; l < nc; ++l) dst[static_cast<size_t>(l) * E + e] = s_src[l * n + i];
+    }
+  }
+}
+
+// true when the experiment is switched on and the shape suits it (rows fit, enough reuse)
+static bool group_smem_wanted(int n, int E) {
+  const char *env = getenv("PN2_GROUP_SMEM");
+  return env != nullptr && env[0] == '1' && n > 0 && static_cast<size_t>(n) * sizeof(float) <= kGsSmemBytes &&
+         static_cast<long long>(E) >= 2LL * n;
+}
+
+static int launch_group_fwd_smem(int b, int c, int n, int E, bool vec, const float *points, const int *idx,
+                                 float *out, cudaStream_t s) {
+  const int ch_max = kGsSmemBytes / (static_cast<int>(sizeof(float)) * n);
+  int ctiles = (c + ch_max - 1) / ch_max;
+  const int want = (2 * kNumSMs + b - 1) / b;  // two waves of CTAs when the channel count allows it
+  if (ctiles < want) ctiles = want < c ? want : c;
+  const int ch_per_cta = (c + ctiles - 1) / ctiles;
+  ctiles = (c + ch_per_cta - 1) / ch_per_cta;
+  const size_t smem = sizeof(float) * static_cast<size_t>(ch_per_cta) * n;
+  auto kern = vec ? group_fwd_smem_kernel<true> : group_fwd_smem_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGsSmemBytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  kern<<<dim3(ctiles, b), kGsThreads, smem, s>>>(c, n, E, ch_per_cta, points, idx, out);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
 static int launch_group_fwd(int b, int c, int n, int E, const float *points,
                             const int *idx, float *out, cudaStream_t s) {
   if (b == 0 || c == 0 || E == 0) return PN2_OK;
   if (b > 65535) return PN2_ERR_UNSUPPORTED;
   const bool vec = (E % 4 == 0) && aligned16(idx) && aligned16(out);
+  if (group_smem_wanted(n, E)) return launch_group_fwd_smem(b, c, n, E, vec, points, idx, out, s);
   const int per_thread = vec ? 4 : 1;
   const int xblocks = (E + kGrpThreads * per_thread - 1) / (kGrpThreads * per_thread);
   // enough CTAs for ~4 waves of 148 SMs, but keep >= 4 channels per idx load

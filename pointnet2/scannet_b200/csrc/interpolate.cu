@@ -12,6 +12,8 @@
 //   reference's expression, interpolate_gpu.cu:98-99, without FMA contraction).
 // Adjoint: a CTA owns (cloud, channel tile) and accumulates g*w into a
 // shared-memory image of its output rows, then writes each row once.
+#include <stdlib.h>
+
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -59,6 +61,72 @@ interp_fwd_kernel(int c, int m, int n, int ch_per_cta, const float *__restrict__
     for (int l = c0; l < c1; ++l, src += m, dst += n)
       dst[j] = interp3(__ldg(src + i1), __ldg(src + i2), __ldg(src + i3), w1, w2, w3);
   }
+}
+
+// ---- EXPERIMENT, off unless PN2_INTERP_SMEM=1 (written after round 1's GPU budget was spent: parity
+// and speed NOT measured yet; tests/test_experimental_gpu.py compare it with the kernel
+// above bit for bit when PN2_EXPERIMENTAL=1).  The kernel above spends its time in L1 gathers (12
+// scattered loads per 4 outputs and channel; 24 % of the HBM peak at FP0).  Here a CTA owns (cloud,
+// channel tile), stages its [channels][m] rows of known features in shared memory once -- they are
+// contiguous, each element leaves HBM exactly once -- and gathers from there.  Same thread mapping,
+// same arithmetic (interp3), same stores.
+constexpr int kIsThreads = 512;
+constexpr int kIsSmemBytes = 56 * 1024;  // four CTAs per SM
+
+template <bool kVec>
+__global__ void __launch_bounds__(kIsThreads)
+interp_fwd_smem_kernel(int c, int m, int n, int ch_per_cta, const float *__restrict__ points,
+                       const int *__restrict__ idx, const float *__restrict__ weight,
+                       float *__restrict__ out) {
+  extern __shared__ __align__(16) float s_src[];  // [channels of this CTA][m]
+  const int cloud = blockIdx.y, tid = threadIdx.x;
+  const int c0 = blockIdx.x * ch_per_cta;
+  const int nc = min(ch_per_cta, c - c0);
+  const float *src = points + (static_cast<size_t>(cloud) * c + c0) * m;
+  const int total = nc * m;
+  if ((m & 3) == 0 && (reinterpret_cast<uintptr_t>(points) & 15u) == 0) {
+    for (int i = tid * 4; i < total; i += kIsThreads * 4)
+      *reinterpret_cast<float4 *>(s_src + i) = __ldg(reinterpret_cast<const float4 *>(src + i));
+  } else {
+    for (int i = tid; i < total; i += kIsThreads) s_src[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int *ix = idx + static_cast<size_t>(cloud) * n * 3;
+  const float *wt = weight + static_cast<size_t>(cloud) * n * 3;
+  float *dst = out + (static_cast<size_t>(cloud) * c + c0) * n;
+  if (kVec) {
+    for (int j = tid * 4; j < n; j += kIsThreads * 4) {
+      const int4 ia = ld_nc_i4(ix + 3 * j), ib = ld_nc_i4(ix + 3 * j + 4), ic = ld_nc_i4(ix + 3 * j + 8);
+      const float4 wa = __ldg(reinterpret_cast<const float4 *>(wt + 3 * j));
+      const float4 wb = __ldg(reinterpret_cast<const float4 *>(wt + 3 * j + 4));
+      const float4 wc = __ldg(reinterpret_cast<const float4 *>(wt + 3 * j + 8));
+#pragma unroll 2
+      for (int l = 0; l < nc; ++l) {
+        const float *row = s_src + l * m;
+        float4 v;
+        v.x = interp3(row[ia.x], row[ia.y], row[ia.z], wa.x, wa.y, wa.z);
+        v.y = interp3(row[ia.w], row[ib.x], row[ib.y], wa.w, wb.x, wb.y);
+        v.z = interp3(row[ib.z], row[ib.w], row[ic.x], wb.z, wb.w, wc.x);
+        v.w = interp3(row[ic.y], row[ic.z], row[ic.w], wc.y, wc.z, wc.w);
+        st_cs_f4(dst + static_cast<size_t>(l) * n + j, v);
+      }
+    }
+  } else {
+    for (int j = tid; j < n; j += kIsThreads) {
+      const int i1 = __ldg(ix + 3 * j), i2 = __ldg(ix + 3 * j + 1), i3 = __ldg(ix + 3 * j + 2);
+      const float w1 = __ldg(wt + 3 * j), w2 = __ldg(wt + 3 * j + 1), w3 = __ldg(wt + 3 * j + 2);
+      for (int l = 0; l < nc; ++l) {
+        const float *row = s_src + l * m;
+        dst[static_cast<size_t>(l) * n + j] = interp3(row[i1], row[i2], row[i3], w1, w2, w3);
+      }
+    }
+  }
+}
+
+static bool interp_smem_wanted(int m, int n) {
+  const char *env = getenv("PN2_INTERP_SMEM");
+  return env != nullptr && env[0] == '1' && m > 0 && static_cast<size_t>(m) * sizeof(float) <= kIsSmemBytes &&
+         3LL * n >= 2LL * m;
 }
 
 constexpr int kItpGradThreads = 512;
@@ -123,6 +191,21 @@ extern "C" int pn2_three_interpolate(int b, int c, int m, int n, const float *po
   if (b > 65535) return PN2_ERR_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool vec = (n % 4 == 0) && aligned16(idx) && aligned16(weight) && aligned16(out);
+  if (interp_smem_wanted(m, n)) {
+    const int ch_max = kIsSmemBytes / (static_cast<int>(sizeof(float)) * m);
+    int tiles = (c + ch_max - 1) / ch_max;
+    const int want = (2 * kNumSMs + b - 1) / b;  // two waves of CTAs when the channel count allows it
+    if (tiles < want) tiles = want < c ? want : c;
+    const int per_cta = (c + tiles - 1) / tiles;
+    tiles = (c + per_cta - 1) / per_cta;
+    const size_t smem = sizeof(float) * static_cast<size_t>(per_cta) * m;
+    auto kern = vec ? interp_fwd_smem_kernel<true> : interp_fwd_smem_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kIsSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    kern<<<dim3(tiles, b), kIsThreads, smem, s>>>(c, m, n, per_cta, points, idx, weight, out);
+    count_launch();
+    PN2_RETURN_LAUNCH_STATUS();
+  }
   const int per_thread = vec ? 4 : 1;
   const int xblocks = (n + kItpThreads * per_thread - 1) / (kItpThreads * per_thread);
   int ctiles = (4 * kNumSMs + b * xblocks - 1) / (b * xblocks);
