@@ -14,6 +14,12 @@ The reference's setup.py cannot be used as is: it pins TORCH_CUDA_ARCH_LIST to
 same source list (setup.py:9-13) is handed to torch.utils.cpp_extension.load
 with the arch overridden to 10.0a.
 
+stage_python() additionally places VERBATIM copies of the reference's own model code
+(pointnet2/{pointnet2_semseg,pointnet2_modules,pointnet2_utils,pytorch_utils}.py and
+lib/loss.py) into oracle/_ref/py/ -- git-ignored like the rest of oracle/_ref, shipped to the
+GPU box -- so that `bench.py --impl reference` runs the unmodified reference end to end
+(its Python over its kernels) where /root/reference does not exist.
+
 Both modules expose the nine functions of bindings.cpp:6-19 and need a GPU to
 run ("CPU not supported", e.g. ball_query.cpp:27-29).
 """
@@ -62,10 +68,31 @@ def build(variant, verbose=False):
     return so_path(variant)
 
 
+def python_dir():
+    return os.path.join(OUT, "py")
+
+
+REF_PY = ["pointnet2_semseg.py", "pointnet2_modules.py", "pointnet2_utils.py", "pytorch_utils.py"]
+
+
+def stage_python():
+    """Verbatim copies of the reference's model code and loss into oracle/_ref/py (see module docstring)."""
+    import shutil
+    ref_root = os.path.dirname(os.path.dirname(REF_SRC))
+    dst = python_dir()
+    os.makedirs(os.path.join(dst, "solver", "lib"), exist_ok=True)
+    for f in REF_PY:
+        shutil.copyfile(os.path.join(ref_root, "pointnet2", f), os.path.join(dst, f))
+    shutil.copyfile(os.path.join(ref_root, "lib", "loss.py"), os.path.join(dst, "solver", "lib", "loss.py"))
+    open(os.path.join(dst, "solver", "lib", "__init__.py"), "w").close()
+    return dst
+
+
 def build_all(verbose=False):
     for v in VARIANTS:
         if not available(v):
             build(v, verbose=verbose)
+    stage_python()
 
 
 def load_ref(variant="nofma"):

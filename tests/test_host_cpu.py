@@ -330,3 +330,81 @@ def test_bench_reference_arm_other_ranks_exit_quietly():
     p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, timeout=300, env=env)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def _product_line(with_per_op):
+    """What run_product hands to the formatter, at its longest (8 GPUs, long kernel name, throttle reasons)."""
+    import bench
+    res = {"metric": bench.METRIC, "value": 123456.7, "unit": bench.UNIT, "n_gpus": 8, "steps": 200, "warmup": 50,
+           "ms_per_step": 12.3456, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": "configs[2] MSG train step 32x8192/GPU C=134", "per_gpu_batch": 32, "npoints": 8192,
+                      "parallelism": "dp8", "launch": "graph(fwd_bwd)+geometry prefetch,split", "mlp": "tcgen05 tf32",
+                      "settle": 50, "l2": "inputs>L2"},
+           "e2e": {"value": 123456.7, "unit": bench.UNIT, "h2d_bytes_per_step": 146800640, "d2h_bytes_per_step": 4},
+           "gpu_launches": 1234567, "loss": 2.99123,
+           "clocks": {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0,
+                      "reasons": ["hw_slowdown", "hw_thermal_slowdown", "sw_power_cap", "sw_thermal_slowdown"]}}
+    if with_per_op:
+        res["roofline"] = {"bound": "hbm", "kernel": "pn2_mlp_bwd_layer(1048576,128,128,128,32)", "achieved": 3518.25,
+                           "peak": 6536.4, "unit": "GB/s", "frac": 0.5367, "traffic": 524600000,
+                           "peak_source": "MEASURED_PEAKS", "share": 0.312}
+        res["fps_ns_per_iter"] = 631.2
+    res["cpu_baseline"] = {"value": 13.37, "unit": bench.UNIT, "cores": 128, "kind": "port",
+                           "sample": "2x8192 pts fwd+bwd+Adam, oracle C ops+torch CPU, median of 10"}
+    return bench.format_line(res)
+
+
+@pytest.mark.parametrize("with_per_op", [True, False])
+def test_bench_product_line_fits_the_drivers_tail(with_per_op):
+    """Round 1's line was 32 KB and the driver, which parses the tail of stdout, recorded nothing."""
+    import json
+    line = _product_line(with_per_op)
+    assert len(line) < 1000 and "\n" not in line
+    d = json.loads(line)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "cpu_baseline"):
+        assert k in d, k
+    assert "workload" in d["config"] and set(d["e2e"]) == {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    if with_per_op:
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+    assert {"value", "unit", "cores", "kind"} <= set(d["cpu_baseline"])
+
+
+def test_reference_arm_runs_the_references_own_python():
+    """bench.py --impl reference imports the reference's pointnet2_semseg / lib.loss from oracle/_ref/py with
+    `pointnet2._ext` set to the extension handed in -- exercised here on the CPU with the oracle's ops table."""
+    from oracle import build_ref
+    if not os.path.exists(os.path.join(build_ref.python_dir(), "pointnet2_semseg.py")):
+        pytest.skip("oracle/_ref/py not staged (needs /root/reference)")
+    import bench
+    import oracle
+    import torch
+    saved = {k: sys.modules.get(k) for k in ("pointnet2._ext", "pointnet2_utils", "pointnet2_modules",
+                                              "pointnet2_semseg", "pytorch_utils")}
+    try:
+        for k in saved:
+            sys.modules.pop(k, None)
+        semseg, loss = bench.load_reference_python(oracle.ext_cpu)
+        assert os.path.realpath(semseg.__file__).startswith(os.path.realpath(build_ref.python_dir()))
+        assert sys.modules["pointnet2_utils"]._ext is oracle.ext_cpu
+        if os.path.isdir("/root/reference/pointnet2"):
+            for f in build_ref.REF_PY:   # verbatim
+                assert open(os.path.join(build_ref.python_dir(), f)).read() == \
+                    open(os.path.join("/root/reference/pointnet2", f)).read()
+        torch.manual_seed(0)
+        m = semseg.get_model(num_classes=20, is_msg=False, input_channels=6, use_xyz=True, bn=True).train()
+        y = m(torch.rand(2, 1024, 9))
+        l = loss.WeightedCrossEntropyLoss()(y.view(-1, 20), torch.zeros(2048, dtype=torch.long), torch.ones(2048))
+        l.backward()
+        assert y.shape == (2, 1024, 20) and torch.isfinite(l)
+    finally:
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
+        import pointnet2
+        if saved["pointnet2._ext"] is not None:
+            pointnet2._ext = saved["pointnet2._ext"]
+        elif hasattr(pointnet2, "_ext"):
+            del pointnet2._ext
