@@ -68,6 +68,8 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-per-op", action="store_true")
     p.add_argument("--cpu-sample-chunks", type=int, default=2)
+    p.add_argument("--settle", type=int, default=SETTLE_STEPS,
+                   help="untimed steps before the clock starts: max(--warmup, this)")
     p.add_argument("--per-kernel-out", default=None,
                    help="where the per-kernel table goes (default gpurun_out/bench_per_kernel_<cfg>_<N>gpu.json)")
     return p.parse_args()
@@ -280,7 +282,7 @@ def run_product(args, world, rank, local):
             sys.stderr.write("CUDA graph capture failed, running eagerly: %r\n" % (e,))
             torch.cuda.synchronize()
             step, launch_mode = eager, "eager (graph capture failed)"
-    settle = max(args.warmup, SETTLE_STEPS)
+    settle = max(args.warmup, args.settle)
     for i in range(settle):
         step(*dev[i % len(dev)])
     torch.cuda.synchronize()
@@ -464,7 +466,7 @@ def run_reference(args, world, rank, local):
         return loss
 
     dev = [tuple(t.cuda() for t in b) for b in batches]
-    settle = max(args.warmup, SETTLE_STEPS)
+    settle = max(args.warmup, args.settle)
     for i in range(settle):
         iteration(*dev[i % len(dev)])
     torch.cuda.synchronize()

@@ -22,12 +22,13 @@ leg() {  # leg <name> <seconds> <command...>
 leg pytest 900 python -m pytest tests -m gpu -x -q
 leg smoke 300 python -c 'import __graft_entry__ as g; g.smoke()'
 leg bench_ref 300 python bench.py --impl reference
+CUDA_LAUNCH_BLOCKING=1 leg bench_ref_blocking 300 python bench.py --impl reference
 leg bench 400 python bench.py
 leg bench_msg 300 python bench.py --msg --no-cpu-baseline --no-per-op
 leg bench_msg_mv 300 python bench.py --msg --multiview --no-cpu-baseline --no-per-op
 leg timeline 300 python tools/timeline.py "$tag"
 leg launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv \
-  --log-file "$out/${tag}_launches.csv" python bench.py --steps 1 --warmup 1 --no-graph --no-prefetch \
+  --log-file "$out/${tag}_launches.csv" python bench.py --steps 1 --warmup 1 --settle 1 --no-graph --no-prefetch \
   --no-cpu-baseline --no-per-op
 tail -n 3 "$out/${tag}_pytest.out"
 cat "$out/${tag}_summary.txt"
