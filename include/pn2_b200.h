@@ -336,6 +336,29 @@ PN2_API int pn2_bwd_stats_finalize(int p, int c, int ld, int nblk, int training,
                                    void *stream);
 
 /* ==========================================================================
+ * Wide layers (n > 128 or lda > 160: SA3 / SA4 / FP1-3 of the reference's models,
+ * pointnet2_semseg.py:32-34, 112-114).  Their adjoint is split in three: dZ written once by
+ * pn2_relu_bn_bwd / pn2_pool_bn_bwd, then two tensor-core products (replacing the two cuBLAS
+ * GEMMs autograd runs for Conv2d 1x1, pytorch_utils.py:87-95):
+ *   dh_prev[p, n_out] = dZ[p, n] * W[n, k]   pn2_mlp_gemm_fwd with a = dZ and the weight tiles of
+ *                                            pn2_mlp_pack_weights_dgrad (columns k..n_out-1 = zeros)
+ *   dW[n, k]          = dZ^T * H_prev        pn2_mlp_wgrad (csrc/mlp_wgrad.cu): both operands read
+ *                                            MN-major straight from their row-major tensors by TMA box
+ *                                            loads; row-split partial images
+ *                                            part[pn2_mlp_wgrad_splits(p, n, ldy)][pn2_mlp_wgrad_rows(n)]
+ *                                                [pn2_mlp_wgrad_cols(ldy)], summed by pn2_sum_partials;
+ *                                            dW is the leading [n, k] block.  x: [p, ldx] (n columns
+ *                                            used), y: [p, ldy]; n, ldx, ldy multiples of 4.
+ * ========================================================================== */
+PN2_API int pn2_mlp_pack_weights_dgrad(int p, int n_out, int n, int k, int ldw, const float *w,
+                                       float *packed, void *stream);
+PN2_API int pn2_mlp_wgrad_splits(int p, int n, int ldy);
+PN2_API int pn2_mlp_wgrad_rows(int n);
+PN2_API int pn2_mlp_wgrad_cols(int ldy);
+PN2_API int pn2_mlp_wgrad(int p, int n, int ldx, int ldy, const float *x, const float *y, float *part,
+                          void *stream);
+
+/* ==========================================================================
  * Training-step utilities on flat fp32 buffers (the step the reference's solver
  * runs after backward, lib/solver.py:171-176, as one launch instead of one per
  * parameter tensor).
@@ -345,6 +368,10 @@ PN2_API int pn2_bwd_stats_finalize(int p, int c, int ld, int nblk, int training,
  * launch is CUDA-graph replayable; the gradient is multiplied by grad_scale first.
  * ========================================================================== */
 PN2_API int pn2_sum_partials(int s, int m, const float *in, float *out, void *stream);
+/* the same sum over padded images in[s][rows_in][cols_in] (cols_in % 4 == 0), written as the DENSE leading
+ * block out[rows_out][cols_out]: the weight gradient in the parameter's own layout */
+PN2_API int pn2_sum_partials_block(int s, int rows_in, int cols_in, int rows_out, int cols_out,
+                                   const float *in, float *out, void *stream);
 /* pn2_dropout_mask: byte keep mask of n elements, P(keep) = keep (resolution 2^-16), counter-based:
  * state = {seed, launch counter} (device int64[2]); the call bumps the counter, so replays of a captured
  * launch draw fresh masks.  The fused chain applies the mask inside the next layer's kernels. */

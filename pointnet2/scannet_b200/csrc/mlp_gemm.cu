@@ -378,7 +378,9 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
 // W [N, K] row-major (a 1x1 conv weight) -> tile images [n_tiles][k_blocks][BN][32], each row's
 // 16-byte chunks XOR-swizzled by (row & 7) exactly as the UMMA SWIZZLE_128B layout expects,
 // rounded to TF32, zero padded.
-__global__ void pack_weights_kernel(const float *__restrict__ W, int N, int K, int ldw, int BN, int n_tiles,
+// (sn, sk): strides of W along the output / reduction index -- (ldw, 1) for the forward product,
+// (1, ldw) for the transposed weight of the data-gradient product dH_prev = dZ * W.
+__global__ void pack_weights_kernel(const float *__restrict__ W, int N, int K, int sn, int sk, int BN, int n_tiles,
                                     int k_blocks, float *__restrict__ Wp) {
   const size_t total = static_cast<size_t>(n_tiles) * k_blocks * BN * BK;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -390,7 +392,7 @@ __global__ void pack_weights_kernel(const float *__restrict__ W, int N, int K, i
     const int kb = static_cast<int>(blk % k_blocks), nt = static_cast<int>(blk / k_blocks);
     const int n = nt * BN + r;
     const int k = kb * BK + ((pc ^ (r & 7)) * 4) + e;
-    float v = (n < N && k < K) ? W[static_cast<size_t>(n) * ldw + k] : 0.f;
+    float v = (n < N && k < K) ? W[static_cast<size_t>(n) * sn + static_cast<size_t>(k) * sk] : 0.f;
     uint32_t t;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
     Wp[i] = __uint_as_float(t);
@@ -403,7 +405,9 @@ __global__ void pack_weights_kernel(const float *__restrict__ W, int N, int K, i
 inline int pick_bn(int p, int n) {
   int bn = n > kMaxBN ? kMaxBN : (n + 15) / 16 * 16;
   const int m_tiles = (p + BM - 1) / BM;
-  while (bn >= 64 && bn % 32 == 0 && m_tiles * ((n + bn - 1) / bn) < kNumSMs) bn /= 2;
+  // (halves stay multiples of 32: the epilogue reads the accumulator out in 32-column blocks, and a block
+  // that straddled the end of a 48- or 80-wide tile would overwrite the next tile's columns of Z)
+  while (bn >= 64 && bn % 64 == 0 && m_tiles * ((n + bn - 1) / bn) < kNumSMs) bn /= 2;
   return bn;
 }
 
@@ -430,7 +434,24 @@ extern "C" int pn2_mlp_pack_weights(int p, int n, int k, int ldw, const float *w
   const size_t total = static_cast<size_t>(nt) * kb * bn * gemm::BK;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-  gemm::pack_weights_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, n, k, ldw, bn, nt, kb, packed);
+  gemm::pack_weights_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, n, k, ldw, 1, bn, nt, kb, packed);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+// Tile images of W^T for the data-gradient product dH_prev[p, n_out] = dZ[p, n] * W[n, k] run on
+// pn2_mlp_gemm_fwd (a = dZ, reduction over the layer's n output channels): output column o < k takes
+// W[:, o]; columns k <= o < n_out (the zero padding of the rows layout) get zero weights, so the
+// product writes zeros there.  Same geometry as pn2_mlp_pack_weights(p, n_out, n).
+extern "C" int pn2_mlp_pack_weights_dgrad(int p, int n_out, int n, int k, int ldw, const float *w, float *packed,
+                                          void *stream) {
+  if (p <= 0 || n <= 0 || k <= 0 || ldw < k || n_out < k) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(w, packed);
+  const int bn = gemm::pick_bn(p, n_out), nt = pn2_mlp_gemm_n_tiles(p, n_out), kb = pn2_mlp_gemm_k_blocks(n);
+  const size_t total = static_cast<size_t>(nt) * kb * bn * gemm::BK;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  gemm::pack_weights_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, k, n, 1, ldw, bn, nt, kb, packed);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

@@ -998,6 +998,55 @@ extern "C" int pn2_sum_partials(int s, int m, const float *in, float *out, void 
   PN2_RETURN_LAUNCH_STATUS();
 }
 
+// The same sum for padded weight-gradient images: in[s][rows_in][cols_in] (cols_in % 4 == 0) -> the dense
+// leading block out[rows_out][cols_out] (any cols_out <= cols_in): the tensor a parameter's .grad takes as
+// it is (no strided view that autograd would have to copy).  Same warp-per-float4 scheme and order.
+__global__ void __launch_bounds__(kRowThreads)
+sum_partials_block_kernel(int S, int rows_in, int cols_in, int rows_out, int cols_out,
+                          const float *__restrict__ in, float *__restrict__ out) {
+  const int c4n = (cols_out + 3) / 4;
+  const int j = blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= rows_out * c4n) return;
+  const int r = j / c4n, c4 = j - r * c4n;
+  const size_t image4 = static_cast<size_t>(rows_in) * cols_in / 4, off4 = (static_cast<size_t>(r) * cols_in) / 4 + c4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int kBatch = 5;
+  for (int s0 = lane; s0 < S; s0 += 32 * kBatch) {
+    float4 v[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i)
+      v[i] = s0 + 32 * i < S ? ld4(in, static_cast<size_t>(s0 + 32 * i) * image4 + off4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i)
+      if (s0 + 32 * i < S) acc.x += v[i].x, acc.y += v[i].y, acc.z += v[i].z, acc.w += v[i].w;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o), acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o), acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+  }
+  if (lane == 0) {
+    float *dst = out + static_cast<size_t>(r) * cols_out + 4 * c4;
+    const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    for (int e = 0; e < 4; ++e)
+      if (4 * c4 + e < cols_out) dst[e] = v[e];
+  }
+}
+
+extern "C" int pn2_sum_partials_block(int s, int rows_in, int cols_in, int rows_out, int cols_out, const float *in,
+                                      float *out, void *stream) {
+  if (s <= 0 || rows_out <= 0 || cols_out <= 0 || rows_out > rows_in || cols_out > cols_in || cols_in % 4 != 0)
+    return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(in, out);
+  if (!aligned16(in)) return PN2_ERR_UNSUPPORTED;
+  const int warps_per_cta = kRowThreads / 32;
+  const int items = rows_out * ((cols_out + 3) / 4);
+  sum_partials_block_kernel<<<(items + warps_per_cta - 1) / warps_per_cta, kRowThreads, 0,
+                              static_cast<cudaStream_t>(stream)>>>(s, rows_in, cols_in, rows_out, cols_out, in, out);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
 // Dropout keep mask (one byte per element) for the classifier's nn.Dropout inside the fused chain
 // (pointnet2_semseg.py:156): counter-based -- element i of launch t keeps iff the i-th 16-bit lane of
 // splitmix64(seed, t, i / 4) is below keep * 65536 -- so the launch is CUDA-graph replayable (the launch

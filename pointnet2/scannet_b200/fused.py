@@ -9,62 +9,26 @@ their adjoints are the streaming kernels of csrc/mlp_rows.cu (C ABI: include/pn2
 (no new parameters: state dicts stay the reference's); running statistics and
 num_batches_tracked are updated exactly like torch.nn.BatchNorm2d does in train mode.
 
-Numerics: BatchNorm statistics fp32 partials + fp64 finalise; GEMMs in TF32 when
-``GEMM_TF32`` (the arithmetic class of the reference's own cuDNN convs, whose
-``cudnn.allow_tf32`` defaults to True) or in fp32 otherwise.
+Numerics: BatchNorm statistics fp32 partials + fp64 finalise; every 1x1 convolution and both of its
+adjoint products run on the hand-written tcgen05 kernels (csrc/mlp_gemm.cu, mlp_bwd.cu, mlp_wgrad.cu)
+with TF32 operands and fp32 accumulation -- the arithmetic class of the reference's own cuDNN convs,
+whose ``cudnn.allow_tf32`` defaults to True.  There is no library GEMM on this path.
 """
 import os
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 from torch.autograd import Function
 
 from . import lib as _lib
 
-GEMM_TF32 = True   # tensor-core TF32 GEMMs, like the reference's cuDNN convs on Ampere+
 ENABLED = True     # module forward()s take the fused path when eligible
-TC_BWD = True      # backward layers on the fused tcgen05 kernel (csrc/mlp_bwd.cu: BN adjoint + dH + dW +
-                   # next statistics in one pass) where the shape is supported and TC_GEMM is on
+TC_BWD = True      # backward layers on the ONE-PASS fused tcgen05 kernel (csrc/mlp_bwd.cu: BN adjoint + dH +
+                   # dW + next statistics) where the shape fits it (N <= 128, lda <= 160); the wider layers --
+                   # and every layer when this is off (tests) -- take the split adjoint: dZ written once by a
+                   # streaming kernel, then the data-gradient product on the forward layer kernel and the
+                   # weight-gradient product on csrc/mlp_wgrad.cu
 POOL_IN_GEMM = True  # pooled last layer: group extrema from the tensor-core layer's epilogue (no pass over Z)
-TC_GEMM = True     # forward layers on the hand-written tcgen05 kernel (csrc/mlp_gemm.cu) when
-                   # GEMM_TF32: BN fold + ReLU of the previous layer in its prologue, BN batch
-                   # statistics in its epilogue; off: cuBLAS GEMM + separate streaming kernels
-
-
-def _mm(a, b):
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = GEMM_TF32
-    try:
-        return torch.mm(a, b)
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
-
-
-def _mm_tn_splitk(dz, h):
-    """dz^T @ h for tall-skinny operands ([P, Cout]^T [P, Cin], P up to 10^6): a single GEMM
-    offers only Cout*Cin/tile CTAs, so the reduction over P is split into S slabs computed as
-    one batched GEMM and summed (fixed order)."""
-    P, cout = dz.shape
-    cin = h.shape[1]
-    tiles = ((cout + 127) // 128) * ((cin + 63) // 64)
-    S = min((2 * 148 + tiles - 1) // tiles, P // 2048)
-    while S > 1 and P % S:
-        S -= 1
-    if S <= 1:
-        return _mm(dz.t(), h)
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = GEMM_TF32
-    try:
-        part = torch.bmm(dz.view(S, P // S, cout).transpose(1, 2), h.view(S, P // S, cin))
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
-    if (cout * cin) % 4:
-        return part.sum(dim=0)
-    out = torch.empty(cout, cin, dtype=torch.float32, device=dz.device)
-    _lib.check(_lib.load().pn2_sum_partials(S, cout * cin, part.data_ptr(), out.data_ptr(), _stream(dz.device)),
-               "sum_partials")
-    return out
 
 
 def _stream(dev):
@@ -257,6 +221,48 @@ def _tc_layer(A, k, W2, fold, relu_in, want_h, want_stats, drop=None, pool_ns=0)
     return z, h, part, (nt * bn, grid)
 
 
+def _pack_dgrad(P, n_out, W2c):
+    """Tile images of W^T for dH_prev[P, n_out] = dZ[P, N] @ W2c[N, K] on the forward layer kernel
+    (columns K..n_out-1, the zero padding of the rows layout, get zero weights)."""
+    L = _lib.load()
+    N, K = W2c.shape
+    bn, nt, kb = L.pn2_mlp_gemm_bn(P, n_out), L.pn2_mlp_gemm_n_tiles(P, n_out), L.pn2_mlp_gemm_k_blocks(N)
+    return _packed("dgrad", W2c, (P, n_out, N, K), nt * kb * bn * 32, lambda ptr, st: _lib.check(
+        L.pn2_mlp_pack_weights_dgrad(P, n_out, N, K, W2c.shape[1], W2c.data_ptr(), ptr, st),
+        "mlp_pack_weights_dgrad"))
+
+
+def _dgrad(dz, W2c, n_out, wp=None):
+    """dH_prev [P, n_out] = dz [P, N] @ W2c [N, K] (zero columns past K): the data-gradient product of a
+    wide layer, on the tcgen05 forward layer kernel with the transposed weight tiles."""
+    L = _lib.load()
+    dev = dz.device
+    P, N = dz.shape
+    if wp is None:
+        wp = _pack_dgrad(P, n_out, W2c)
+    out = torch.empty(P, n_out, dtype=torch.float32, device=dev)
+    _lib.check(L.pn2_mlp_gemm_fwd(P, N, N, n_out, n_out, dz.data_ptr(), None, None, 0, None, wp.data_ptr(),
+                                  out.data_ptr(), None, None, 1.0, 0, None, None, None, None, _stream(dev)),
+               "mlp_gemm_fwd (dgrad)")
+    return out
+
+
+def _wgrad(dz, h, K):
+    """(dz^T @ h)[:, :K] -> dense [N, K]: csrc/mlp_wgrad.cu, row-split partial images summed in fixed order
+    straight into the parameter's layout (autograd takes the tensor as .grad without a copy)."""
+    L = _lib.load()
+    dev = dz.device
+    P, N = dz.shape
+    ldy = h.shape[1]
+    S, R, Cc = L.pn2_mlp_wgrad_splits(P, N, ldy), L.pn2_mlp_wgrad_rows(N), L.pn2_mlp_wgrad_cols(ldy)
+    part = torch.empty(S, R, Cc, dtype=torch.float32, device=dev)
+    _lib.check(L.pn2_mlp_wgrad(P, N, N, ldy, dz.data_ptr(), h.data_ptr(), part.data_ptr(), _stream(dev)), "mlp_wgrad")
+    out = torch.empty(N, K, dtype=torch.float32, device=dev)
+    _lib.check(L.pn2_sum_partials_block(S, R, Cc, N, K, part.data_ptr(), out.data_ptr(), _stream(dev)),
+               "sum_partials_block")
+    return out
+
+
 def _bn_finalize(P, C, part, ld, nblk, gamma, beta, rm, rv, eps, momentum, nbt=None):
     L = _lib.load()
     dev = part.device
@@ -288,7 +294,6 @@ class SharedMLPRows(Function):
         P = x0.shape[0]
         layers, hs = [], [x0]
         out = argmax = zsel = None
-        use_tc = TC_GEMM and GEMM_TF32
         want_grad = any(ctx.needs_input_grad)
         bwd_fused = [False] * nl
         wt_packed = [None] * nl   # transposed tile images for the fused backward layers, packed beside the forward pass
@@ -297,56 +302,50 @@ class SharedMLPRows(Function):
                 W, gamma, beta = params[3 * l:3 * l + 3]
                 W2 = W.reshape(W.shape[0], -1)
                 lda = x0.shape[1] if l == 0 else layers[l - 1].cout
-                bwd_fused[l] = bool(use_tc and TC_BWD and want_grad and
+                bwd_fused[l] = bool(TC_BWD and want_grad and
                                     L.pn2_mlp_bwd_supported(P, W2.shape[0], W2.shape[1], lda, int(l > 0)) and
                                     not (l == nl - 1 and ns > 0 and ns % 4 != 0))
                 want_h = want_grad and not bwd_fused[l]   # the fused adjoint recomputes H_{l-1} from Z_{l-1}
                 st = _BNLayer()
                 st.cout = W2.shape[0]
                 rm, rv, nbt = buffers[l]
-                if use_tc:
-                    # tensor-core layer: the previous layer's BN fold + ReLU is applied to the A tile
-                    # on chip (its normalised output is only written out, once, for the backward
-                    # weight-gradient GEMM); this layer's BN statistics come out of the epilogue
-                    prev = layers[l - 1] if l > 0 else None
-                    A = prev.z if prev is not None else x0
-                    fold = (prev.a, prev.b) if prev is not None else None
-                    drop = drops[l - 1] if l > 0 else None
-                    assert drop is None or (bwd_fused[l] and bwd_fused[l - 1]), "dropout needs the fused backward layers"
-                    # pooled last layer: the group extrema of z come out of the same kernel
-                    ext = None
-                    pool_here = (l == nl - 1 and ns > 0 and POOL_IN_GEMM and P % ns == 0
-                                 and bool(L.pn2_mlp_gemm_pool_supported(ns)))
-                    res = _tc_layer(A, W2.shape[1], W2, fold, relus[l - 1] if l > 0 else False, want_h, training,
-                                    drop, ns if pool_here else 0)
-                    st.z, h, part, (ld, nblk) = res[:4]
-                    if pool_here:
-                        ext = res[4]
-                    if bwd_fused[l] and _pack_state["active"] and (l > 0 or ctx.needs_input_grad[0]):
-                        W2c, Cn, Kk = W2.contiguous(), W2.shape[0], W2.shape[1]
+                # tensor-core layer: the previous layer's BN fold + ReLU is applied to the A tile
+                # on chip (its normalised output is only written out, once, where the split adjoint's
+                # weight-gradient product needs it); this layer's BN statistics come out of the epilogue
+                prev = layers[l - 1] if l > 0 else None
+                A = prev.z if prev is not None else x0
+                fold = (prev.a, prev.b) if prev is not None else None
+                drop = drops[l - 1] if l > 0 else None
+                assert drop is None or (bwd_fused[l] and bwd_fused[l - 1]), "dropout needs the fused backward layers"
+                # pooled last layer: the group extrema of z come out of the same kernel
+                ext = None
+                pool_here = (l == nl - 1 and ns > 0 and POOL_IN_GEMM and P % ns == 0
+                             and bool(L.pn2_mlp_gemm_pool_supported(ns)))
+                res = _tc_layer(A, W2.shape[1], W2, fold, relus[l - 1] if l > 0 else False, want_h, training,
+                                drop, ns if pool_here else 0)
+                st.z, h, part, (ld, nblk) = res[:4]
+                if pool_here:
+                    ext = res[4]
+                if _pack_state["active"] and want_grad and (l > 0 or ctx.needs_input_grad[0]):
+                    W2c, Cn, Kk = W2.contiguous(), W2.shape[0], W2.shape[1]
+                    if bwd_fused[l]:
                         wt_packed[l] = _packed(
                             "bwd", W2c, (Cn, Kk, lda), L.pn2_mlp_bwd_nb(Cn) * L.pn2_mlp_bwd_kpad(lda) * 32,
                             lambda ptr, strm: _lib.check(L.pn2_mlp_pack_weights_t(
                                 Cn, Kk, lda, W2c.shape[1], W2c.data_ptr(), ptr, strm), "mlp_pack_weights_t"))
-                    if l > 0:
-                        hs.append(h)          # None when the fused backward layer will recompute it
-                    if training:
-                        st.a, st.b, st.mean, st.invstd = _bn_finalize(P, st.cout, part, ld, nblk, gamma, beta,
-                                                                      rm, rv, eps, momentum, nbt)
                     else:
-                        st.a, st.b, st.mean, st.invstd = _bn_forward(st.z, gamma, beta, rm, rv, eps, momentum, False)
-                    layers.append(st)
-                    C = st.cout
-                    if l < nl - 1:
-                        continue
+                        wt_packed[l] = _pack_dgrad(P, lda, W2c)
+                if l > 0:
+                    hs.append(h)          # None when the fused backward layer will recompute it
+                if training:
+                    st.a, st.b, st.mean, st.invstd = _bn_finalize(P, st.cout, part, ld, nblk, gamma, beta,
+                                                                  rm, rv, eps, momentum, nbt)
                 else:
-                    cin = hs[-1].shape[1]
-                    if W2.shape[1] != cin:  # first layer: rows are zero-padded to a multiple of 4
-                        W2 = F.pad(W2, (0, cin - W2.shape[1]))
-                    st.z = _mm(hs[-1], W2.t())
-                    st.a, st.b, st.mean, st.invstd = _bn_forward(st.z, gamma, beta, rm, rv, eps, momentum, training, nbt)
-                    layers.append(st)
-                    C = st.cout
+                    st.a, st.b, st.mean, st.invstd = _bn_forward(st.z, gamma, beta, rm, rv, eps, momentum, False)
+                layers.append(st)
+                C = st.cout
+                if l < nl - 1:
+                    continue
                 if l < nl - 1 or ns == 0:
                     h = torch.empty_like(st.z)
                     _lib.check(L.pn2_bn_relu_apply(P, C, st.z.data_ptr(), st.a.data_ptr(), st.b.data_ptr(),
@@ -355,7 +354,7 @@ class SharedMLPRows(Function):
                         hs.append(h)
                     else:
                         out = h
-                elif use_tc and ext is not None:
+                elif ext is not None:
                     G = P // ns
                     out = torch.empty(G, C, dtype=torch.float32, device=dev)
                     argmax = torch.empty(G, C, dtype=torch.int32, device=dev)
@@ -375,7 +374,6 @@ class SharedMLPRows(Function):
                                                       _stream(dev)), "bn_relu_groupmax")
         ctx.layers, ctx.hs, ctx.argmax, ctx.bwd_fused, ctx.wt_packed = layers, hs, argmax, bwd_fused, wt_packed
         ctx.zsel = zsel
-        assert use_tc or not any(d is not None for d in drops), "dropout inside the chain needs the tensor-core path"
         ctx.ns, ctx.training, ctx.nl, ctx.relus, ctx.drops = ns, training, nl, relus, drops
         ctx.weights = [params[3 * l] for l in range(nl)]
         return out
@@ -456,9 +454,9 @@ class SharedMLPRows(Function):
                         d_out[0].data_ptr() if d_out is not None else None, float(d_out[1]) if d_out is not None else 1.0,
                         d_in[0].data_ptr() if d_in is not None else None, float(d_in[1]) if d_in is not None else 1.0, s),
                         "mlp_bwd_layer")
-                    dW = f32(nb * 32, kb * 32)
                     pending = None
                     if sp is not None:   # weight-gradient partials + the statistics of the layer below: one launch
+                        dW = f32(nb * 32, kb * 32)
                         Kc = prev.cout
                         pg, pb, pc = f32(Kc), f32(Kc), f32(2 * Kc)
                         scratch = f32(L.pn2_mlp_bwd_finalize_scratch_floats(C, lda))
@@ -470,14 +468,20 @@ class SharedMLPRows(Function):
                                                           _sched_counters(dev)[8:].data_ptr(), s),
                                    "mlp_bwd_finalize")
                         pending = (pg, pb, pc)
+                        grads[3 * l] = dW[:C, :K].reshape(W.shape)
                     else:
-                        _on_dw_branch(dev, (dwp, dW), lambda: _lib.check(L.pn2_sum_partials(
-                            grid, nb * 32 * kb * 32, dwp.data_ptr(), dW.data_ptr(), _stream(dev)), "sum_partials"))
-                    grads[3 * l] = dW[:C, :K].reshape(W.shape)
+                        # dense [C, K] written on the branch: autograd takes it as .grad as it is (a strided
+                        # view of a padded image would be COPIED by AccumulateGrad on the main stream, beside
+                        # the branch that is still summing it)
+                        dWd = f32(C, K)
+                        _on_dw_branch(dev, (dwp, dWd), lambda: _lib.check(L.pn2_sum_partials_block(
+                            grid, nb * 32, kb * 32, C, K, dwp.data_ptr(), dWd.data_ptr(), _stream(dev)),
+                            "sum_partials_block"))
+                        grads[3 * l] = dWd.reshape(W.shape)
                     grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
                     dh = dh_prev
                     continue
-                # ---- streaming adjoint kernels + cuBLAS GEMMs ----
+                # ---- split adjoint (wide layers): dZ by a streaming kernel, then two tensor-core products ----
                 pending = None
                 dz = torch.empty_like(st.z)
                 dgamma, dbeta = f32(C), f32(C)
@@ -494,17 +498,10 @@ class SharedMLPRows(Function):
                                                  st.invstd.data_ptr(), dz.data_ptr(), dgamma.data_ptr(),
                                                  dbeta.data_ptr(), ws.data_ptr(), s), "relu_bn_bwd")
                 h_prev = hs[l]
-                dW = _on_dw_branch(dev, (dz, h_prev), lambda: _mm_tn_splitk(dz, h_prev))   # [Cout, Cin(_pad)]
-                if dW.shape[1] != W2.shape[1]:
-                    dW = dW[:, :W2.shape[1]]
+                dW = _on_dw_branch(dev, (dz, h_prev), lambda: _wgrad(dz, h_prev, K))   # dense [C, K]
                 grads[3 * l] = dW.reshape(W.shape)
                 grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
-                if need_dh:
-                    if W2.shape[1] != h_prev.shape[1]:
-                        W2 = F.pad(W2, (0, h_prev.shape[1] - W2.shape[1]))
-                    dh = _mm(dz, W2)                           # [P, Cin]
-                else:
-                    dh = None
+                dh = _dgrad(dz, W2.contiguous(), h_prev.shape[1], ctx.wt_packed[l]) if need_dh else None
         return (dh if ctx.needs_input_grad[0] else None, None, None, None, None, None, None, None) + tuple(grads)
 
 
@@ -688,7 +685,7 @@ def _dropout_mask(rows, cols, keep, dev):
 def chain_supports_dropout(units, x0, i):
     """Can nn.Dropout after unit ``i`` of the chain be applied inside the kernels of unit i + 1?  Needs the
     tensor-core forward layer and the fused backward layers for units i and i + 1."""
-    if not (TC_GEMM and GEMM_TF32 and TC_BWD and ENABLED) or i + 1 >= len(units):
+    if not (TC_BWD and ENABLED) or i + 1 >= len(units):
         return False
     L = _lib.load()
     shape = tuple(x0.shape) if hasattr(x0, "shape") else tuple(x0)   # rows [P, width] or just their shape

@@ -64,8 +64,15 @@ SIGNATURES = {
     "pn2_pool_bn_bwd_stats": [_i, _i, _i, _i] + [_vp] * 13,
     "pn2_relu_bn_bwd_stats": [_i, _i, _i, _i] + [_vp] * 11,
     "pn2_bwd_stats_finalize": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    # wide layers: data-gradient weight tiles, weight-gradient product
+    "pn2_mlp_pack_weights_dgrad": [_i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "pn2_mlp_wgrad_splits": [_i, _i, _i],
+    "pn2_mlp_wgrad_rows": [_i],
+    "pn2_mlp_wgrad_cols": [_i],
+    "pn2_mlp_wgrad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     # flat-buffer training-step utilities
     "pn2_sum_partials": [_i, _i, _vp, _vp, _vp],
+    "pn2_sum_partials_block": [_i, _i, _i, _i, _i, _vp, _vp, _vp],
     "pn2_dropout_mask": [ctypes.c_longlong, _f, _vp, _vp, _vp],
     "pn2_adam_flat": [ctypes.c_longlong, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp],
     # weighted cross-entropy of the training step

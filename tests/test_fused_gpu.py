@@ -1,11 +1,19 @@
-"""GPU parity of the fused shared-MLP blocks (rows layout, csrc/mlp_rows.cu + GEMM) against
-the SAME module run through the reference's formulation (torch.nn Conv2d + BatchNorm2d +
-ReLU + max_pool2d on (B, C, npoint, nsample)).
+"""GPU parity of the fused shared-MLP blocks (rows layout, tcgen05 layers) against the SAME module run
+through the reference's formulation (torch.nn Conv2d + BatchNorm2d + ReLU + max_pool2d on
+(B, C, npoint, nsample)).
 
-Tolerances.  With fp32 GEMMs on both sides (TF32 off) the two paths differ only by
-summation order: outputs, input gradients and parameter gradients within 2e-4 of the
-tensor's max magnitude, BatchNorm running statistics within 1e-5.  With TF32 GEMMs (the
-reference's default arithmetic for its convs) the bar is 5e-3 of the max magnitude.
+Every 1x1 convolution of the fused path and both of its adjoint products run on the hand-written
+tensor-core kernels with TF32 operands and fp32 accumulation -- there is no fp32 or library GEMM mode.
+The stated tolerance: the fused path's deviation from the fp32 result of the
+reference formulation (``allow_tf32 = False``: the truth) is at most 4x the deviation the reference
+formulation ITSELF shows under its default arithmetic (``cudnn.allow_tf32 = True``), with a floor of
+5e-3 of the tensor's max magnitude for outputs (entry by entry) and 1e-2 in the L2 norm for gradients.
+Gradients are compared in the L2 norm because under TF32 a pooled value can change its arg-max row or
+cross the ReLU threshold, which re-routes ONE gradient entry completely (the reference formulation shows
+4-40 % max-entry deviations on these inputs for the same reason).  (4x: the tensor core truncates the
+activation operands to TF32 where cuDNN's kernels may round them; truncation doubles the operand error.)
+The kernels' arithmetic itself is pinned to 2e-5 .. 4e-4 against fp64 products of the TF32-reduced
+operands in test_gemm_gpu.py / test_bwd_gpu.py / test_wide_gpu.py.
 """
 import copy
 
@@ -28,18 +36,19 @@ def l2_err(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-20))
 
 
-class precision(object):
+class torch_tf32(object):
+    """arithmetic of the torch.nn formulation: TF32 convs / matmuls on (the reference's default) or off"""
+
     def __init__(self, tf32):
         self.tf32 = tf32
 
-    def __enter__(self):  # fp32 mode also takes the cuBLAS + streaming-kernel path (TC_GEMM needs TF32)
-        self.saved = (fused.GEMM_TF32, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-        fused.GEMM_TF32 = self.tf32
+    def __enter__(self):
+        self.saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
         torch.backends.cudnn.allow_tf32 = self.tf32
         torch.backends.cuda.matmul.allow_tf32 = self.tf32
 
     def __exit__(self, *a):
-        fused.GEMM_TF32, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.saved
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.saved
 
 
 def run(module, enabled, *inputs, train=True):
@@ -61,21 +70,29 @@ def run(module, enabled, *inputs, train=True):
     return out.detach(), grads, bufs, in_grads
 
 
-def compare(module, inputs, tol, stat_tol):
+def class_bound(module, inputs, factor=4.0, out_floor=5e-3, grad_floor=1e-2, stat_tol=2e-3):
+    """fused (tcgen05, TF32) vs the torch.nn formulation in fp32, bounded by what the torch.nn
+    formulation itself loses under TF32.  Returns the measured deviations (printed on failure)."""
+    with torch_tf32(False):
+        out_t, g_t, b_t, ig_t = run(module, False, *inputs)
+    with torch_tf32(True):
+        out_r, g_r, _, ig_r = run(module, False, *inputs)
     out_f, g_f, b_f, ig_f = run(module, True, *inputs)
-    out_r, g_r, b_r, ig_r = run(module, False, *inputs)
-    assert out_f.shape == out_r.shape
-    assert rel_err(out_f, out_r) < tol, "output %g" % rel_err(out_f, out_r)
-    for n in g_r:
-        assert rel_err(g_f[n], g_r[n]) < tol, "grad %s %g" % (n, rel_err(g_f[n], g_r[n]))
-    for n in b_r:
-        if b_r[n].dtype == torch.long:
-            assert torch.equal(b_f[n], b_r[n]), n
+    assert out_f.shape == out_t.shape
+    report = {"out": (rel_err(out_f, out_t), rel_err(out_r, out_t))}
+    assert report["out"][0] <= max(factor * report["out"][1], out_floor), report
+    pairs = [(n, g_f[n], g_r[n], g_t[n]) for n in g_t]
+    pairs += [("input%d" % i, f, r, t) for i, (f, r, t) in enumerate(zip(ig_f, ig_r, ig_t)) if t is not None]
+    for n, f, r, t in pairs:
+        assert f is not None, n
+        report[n] = (l2_err(f, t), l2_err(r, t))
+        assert report[n][0] <= max(factor * report[n][1], grad_floor), (n, report[n])
+    for n in b_t:
+        if b_t[n].dtype == torch.long:
+            assert torch.equal(b_f[n], b_t[n]), n
         else:
-            assert rel_err(b_f[n], b_r[n]) < stat_tol, "buffer %s %g" % (n, rel_err(b_f[n], b_r[n]))
-    for a, b in zip(ig_f, ig_r):
-        if b is not None:
-            assert rel_err(a, b) < tol, "input grad %g" % rel_err(a, b)
+            assert rel_err(b_f[n], b_t[n]) < stat_tol, "buffer %s %g" % (n, rel_err(b_f[n], b_t[n]))
+    return report
 
 
 def sa_inputs(B, N, C, seed=0):
@@ -88,52 +105,50 @@ def sa_inputs(B, N, C, seed=0):
 def test_sa_module_ssg():
     torch.manual_seed(0)
     sa = M.PointnetSAModule(npoint=256, radius=0.2, nsample=32, mlp=[6, 32, 32, 64]).to(DEV)
-    with precision(False):
-        compare(sa, sa_inputs(2, 2048, 6), 2e-4, 1e-5)
+    class_bound(sa, sa_inputs(2, 2048, 6))
 
 
-def test_sa_module_tf32_error_is_the_references_class():
-    """TF32 GEMMs: the fused path's deviation from the fp32 result must be of the size of the
-    deviation the reference's own formulation shows when ITS convs run in TF32 (the torch
-    default): no worse than 3x that, or 5e-3 of the max magnitude, whichever is larger."""
+def test_sa_module_ssg_wide():
+    """SA3 / SA4 of the SSG model (pointnet2_semseg.py:112-114): the pooled 256- and 512-wide layers and the
+    259-channel first layer take the split adjoint (mlp_wgrad.cu + data gradient on the forward kernel)."""
     torch.manual_seed(0)
-    sa = M.PointnetSAModule(npoint=256, radius=0.2, nsample=32, mlp=[6, 32, 32, 64]).to(DEV)
-    ins = sa_inputs(2, 2048, 6)
-    with precision(False):
-        out_t, g_t, _, ig_t = run(sa, False, *ins)
-    with precision(True):
-        out_f, g_f, _, ig_f = run(sa, True, *ins)
-        out_r, g_r, _, ig_r = run(sa, False, *ins)
-    # The output is compared entry by entry.  Gradients are compared in the L2 norm: under TF32 a
-    # pooled value can change its arg-max row or cross the ReLU threshold, which re-routes ONE
-    # gradient entry completely (the reference formulation shows 4-40 % max-entry deviations on this
-    # very input for the same reason), so a max-entry bound would test luck, not arithmetic.
-    assert rel_err(out_f, out_t) <= max(3 * rel_err(out_r, out_t), 5e-3), (rel_err(out_f, out_t), rel_err(out_r, out_t))
-    pairs = [(n, g_f[n], g_r[n], g_t[n]) for n in g_t] + [("input", ig_f[1], ig_r[1], ig_t[1])]
-    for n, f, r, t in pairs:
-        ef, er = l2_err(f, t), l2_err(r, t)
-        assert ef <= max(3 * er, 1e-2), (n, ef, er)
+    sa3 = M.PointnetSAModule(npoint=64, radius=0.4, nsample=32, mlp=[128, 128, 128, 256]).to(DEV)
+    # (8 / 16 clouds: a pooled channel's bias gradient sums one term per group, and with only ~100 groups a
+    # single ReLU decision that TF32 flips moves it by a percent)
+    class_bound(sa3, sa_inputs(8, 256, 128, seed=1), grad_floor=2e-2)
+    sa4 = M.PointnetSAModule(npoint=16, radius=0.8, nsample=32, mlp=[256, 256, 256, 512]).to(DEV)
+    class_bound(sa4, sa_inputs(16, 64, 256, seed=2), grad_floor=2e-2)
 
 
 def test_sa_module_msg_odd_widths():
     torch.manual_seed(0)
     sa = M.PointnetSAModuleMSG(npoint=128, radii=[0.1, 0.2], nsamples=[16, 32],
                                mlps=[[64, 64, 96, 128], [64, 128, 196, 256]]).to(DEV)
-    with precision(False):
-        compare(sa, sa_inputs(2, 1024, 64, seed=3), 2e-4, 1e-5)
+    class_bound(sa, sa_inputs(2, 1024, 64, seed=3))
+
+
+def fp_inputs(n, m, c1, c2, seed=1):
+    xyz, _ = cases.chunk_xyz(2, npoints=n)
+    unknown = cases.t(xyz, DEV)
+    known = unknown[:, :m].contiguous()
+    rng = np.random.default_rng(seed)
+    uf = cases.t(rng.standard_normal((2, c1, n)).astype(np.float32), DEV)
+    kf = cases.t(rng.standard_normal((2, c2, m)).astype(np.float32), DEV)
+    return [(unknown, False), (known, False), (uf, True), (kf, True)]
 
 
 def test_fp_module():
     torch.manual_seed(0)
     fp = M.PointnetFPModule(mlp=[128 + 6, 128, 128]).to(DEV)
-    xyz, _ = cases.chunk_xyz(2, npoints=2048)
-    unknown = cases.t(xyz, DEV)
-    known = unknown[:, :256].contiguous()
-    rng = np.random.default_rng(1)
-    uf = cases.t(rng.standard_normal((2, 6, 2048)).astype(np.float32), DEV)
-    kf = cases.t(rng.standard_normal((2, 128, 256)).astype(np.float32), DEV)
-    with precision(False):
-        compare(fp, [(unknown, False), (known, False), (uf, True), (kf, True)], 2e-4, 1e-5)
+    class_bound(fp, fp_inputs(2048, 256, 6, 128))
+
+
+def test_fp_module_wide():
+    """FP1 / FP3 of the SSG model ([320, 256, 128] and [768, 256, 256]): split adjoint with 320- / 768-column
+    data gradients."""
+    torch.manual_seed(0)
+    class_bound(M.PointnetFPModule(mlp=[256 + 64, 256, 128]).to(DEV), fp_inputs(1024, 256, 64, 256, seed=2))
+    class_bound(M.PointnetFPModule(mlp=[512 + 256, 256, 256]).to(DEV), fp_inputs(64, 16, 256, 512, seed=3))
 
 
 def test_eval_mode_uses_running_stats():
@@ -143,10 +158,13 @@ def test_eval_mode_uses_running_stats():
         if isinstance(m, torch.nn.BatchNorm2d):
             m.running_mean.normal_(), m.running_var.uniform_(0.5, 2.0)
     ins = sa_inputs(2, 512, 6)
-    with precision(False), torch.no_grad():
+    with torch.no_grad():
+        with torch_tf32(False):
+            out_t = run_noback(sa, False, ins)
+        with torch_tf32(True):
+            out_r = run_noback(sa, False, ins)
         out_f = run_noback(sa, True, ins)
-        out_r = run_noback(sa, False, ins)
-    assert rel_err(out_f, out_r) < 2e-4
+    assert rel_err(out_f, out_t) <= max(4 * rel_err(out_r, out_t), 5e-3), (rel_err(out_f, out_t), rel_err(out_r, out_t))
 
 
 def run_noback(module, enabled, inputs):
@@ -158,71 +176,48 @@ def run_noback(module, enabled, inputs):
         fused.ENABLED = True
 
 
-def test_full_ssg_model_step_matches_unfused():
-    """Whole SSG network, one forward/backward: fused vs torch.nn formulation."""
+def model_step(model, pc, enabled):
+    m = copy.deepcopy(model).train()
+    m.cls_layer[1].p = 0.0  # the dropout mask is drawn per layout; keep the comparison deterministic
+    fused.ENABLED = enabled
+    try:
+        logits = m(pc)
+        torch.manual_seed(6)
+        (logits * torch.randn_like(logits)).sum().backward()  # (a mean of squares after the
+        # final BatchNorm would be constant: every gradient would be rounding noise)
+    finally:
+        fused.ENABLED = True
+    return logits.detach(), {n: p.grad for n, p in m.named_parameters()}
+
+
+@pytest.mark.parametrize("is_msg,c0", [(False, 6), (True, 6), (False, 131), (True, 131)])
+def test_full_model_step_matches_torch_nn(is_msg, c0):
+    """Whole SSG / MSG network (BASELINE configs 2, 3, 5: 6 or 131 feature channels), one forward/backward on
+    the tcgen05 path against the torch.nn formulation in fp32, bounded by the torch.nn formulation's own
+    TF32 deviation.  Through 4 SA + 4 FP levels TF32 differences flip ReLU / max-pool decisions, so the
+    gradient is compared in the L2 norm over all parameters and single parameters loosely."""
+    from pointnet2.scannet_b200 import synthetic
     torch.manual_seed(0)
-    model = pointnet2_semseg.get_model(20, is_msg=False, input_channels=6).to(DEV)
-    x, _, _ = __import__("pointnet2.scannet_b200.synthetic", fromlist=["x"]).make_batch(2, 2, 8192)
+    model = pointnet2_semseg.get_model(20, is_msg=is_msg, input_channels=c0).to(DEV)
+    x, _, _ = synthetic.make_batch(2, 2, 8192, use_multiview=(c0 == 131), use_color=(c0 != 131))
     pc = cases.t(x, DEV)
-    with precision(False):
-        outs = []
-        for enabled in (True, False):
-            m = copy.deepcopy(model).train()
-            m.cls_layer[1].p = 0.0  # the dropout mask is drawn per layout; keep the comparison deterministic
-            fused.ENABLED = enabled
-            try:
-                torch.manual_seed(5)  # dropout mask
-                logits = m(pc)
-                torch.manual_seed(6)
-                (logits * torch.randn_like(logits)).sum().backward()  # (a mean of squares after the
-                # final BatchNorm would be constant: every gradient would be rounding noise)
-            finally:
-                fused.ENABLED = True
-            outs.append((logits.detach(), {n: p.grad for n, p in m.named_parameters()}))
-    (lf, gf), (lr, gr) = outs
-    assert rel_err(lf, lr) < 1e-3, rel_err(lf, lr)
-    # through 4 SA + 4 FP levels fp32 summation-order differences flip a few ReLU / max-pool
-    # decisions, so single parameters are compared loosely and the whole gradient in L2
-    flat_f = torch.cat([gf[n].flatten() for n in gr])
-    flat_r = torch.cat([gr[n].flatten() for n in gr])
-    l2 = float((flat_f - flat_r).norm() / flat_r.norm())
-    worst = max((rel_err(gf[n], gr[n]), n) for n in gr)
-    assert l2 < 1e-2, (l2, worst)
-    assert worst[0] < 0.1, worst
+    assert pc.shape[2] == 3 + c0
+    with torch_tf32(False):
+        lt, gt = model_step(model, pc, False)
+    with torch_tf32(True):
+        lr, gr = model_step(model, pc, False)
+    lf, gf = model_step(model, pc, True)
+    e_f, e_r = rel_err(lf, lt), rel_err(lr, lt)
+    assert e_f <= max(4 * e_r, 2e-2), (e_f, e_r)
 
+    def flat(g):
+        return torch.cat([g[n].flatten() for n in gt])
 
-def test_tensor_core_path_matches_cublas_path():
-    """Same fused block, TF32 both ways: hand-written tcgen05 layers (BN fold/ReLU in the prologue,
-    statistics in the epilogue, fused backward layers) vs cuBLAS GEMMs + streaming kernels.  Both
-    use TF32 operands (the tcgen05 path truncates the activation operand, cuBLAS does whatever it
-    does) and accumulate in fp32: outputs agree to 3e-3 of the max magnitude; gradients -- long
-    cancelling sums of TF32 products, with arg-max rows / ReLU masks that flip on near-ties, which
-    re-routes single entries completely -- to 5e-2 in the L2 norm.
-    The principled bound is test_sa_module_tf32_error_is_the_references_class (vs fp32 truth)."""
-    torch.manual_seed(0)
-    sa = M.PointnetSAModule(npoint=256, radius=0.2, nsample=32, mlp=[6, 32, 32, 64]).to(DEV)
-    fp = M.PointnetFPModule(mlp=[128 + 6, 128, 128]).to(DEV)
-    ins = sa_inputs(2, 2048, 6)
-    xyz, _ = cases.chunk_xyz(2, npoints=2048)
-    rng = np.random.default_rng(1)
-    fp_ins = [(cases.t(xyz, DEV), False), (cases.t(xyz[:, :256].copy(), DEV), False),
-              (cases.t(rng.standard_normal((2, 6, 2048)).astype(np.float32), DEV), True),
-              (cases.t(rng.standard_normal((2, 128, 256)).astype(np.float32), DEV), True)]
-    for module, inputs in ((sa, ins), (fp, fp_ins)):
-        res = []
-        for tc in (True, False):
-            fused.TC_GEMM = tc
-            try:
-                res.append(run(module, True, *inputs))
-            finally:
-                fused.TC_GEMM = True
-        (o1, g1, b1, i1), (o2, g2, b2, i2) = res
-        assert rel_err(o1, o2) < 3e-3, rel_err(o1, o2)
-        for n in g2:
-            assert l2_err(g1[n], g2[n]) < 5e-2, (n, l2_err(g1[n], g2[n]))
-        for n in b2:
-            if b2[n].dtype != torch.long:
-                assert rel_err(b1[n], b2[n]) < 2e-3, n
+    l2_f, l2_r = l2_err(flat(gf), flat(gt)), l2_err(flat(gr), flat(gt))
+    assert l2_f <= max(4 * l2_r, 5e-2), (l2_f, l2_r)
+    worst = max((l2_err(gf[n], gt[n]), n) for n in gt)
+    worst_r = max((l2_err(gr[n], gt[n]), n) for n in gt)
+    assert worst[0] <= max(4 * worst_r[0], 0.2), (worst, worst_r)
 
 
 def test_flat_adam_matches_torch_adam():

@@ -60,7 +60,9 @@ def run_gemm(A, W, k, a_in=None, b_in=None, relu=False, want_h=False):
 @pytest.mark.parametrize("P,K,lda,N", [
     (1000, 9, 12, 32), (4096, 32, 32, 32), (5000, 64, 64, 128), (3000, 131, 132, 128),
     (2048, 256, 256, 512), (777, 64, 64, 20), (1024, 128, 128, 196), (70000, 32, 32, 64),
-    (128, 8, 8, 16), (130, 260, 260, 256)])
+    (128, 8, 8, 16), (130, 260, 260, 256),
+    # few row tiles: the launcher narrows the N tile to cover the machine (96 -> must not become 48, 160 -> not 80)
+    (4096, 64, 64, 96), (2000, 128, 128, 160), (8192, 96, 96, 128), (3000, 64, 64, 224), (1500, 32, 32, 320)])
 def test_gemm_plain(P, K, lda, N):
     rng = np.random.default_rng(P + N)
     A = np.zeros((P, lda), np.float32)
