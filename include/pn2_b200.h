@@ -218,6 +218,24 @@ PN2_API int pn2_fp_interp_rows_grad(int b, int n, int m, int c2, int c1, const f
                                     const int *idx, const float *weight, float *grad_known,
                                     float *grad_skip, void *stream);
 
+/* Adjoints of the two row gathers as segmented gather-sums over an INVERSE MAP (csrc/inverse_map.cu): no
+ * atomics, no zero fill, fixed summation order (bit-reproducible) -- replacing the atomicAdd scatters of
+ * group_points_grad / three_interpolate_grad (group_points_gpu.cu:43-75, interpolate_gpu.cu:116-154).
+ * pn2_inverse_map: keys [b, n_items] with values in [0, n_src) (the ball-query idx flattened to
+ * [b, npoint * nsample], or the 3-NN idx flattened to [b, 3 * n]) -> offsets [b, n_src + 1] and items
+ * [b, n_items]: segment k of cloud i = items[i, offsets[i, k] .. offsets[i, k + 1]) = the item ids whose key
+ * is k, ascending (out-of-range keys are dropped; unused tail = -1).  The map depends on coordinates only
+ * and is built once per batch beside the ball query / 3-NN.  Supported sizes: pn2_inverse_map_supported. */
+PN2_API int pn2_inverse_map_supported(int n_src, int n_items);
+PN2_API int pn2_inverse_map(int b, int n_src, int n_items, const int *keys, int *offsets, int *items,
+                            void *stream);
+PN2_API int pn2_sa_group_rows_grad_inv(int b, int n, int npoint, int nsample, int ct,
+                                       const float *grad_rows, const int *offsets, const int *items,
+                                       float *grad_table, void *stream);
+PN2_API int pn2_fp_interp_rows_grad_inv(int b, int n, int m, int c2, int c1, const float *grad_rows,
+                                        const int *offsets, const int *items, const float *weight,
+                                        float *grad_known, float *grad_skip, void *stream);
+
 /* ==========================================================================
  * Shared-MLP layer on the tensor cores (tcgen05 / TMEM, TF32 operands, fp32
  * accumulation):  z[p, n] = act(a)[p, k] * w[n, k]^T  with

@@ -91,7 +91,6 @@ struct Params {
   int sets, w_slot_bytes, tmem_cols;     // dZ sets (2, or 1 when N > 64)
   int out_bytes;                         // 16 KB of staging blocks when dH_prev leaves through the tensor map, else 0
   int dbg;                               // PN2_BWD_DBG timing experiments (results invalid when != 0)
-  int prefetch;                          // row tiles ahead whose dH / Z / Z_prev blocks are prefetched into L2 (0: off)
   int *sched;                            // [2] {next tile, CTAs finished}, zero between launches (self-resetting)
   const unsigned char *drop_out, *drop_in;  // [P, N] / [P, K] dropout keep masks (nullptr: none)
   float drop_out_scale, drop_in_scale;
@@ -462,32 +461,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
           mbar_arrive(&bars->tile_full[tl & 7]);
         }
       };
-      // A row tile of a row-major [P, C] tensor is ONE contiguous block: three bulk L2 prefetches per tile
-      // (dH, Z, Z_prev; 16 - 68 KB each), issued a tile or two before the loaders' LDGs, turn their DRAM
-      // latency into L2-hit latency -- the loaders keep only ~24 KB of loads in flight per SM
-      // (long_scoreboard was 44 % of this kernel's stall cycles).
-      auto prefetch_tile = [&](int id) {
-        if (id < 0) return;
-        const size_t r0 = static_cast<size_t>(id) * BM;
-        const int rows = min(BM, p.P - id * BM);
-        const float *src = nullptr;
-        int ld = 0;
-        if (lane == 1) src = p.Z, ld = p.N;
-        if (lane == 2) src = p.dH, ld = p.N;
-        if (lane == 3) src = p.Aprev, ld = p.lda;
-        if (src != nullptr)
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + r0 * ld),
-                       "r"(static_cast<uint32_t>(rows) * ld * 4u)
-                       : "memory");
-      };
       int id_cur = fetch(true), id_next = fetch(id_cur >= 0);
       publish(0, id_cur), publish(1, id_next);
-      if (p.prefetch >= 1) prefetch_tile(id_next);
       int tl = 0;
       for (; id_cur >= 0; ++tl) {
         const int id_after = fetch(id_next >= 0);   // lands while this tile's MMAs are issued
-        if (p.prefetch >= 2) prefetch_tile(id_after);
-        else if (p.prefetch == 1 && tl > 0) prefetch_tile(id_next);
         const int acc = tl & 1, acc_use = tl >> 1;
         const int set = p.sets == 2 ? (tl & 1) : 0, use = p.sets == 2 ? (tl >> 1) : tl;
         const uint64_t dz_desc = mn_hi | addr(smem_u32(s_dz + set * nb * SLAB));
@@ -854,7 +832,6 @@ extern "C" int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu,
   if ((drop_out != nullptr && dh == nullptr) || (drop_in != nullptr && a_in == nullptr)) return PN2_ERR_INVALID_ARG;
   prm.drop_out = drop_out, prm.drop_in = drop_in, prm.drop_out_scale = drop_out_scale, prm.drop_in_scale = drop_in_scale;
   prm.dbg = getenv("PN2_BWD_DBG") != nullptr ? atoi(getenv("PN2_BWD_DBG")) : 0;
-  prm.prefetch = getenv("PN2_BWD_PREFETCH") != nullptr ? atoi(getenv("PN2_BWD_PREFETCH")) : 2;
   prm.ns_shift = -1;
   for (int sh = 0; sh < 31; ++sh)
     if ((1 << sh) == prm.ns) prm.ns_shift = sh;

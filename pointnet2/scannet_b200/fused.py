@@ -498,19 +498,38 @@ class SharedMLPRows(Function):
                                                  st.invstd.data_ptr(), dz.data_ptr(), dgamma.data_ptr(),
                                                  dbeta.data_ptr(), ws.data_ptr(), s), "relu_bn_bwd")
                 h_prev = hs[l]
+                # the data gradient first: the next kernel of the chain waits for it, nobody waits for dW
+                # (measured neutral for the step, 3.72 vs 3.74 ms: the two compete for the same L2 bandwidth)
+                dh = _dgrad(dz, W2.contiguous(), h_prev.shape[1], ctx.wt_packed[l]) if need_dh else None
                 dW = _on_dw_branch(dev, (dz, h_prev), lambda: _wgrad(dz, h_prev, K))   # dense [C, K]
                 grads[3 * l] = dW.reshape(W.shape)
                 grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
-                dh = _dgrad(dz, W2.contiguous(), h_prev.shape[1], ctx.wt_packed[l]) if need_dh else None
         return (dh if ctx.needs_input_grad[0] else None, None, None, None, None, None, None, None) + tuple(grads)
+
+
+# Adjoints of the two row gathers through an inverse map (csrc/inverse_map.cu): deterministic, atomic-free --
+# and, measured, not faster than the vector-reduction scatters (see that file's header), so off by default.
+INVERSE_ADJOINT = os.environ.get("PN2_INVERSE_ADJOINT", "0") == "1"
+
+
+def _inv_or_build(inv, keys, n_src, needed):
+    """(offsets, items) of ``keys``: the one handed in (geometry.build_plan made it ahead of time) or, when a
+    gradient will be wanted, built here; None -> the adjoint scatters with atomics."""
+    if not INVERSE_ADJOINT:
+        return None
+    if inv is not None or not needed:
+        return inv
+    from . import geometry
+    return geometry.inverse_map(keys, n_src)
 
 
 class SAGroupRows(Function):
     """QueryAndGroup in rows layout: table (B, N, ct) [xyz | features | 0 pad], new_xyz (B, np, 3),
-    idx (B, np, ns) -> rows (B*np*ns, ct) with the xyz columns centred on their query point."""
+    idx (B, np, ns) -> rows (B*np*ns, ct) with the xyz columns centred on their query point.
+    inv_off / inv_items: the inverse map of idx (geometry.inverse_map), or None."""
 
     @staticmethod
-    def forward(ctx, table, new_xyz, idx):
+    def forward(ctx, table, new_xyz, idx, inv_off=None, inv_items=None):
         B, N, ct = table.shape
         _, npoint, ns = idx.shape
         dev = table.device
@@ -519,6 +538,8 @@ class SAGroupRows(Function):
             _lib.check(_lib.load().pn2_sa_group_rows(B, N, npoint, ns, ct, table.data_ptr(),
                                                      new_xyz.data_ptr(), idx.data_ptr(), rows.data_ptr(),
                                                      _stream(dev)), "sa_group_rows")
+            ctx.inv = _inv_or_build((inv_off, inv_items) if inv_off is not None else None, idx, N,
+                                    ctx.needs_input_grad[0])
         ctx.idx, ctx.shape = idx, (B, N, ct, npoint, ns)
         return rows
 
@@ -528,21 +549,37 @@ class SAGroupRows(Function):
         dev = grad_rows.device
         grad_rows = grad_rows.contiguous()
         grad_table = torch.empty(B, N, ct, dtype=torch.float32, device=dev)
+        L = _lib.load()
         with torch.cuda.device(dev):
-            _lib.check(_lib.load().pn2_sa_group_rows_grad(B, N, npoint, ns, ct, grad_rows.data_ptr(),
-                                                          ctx.idx.data_ptr(), grad_table.data_ptr(),
-                                                          _stream(dev)), "sa_group_rows_grad")
+            if ctx.inv is not None:   # segmented gather-sum over the inverse map: no atomics, fixed order
+                _lib.check(L.pn2_sa_group_rows_grad_inv(B, N, npoint, ns, ct, grad_rows.data_ptr(),
+                                                        ctx.inv[0].data_ptr(), ctx.inv[1].data_ptr(),
+                                                        grad_table.data_ptr(), _stream(dev)), "sa_group_rows_grad_inv")
+            else:
+                _lib.check(L.pn2_sa_group_rows_grad(B, N, npoint, ns, ct, grad_rows.data_ptr(),
+                                                    ctx.idx.data_ptr(), grad_table.data_ptr(),
+                                                    _stream(dev)), "sa_group_rows_grad")
         # new_xyz is a gather of input coordinates; like the reference's semseg models this path
         # does not propagate a gradient into it
-        return grad_table, None, None
+        return grad_table, None, None, None, None
+
+
+# A trainer can ask to be told when the backward pass leaves the finest level: the event (created with
+# external=True, so that it may be recorded inside a captured graph and waited for outside it) is recorded
+# right after the adjoint of the FINEST FP block's interpolation -- from there to the SA2 adjoint the step
+# is ~60 short, latency-bound kernels of the coarse levels that leave most SMs idle
+# (train.PipelinedTrainStep releases the next batch's FPS there).
+BWD_MARK_EVENT = None
 
 
 class FPInterpRows(Function):
     """three_interpolate + concat of PointnetFPModule in rows layout: known (B, m, C2) and skip
-    (B, n, C1) point-major, idx / weight (B, n, 3) -> rows (B*n, pad4(C2 + C1))."""
+    (B, n, C1) point-major, idx / weight (B, n, 3) -> rows (B*n, pad4(C2 + C1)).  ``mark``: record
+    BWD_MARK_EVENT after this call's adjoint."""
 
     @staticmethod
-    def forward(ctx, known, skip, idx, weight):
+    def forward(ctx, known, skip, idx, weight, mark=False, inv_off=None, inv_items=None):
+        ctx.mark = mark
         B, m, c2 = known.shape
         n = idx.shape[1]
         c1 = skip.shape[2] if skip is not None else 0
@@ -552,6 +589,8 @@ class FPInterpRows(Function):
             _lib.check(_lib.load().pn2_fp_interp_rows(
                 B, n, m, c2, c1, known.data_ptr(), skip.data_ptr() if skip is not None else None,
                 idx.data_ptr(), weight.data_ptr(), rows.data_ptr(), _stream(dev)), "fp_interp_rows")
+            ctx.inv = _inv_or_build((inv_off, inv_items) if inv_off is not None else None, idx, m,
+                                    ctx.needs_input_grad[0])
         ctx.saved = (idx, weight, B, n, m, c2, c1)
         return rows
 
@@ -565,10 +604,18 @@ class FPInterpRows(Function):
         if c1 > 0 and ctx.needs_input_grad[1]:
             gs = torch.empty(B, n, c1, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(_lib.load().pn2_fp_interp_rows_grad(
-                B, n, m, c2, c1, grad_rows.data_ptr(), idx.data_ptr(), weight.data_ptr(), gk.data_ptr(),
-                gs.data_ptr() if gs is not None else None, _stream(dev)), "fp_interp_rows_grad")
-        return gk, gs, None, None
+            if ctx.inv is not None:   # segmented gather-sum over the inverse map: no atomics, fixed order
+                _lib.check(_lib.load().pn2_fp_interp_rows_grad_inv(
+                    B, n, m, c2, c1, grad_rows.data_ptr(), ctx.inv[0].data_ptr(), ctx.inv[1].data_ptr(),
+                    weight.data_ptr(), gk.data_ptr(), gs.data_ptr() if gs is not None else None, _stream(dev)),
+                    "fp_interp_rows_grad_inv")
+            else:
+                _lib.check(_lib.load().pn2_fp_interp_rows_grad(
+                    B, n, m, c2, c1, grad_rows.data_ptr(), idx.data_ptr(), weight.data_ptr(), gk.data_ptr(),
+                    gs.data_ptr() if gs is not None else None, _stream(dev)), "fp_interp_rows_grad")
+        if ctx.mark and BWD_MARK_EVENT is not None:
+            BWD_MARK_EVENT.record(torch.cuda.current_stream(dev))
+        return gk, gs, None, None, None, None, None
 
 
 def rows_of(t):

@@ -40,6 +40,10 @@ SIGNATURES = {
     "pn2_sa_group_rows_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pn2_fp_interp_rows": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_fp_interp_rows_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pn2_inverse_map_supported": [_i, _i],
+    "pn2_inverse_map": [_i, _i, _i, _vp, _vp, _vp, _vp],
+    "pn2_sa_group_rows_grad_inv": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "pn2_fp_interp_rows_grad_inv": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     # shared-MLP layer on the tensor cores
     "pn2_mlp_gemm_bn": [_i, _i],
     "pn2_mlp_gemm_n_tiles": [_i, _i],

@@ -29,9 +29,11 @@ class _PointnetSAModuleBase(nn.Module):
         self.mlps = None
 
     def forward(self, xyz, features=None, geometry=None):
-        """``geometry`` (optional) = (new_xyz, [idx per scale]) computed ahead by geometry.build_plan."""
+        """``geometry`` (optional) = (new_xyz, [idx per scale][, [inverse map of idx per scale]]) computed ahead
+        by geometry.build_plan."""
         if geometry is not None and self._fused_ok(xyz, features):
-            return geometry[0], self._forward_rows(xyz, geometry[0], features, geometry[1])
+            return geometry[0], self._forward_rows(xyz, geometry[0], features, geometry[1],
+                                                   geometry[2] if len(geometry) > 2 else None)
         new_xyz = None
         if self.npoint is not None:
             # FPS on (B, N, 3); the centres are gathered from the channel-major copy
@@ -64,7 +66,7 @@ class _PointnetSAModuleBase(nn.Module):
                 return False
         return True
 
-    def _forward_rows(self, xyz, new_xyz, features, idxs=None):
+    def _forward_rows(self, xyz, new_xyz, features, idxs=None, invs=None):
         B, N, _ = xyz.shape
         cols = [xyz] if features is None else [xyz, fused.rows_of(features)]
         width = sum(c.size(2) for c in cols)
@@ -75,7 +77,8 @@ class _PointnetSAModuleBase(nn.Module):
         for i, (grouper, mlp) in enumerate(zip(self.groupers, self.mlps)):
             idx = idxs[i] if idxs is not None else pointnet2_utils.ball_query(
                 grouper.radius, grouper.nsample, xyz, new_xyz)
-            rows = fused.SAGroupRows.apply(table, new_xyz, idx)          # (B*npoint*nsample, ct)
+            inv = invs[i] if invs is not None and invs[i] is not None else (None, None)
+            rows = fused.SAGroupRows.apply(table, new_xyz, idx, inv[0], inv[1])   # (B*npoint*nsample, ct)
             out = fused.run_mlp_rows(mlp, rows, grouper.nsample)          # (B*npoint, mlp[-1])
             pooled.append(out.view(B, self.npoint, -1))
         rows = torch.cat(pooled, dim=2) if len(pooled) > 1 else pooled[0]   # (B, npoint, sum C)
@@ -143,20 +146,24 @@ class PointnetFPModule(nn.Module):
             [interpolated, unknow_feats], dim=1)             # (B, C2 + C1, n)
         return self.mlp(feats.unsqueeze(-1)).squeeze(-1)
 
-    def forward_rows(self, unknown, known, unknow_feats, known_feats, geometry=None, tail=(), tail_dropouts=None):
+    def forward_rows(self, unknown, known, unknow_feats, known_feats, geometry=None, tail=(), tail_dropouts=None,
+                     mark=False):
         """Fused path, point-major result (B, n, mlp[-1]): interpolation + concat written straight
         into [positions, channels] rows, then the shared MLP on rows (fused.py).  ``tail``: further
         conv + BN (+ ReLU) units applied to the result in the same chain (the classifier's first unit:
         this block's last activation is then never written out or re-read); ``tail_dropouts``:
         {index into tail: p} -- nn.Dropout(p) after that tail unit, applied inside the next unit."""
         B, n, _ = unknown.shape
+        inv = (None, None)
         if geometry is not None:
-            idx, weight = geometry
+            idx, weight = geometry[0], geometry[1]
+            if len(geometry) > 2 and geometry[2] is not None:
+                inv = geometry[2]
         else:
             dist, idx = pointnet2_utils.three_nn(unknown, known)
             recip = 1.0 / (dist + 1e-8)                      # ref :395-397
             weight = recip / torch.sum(recip, dim=2, keepdim=True)
         skip = fused.rows_of(unknow_feats) if unknow_feats is not None else None
-        rows = fused.FPInterpRows.apply(fused.rows_of(known_feats), skip, idx, weight)
+        rows = fused.FPInterpRows.apply(fused.rows_of(known_feats), skip, idx, weight, mark, inv[0], inv[1])
         drops = {len(self.mlp) + i: p for i, p in (tail_dropouts or {}).items()}
         return fused.run_mlp_rows(list(self.mlp) + list(tail), rows, 0, drops).view(B, n, -1)

@@ -119,11 +119,12 @@ class _Pointnet2SemSeg(nn.Module):
         xyz, features = self._break_up_pc(pointcloud)
         l_xyz, l_features = [xyz], [features]
         for k, sa in enumerate(self.SA_modules):
-            nxt_xyz, nxt_feat = sa(l_xyz[-1], l_features[-1], plan.sa[k] if plan is not None else None)
+            nxt_xyz, nxt_feat = sa(l_xyz[-1], l_features[-1],
+                                   tuple(plan.sa[k]) + (plan.sa_inv[k],) if plan is not None else None)
             l_xyz.append(nxt_xyz)
             l_features.append(nxt_feat)
         nfp = len(self.FP_modules)
-        geo = (lambda k: plan.fp[k]) if plan is not None else (lambda k: None)
+        geo = (lambda k: tuple(plan.fp[k]) + (plan.fp_inv[k],)) if plan is not None else (lambda k: None)
         for i in range(-1, -nfp, -1):  # coarse -> fine, all but the finest level
             l_features[i - 1] = self.FP_modules[i](
                 l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i], geo(nfp + i))
@@ -133,7 +134,7 @@ class _Pointnet2SemSeg(nn.Module):
             # output rows ARE the (B, N, num_classes) result, no transpose anywhere
             lead, drops, used = self._head_lead(fp0, l_features[0], l_features[1])
             rows = fp0.forward_rows(l_xyz[0], l_xyz[1], l_features[0], l_features[1], geo(0), tail=lead,
-                                    tail_dropouts=drops)
+                                    tail_dropouts=drops, mark=True)
             return self._head_rows(rows, skip=used)
         l_features[0] = fp0(l_xyz[0], l_xyz[1], l_features[0], l_features[1], geo(0))
         return self.cls_layer(l_features[0]).transpose(1, 2).contiguous()

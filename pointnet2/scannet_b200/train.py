@@ -262,17 +262,29 @@ class PipelinedTrainStep(object):
         # keep their speed when FPS holds 32 SMs -- instead of the forward pass, whose statically tiled
         # layers wait for the CTAs that cannot become resident (measured: 0.48 ms of the 1.0 ms of geometry
         # work stayed exposed when it started together with the step).
+        # Where in the step the geometry graph starts (PN2_GEO_RELEASE): "fwd" (default) = after the forward
+        # pass, beside the finest level's backward layers; "mid" = after the finest FP block's interpolation
+        # adjoint, beside the ~60 short kernels of the coarse levels.  Measured in one run on one box (round 2):
+        # "mid" gives the FP0 / head backward layers all 148 SMs (-66 us) but moves 3-NN / ball query beside
+        # the SA2 / SA1 backward layers: 3.77-3.80 vs 3.72-3.74 ms per step, so "fwd" stays.
+        self.release = _os.environ.get("PN2_GEO_RELEASE", "fwd")
         self.split = split_fwd_bwd
         self.fwd_done = torch.cuda.Event()
+        self.mid_bwd = torch.cuda.Event(external=True) if (self.split and self.release == "mid") else None
         self.graph = torch.cuda.CUDAGraph()
         if self.split:
             with torch.cuda.graph(self.graph):
                 self.loss = self.step.forward_loss(*self.static, plan=self.plan)
             self.graph_bwd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_bwd, pool=self.graph.pool()):
-                self.step.backward_pack(self.loss)
-                if self.scope == "step":
-                    self.step.reduce_and_update()
+            from . import fused
+            fused.BWD_MARK_EVENT = self.mid_bwd
+            try:
+                with torch.cuda.graph(self.graph_bwd, pool=self.graph.pool()):
+                    self.step.backward_pack(self.loss)
+                    if self.scope == "step":
+                        self.step.reduce_and_update()
+            finally:
+                fused.BWD_MARK_EVENT = None
         else:
             with torch.cuda.graph(self.graph):
                 self.loss = self._body()
@@ -294,7 +306,8 @@ class PipelinedTrainStep(object):
             for s, t in zip(self.next, (pointcloud, targets, weights)):
                 s.copy_(t, non_blocking=True)
             if self.split and self._fwd_recorded:
-                self.side.wait_event(self.fwd_done)   # start beside the backward pass of the running step
+                # start beside the backward pass of the running step (the event node of the replayed graph)
+                self.side.wait_event(self.mid_bwd if self.mid_bwd is not None else self.fwd_done)
             if not _STALE_GEOMETRY:
                 self.geo_graph.replay()
             self.ready.record(self.side)

@@ -64,6 +64,15 @@ def main_one():
                                                                 gt.data_ptr(), s), "gg"))
         by = 4 * P + 4 * P * ct + 4 * B * N * ct
         out.append(("sa_group_rows_grad(%d,%d,%d,%d)" % (N, npnt, ns, ct), us, by))
+        if L.pn2_inverse_map_supported(N, npnt * ns):
+            off = torch.empty(B, N + 1, dtype=torch.int32, device=dev)
+            items = torch.empty(B, npnt * ns, dtype=torch.int32, device=dev)
+            us = timed(lambda: _lib.check(L.pn2_inverse_map(B, N, npnt * ns, idx.data_ptr(), off.data_ptr(),
+                                                             items.data_ptr(), s), "inv"))
+            out.append(("inverse_map(%d,%d)" % (N, npnt * ns), us, 8 * P + 4 * B * N))
+            us = timed(lambda: _lib.check(L.pn2_sa_group_rows_grad_inv(B, N, npnt, ns, ct, rows.data_ptr(), off.data_ptr(),
+                                                                        items.data_ptr(), gt.data_ptr(), s), "ggi"))
+            out.append(("sa_group_rows_grad_inv(%d,%d,%d,%d)" % (N, npnt, ns, ct), us, by))
     # FP levels: (n, m, c2, c1)
     for (n, m, c2, c1) in [(8192, 1024, 128, 6), (1024, 256, 256, 64), (256, 64, 256, 128), (64, 16, 512, 256)]:
         known = torch.randn(B, m, c2, generator=g).to(dev)
@@ -83,6 +92,21 @@ def main_one():
                                                                  w.data_ptr(), gk.data_ptr(), gs.data_ptr(), s), "ig"))
         by = 24 * P + 4 * P * ct + 4 * B * m * c2 + 4 * P * c1
         out.append(("fp_interp_rows_grad(%d,%d,%d,%d)" % (n, m, c2, c1), us, by))
+        if L.pn2_inverse_map_supported(m, 3 * n):
+            off = torch.empty(B, m + 1, dtype=torch.int32, device=dev)
+            items = torch.empty(B, 3 * n, dtype=torch.int32, device=dev)
+            us = timed(lambda: _lib.check(L.pn2_inverse_map(B, m, 3 * n, idx.data_ptr(), off.data_ptr(),
+                                                             items.data_ptr(), s), "inv"))
+            out.append(("inverse_map(%d,%d)" % (m, 3 * n), us, 24 * P + 4 * B * m))
+            us = timed(lambda: _lib.check(L.pn2_fp_interp_rows_grad_inv(
+                B, n, m, c2, c1, rows.data_ptr(), off.data_ptr(), items.data_ptr(), w.data_ptr(), gk.data_ptr(),
+                gs.data_ptr(), s), "igi"))
+            out.append(("fp_interp_rows_grad_inv(%d,%d,%d,%d)" % (n, m, c2, c1), us, by))
+            us = timed(lambda: _lib.check(L.pn2_fp_interp_rows_grad_inv(
+                B, n, m, c2, c1, rows.data_ptr(), off.data_ptr(), items.data_ptr(), w.data_ptr(), gk.data_ptr(),
+                None, s), "igi"))
+            out.append(("fp_interp_rows_grad_inv(%d,%d,%d,%d) no skip grad" % (n, m, c2, c1), us,
+                        24 * P + 4 * P * c2 + 4 * B * m * c2))
     res = {"PN2_ROWS_U": os.environ.get("PN2_ROWS_U", "default"), "hbm_peak_gbs": PEAK, "kernels": [
         {"call": k, "us": round(us, 2), "MB": round(by / 1e6, 1), "GBs": round(by / us / 1e3, 1),
          "frac_of_hbm_peak": round(by / us / 1e3 / PEAK, 3)} for k, us, by in out]}
