@@ -152,6 +152,7 @@ ball_query_kernel(BqParams p, const float *__restrict__ new_xyz,
 // ---------------------------------------------------------------------------------------------
 constexpr int kGridThreads = 1024, kGridWarps = kGridThreads / 32;
 constexpr int kGridBuckets = 4096, kGridHitCap = 128;
+constexpr float kMaxCellCoord = 4096.f;   // largest |coordinate / cell size| the 27-cell search is trusted for
 
 __global__ void __launch_bounds__(kGridThreads, 1)
 ball_query_grid_kernel(BqParams p, float inv, const float *__restrict__ new_xyz,
@@ -175,6 +176,17 @@ ball_query_grid_kernel(BqParams p, float inv, const float *__restrict__ new_xyz,
   for (int i = tid; i < kGridBuckets; i += kGridThreads) s_cnt[i] = 0;
   __syncthreads();
   grid_build<kGridThreads>(pts, p.n, inv, kGridBuckets, s_cnt, s_start, s_pts, s_scratch);
+  // The 27-cell search is complete only while the fp32 rounding of x * inv stays inside the 0.1 % margin
+  // of the cell size and no cell index is clamped: |x * inv| <= kMaxCellCoord (rounding error of one
+  // product <= 4096 * 2^-24 = 2.4e-4 of a cell, two products < 1e-3).  A cloud (or a centre) outside that
+  // range -- millimetre radii on metre-scale coordinates, chunks at large world offsets, non-finite input --
+  // takes the reference's scan over all points instead, so the result never depends on the grid.
+  bool far = false;
+  for (int k = tid; k < p.n; k += kGridThreads) {
+    const float4 q = s_pts[k];
+    far |= !(fabsf(q.x * inv) <= kMaxCellCoord && fabsf(q.y * inv) <= kMaxCellCoord && fabsf(q.z * inv) <= kMaxCellCoord);
+  }
+  const bool scan_all = __syncthreads_or(far) != 0;
 
   const int j0 = blockIdx.x * p.centres_per_cta;
   const int j1 = min(j0 + p.centres_per_cta, p.m);
@@ -182,9 +194,11 @@ ball_query_grid_kernel(BqParams p, float inv, const float *__restrict__ new_xyz,
   int *row = s_rows + warp * p.nsample;
   for (int j = j0 + warp; j < j1; j += kGridWarps) {
     const float cx = __ldg(ctr + 3 * j), cy = __ldg(ctr + 3 * j + 1), cz = __ldg(ctr + 3 * j + 2);
+    const bool use_scan = scan_all || !(fabsf(cx * inv) <= kMaxCellCoord && fabsf(cy * inv) <= kMaxCellCoord &&
+                                         fabsf(cz * inv) <= kMaxCellCoord);   // warp-uniform
     int tx = grid_cell(cx, inv), ty = grid_cell(cy, inv), tz = grid_cell(cz, inv);
     int s = 0, e = 0;
-    if (lane < 27) {
+    if (lane < 27 && !use_scan) {
       tx += lane % 3 - 1, ty += (lane / 3) % 3 - 1, tz += lane / 9 - 1;
       const unsigned b = grid_hash(tx, ty, tz, kGridBuckets - 1);
       s = s_start[b], e = s_start[b + 1];
@@ -204,7 +218,7 @@ ball_query_grid_kernel(BqParams p, float inv, const float *__restrict__ new_xyz,
       }
     }
     __syncwarp();
-    const int H = s_hitcnt[warp];
+    const int H = use_scan ? kGridHitCap + 1 : s_hitcnt[warp];
     int *dst = out + static_cast<size_t>(j) * p.nsample;
     if (H > kGridHitCap) {
       // more hits than the list holds: the reference's scan over all points, in index order

@@ -58,13 +58,15 @@ group_fwd_kernel(int c, int n, int E, int ch_per_cta, const float *__restrict__ 
   }
 }
 
-// ---- EXPERIMENT, off unless PN2_GROUP_SMEM=1 (written after round 1's GPU budget was spent: parity
-// and speed NOT measured yet; tests/test_experimental_gpu.py compare it with the kernel
-// above bit for bit when PN2_EXPERIMENTAL=1).  The kernel above is bound by L1 gathers (a warp's 32
-// indices touch up to 32 sectors per load instruction).  Here a CTA owns (cloud, channel tile),
-// copies its [channels][n] rows -- contiguous in memory, each element read from HBM exactly once --
-// into shared memory with 128-bit loads, and gathers from there: a 32-way scattered LDS costs a few
-// bank-conflict replays instead of 32 sector lookups.  Same thread mapping and stores as above.
+// ---- Shared-memory gather (the default where the shape suits it; PN2_GROUP_SMEM=0 selects the kernel above).
+// The kernel above is bound by L1 gathers (a warp's 32 indices touch up to 32 sectors per load
+// instruction).  Here a CTA owns (cloud, channel tile), copies its [channels][n] rows -- contiguous in
+// memory, each element read from HBM exactly once -- into shared memory with 128-bit loads, and gathers
+// from there: a 32-way scattered LDS costs a few bank-conflict replays instead of 32 sector lookups.
+// Same thread mapping and stores as above; bit-identical output (tests/test_gather_variants_gpu.py).
+// Measured (B200, B = 32, profiles/r02_gather_smem_vs_l1.txt): SA2 features 64 x 1024 -> 256 x 32:
+// 31.9 -> 21.5 us (37 -> 54 % of the HBM peak); multiview SA1 131 x 8192 -> 1024 x 32: 476 -> 155 us
+// (22 -> 68 %).
 constexpr int kGsThreads = 512;
 constexpr int kGsSmemBytes = 56 * 1024;  // four CTAs per SM
 
@@ -104,10 +106,10 @@ group_fwd_smem_kernel(int c, int n, int E, int ch_per_cta, const float *__restri
   }
 }
 
-// true when the experiment is switched on and the shape suits it (rows fit, enough reuse)
+// true unless switched off, when the shape suits it (rows fit, enough reuse)
 static bool group_smem_wanted(int n, int E) {
   const char *env = getenv("PN2_GROUP_SMEM");
-  return env != nullptr && env[0] == '1' && n > 0 && static_cast<size_t>(n) * sizeof(float) <= kGsSmemBytes &&
+  return !(env != nullptr && env[0] == '0') && n > 0 && static_cast<size_t>(n) * sizeof(float) <= kGsSmemBytes &&
          static_cast<long long>(E) >= 2LL * n;
 }
 

@@ -63,13 +63,13 @@ interp_fwd_kernel(int c, int m, int n, int ch_per_cta, const float *__restrict__
   }
 }
 
-// ---- EXPERIMENT, off unless PN2_INTERP_SMEM=1 (written after round 1's GPU budget was spent: parity
-// and speed NOT measured yet; tests/test_experimental_gpu.py compare it with the kernel
-// above bit for bit when PN2_EXPERIMENTAL=1).  The kernel above spends its time in L1 gathers (12
-// scattered loads per 4 outputs and channel; 24 % of the HBM peak at FP0).  Here a CTA owns (cloud,
-// channel tile), stages its [channels][m] rows of known features in shared memory once -- they are
-// contiguous, each element leaves HBM exactly once -- and gathers from there.  Same thread mapping,
-// same arithmetic (interp3), same stores.
+// ---- Shared-memory gather (the default where the shape suits it; PN2_INTERP_SMEM=0 selects the kernel
+// above).  The kernel above spends its time in L1 gathers (12 scattered loads per 4 outputs and channel).
+// Here a CTA owns (cloud, channel tile), stages its [channels][m] rows of known features in shared memory
+// once -- they are contiguous, each element leaves HBM exactly once -- and gathers from there.  Same
+// thread mapping, same arithmetic (interp3), same stores; bit-identical output
+// (tests/test_gather_variants_gpu.py).  Measured (B200, B = 32, profiles/r02_gather_smem_vs_l1.txt):
+// FP0 128 x 1024 -> 8192: 112.5 -> 72.9 us (21 -> 33 % of the HBM peak).
 constexpr int kIsThreads = 512;
 constexpr int kIsSmemBytes = 56 * 1024;  // four CTAs per SM
 
@@ -125,7 +125,7 @@ interp_fwd_smem_kernel(int c, int m, int n, int ch_per_cta, const float *__restr
 
 static bool interp_smem_wanted(int m, int n) {
   const char *env = getenv("PN2_INTERP_SMEM");
-  return env != nullptr && env[0] == '1' && m > 0 && static_cast<size_t>(m) * sizeof(float) <= kIsSmemBytes &&
+  return !(env != nullptr && env[0] == '0') && m > 0 && static_cast<size_t>(m) * sizeof(float) <= kIsSmemBytes &&
          3LL * n >= 2LL * m;
 }
 

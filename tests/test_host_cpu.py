@@ -125,6 +125,43 @@ def test_mirror_modules_equal_reference_modules_on_cpu(oracle):
     assert all(torch.equal(sa[k], sb[k]) for k in sa)
 
 
+@pytest.mark.skipif(not have_ref, reason="/root/reference not present")
+@pytest.mark.parametrize("msg,channels", [(False, 6), (True, 131)])
+def test_reference_checkpoint_round_trip_on_cpu(oracle, tmp_path, msg, channels):
+    """a model.pth in the reference's format -- ``torch.save(model.state_dict(), ...)`` of the
+    reference's own ``get_model`` (lib/solver.py:142, 325) -- loads into the mirror with ``strict=True`` as
+    scripts/eval.py:183-188 loads it, and the mirror in eval mode reproduces the reference's logits bit for
+    bit (both on the oracle's CPU ops table)."""
+    from pointnet2.scannet_b200 import pointnet2_semseg as mine, pointnet2_utils as my_utils, synthetic
+    ref = _import_reference("pointnet2_semseg")
+    ref_utils = _import_reference("pointnet2_utils")
+    saved = (my_utils._ext, ref_utils._ext)
+    my_utils._ext = ref_utils._ext = oracle.ext_cpu
+    try:
+        torch.manual_seed(3)
+        ref_model = ref.get_model(20, is_msg=msg, input_channels=channels)
+        g = torch.Generator().manual_seed(4)
+        for m in ref_model.modules():          # a trained-looking checkpoint: non-trivial BatchNorm state
+            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+                m.running_mean.normal_(0, 0.2, generator=g), m.running_var.uniform_(0.5, 2.0, generator=g)
+                m.weight.data.uniform_(0.5, 1.5, generator=g), m.bias.data.normal_(0, 0.1, generator=g)
+                m.num_batches_tracked.fill_(1234)
+        path = str(tmp_path / "model.pth")
+        torch.save(ref_model.state_dict(), path)                      # lib/solver.py:325
+        mirror = mine.get_model(20, is_msg=msg, input_channels=channels)
+        missing = mirror.load_state_dict(torch.load(path), strict=True)   # scripts/eval.py:183-188
+        assert not missing.missing_keys and not missing.unexpected_keys
+        x, _, _ = synthetic.make_batch(2, 1, npoints=1024, use_multiview=(channels == 131), use_color=(channels != 131))
+        pc = torch.from_numpy(x)
+        with torch.no_grad():
+            want = ref_model.eval()(pc)
+            got = mirror.eval()(pc)
+    finally:
+        my_utils._ext, ref_utils._ext = saved
+    assert got.shape == want.shape == (1, 1024, 20)
+    assert torch.equal(got, want)
+
+
 def test_groupall_and_surface_names():
     from pointnet2.scannet_b200 import pointnet2_utils as U
     for name in ("furthest_point_sample", "gather_operation", "three_nn", "three_interpolate",

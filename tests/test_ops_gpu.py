@@ -166,6 +166,25 @@ def test_ball_query_edge_cases(ext, oracle):
     assert (got == 0).all()
 
 
+@pytest.mark.parametrize("offset,radius", [(100.0, 1e-3), (1000.0, 1e-3), (100.0, 0.01), (1000.0, 0.01),
+                                           (30.0, 0.01), (3.0, 1e-3), (5000.0, 0.1), (0.0, 2e-3)])
+def test_ball_query_grid_path_large_offsets_small_radii(ext, oracle, offset, radius):
+    """The spatial-hash path (512 <= n <= 8192) with coordinates far from the origin and radii down to a
+    millimetre: fp32 rounding of coordinate / cell size exceeds the cell margin once |x| / r > ~4000, and the
+    cell index clamps at 2^20; the kernel must notice and scan (results stay the reference's, bit for bit).
+    Points are laid on a lattice of pitch ~r/2 so that balls are well filled at every radius."""
+    rng = np.random.default_rng(int(offset) + int(radius * 1e4))
+    n, m, ns = 2048, 256, 32
+    base = rng.integers(0, 24, (2, n, 3)).astype(np.float32) * np.float32(radius * 0.45)
+    base += rng.normal(0, radius * 0.02, base.shape).astype(np.float32)
+    pts = (base + np.float32(offset)).astype(np.float32)
+    ctr = pts[:, rng.choice(n, m, replace=False)].copy()
+    want = oracle.ext_cpu.ball_query(cases.t(ctr), cases.t(pts), radius, ns).numpy()
+    got = ext.ball_query(g(ctr), g(pts), radius, ns).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    assert (want != want[:, :, :1]).any()          # the balls are not all singletons / empty
+
+
 def test_ball_query_whole_scene_cloud(ext, oracle):
     """n > 8192: scanned from L2 instead of the shared-memory stage."""
     from pointnet2.scannet_b200 import synthetic as syn

@@ -49,3 +49,21 @@ def test_oracle_vs_live_reference(oracle):
     want = ref.furthest_point_sampling(cases.t(xyz, "cuda:0"), 512).cpu()
     got = oracle.ext_cpu.furthest_point_sampling(cases.t(xyz), 512)
     assert (want == got).all()
+
+
+@pytest.mark.parametrize("flags", [[], ["--msg", "--multiview"]])
+def test_reference_checkpoint_round_trip(flags):
+    """model.pth saved by the reference's own get_model (its Python + its CUDA extension),
+    loaded by the mirror, evaluated unfused (bit-identical logits) and on the fused tcgen05 path (TF32 class
+    bound): tools/checkpoint_roundtrip.py, in its own process."""
+    import os
+    import subprocess
+    import sys
+    from oracle import build_ref
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not build_ref.available("nofma") or not os.path.exists(os.path.join(build_ref.python_dir(), "pointnet2_semseg.py")):
+        pytest.skip("oracle/_ref (reference extension + staged Python) not built")
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "checkpoint_roundtrip.py")] + flags,
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    assert "bit for bit" in p.stdout

@@ -29,10 +29,20 @@ for name, P, N, K, lda, ns, fold, dgrad in CASES:
         continue
     g = torch.Generator(device=DEV).manual_seed(0)
     r = lambda *sh: torch.randn(*sh, device=DEV, generator=g)
-    z, aprev = r(P, N), r(P, lda)
+    if os.environ.get("CARVE"):   # the four big tensors as consecutive pieces of ONE allocation (as the step's allocator places them)
+        big = torch.empty(P * (3 * N + 2 * lda) + 1024, device=DEV)
+        def carve(off, rows, cols):
+            return big[off:off + rows * cols].view(rows, cols)
+        z = carve(0, P, N); z.normal_(generator=g)
+        aprev = carve(P * N, P, lda); aprev.normal_(generator=g)
+    else:
+        z, aprev = r(P, N), r(P, lda)
     a, b, mean, invstd, c1c2 = r(N), r(N), r(N), r(N).abs() + .5, 0.01 * r(2 * N)
     a_in, b_in, mean_in, invstd_in = (r(K), r(K), r(K), r(K).abs() + .5) if fold else (None,) * 4
-    dh = r(P, N) if not ns else None
+    if os.environ.get("CARVE") and not ns:
+        dh = carve(P * (N + lda), P, N); dh.normal_(generator=g)
+    else:
+        dh = r(P, N) if not ns else None
     dout = r(P // ns, N) if ns else None
     am = torch.randint(0, ns, (P // ns, N), device=DEV, dtype=torch.int32) if ns else None
     W = r(N, K)
@@ -40,7 +50,7 @@ for name, P, N, K, lda, ns, fold, dgrad in CASES:
     wtp = torch.empty(nb * kpad * 32, device=DEV) if dgrad else None
     if dgrad:
         lib.check(L.pn2_mlp_pack_weights_t(N, K, lda, K, W.data_ptr(), wtp.data_ptr(), s), "pack")
-    dhp = torch.empty(P, lda, device=DEV) if dgrad else None
+    dhp = (carve(P * (2 * N + lda), P, lda) if os.environ.get("CARVE") else torch.empty(P, lda, device=DEV)) if dgrad else None
     dwp = torch.empty(grid, nb * 32 * kb * 32, device=DEV)
     sp = torch.empty(grid, nb * 32 * kb * 32, device=DEV) if (dgrad and fold) else None
     p = lambda t: t.data_ptr() if t is not None else None
@@ -53,11 +63,12 @@ for name, P, N, K, lda, ns, fold, dgrad in CASES:
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(10):
+    REPS = int(os.environ.get("REPS", "10"))
+    for _ in range(REPS):
         call()
     e1.record()
     torch.cuda.synchronize()
-    us = 1e3 * e0.elapsed_time(e1) / 10
+    us = 1e3 * e0.elapsed_time(e1) / REPS
     byt = 4 * P * (N + lda + (lda if dgrad else 0) + (N if not ns else 0)) + (8 * (P // ns) * N if ns else 0)
     if os.environ.get("PN2_BWD_DBG") and int(os.environ["PN2_BWD_DBG"]) & 32:
         import ctypes, numpy as np

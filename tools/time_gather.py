@@ -1,6 +1,6 @@
 """A/B timing (CUDA events) of the channel-major grouping / interpolation forward kernels at the SSG and
-multiview shapes: default kernels against the shared-memory-gather experiments (PN2_GROUP_SMEM /
-PN2_INTERP_SMEM), with the algorithmic bytes of SURVEY.md 8(d) and the measured HBM peak.
+multiview shapes: the L1-gather kernels (PN2_GROUP_SMEM=0 / PN2_INTERP_SMEM=0) against the shared-memory
+gather that is the default, with the algorithmic bytes of SURVEY.md 8(d) and the measured HBM peak.
 
     python tools/time_gather.py [B]
 """
@@ -41,15 +41,14 @@ def timed(fn):
 
 
 def ab(name, env, nbytes, fn):
-    os.environ.pop(env, None)
+    os.environ[env] = "0"          # the L1-gather kernel
     base = fn()
     t0 = timed(fn)
-    os.environ[env] = "1"
+    os.environ.pop(env, None)      # default: the shared-memory gather where the shape suits it
     same = torch.equal(fn(), base)
     t1 = timed(fn)
-    os.environ.pop(env, None)
-    print("%-44s default %8.1f us %5.1f%%   %s=1 %8.1f us %5.1f%%   bit-equal %s" % (
-        name, t0, 100 * nbytes / t0 / 1e3 / PEAK, env, t1, 100 * nbytes / t1 / 1e3 / PEAK, same))
+    print("%-44s L1 gather (%s=0) %8.1f us %5.1f%%   shared-memory gather (default) %8.1f us %5.1f%%   bit-equal %s" % (
+        name, env, t0, 100 * nbytes / t0 / 1e3 / PEAK, t1, 100 * nbytes / t1 / 1e3 / PEAK, same))
 
 
 rng = np.random.default_rng(0)
