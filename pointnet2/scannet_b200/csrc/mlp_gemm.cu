@@ -74,6 +74,7 @@ struct Params {
   float *zmax, *zmin;
   int *imax, *imin;
   int stages, b_stage_bytes;  // pipeline depth; bytes reserved per weight stage (multiple of 1024)
+  int resident;               // all k_blocks weight tiles of this CTA's N tile stay in shared memory (loaded once)
   int tmem_cols;              // 512 (one CTA per SM) or 256 (two): two accumulators of tmem_cols / 2
   // dropout between the previous layer's activation and this layer (nn.Dropout in the classifier,
   // pointnet2_semseg.py:156): act(x) is multiplied by drop[p, k] ? drop_scale : 0 on the A tile
@@ -90,6 +91,7 @@ struct __align__(16) Barriers {
   uint64_t empty[kMaxStages];  // MMAs that read the stage have retired  (1 commit)
   uint64_t acc_full[2];    // accumulator complete                   (1 commit)
   uint64_t acc_empty[2];   // accumulator drained by the epilogue    (128 arrivals)
+  uint64_t w_full;         // resident weight tiles landed           (1 arrival + tx bytes)
   uint32_t tmem_base;
 };
 
@@ -98,9 +100,13 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
                                                                      const __grid_constant__ CUtensorMap tm_a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int STAGES = p.stages, B_STAGE_BYTES = p.b_stage_bytes;
+  // Weight tiles: one per pipeline stage (streamed with the A tiles), or -- `resident` -- all k_blocks of
+  // them loaded ONCE per CTA.  The wide layers of the coarse levels (N tile 256, K = 128 .. 768) re-fetched
+  // 32 KB of weights from L2 for every 16 KB of activations: 2/3 of their shared-memory fill traffic.
+  const int b_slots = p.resident ? p.k_blocks : STAGES;
   unsigned char *smem_a = smem;                                  // STAGES x 16 KB
-  unsigned char *smem_b = smem + STAGES * A_STAGE_BYTES;         // STAGES x b_stage_bytes
-  unsigned char *smem_out = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);  // kEpiWarps x 4 KB, 1024-aligned
+  unsigned char *smem_b = smem + STAGES * A_STAGE_BYTES;         // b_slots x b_stage_bytes
+  unsigned char *smem_out = smem_b + b_slots * B_STAGE_BYTES;    // kEpiWarps x 4 KB, 1024-aligned
   Barriers *bars = reinterpret_cast<Barriers *>(smem_out + kOutBytes);
   float *s_stats = reinterpret_cast<float *>(bars + 1);          // [kEpiWarps][2][kMaxBN]
   float *s_fold = s_stats + kEpiWarps * 2 * kMaxBN;              // [2][k_blocks * BK]: a_in, b_in of the fold
@@ -114,14 +120,21 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&bars->raw[s], p.tma_load ? 1 : 32 * kLoadWarps);
-      mbar_init(&bars->full[s], 32 * kLoadWarps + 1);
+      mbar_init(&bars->full[s], 32 * kLoadWarps + (p.resident ? 0 : 1));
       mbar_init(&bars->empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->acc_full[a], 1);
       mbar_init(&bars->acc_empty[a], 32 * kEpiWarps);
     }
+    mbar_init(&bars->w_full, 1);
     mbar_fence_init();
+    if (p.resident && my_tiles > 0) {  // the CTA's whole weight set: k_blocks contiguous, pre-swizzled images
+      mbar_expect_tx(&bars->w_full, b_bytes * static_cast<uint32_t>(p.k_blocks));
+      for (int kb = 0; kb < p.k_blocks; ++kb)
+        tma_load_1d(smem_b + kb * B_STAGE_BYTES, p.Wp + (static_cast<size_t>(n_tile) * p.k_blocks + kb) * p.BN * BK,
+                    b_bytes, &bars->w_full);
+    }
   }
   if (warp == kLoadWarps + kEpiWarps) {  // the MMA warp owns the tensor memory
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -153,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
     auto issue = [&]() {                  // cp.async of the next K block into stage is_s
       const int s = is_s, tile = is_tile, kb = is_kb;
       mbar_wait(&bars->empty[s], is_par);
-      if (tid == 0) {  // weight tile: one contiguous, pre-swizzled image
+      if (tid == 0 && !p.resident) {  // weight tile: one contiguous, pre-swizzled image
         mbar_expect_tx(&bars->full[s], b_bytes);
         tma_load_1d(smem_b + s * B_STAGE_BYTES,
                     p.Wp + (static_cast<size_t>(n_tile) * p.k_blocks + kb) * p.BN * BK, b_bytes,
@@ -246,6 +259,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
       const uint32_t idesc = make_idesc(BM, p.BN);
       const uint64_t k_hi = make_desc(0);
       int s = 0, par = 0, t = 0, kb = 0;
+      if (p.resident && total_kb > 0) mbar_wait(&bars->w_full, 0);
       for (int it = 0; it < total_kb; ++it) {
         const int acc = t & 1;
         if (kb == 0) {
@@ -255,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
         mbar_wait(&bars->full[s], par);
         tc_fence_after();
         const uint64_t da = k_hi | static_cast<uint64_t>((smem_u32(smem_a + s * A_STAGE_BYTES) & 0x3ffff) >> 4);
-        const uint64_t db = k_hi | static_cast<uint64_t>((smem_u32(smem_b + s * B_STAGE_BYTES) & 0x3ffff) >> 4);
+        const uint64_t db = k_hi | static_cast<uint64_t>((smem_u32(smem_b + (p.resident ? kb : s) * B_STAGE_BYTES) & 0x3ffff) >> 4);
         if (leader) {
           tc_mma_tf32(tmem_base + acc * acc_cols, da, db, idesc, kb != 0);
 #pragma unroll
@@ -484,12 +498,20 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   // stages each) double the loads in flight and the warps available to hide latency.
   const bool two_per_sm = prm.BN <= 128;
   prm.tmem_cols = two_per_sm ? 256 : 512;
+  const int budget = (two_per_sm ? gemm::kSmemBudgetHalf : gemm::kSmemBudget) - gemm::kOutBytes;
+  // Resident weights: when the whole weight set of an N tile fits beside >= 3 activation stages and the
+  // per-stage weight tile is at least as large as the activation tile (the wide layers, one CTA per SM).
+  // PN2_GEMM_RESIDENT = 0 / 1 forces it off / on where it fits (timing experiments).
+  const int w_all = prm.k_blocks * prm.b_stage_bytes;
+  const char *renv = getenv("PN2_GEMM_RESIDENT");
+  const bool fits = drop == nullptr && budget - w_all >= 3 * gemm::A_STAGE_BYTES;
+  prm.resident = (fits && (renv != nullptr ? renv[0] == '1' : prm.b_stage_bytes >= gemm::A_STAGE_BYTES && !two_per_sm)) ? 1 : 0;
   // the epilogue's staging blocks come out of the same budget (two CTAs of <= 113 KB share an SM)
-  prm.stages = ((two_per_sm ? gemm::kSmemBudgetHalf : gemm::kSmemBudget) - gemm::kOutBytes) /
-               (gemm::A_STAGE_BYTES + prm.b_stage_bytes);
+  prm.stages = prm.resident ? (budget - w_all) / gemm::A_STAGE_BYTES : budget / (gemm::A_STAGE_BYTES + prm.b_stage_bytes);
   if (prm.stages > gemm::kMaxStages) prm.stages = gemm::kMaxStages;
   if (prm.stages < 2) return PN2_ERR_UNSUPPORTED;
-  const size_t smem = static_cast<size_t>(prm.stages) * (gemm::A_STAGE_BYTES + prm.b_stage_bytes) + gemm::kOutBytes +
+  const size_t smem = static_cast<size_t>(prm.stages) * gemm::A_STAGE_BYTES +
+                      static_cast<size_t>(prm.resident ? prm.k_blocks : prm.stages) * prm.b_stage_bytes + gemm::kOutBytes +
                       sizeof(gemm::Barriers) + sizeof(float) * gemm::kEpiWarps * 2 * gemm::kMaxBN +
                       sizeof(float) * 2 * prm.k_blocks * gemm::BK;
   CUtensorMap tm_z;

@@ -704,6 +704,11 @@ def _dropout_mask(rows, cols, keep, dev):
     st = _drop_state.get(dev)
     if st is None:
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        # data-parallel ranks seed torch identically (same initial weights): without the rank every replica
+        # would draw the same keep masks
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            seed = (seed ^ (0x9E3779B97F4A7C15 * (dist.get_rank() + 1))) & (2 ** 62 - 1)
         st = _drop_state[dev] = torch.tensor([seed, 0], dtype=torch.int64, device=dev)
     def launch(ptr, strm):
         with torch.cuda.device(dev):

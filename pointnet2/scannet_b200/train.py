@@ -178,6 +178,37 @@ class TrainStep(object):
         return loss
 
 
+class _Snapshot(object):
+    """Parameters, optimiser state and BatchNorm buffers of a TrainStep, to be put back after the warm-up
+    passes a graph capture needs (allocator, lazy initialisations): building a graphed step must not train
+    the model, move its running statistics or advance Adam's step count."""
+
+    def __init__(self, step):
+        self.step = step
+        self.buffers = [b.detach().clone() for b in step.model.buffers()]
+        if step.flat_mode:
+            o = step.opt
+            self.opt = [t.detach().clone() for t in (o.flat, o.exp_avg, o.exp_avg_sq, o.step_count)]
+        else:
+            import copy
+            self.params = [p.detach().clone() for p in step.bucket.params]
+            self.opt = copy.deepcopy(step.optimizer.state_dict())
+
+    def restore(self):
+        step = self.step
+        with torch.no_grad():
+            for b, saved in zip(step.model.buffers(), self.buffers):
+                b.copy_(saved)
+            if step.flat_mode:
+                o = step.opt
+                for t, saved in zip((o.flat, o.exp_avg, o.exp_avg_sq, o.step_count), self.opt):
+                    t.copy_(saved)
+            else:
+                for p, saved in zip(step.bucket.params, self.params):
+                    p.copy_(saved)
+                step.optimizer.load_state_dict(self.opt)
+
+
 class GraphedTrainStep(object):
     """The same step replayed from a CUDA graph: the ~470 kernel launches of one SSG step
     (libpn2_b200.so kernels, cuBLAS GEMMs, the fused Adam) become one graph launch, which removes
@@ -195,9 +226,11 @@ class GraphedTrainStep(object):
             s.copy_(t)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):  # allocator / cuBLAS workspaces / lazy inits outside capture
+        snap = _Snapshot(step)
+        with torch.cuda.stream(side):  # allocator / workspaces / lazy inits outside capture
             for _ in range(warmup):
                 self._body()
+            snap.restore()             # the warm-up passes leave no trace in the model or the optimiser
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
@@ -247,8 +280,10 @@ class PipelinedTrainStep(object):
             # both plans live in flat buffers: handing the prefetched plan over is one device copy
             self.plan = geometry.build_plan(model, self.static[0][..., 0:3].contiguous()).pack()
             self.plan_next = geometry.build_plan(model, self.next[0][..., 0:3].contiguous()).pack()
+            snap = _Snapshot(step)
             for _ in range(warmup):
                 self._body()
+            snap.restore()             # the warm-up passes leave no trace in the model or the optimiser
         torch.cuda.current_stream().wait_stream(warm)
         torch.cuda.synchronize()
         # graph 1 (side stream): next batch's coordinates -> plan_next

@@ -263,13 +263,15 @@ def test_pipelined_step_equals_eager_step(warmup):
         m.cls_layer[1].p = 0.0
         return train.TrainStep(m, lr=1e-3)
 
-    eager = make()
-    for _ in range(warmup):          # the pipelined step's warm-up is a real optimisation step on its example batch
-        eager(*batches[2])
-    want = [float(eager(*batches[i % 3]).item()) for i in range(5)]
+    eager = make()                   # (the pipelined step's warm-up passes are undone: parameters, Adam state
+    want = [float(eager(*batches[i % 3]).item()) for i in range(5)]   # and BatchNorm buffers are restored)
     # warmup = 1: the weight-tile packing runs as a forked branch of the captured graph (fused.pack_branch);
     # warmup = 0: no eager step allocated its persistent buffers, so the graph packs in line
     piped = train.PipelinedTrainStep(make(), batches[2], warmup=warmup)
+    fresh_model = make().model               # building the graphed step must not have trained the model
+    for (n, a), (_, b) in zip(piped.step.model.state_dict().items(), fresh_model.state_dict().items()):
+        assert torch.equal(a, b), "warm-up changed %s" % n
+    assert int(piped.step.opt.step_count.item()) == 0 and float(piped.step.opt.exp_avg.abs().max()) == 0.0
     piped.prefetch(*batches[0])
     got = []
     for i in range(5):
