@@ -284,6 +284,23 @@ PN2_API int pn2_bn_finalize(int p, int c, int ld, int nblk, const float *partial
                             float *a, float *b, float *mean, float *invstd, void *stream);
 
 /* ==========================================================================
+ * Whole set-abstraction block in one kernel, inference (csrc/sa_chain.cu): QueryAndGroup ->
+ * three Conv2d(1x1) + folded BatchNorm + ReLU -> max over nsample
+ * (PointnetSAModule(MSG).forward in eval mode, pointnet2_modules.py:60-75).  table [b, n, ct] =
+ * [xyz | features | 0 pad] point rows, new_xyz [b, npoint, 3], idx [b, npoint, ns]; w1p / w2p / w3p:
+ * the layers' weights [c_l, c_{l-1}] packed by pn2_mlp_pack_weights_bn (pn2_sa_chain_weight_floats(n, k)
+ * floats each; layer 1's k = ct); fold = [a1 | b1 | a2 | b2 | a3 | b3] (pn2_bn_fold_eval); out
+ * [b * npoint, c3].  Activations never leave the SM.  Supported shapes: pn2_sa_chain_supported.
+ * ========================================================================== */
+PN2_API int pn2_sa_chain_supported(int ns, int ct, int c1, int c2, int c3);
+PN2_API int pn2_sa_chain_weight_floats(int n, int k);
+PN2_API int pn2_mlp_pack_weights_bn(int n, int k, int ldw, const float *w, float *packed, void *stream);
+PN2_API int pn2_sa_chain_eval(int b, int n, int npoint, int ns, int ct, const float *table,
+                              const float *new_xyz, const int *idx, int c1, int c2, int c3,
+                              const float *w1p, const float *w2p, const float *w3p, const float *fold,
+                              float *out, void *stream);
+
+/* ==========================================================================
  * Fused backward of one shared-MLP layer on the tensor cores (csrc/mlp_bwd.cu):
  * the adjoint of Conv2d(1x1) -> BatchNorm2d(train) -> ReLU (pytorch_utils.py:11-36)
  * in ONE pass over the rows, replacing autograd's threshold_backward + cudnn

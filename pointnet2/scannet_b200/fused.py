@@ -618,6 +618,68 @@ class FPInterpRows(Function):
         return gk, gs, None, None, None, None, None
 
 
+CHAIN_EVAL = True   # inference: a whole SA block (gather + 3 layers + max) in one kernel where it fits
+_chain_cache = {}
+
+
+def sa_chain_eval(mlp, table, new_xyz, idx):
+    """QueryAndGroup + SharedMLP + max-pool of one SA scale in ONE kernel (csrc/sa_chain.cu), inference only:
+    table (B, N, ct), new_xyz (B, np, 3), idx (B, np, ns) -> (B * np, C3), or None when the block does not fit
+    the kernel (then the caller runs it layer by layer).  BatchNorm is folded from the running statistics."""
+    layers = list(mlp)
+    if not CHAIN_EVAL or len(layers) != 3 or torch.is_grad_enabled() or any(l.training for l in layers):
+        return None
+    if not all(getattr(l, "activation", None) is not None for l in layers):
+        return None
+    L = _lib.load()
+    B, N, ct = table.shape
+    _, npoint, ns = idx.shape
+    Ws = [l.conv.weight.reshape(l.conv.weight.shape[0], -1) for l in layers]
+    cs = [w.shape[0] for w in Ws]
+    if Ws[0].shape[1] > ct or not L.pn2_sa_chain_supported(ns, ct, cs[0], cs[1], cs[2]):
+        return None
+    dev = table.device
+    s = _stream(dev)
+    # weight tiles and folds depend on the parameters / running statistics only: kept per SharedMLP until any
+    # of them changes (inference evaluates many batches with the same weights)
+    state = [t for layer in layers for t in (layer.conv.weight, layer.bn.bn.weight, layer.bn.bn.bias,
+                                             layer.bn.bn.running_mean, layer.bn.bn.running_var)]
+    key = (ct, dev) + tuple((t.data_ptr(), t._version) for t in state)
+    hit = _chain_cache.get(id(mlp))
+    if hit is not None and hit[0] == key and not torch.cuda.is_current_stream_capturing():
+        packed, fold = hit[1], hit[2]
+        out = torch.empty(B * npoint, cs[2], dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.pn2_sa_chain_eval(B, N, npoint, ns, ct, table.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(),
+                                           cs[0], cs[1], cs[2], packed[0].data_ptr(), packed[1].data_ptr(),
+                                           packed[2].data_ptr(), fold.data_ptr(), out.data_ptr(), s), "sa_chain_eval")
+        return out
+    with torch.cuda.device(dev):
+        packed, folds = [], []
+        for l, (layer, W2) in enumerate(zip(layers, Ws)):
+            W2 = W2.contiguous()
+            k = ct if l == 0 else cs[l - 1]
+            wp = torch.empty(L.pn2_sa_chain_weight_floats(cs[l], k), dtype=torch.float32, device=dev)
+            _lib.check(L.pn2_mlp_pack_weights_bn(cs[l], W2.shape[1], W2.shape[1], W2.data_ptr(), wp.data_ptr(), s),
+                       "mlp_pack_weights_bn")
+            packed.append(wp)
+            norm = layer.bn.bn
+            ab = torch.empty(4, cs[l], dtype=torch.float32, device=dev)   # a | b | mean | invstd
+            _lib.check(L.pn2_bn_fold_eval(cs[l], norm.weight.data_ptr(), norm.bias.data_ptr(),
+                                          norm.running_mean.data_ptr(), norm.running_var.data_ptr(), float(norm.eps),
+                                          ab[0].data_ptr(), ab[1].data_ptr(), ab[2].data_ptr(), ab[3].data_ptr(), s),
+                       "bn_fold_eval")
+            folds.append(ab[:2].reshape(-1))
+        fold = torch.cat(folds)
+        if not torch.cuda.is_current_stream_capturing():
+            _chain_cache[id(mlp)] = (key, packed, fold)
+        out = torch.empty(B * npoint, cs[2], dtype=torch.float32, device=dev)
+        _lib.check(L.pn2_sa_chain_eval(B, N, npoint, ns, ct, table.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(),
+                                       cs[0], cs[1], cs[2], packed[0].data_ptr(), packed[1].data_ptr(),
+                                       packed[2].data_ptr(), fold.data_ptr(), out.data_ptr(), s), "sa_chain_eval")
+    return out
+
+
 def rows_of(t):
     """Point-major (B, N, C) contiguous alias of a channel-major (B, C, N) feature tensor: the
     rows tensor a fused module produced it from when there is one, else a transposed copy."""

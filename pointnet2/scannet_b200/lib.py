@@ -55,6 +55,11 @@ SIGNATURES = {
                          _i, _vp, _vp, _vp, _vp, _vp],
     "pn2_groupmax_from_extrema": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_bn_finalize": [_i, _i, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    # whole SA block in one kernel (inference)
+    "pn2_sa_chain_supported": [_i, _i, _i, _i, _i],
+    "pn2_sa_chain_weight_floats": [_i, _i],
+    "pn2_mlp_pack_weights_bn": [_i, _i, _i, _vp, _vp, _vp],
+    "pn2_sa_chain_eval": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     # fused backward layer on the tensor cores
     "pn2_mlp_bwd_supported": [_i, _i, _i, _i, _i],
     "pn2_mlp_bwd_grid": [_i],

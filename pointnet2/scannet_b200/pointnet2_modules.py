@@ -77,9 +77,11 @@ class _PointnetSAModuleBase(nn.Module):
         for i, (grouper, mlp) in enumerate(zip(self.groupers, self.mlps)):
             idx = idxs[i] if idxs is not None else pointnet2_utils.ball_query(
                 grouper.radius, grouper.nsample, xyz, new_xyz)
-            inv = invs[i] if invs is not None and invs[i] is not None else (None, None)
-            rows = fused.SAGroupRows.apply(table, new_xyz, idx, inv[0], inv[1])   # (B*npoint*nsample, ct)
-            out = fused.run_mlp_rows(mlp, rows, grouper.nsample)          # (B*npoint, mlp[-1])
+            out = fused.sa_chain_eval(mlp, table, new_xyz, idx)           # inference: the whole block in one kernel
+            if out is None:
+                inv = invs[i] if invs is not None and invs[i] is not None else (None, None)
+                rows = fused.SAGroupRows.apply(table, new_xyz, idx, inv[0], inv[1])   # (B*npoint*nsample, ct)
+                out = fused.run_mlp_rows(mlp, rows, grouper.nsample)      # (B*npoint, mlp[-1])
             pooled.append(out.view(B, self.npoint, -1))
         rows = torch.cat(pooled, dim=2) if len(pooled) > 1 else pooled[0]   # (B, npoint, sum C)
         return fused.channel_major(rows)

@@ -37,6 +37,33 @@ def eval_scene():
 
 
 ms_eval, pred = timed(eval_scene)
+# the same evaluation without the one-kernel SA blocks (layer by layer), and both replayed from a CUDA graph
+from pointnet2.scannet_b200 import fused
+fused.CHAIN_EVAL = False
+ms_eval_layers, pred_layers = timed(eval_scene)
+fused.CHAIN_EVAL = True
+assert torch.equal(pred, pred_layers)
+
+
+def graphed(chain):
+    fused.CHAIN_EVAL = chain
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        eval_scene()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = eval_scene()
+    ms, _ = timed(lambda: g.replay(), reps=5)
+    fused.CHAIN_EVAL = True
+    return ms, out
+
+
+ms_graph_chain, pred_g = graphed(True)
+ms_graph_layers, _ = graphed(False)
+assert torch.equal(pred_g, pred)
 xyz = torch.from_numpy(np.ascontiguousarray(scene[None, :, :3])).cuda()
 ms_fps8k, idx8k = timed(lambda: ext.furthest_point_sampling(xyz, 8192), reps=1)
 ms_fps1k, idx1k = timed(lambda: ext.furthest_point_sampling(xyz, 1024), reps=2)
@@ -46,6 +73,10 @@ print(json.dumps({
     "scene_points": int(scene.shape[0]), "tiles": int(tiles.shape[0]),
     "ssg_eval_ms_per_scene": round(ms_eval, 3), "scenes_per_s": round(1e3 / ms_eval, 2),
     "chunks_per_s_eval": round(tiles.shape[0] / ms_eval * 1e3, 1),
+    "ssg_eval_ms_per_scene_layer_by_layer": round(ms_eval_layers, 3),
+    "ssg_eval_ms_per_scene_graph_replay": round(ms_graph_chain, 3),
+    "ssg_eval_ms_per_scene_graph_replay_layer_by_layer": round(ms_graph_layers, 3),
+    "scenes_per_s_graph_replay": round(1e3 / ms_graph_chain, 2),
     "fps_150k_to_8192_ms": round(ms_fps8k, 2), "fps_150k_to_8192_us_per_iteration": round(1e3 * ms_fps8k / 8191, 2),
     "fps_150k_to_1024_ms": round(ms_fps1k, 2),
     "ball_query_150k_x_1024_ms": round(ms_bq, 3),
