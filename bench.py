@@ -275,7 +275,9 @@ def run_product(args, world, rank, local):
         try:  # single GPU: the whole step; DP: forward+backward in the graph, NCCL + Adam after it
             cls = train.GraphedTrainStep if args.no_prefetch else train.PipelinedTrainStep
             kw = {} if args.no_prefetch else {"split_fwd_bwd": not args.no_split}
-            step = cls(eager, dev[0], scope="step" if world == 1 else "fwd_bwd", **kw)
+            # PN2_DP_SCOPE=step: the gradient all-reduce and Adam captured inside the step graph as well
+            scope = "step" if world == 1 else os.environ.get("PN2_DP_SCOPE", "fwd_bwd")
+            step = cls(eager, dev[0], scope=scope, **kw)
             launch_mode = "graph(%s)%s" % (step.scope, "" if args.no_prefetch else
                                            "+geometry prefetch" + ("" if args.no_split else ",split"))
         except Exception as e:  # noqa: BLE001

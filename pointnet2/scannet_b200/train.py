@@ -302,12 +302,23 @@ class PipelinedTrainStep(object):
         # adjoint, beside the ~60 short kernels of the coarse levels.  Measured in one run on one box (round 2):
         # "mid" gives the FP0 / head backward layers all 148 SMs (-66 us) but moves 3-NN / ball query beside
         # the SA2 / SA1 backward layers: 3.77-3.80 vs 3.72-3.74 ms per step, so "fwd" stays.
-        self.release = _os.environ.get("PN2_GEO_RELEASE", "fwd")
+        # "fwd1": the same release point as "fwd", but forward and backward stay ONE graph and the release is
+        # an external event-record node after the forward pass (no second graph launch, whose ~30 us gap sat
+        # on the critical path between the loss and the first backward kernel).
+        self.release = _os.environ.get("PN2_GEO_RELEASE", "fwd1")
         self.split = split_fwd_bwd
         self.fwd_done = torch.cuda.Event()
-        self.mid_bwd = torch.cuda.Event(external=True) if (self.split and self.release == "mid") else None
+        self.mid_bwd = torch.cuda.Event(external=True) if (self.split and self.release in ("mid", "fwd1")) else None
         self.graph = torch.cuda.CUDAGraph()
-        if self.split:
+        self.one_graph = self.split and self.release == "fwd1"
+        if self.one_graph:
+            with torch.cuda.graph(self.graph):
+                self.loss = self.step.forward_loss(*self.static, plan=self.plan)
+                self.mid_bwd.record(torch.cuda.current_stream())
+                self.step.backward_pack(self.loss)
+                if self.scope == "step":
+                    self.step.reduce_and_update()
+        elif self.split:
             with torch.cuda.graph(self.graph):
                 self.loss = self.step.forward_loss(*self.static, plan=self.plan)
             self.graph_bwd = torch.cuda.CUDAGraph()
@@ -361,7 +372,9 @@ class PipelinedTrainStep(object):
         self.copied.record(main)
         self._have_next = False
         self.graph.replay()
-        if self.split:
+        if self.one_graph:
+            self._fwd_recorded = True
+        elif self.split:
             self.fwd_done.record(main)
             self._fwd_recorded = True
             self.graph_bwd.replay()
