@@ -46,7 +46,7 @@ constexpr int BM = 128;          // rows (positions) per tile = UMMA M
 constexpr int BK = 32;           // fp32 per K block = one 128-byte swizzle row
 constexpr int kMaxStages = 12;   // stage count is chosen per launch: as many as fit (see launcher)
 constexpr int kLoadWarps = 4, kEpiWarps = 4;
-constexpr int kThreads = 32 * (kLoadWarps + kEpiWarps + 1);
+constexpr int kThreads = 32 * (kLoadWarps + kEpiWarps + 2);   // + MMA warp + weight-tile producer warp
 constexpr int kMaxBN = 256;
 constexpr int A_STAGE_BYTES = BM * BK * 4;        // 16 KB
 constexpr int kSmemBudget = 200 * 1024;           // A + B stages, one CTA per SM (BN > 128)
@@ -73,14 +73,15 @@ struct Params {
   int pool_ns;
   float *zmax, *zmin;
   int *imax, *imin;
-  int stages, b_stage_bytes;  // pipeline depth; bytes reserved per weight stage (multiple of 1024)
-  int resident;               // all k_blocks weight tiles of this CTA's N tile stay in shared memory (loaded once)
+  int stages, b_stage_bytes;  // A pipeline depth; bytes reserved per weight slot (multiple of 1024)
+  int b_slots;                // weight-tile ring: its own, shorter pipeline (the tiles come from L2, not HBM)
+  int resident;               // b_slots == k_blocks: every weight tile of this CTA's N tile is loaded once
   int tmem_cols;              // 512 (one CTA per SM) or 256 (two): two accumulators of tmem_cols / 2
   // dropout between the previous layer's activation and this layer (nn.Dropout in the classifier,
   // pointnet2_semseg.py:156): act(x) is multiplied by drop[p, k] ? drop_scale : 0 on the A tile
   const unsigned char *drop;  // [P, K] keep mask (nullptr: none); requires a_in
   float drop_scale;
-  int mask_off;               // offset of the stage's mask tile inside its weight stage
+  int mask_off;               // byte offset of the A stages' dropout mask tiles ([stages][128 rows][32 bytes])
 };
 
 using namespace tc;
@@ -91,7 +92,8 @@ struct __align__(16) Barriers {
   uint64_t empty[kMaxStages];  // MMAs that read the stage have retired  (1 commit)
   uint64_t acc_full[2];    // accumulator complete                   (1 commit)
   uint64_t acc_empty[2];   // accumulator drained by the epilogue    (128 arrivals)
-  uint64_t w_full;         // resident weight tiles landed           (1 arrival + tx bytes)
+  uint64_t b_full[kMaxStages];   // weight tile landed in its slot         (1 arrival + tx bytes)
+  uint64_t b_empty[kMaxStages];  // MMAs that read the slot have retired   (1 commit)
   uint32_t tmem_base;
 };
 
@@ -100,13 +102,15 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
                                                                      const __grid_constant__ CUtensorMap tm_a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int STAGES = p.stages, B_STAGE_BYTES = p.b_stage_bytes;
-  // Weight tiles: one per pipeline stage (streamed with the A tiles), or -- `resident` -- all k_blocks of
-  // them loaded ONCE per CTA.  The wide layers of the coarse levels (N tile 256, K = 128 .. 768) re-fetched
-  // 32 KB of weights from L2 for every 16 KB of activations: 2/3 of their shared-memory fill traffic.
-  const int b_slots = p.resident ? p.k_blocks : STAGES;
+  // The weight tiles have their OWN ring (b_slots, usually 2): they are re-read from L2 for every row tile and
+  // need little run-ahead, while the activation tiles stream from HBM and need all the depth shared memory
+  // allows -- with one ring for both, a 128-wide layer had 2 stages of (16 + 16) KB and ONE activation tile in
+  // flight per CTA.  `resident`: b_slots == k_blocks, every tile loaded once.
+  const int b_slots = p.b_slots;
   unsigned char *smem_a = smem;                                  // STAGES x 16 KB
   unsigned char *smem_b = smem + STAGES * A_STAGE_BYTES;         // b_slots x b_stage_bytes
-  unsigned char *smem_out = smem_b + b_slots * B_STAGE_BYTES;    // kEpiWarps x 4 KB, 1024-aligned
+  unsigned char *smem_mask = smem + p.mask_off;                  // STAGES x 4 KB (dropout only)
+  unsigned char *smem_out = smem_b + b_slots * B_STAGE_BYTES + (kDrop ? STAGES * BM * BK : 0);  // kEpiWarps x 4 KB
   Barriers *bars = reinterpret_cast<Barriers *>(smem_out + kOutBytes);
   float *s_stats = reinterpret_cast<float *>(bars + 1);          // [kEpiWarps][2][kMaxBN]
   float *s_fold = s_stats + kEpiWarps * 2 * kMaxBN;              // [2][k_blocks * BK]: a_in, b_in of the fold
@@ -120,21 +124,18 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&bars->raw[s], p.tma_load ? 1 : 32 * kLoadWarps);
-      mbar_init(&bars->full[s], 32 * kLoadWarps + (p.resident ? 0 : 1));
+      mbar_init(&bars->full[s], 32 * kLoadWarps);
       mbar_init(&bars->empty[s], 1);
+    }
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(&bars->b_full[s], 1);
+      mbar_init(&bars->b_empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->acc_full[a], 1);
       mbar_init(&bars->acc_empty[a], 32 * kEpiWarps);
     }
-    mbar_init(&bars->w_full, 1);
     mbar_fence_init();
-    if (p.resident && my_tiles > 0) {  // the CTA's whole weight set: k_blocks contiguous, pre-swizzled images
-      mbar_expect_tx(&bars->w_full, b_bytes * static_cast<uint32_t>(p.k_blocks));
-      for (int kb = 0; kb < p.k_blocks; ++kb)
-        tma_load_1d(smem_b + kb * B_STAGE_BYTES, p.Wp + (static_cast<size_t>(n_tile) * p.k_blocks + kb) * p.BN * BK,
-                    b_bytes, &bars->w_full);
-    }
   }
   if (warp == kLoadWarps + kEpiWarps) {  // the MMA warp owns the tensor memory
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -166,12 +167,6 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
     auto issue = [&]() {                  // cp.async of the next K block into stage is_s
       const int s = is_s, tile = is_tile, kb = is_kb;
       mbar_wait(&bars->empty[s], is_par);
-      if (tid == 0 && !p.resident) {  // weight tile: one contiguous, pre-swizzled image
-        mbar_expect_tx(&bars->full[s], b_bytes);
-        tma_load_1d(smem_b + s * B_STAGE_BYTES,
-                    p.Wp + (static_cast<size_t>(n_tile) * p.k_blocks + kb) * p.BN * BK, b_bytes,
-                    &bars->full[s]);
-      }
       if (!kDrop && p.tma_load) {
         // the whole 128 x 32 K block by ONE tensor load: same swizzled image as the cp.async path writes,
         // rows past P / columns past lda zero-filled by the TMA unit, no LSU wavefronts, no address math
@@ -194,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
         cp_async16(dst0 + r * 128 + ((chunk ^ (r & 7)) << 4), src, ok ? 16u : 0u);
         if (kDrop) {  // this thread's 4 mask bytes of the row ([128 rows][32 bytes] per stage)
           const bool mok = grow < p.P && col < p.K;
-          cp_async4(smem_u32(smem_b + s * B_STAGE_BYTES + p.mask_off) + r * 32 + chunk * 4,
+          cp_async4(smem_u32(smem_mask + s * BM * BK) + r * 32 + chunk * 4,
                     mok ? p.drop + static_cast<size_t>(grow) * p.K + col : p.drop, mok ? 4u : 0u);
         }
       }
@@ -235,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
           const float2 y01 = fma2(a01, make_float2(v.x, v.y), b01), y23 = fma2(a23, make_float2(v.z, v.w), b23);
           v = make_float4(fmaxf(y01.x, lo), fmaxf(y01.y, lo), fmaxf(y23.x, lo), fmaxf(y23.y, lo));
           if (kDrop) {
-            const uint32_t m = *reinterpret_cast<const uint32_t *>(smem_b + s * B_STAGE_BYTES + p.mask_off + r * 32 + chunk * 4);
+            const uint32_t m = *reinterpret_cast<const uint32_t *>(smem_mask + s * BM * BK + r * 32 + chunk * 4);
             v.x = (m & 0xffu) ? v.x * p.drop_scale : 0.f, v.y = (m & 0xff00u) ? v.y * p.drop_scale : 0.f;
             v.z = (m & 0xff0000u) ? v.z * p.drop_scale : 0.f, v.w = (m & 0xff000000u) ? v.w * p.drop_scale : 0.f;
           }
@@ -259,28 +254,46 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
       const uint32_t idesc = make_idesc(BM, p.BN);
       const uint64_t k_hi = make_desc(0);
       int s = 0, par = 0, t = 0, kb = 0;
-      if (p.resident && total_kb > 0) mbar_wait(&bars->w_full, 0);
+      int bs = 0, bpar = 0;   // weight ring slot / parity (resident: slot = K block, loaded once, parity stays 0)
       for (int it = 0; it < total_kb; ++it) {
         const int acc = t & 1;
         if (kb == 0) {
           mbar_wait(&bars->acc_empty[acc], ((t >> 1) & 1) ^ 1);
           tc_fence_after();
         }
+        const int wslot = p.resident ? kb : bs;
+        mbar_wait(&bars->b_full[wslot], p.resident ? 0 : bpar);
         mbar_wait(&bars->full[s], par);
         tc_fence_after();
         const uint64_t da = k_hi | static_cast<uint64_t>((smem_u32(smem_a + s * A_STAGE_BYTES) & 0x3ffff) >> 4);
-        const uint64_t db = k_hi | static_cast<uint64_t>((smem_u32(smem_b + (p.resident ? kb : s) * B_STAGE_BYTES) & 0x3ffff) >> 4);
+        const uint64_t db = k_hi | static_cast<uint64_t>((smem_u32(smem_b + wslot * B_STAGE_BYTES) & 0x3ffff) >> 4);
         if (leader) {
           tc_mma_tf32(tmem_base + acc * acc_cols, da, db, idesc, kb != 0);
 #pragma unroll
           for (int k = 1; k < BK / 8; ++k)  // 32 bytes (8 x tf32) further along K per instruction
             tc_mma_tf32(tmem_base + acc * acc_cols, da + 2 * k, db + 2 * k, idesc, 1);
           tc_commit(&bars->empty[s]);                       // stage reusable once these MMAs retire
+          if (!p.resident) tc_commit(&bars->b_empty[wslot]);
           if (kb == p.k_blocks - 1) tc_commit(&bars->acc_full[acc]);
         }
         __syncwarp();
         if (++s == STAGES) s = 0, par ^= 1;
+        if (++bs == b_slots) bs = 0, bpar ^= 1;
         if (++kb == p.k_blocks) kb = 0, ++t;
+      }
+    }
+  } else if (warp == kLoadWarps + kEpiWarps + 1) {
+    // ================================ weight-tile producer (one thread) ================================
+    if (lane == 0) {
+      const int total = p.resident ? min(total_kb, p.k_blocks) : total_kb;
+      int bs = 0, bpar = 1, kb = 0;
+      for (int q = 0; q < total; ++q) {
+        if (!p.resident) mbar_wait(&bars->b_empty[bs], bpar);
+        mbar_expect_tx(&bars->b_full[bs], b_bytes);
+        tma_load_1d(smem_b + bs * B_STAGE_BYTES, p.Wp + (static_cast<size_t>(n_tile) * p.k_blocks + kb) * p.BN * BK,
+                    b_bytes, &bars->b_full[bs]);
+        if (++bs == b_slots) bs = 0, bpar ^= 1;
+        if (++kb == p.k_blocks) kb = 0;
       }
     }
   } else {
@@ -418,6 +431,14 @@ __global__ void pack_weights_kernel(const float *__restrict__ W, int N, int K, i
 // covers the machine (the A tile is then re-read from L2 by each N tile's CTA).
 inline int pick_bn(int p, int n) {
   int bn = n > kMaxBN ? kMaxBN : (n + 15) / 16 * 16;
+  // Wide layers: N tiles of <= 128 columns, two CTAs per SM, instead of one 256-wide tile per SM.  Measured
+  // at 65536 x 128 -> 256: the 256-wide tile runs 10 us per row tile with 9 warps per SM, two 128-wide CTAs
+  // 4.4 us per row tile each (FP0 shapes): warps to hide latency matter more than the A tile re-read from L2.
+  static const bool wide_tiles = getenv("PN2_GEMM_WIDE_TILES") == nullptr || getenv("PN2_GEMM_WIDE_TILES")[0] != '0';
+  if (n > 128 && wide_tiles) {
+    const int nt = (n + 127) / 128;
+    bn = ((n + nt - 1) / nt + 31) / 32 * 32;
+  }
   const int m_tiles = (p + BM - 1) / BM;
   // (halves stay multiples of 32: the epilogue reads the accumulator out in 32-column blocks, and a block
   // that straddled the end of a 48- or 80-wide tile would overwrite the next tile's columns of Z)
@@ -492,26 +513,34 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   // loads in flight per SM to cover HBM latency; the wide ones get 4 x 48 KB
   prm.b_stage_bytes = (prm.BN * gemm::BK * 4 + 1023) / 1024 * 1024;
   if (drop != nullptr && (a_in == nullptr || h_out != nullptr || k % 4 != 0)) return PN2_ERR_INVALID_ARG;
-  prm.drop = drop, prm.drop_scale = drop_scale, prm.mask_off = prm.b_stage_bytes;
-  if (drop != nullptr) prm.b_stage_bytes += gemm::BM * gemm::BK;  // + [128 rows][32 mask bytes]
+  prm.drop = drop, prm.drop_scale = drop_scale;
+  const int mask_stage = drop != nullptr ? gemm::BM * gemm::BK : 0;   // [128 rows][32 mask bytes] per A stage
   // Narrow layers (BN <= 128) are pure streaming: two CTAs per SM (256 TMEM columns and <= 96 KB of
-  // stages each) double the loads in flight and the warps available to hide latency.
-  const bool two_per_sm = prm.BN <= 128;
+  // stages each) double the warps available to hide latency.
+  const char *oenv = getenv("PN2_GEMM_ONE_PER_SM");   // timing experiment: N tiles of 128 as one CTA per SM
+  const bool two_per_sm = prm.BN <= 128 && !(oenv != nullptr && oenv[0] == '1' && prm.BN == 128);
   prm.tmem_cols = two_per_sm ? 256 : 512;
+  // the epilogue's staging blocks come out of the same budget (two CTAs of <= 113 KB share an SM)
   const int budget = (two_per_sm ? gemm::kSmemBudgetHalf : gemm::kSmemBudget) - gemm::kOutBytes;
-  // Resident weights: when the whole weight set of an N tile fits beside >= 3 activation stages and the
-  // per-stage weight tile is at least as large as the activation tile (the wide layers, one CTA per SM).
-  // PN2_GEMM_RESIDENT = 0 / 1 forces it off / on where it fits (timing experiments).
+  // Weight ring: all K blocks once (resident) when the whole set fits beside >= 3 activation stages and the
+  // tiles are large (PN2_GEMM_RESIDENT = 0 / 1 forces it where it fits); else 2 slots (PN2_GEMM_BSLOTS).
   const int w_all = prm.k_blocks * prm.b_stage_bytes;
   const char *renv = getenv("PN2_GEMM_RESIDENT");
-  const bool fits = drop == nullptr && budget - w_all >= 3 * gemm::A_STAGE_BYTES;
+  const bool fits = budget - w_all >= 3 * (gemm::A_STAGE_BYTES + mask_stage) && prm.k_blocks <= gemm::kMaxStages;
   prm.resident = (fits && (renv != nullptr ? renv[0] == '1' : prm.b_stage_bytes >= gemm::A_STAGE_BYTES && !two_per_sm)) ? 1 : 0;
-  // the epilogue's staging blocks come out of the same budget (two CTAs of <= 113 KB share an SM)
-  prm.stages = prm.resident ? (budget - w_all) / gemm::A_STAGE_BYTES : budget / (gemm::A_STAGE_BYTES + prm.b_stage_bytes);
+  const char *benv = getenv("PN2_GEMM_BSLOTS");
+  prm.b_slots = prm.resident ? prm.k_blocks : (benv != nullptr ? atoi(benv) : 2);
+  if (prm.b_slots < 1) prm.b_slots = 1;
+  if (prm.b_slots > gemm::kMaxStages) prm.b_slots = gemm::kMaxStages;
+  if (benv != nullptr && atoi(benv) == 0 && !prm.resident)   // experiment: one ring depth for both, as before the split
+    prm.b_slots = budget / (gemm::A_STAGE_BYTES + mask_stage + prm.b_stage_bytes);
+  prm.stages = (budget - prm.b_slots * prm.b_stage_bytes) / (gemm::A_STAGE_BYTES + mask_stage);
+  if (benv != nullptr && atoi(benv) == 0 && !prm.resident) prm.stages = prm.b_slots;
   if (prm.stages > gemm::kMaxStages) prm.stages = gemm::kMaxStages;
   if (prm.stages < 2) return PN2_ERR_UNSUPPORTED;
-  const size_t smem = static_cast<size_t>(prm.stages) * gemm::A_STAGE_BYTES +
-                      static_cast<size_t>(prm.resident ? prm.k_blocks : prm.stages) * prm.b_stage_bytes + gemm::kOutBytes +
+  prm.mask_off = prm.stages * gemm::A_STAGE_BYTES + prm.b_slots * prm.b_stage_bytes;
+  const size_t smem = static_cast<size_t>(prm.stages) * (gemm::A_STAGE_BYTES + mask_stage) +
+                      static_cast<size_t>(prm.b_slots) * prm.b_stage_bytes + gemm::kOutBytes +
                       sizeof(gemm::Barriers) + sizeof(float) * gemm::kEpiWarps * 2 * gemm::kMaxBN +
                       sizeof(float) * 2 * prm.k_blocks * gemm::BK;
   CUtensorMap tm_z;
