@@ -11,12 +11,13 @@
 // (from the L2-resident point table) and the pooled output touches memory: the activations go
 // TMEM -> registers (fold + ReLU) -> shared memory (next layer's A operand) -> tensor core.
 //
-// Per CTA (persistent over 128-row tiles = 128 / nsample whole groups), 9 warps:
-//   warps 4-7  gather: thread r builds row r of the tile's A0 operand -- 16-byte loads of table[b, idx[p], :],
+// Per CTA (persistent over 128-row tiles = 128 / nsample whole groups), 13 warps:
+//   warps 8-11 gather: thread r builds row r of the tile's A0 operand -- 16-byte loads of table[b, idx[p], :],
 //              centre subtracted from the first three columns -- in the 128B-swizzled K-major UMMA layout
-//   warp  8    one elected thread issues tcgen05.mma.kind::tf32 for the three layers (weights resident in
+//   warp  12   one elected thread issues tcgen05.mma.kind::tf32 for the three layers (weights resident in
 //              shared memory as pre-packed tile images, loaded once by 1-D TMA bulk copies)
-//   warps 0-3  epilogues: layers 1, 2: tcgen05.ld -> relu(a z + b) -> next A operand; layer 3:
+//   warps 0-7  epilogues (two warpgroups: one per tile in flight, or alternating 32-column chunks of the
+//              single tile): layers 1, 2: tcgen05.ld -> relu(a z + b) -> next A operand; layer 3:
 //              relu(a z + b) and a shuffle butterfly max over the 32 (or 2 x 16) lanes of the warp, which are
 //              exactly the rows of one (two) group(s); one 128-byte store per group and 32 channels
 // Two tiles are in flight (two sets of operand tiles and accumulators) where shared / tensor memory
@@ -37,7 +38,7 @@ using namespace tc;
 
 constexpr int BM = 128;
 constexpr int SLAB = BM * 128;               // [128 rows][32 fp32] = 16 KB
-constexpr int kEpiWarps = 4, kGatherWarps = 4;
+constexpr int kEpiWarps = 8, kGatherWarps = 4;   // two epilogue warpgroups (TMEM lane quarter = warp % 4)
 constexpr int kThreads = 32 * (kEpiWarps + kGatherWarps + 1);
 constexpr int kSmemMax = 220 * 1024;
 
@@ -106,8 +107,11 @@ __global__ void __launch_bounds__(kThreads, 1) sa_chain_eval_kernel(Params p) {
       mbar_init(&bars->a0_full[s], 32 * kGatherWarps);
       mbar_init(&bars->a0_empty[s], 1);
       for (int l = 0; l < 3; ++l) mbar_init(&bars->d_full[s][l], 1);
-      for (int l = 0; l < 2; ++l) mbar_init(&bars->a_full[s][l], 32 * kEpiWarps);
-      mbar_init(&bars->tile_done[s], 32 * kEpiWarps);
+      // two tiles in flight: one epilogue warpgroup per slot (128 arrivals); one tile: both warpgroups share
+      // the slot, alternating 32-column chunks (256 arrivals)
+      const int epi = p.slots == 2 ? 128 : 256;
+      for (int l = 0; l < 2; ++l) mbar_init(&bars->a_full[s][l], epi);
+      mbar_init(&bars->tile_done[s], epi);
     }
     mbar_fence_init();
     if (my_tiles > 0) {
@@ -135,40 +139,74 @@ __global__ void __launch_bounds__(kThreads, 1) sa_chain_eval_kernel(Params p) {
 
   if (warp >= kEpiWarps && warp < kEpiWarps + kGatherWarps) {
     // ========================================= gather =========================================
+    // Two dependent global-memory latencies per row (index -> point row) bound this role: the indices and
+    // centres of the NEXT pair of tiles are fetched while the current pair is gathered, and when a row fits
+    // one K block (ct <= 32) the rows of both tiles are in flight together.
     const int r = tid - 32 * kEpiWarps;                 // row of the tile
     const int np_ns = p.npoint * p.ns, ct4 = p.ct / 4;
+    struct Row { const float4 *src; float cx, cy, cz; bool ok; };
+    auto fetch = [&](int t) -> Row {                    // t = index into this CTA's tile sequence
+      Row q;
+      q.src = nullptr, q.cx = q.cy = q.cz = 0.f, q.ok = false;
+      if (t >= my_tiles) return q;
+      const int tile = blockIdx.x + t * gridDim.x;
+      const long long row = static_cast<long long>(tile) * BM + r;
+      if (row >= p.P) return q;
+      const long long cloud = row / np_ns;
+      const int k = __ldg(p.idx + row);
+      q.src = reinterpret_cast<const float4 *>(p.table + (cloud * p.n + k) * p.ct);
+      const float *ctr = p.new_xyz + (row / p.ns) * 3;
+      q.cx = __ldg(ctr), q.cy = __ldg(ctr + 1), q.cz = __ldg(ctr + 2);
+      q.ok = true;
+      return q;
+    };
+    Row nxt[2] = {fetch(0), fetch(1)};
     for (int it = 0, t0 = 0; t0 < my_tiles; t0 += p.slots, ++it) {
       const int nt = min(p.slots, my_tiles - t0);
-      for (int s = 0; s < nt; ++s) {
-        const int tile = blockIdx.x + (t0 + s) * gridDim.x;
-        const long long row = static_cast<long long>(tile) * BM + r;
-        mbar_wait(&bars->a0_empty[s], (it & 1) ^ 1);    // layer-1 MMAs of the slot's previous tile retired
-        unsigned char *a0 = slot_base(s) + p.a_off[0];
-        const bool ok = row < p.P;
-        const float4 *src = nullptr;
-        float cx = 0.f, cy = 0.f, cz = 0.f;
-        if (ok) {
-          const long long cloud = row / np_ns;
-          const int k = __ldg(p.idx + row);
-          src = reinterpret_cast<const float4 *>(p.table + (cloud * p.n + k) * p.ct);
-          const float *ctr = p.new_xyz + (row / p.ns) * 3;
-          cx = __ldg(ctr), cy = __ldg(ctr + 1), cz = __ldg(ctr + 2);
-        }
-        for (int kb = 0; kb < p.kb[0]; ++kb) {
-          float4 v[8];
+      Row cur[2] = {nxt[0], nxt[1]};
+      if (p.slots == 2) nxt[0] = fetch(t0 + 2), nxt[1] = fetch(t0 + 3);
+      else nxt[0] = fetch(t0 + 1);
+      if (p.kb[0] == 1) {
+        float4 v[2][8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c4 = kb * 8 + j;
-            v[j] = (ok && c4 < ct4) ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          if (kb == 0 && ok) v[0].x -= cx, v[0].y -= cy, v[0].z -= cz;
-          unsigned char *slab = a0 + kb * SLAB + r * 128;
+        for (int s = 0; s < 2; ++s)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if ((kb * 8 + j) * 4 < p.c[0]) *reinterpret_cast<float4 *>(slab + ((j ^ (r & 7)) << 4)) = v[j];
+            v[s][j] = (s < nt && cur[s].ok && j < ct4) ? __ldg(cur[s].src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (s < nt) {
+            mbar_wait(&bars->a0_empty[s], (it & 1) ^ 1);    // layer-1 MMAs of the slot's previous tile retired
+            if (cur[s].ok) v[s][0].x -= cur[s].cx, v[s][0].y -= cur[s].cy, v[s][0].z -= cur[s].cz;
+            unsigned char *slab = slot_base(s) + p.a_off[0] + r * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j * 4 < p.c[0]) *reinterpret_cast<float4 *>(slab + ((j ^ (r & 7)) << 4)) = v[s][j];
+            fence_proxy_async();
+            mbar_arrive(&bars->a0_full[s]);
+          }
         }
-        fence_proxy_async();
-        mbar_arrive(&bars->a0_full[s]);
+      } else {
+        for (int s = 0; s < nt; ++s) {
+          mbar_wait(&bars->a0_empty[s], (it & 1) ^ 1);
+          unsigned char *a0 = slot_base(s) + p.a_off[0];
+          const Row q = cur[s];
+          for (int kb = 0; kb < p.kb[0]; ++kb) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c4 = kb * 8 + j;
+              v[j] = (q.ok && c4 < ct4) ? __ldg(q.src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (kb == 0 && q.ok) v[0].x -= q.cx, v[0].y -= q.cy, v[0].z -= q.cz;
+            unsigned char *slab = a0 + kb * SLAB + r * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if ((kb * 8 + j) * 4 < p.c[0]) *reinterpret_cast<float4 *>(slab + ((j ^ (r & 7)) << 4)) = v[j];
+          }
+          fence_proxy_async();
+          mbar_arrive(&bars->a0_full[s]);
+        }
       }
     }
   } else if (warp == kEpiWarps + kGatherWarps) {
@@ -209,66 +247,67 @@ __global__ void __launch_bounds__(kThreads, 1) sa_chain_eval_kernel(Params p) {
     }
   } else {
     // ======================================== epilogues ========================================
-    const int wq = warp;                                  // TMEM lane quarter = rows 32 wq .. 32 wq + 31
+    const int wg = warp >> 2, wq = warp & 3;              // warpgroup; TMEM lane quarter = rows 32 wq .. 32 wq + 31
     const int r = wq * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const bool share = p.slots == 1;                      // both warpgroups work on slot 0, alternating chunks
     for (int it = 0, t0 = 0; t0 < my_tiles; t0 += p.slots, ++it) {
       const int nt = min(p.slots, my_tiles - t0);
+      const int s = share ? 0 : wg;
+      if (s >= nt) continue;
       for (int l = 0; l < 3; ++l) {
         const int C = p.c[l + 1];
         const float *fa = s_fold + 2 * (l > 0 ? p.c[1] : 0) + 2 * (l > 1 ? p.c[2] : 0), *fb = fa + C;
-        for (int s = 0; s < nt; ++s) {
-          mbar_wait(&bars->d_full[s][l], it & 1);
-          tc_fence_after();
-          const uint32_t d = tmem_base + lane_off + s * p.slot_cols + p.d_off[l];
-          if (l < 2) {
-            unsigned char *a_next = slot_base(s) + p.a_off[l + 1] + r * 128;
-            for (int c0 = 0; c0 < C; c0 += 32) {
-              float v[32];
-              tc_ld32(d + c0, v);
-              unsigned char *slab = a_next + (c0 >> 5) * SLAB;
+        mbar_wait(&bars->d_full[s][l], it & 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + lane_off + s * p.slot_cols + p.d_off[l];
+        if (l < 2) {
+          unsigned char *a_next = slot_base(s) + p.a_off[l + 1] + r * 128;
+          for (int c0 = share ? 32 * wg : 0; c0 < C; c0 += share ? 64 : 32) {
+            float v[32];
+            tc_ld32(d + c0, v);
+            unsigned char *slab = a_next + (c0 >> 5) * SLAB;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (c0 + 4 * j < C) {
-                  const float4 a4 = *reinterpret_cast<const float4 *>(fa + c0 + 4 * j);
-                  const float4 b4 = *reinterpret_cast<const float4 *>(fb + c0 + 4 * j);
-                  float4 y;
-                  y.x = fmaxf(fmaf(a4.x, v[4 * j], b4.x), 0.f), y.y = fmaxf(fmaf(a4.y, v[4 * j + 1], b4.y), 0.f);
-                  y.z = fmaxf(fmaf(a4.z, v[4 * j + 2], b4.z), 0.f), y.w = fmaxf(fmaf(a4.w, v[4 * j + 3], b4.w), 0.f);
-                  *reinterpret_cast<float4 *>(slab + ((j ^ (r & 7)) << 4)) = y;
-                }
+            for (int j = 0; j < 8; ++j) {
+              if (c0 + 4 * j < C) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(fa + c0 + 4 * j);
+                const float4 b4 = *reinterpret_cast<const float4 *>(fb + c0 + 4 * j);
+                float4 y;
+                y.x = fmaxf(fmaf(a4.x, v[4 * j], b4.x), 0.f), y.y = fmaxf(fmaf(a4.y, v[4 * j + 1], b4.y), 0.f);
+                y.z = fmaxf(fmaf(a4.z, v[4 * j + 2], b4.z), 0.f), y.w = fmaxf(fmaf(a4.w, v[4 * j + 3], b4.w), 0.f);
+                *reinterpret_cast<float4 *>(slab + ((j ^ (r & 7)) << 4)) = y;
               }
             }
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(&bars->a_full[s][l]);
-          } else {
-            const int tile = blockIdx.x + (t0 + s) * gridDim.x;
-            const long long g0 = (static_cast<long long>(tile) * BM + wq * 32) / p.ns;   // first group of this warp
-            for (int c0 = 0; c0 < C; c0 += 32) {
-              float v[32];
-              tc_ld32(d + c0, v);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const bool in = c0 + j < C;
-                v[j] = fmaxf(fmaf(in ? fa[c0 + j] : 0.f, v[j], in ? fb[c0 + j] : 0.f), 0.f);
-              }
-              if (p.ns == 32) {
-                group_colmax<false>(v, lane);
-                if (g0 < p.G && c0 + lane < C) p.out[g0 * C + c0 + lane] = v[0];
-              } else {   // ns == 16: lanes 0-15 and 16-31 are two groups
-                group_colmax<true>(v, lane);
-                const long long g = g0 + (lane >> 4);
-                const int col = c0 + 2 * (lane & 15);
-                if (g < p.G && col < C) {
-                  p.out[g * C + col] = v[0];
-                  if (col + 1 < C) p.out[g * C + col + 1] = v[1];
-                }
-              }
-            }
-            tc_fence_before();
-            mbar_arrive(&bars->tile_done[s]);
           }
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(&bars->a_full[s][l]);
+        } else {
+          const int tile = blockIdx.x + (t0 + s) * gridDim.x;
+          const long long g0 = (static_cast<long long>(tile) * BM + wq * 32) / p.ns;   // first group of this warp
+          for (int c0 = share ? 32 * wg : 0; c0 < C; c0 += share ? 64 : 32) {
+            float v[32];
+            tc_ld32(d + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const bool in = c0 + j < C;
+              v[j] = fmaxf(fmaf(in ? fa[c0 + j] : 0.f, v[j], in ? fb[c0 + j] : 0.f), 0.f);
+            }
+            if (p.ns == 32) {
+              group_colmax<false>(v, lane);
+              if (g0 < p.G && c0 + lane < C) p.out[g0 * C + c0 + lane] = v[0];
+            } else {   // ns == 16: lanes 0-15 and 16-31 are two groups
+              group_colmax<true>(v, lane);
+              const long long g = g0 + (lane >> 4);
+              const int col = c0 + 2 * (lane & 15);
+              if (g < p.G && col < C) {
+                p.out[g * C + col] = v[0];
+                if (col + 1 < C) p.out[g * C + col + 1] = v[1];
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&bars->tile_done[s]);
         }
       }
     }

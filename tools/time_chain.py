@@ -52,11 +52,19 @@ with torch.no_grad():
             res[chain] = (timed(lambda: sa._forward_rows(xyz, new_xyz, feat, [bq])), out)
         fused.CHAIN_EVAL = True
         assert torch.equal(res[True][1], res[False][1])
+        # the kernel alone (point table already concatenated)
+        cols = [xyz, fused.rows_of(feat)]
+        width = sum(c.size(2) for c in cols)
+        if fused.pad4(width) != width:
+            cols.append(xyz.new_zeros(B, xyz.shape[1], fused.pad4(width) - width))
+        table = torch.cat(cols, dim=2)
+        t_kernel = timed(lambda: fused.sa_chain_eval(sa.mlps[0], table, new_xyz, bq))
         N, ct, P = xyz.shape[1], fused.pad4(3 + feat.shape[1]), B * npoint * ns
         nbytes = 4 * P + 4 * ct * min(B * N, P) + 4 * B * npoint * mlp[3]
         layer_bytes = nbytes + 4 * P * (2 * ct + 2 * mlp[1] + 2 * mlp[2] + mlp[3])
-        print("%s B=%d: chain %7.1f us (%5.1f MB algorithmic, %5.0f GB/s, %.2f of the HBM peak) | layer by layer %7.1f us "
-              "(%6.1f MB) | %.1fx, bit-identical" % (name, B, res[True][0], nbytes / 1e6, nbytes / res[True][0] / 1e3,
-                                                    nbytes / res[True][0] / 1e3 / PEAK, res[False][0], layer_bytes / 1e6,
-                                                    res[False][0] / res[True][0]))
+        flops = 2.0 * P * (fused.pad4(3 + feat.shape[1]) * mlp[1] + mlp[1] * mlp[2] + mlp[2] * mlp[3])
+        print("%s B=%d: block with the chain kernel %7.1f us (kernel alone %6.1f us = %5.1f TFLOP/s TF32, %5.1f MB algorithmic) | "
+              "layer by layer %7.1f us (%6.1f MB) | %.1fx, bit-identical" % (
+                  name, B, res[True][0], t_kernel, flops / t_kernel / 1e6, nbytes / 1e6, res[False][0], layer_bytes / 1e6,
+                  res[False][0] / res[True][0]))
         xyz, feat = new_xyz, res[True][1]
