@@ -387,6 +387,15 @@ PN2_API int pn2_bwd_stats_finalize(int p, int c, int ld, int nblk, int training,
  * ========================================================================== */
 PN2_API int pn2_mlp_pack_weights_dgrad(int p, int n_out, int n, int k, int ldw, const float *w,
                                        float *packed, void *stream);
+/* the data-gradient product with the BatchNorm-adjoint statistics of the layer BELOW from its epilogue (z_prev
+ * [p, n_out], fold_prev = [a | b | mean | invstd] of that layer, [4][n_out]; partials as pn2_mlp_gemm_fwd's, finalised
+ * by pn2_bwd_stats_finalize), and the dZ half of pn2_relu_bn_bwd for a layer whose c1c2 came that way */
+PN2_API int pn2_mlp_dgrad_stats(int p, int n, int n_out, const float *dz, const float *w_packed,
+                                float *dh_prev, const float *z_prev, const float *fold_prev, int relu_prev,
+                                float *partials, void *stream);
+PN2_API int pn2_relu_bn_bwd_dz(int p, int c, int relu, const float *dh, const float *z, const float *a,
+                               const float *b, const float *mean, const float *invstd, const float *c1c2,
+                               float *dz, void *stream);
 PN2_API int pn2_mlp_wgrad_splits(int p, int n, int ldy);
 PN2_API int pn2_mlp_wgrad_rows(int n);
 PN2_API int pn2_mlp_wgrad_cols(int ldy);

@@ -82,6 +82,12 @@ struct Params {
   const unsigned char *drop;  // [P, K] keep mask (nullptr: none); requires a_in
   float drop_scale;
   int mask_off;               // byte offset of the A stages' dropout mask tiles ([stages][128 rows][32 bytes])
+  // Data-gradient use (A = dZ of a layer, Z = dH_prev): BatchNorm-adjoint statistics of the layer BELOW from the
+  // epilogue -- column sums of dY = relu'(a z + b) .* dH_prev and of dY .* zhat over this CTA's rows, written to
+  // `partials` like the forward statistics (pn2_bwd_stats_finalize turns them into dbeta, dgamma, c1, c2).
+  // zs: that layer's pre-BN output [P, ldzs]; zs_fold: its a | b | mean | invstd ([4][N]); nullptr: off.
+  const float *zs, *zs_fold;
+  int ldzs, zs_relu;
 };
 
 using namespace tc;
@@ -114,6 +120,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
   Barriers *bars = reinterpret_cast<Barriers *>(smem_out + kOutBytes);
   float *s_stats = reinterpret_cast<float *>(bars + 1);          // [kEpiWarps][2][kMaxBN]
   float *s_fold = s_stats + kEpiWarps * 2 * kMaxBN;              // [2][k_blocks * BK]: a_in, b_in of the fold
+  float *s_zs = s_fold + 2 * p.k_blocks * BK;                    // [4][kMaxBN]: a | b | mean | invstd of the layer below
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tile = blockIdx.y;
@@ -149,6 +156,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
     s_fold[i] = ok ? p.a_in[i] : 1.f;
     s_fold[p.k_blocks * BK + i] = ok ? p.b_in[i] : 0.f;
   }
+  if (p.zs != nullptr)
+    for (int i = tid; i < 4 * p.BN; i += kThreads) {
+      const int which = i / p.BN, col = n_tile * p.BN + (i - which * p.BN);
+      s_zs[which * kMaxBN + (i - which * p.BN)] = col < p.N ? p.zs_fold[static_cast<size_t>(which) * p.N + col] : 0.f;
+    }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -360,6 +372,27 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
               }
             }
             csum[c] += s0, csq[c] += q0;
+          } else if (p.zs != nullptr) {
+            // adjoint statistics of the layer below: dY = dH_prev where that layer's ReLU passed, zhat from its z
+            float dy[32], dq[32];
+            const bool rok = grow < p.P;
+            const float *zr = p.zs + static_cast<size_t>(rok ? grow : 0) * p.ldzs + n0;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const bool in = rok && n0 + 4 * j4 < p.N;
+              const float4 zz = in ? __ldg(reinterpret_cast<const float4 *>(zr + 4 * j4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float zv[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = 4 * j4 + e, cc = c * 32 + j;
+                const float ya = fmaf(s_zs[cc], zv[e], s_zs[kMaxBN + cc]);
+                const float d = (in && (!p.zs_relu || ya > 0.f)) ? v[j] : 0.f;
+                dy[j] = d;
+                dq[j] = d * ((zv[e] - s_zs[2 * kMaxBN + cc]) * s_zs[3 * kMaxBN + cc]);
+              }
+            }
+            csum[c] += warp_colsum32(dy, lane);
+            csq[c] += warp_colsum32(dq, lane);
           } else if (p.partials != nullptr) {  // rows past P are zero (zero-filled A): they add nothing
             float sq[32];
 #pragma unroll
@@ -493,10 +526,11 @@ extern "C" int pn2_mlp_pack_weights_dgrad(int p, int n_out, int n, int k, int ld
 
 extern "C" int pn2_mlp_gemm_pool_supported(int ns) { return (ns == 16 || ns == 32) ? 1 : 0; }
 
-extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const float *a, const float *a_in,
-                                const float *b_in, int relu_in, float *h_out, const float *w_packed,
-                                float *z, float *partials, const unsigned char *drop, float drop_scale,
-                                int pool_ns, float *zmax, float *zmin, int *imax, int *imin, void *stream) {
+static int launch_gemm(int p, int k, int lda, int n, int ldz, const float *a, const float *a_in,
+                       const float *b_in, int relu_in, float *h_out, const float *w_packed,
+                       float *z, float *partials, const unsigned char *drop, float drop_scale,
+                       int pool_ns, float *zmax, float *zmin, int *imax, int *imin, const float *zs,
+                       const float *zs_fold, int ldzs, int zs_relu, void *stream) {
   if (p <= 0 || k <= 0 || n <= 0 || lda < 4 || lda % 4 != 0) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(a, w_packed);
   if (!aligned16(a) || !aligned16(w_packed)) return PN2_ERR_UNSUPPORTED;
@@ -506,6 +540,10 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   gemm::Params prm;
   prm.A = a, prm.a_in = a_in, prm.b_in = b_in, prm.H_out = h_out, prm.Wp = w_packed, prm.Z = z;
   prm.partials = partials;
+  prm.zs = zs, prm.zs_fold = zs_fold, prm.ldzs = ldzs, prm.zs_relu = zs_relu;
+  if (zs != nullptr && (partials == nullptr || zs_fold == nullptr || pool_ns != 0 || ldzs < n || ldzs % 4 != 0 ||
+                        !aligned16(zs)))
+    return PN2_ERR_INVALID_ARG;
   prm.P = p, prm.lda = lda, prm.K = k, prm.k_blocks = pn2_mlp_gemm_k_blocks(k);
   prm.N = n, prm.ldz = ldz, prm.BN = gemm::pick_bn(p, n), prm.n_tiles = pn2_mlp_gemm_n_tiles(p, n);
   prm.relu_in = relu_in;
@@ -542,7 +580,7 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   const size_t smem = static_cast<size_t>(prm.stages) * (gemm::A_STAGE_BYTES + mask_stage) +
                       static_cast<size_t>(prm.b_slots) * prm.b_stage_bytes + gemm::kOutBytes +
                       sizeof(gemm::Barriers) + sizeof(float) * gemm::kEpiWarps * 2 * gemm::kMaxBN +
-                      sizeof(float) * 2 * prm.k_blocks * gemm::BK;
+                      sizeof(float) * 2 * prm.k_blocks * gemm::BK + (zs != nullptr ? sizeof(float) * 4 * gemm::kMaxBN : 0);
   CUtensorMap tm_z;
   memset(&tm_z, 0, sizeof(tm_z));
   static const bool no_tma = getenv("PN2_GEMM_NO_TMA_STORE") != nullptr;   // timing experiments only
@@ -564,4 +602,25 @@ extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const flo
   kern<<<grid, gemm::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(prm, tm_z, tm_a);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_mlp_gemm_fwd(int p, int k, int lda, int n, int ldz, const float *a, const float *a_in,
+                                const float *b_in, int relu_in, float *h_out, const float *w_packed,
+                                float *z, float *partials, const unsigned char *drop, float drop_scale,
+                                int pool_ns, float *zmax, float *zmin, int *imax, int *imin, void *stream) {
+  return launch_gemm(p, k, lda, n, ldz, a, a_in, b_in, relu_in, h_out, w_packed, z, partials, drop, drop_scale, pool_ns,
+                     zmax, zmin, imax, imin, nullptr, nullptr, 0, 0, stream);
+}
+
+// Data gradient of a wide layer, dh_prev[p, n_out] = dz[p, n] * W (tile images of pn2_mlp_pack_weights_dgrad), with the
+// BatchNorm-adjoint statistics of the layer BELOW out of the epilogue: z_prev [p, n_out] is that layer's pre-BN output,
+// fold_prev = its [a | b | mean | invstd] ([4][n_out]); partials: [pn2_mlp_gemm_grid(p, n_out)][2][n_tiles * bn] column
+// sums of dY_prev and dY_prev .* zhat_prev, to be finalised by pn2_bwd_stats_finalize (ld = n_tiles * bn).  Removes the
+// statistics pass over (dh_prev, z_prev) that pn2_relu_bn_bwd(_stats) would make.
+extern "C" int pn2_mlp_dgrad_stats(int p, int n, int n_out, const float *dz, const float *w_packed, float *dh_prev,
+                                   const float *z_prev, const float *fold_prev, int relu_prev, float *partials,
+                                   void *stream) {
+  if (z_prev == nullptr || fold_prev == nullptr || partials == nullptr || dh_prev == nullptr) return PN2_ERR_INVALID_ARG;
+  return launch_gemm(p, n, n, n_out, n_out, dz, nullptr, nullptr, 0, nullptr, w_packed, dh_prev, partials, nullptr, 1.0f,
+                     0, nullptr, nullptr, nullptr, nullptr, z_prev, fold_prev, n_out, relu_prev, stream);
 }

@@ -794,6 +794,21 @@ extern "C" int pn2_relu_bn_bwd(int p, int c, int training, int relu, const float
   PN2_RETURN_LAUNCH_STATUS();
 }
 
+// The dZ half of pn2_relu_bn_bwd alone, for a layer whose statistics c1c2 = [dbeta / P | dgamma / P] came from
+// elsewhere (the data-gradient product's epilogue, pn2_mlp_dgrad_stats + pn2_bwd_stats_finalize).
+extern "C" int pn2_relu_bn_bwd_dz(int p, int c, int relu, const float *dh, const float *z, const float *a,
+                                  const float *b, const float *mean, const float *invstd, const float *c1c2,
+                                  float *dz, void *stream) {
+  if (p <= 0 || c <= 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(dh, z, a, b, mean, invstd, c1c2, dz);
+  if (!rows_ok(c, z) || !aligned16(dh) || !aligned16(dz) || !aligned16(c1c2)) return PN2_ERR_UNSUPPORTED;
+  const size_t total4 = static_cast<size_t>(p) * (c / 4);
+  relu_bwd_dz_kernel<<<blocks_for(total4, 16 * kNumSMs), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      total4, c / 4, relu, dh, z, a, b, mean, invstd, c1c2, c1c2 + c, dz);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
 // Statistics halves of the two adjoints above, for the fused tensor-core backward layer
 // (mlp_bwd.cu), which forms dZ on chip: dgamma, dbeta and c1c2 = [dbeta / P | dgamma / P].
 extern "C" int pn2_pool_bn_bwd_stats(int g, int ns, int c, int training, const float *dout, const int *argmax,

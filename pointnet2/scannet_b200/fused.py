@@ -161,7 +161,7 @@ def _ws(c, dev):
 
 class _BNLayer(object):
     """Per-layer state shared between forward and backward."""
-    __slots__ = ("z", "a", "b", "mean", "invstd", "cout")
+    __slots__ = ("z", "a", "b", "mean", "invstd", "cout", "fold4")
 
 
 def _bn_forward(z, gamma, beta, rm, rv, eps, momentum, training, nbt=None):
@@ -169,7 +169,7 @@ def _bn_forward(z, gamma, beta, rm, rv, eps, momentum, training, nbt=None):
     L = _lib.load()
     P, C = z.shape
     dev = z.device
-    a, b, mean, invstd = (torch.empty(C, dtype=torch.float32, device=dev) for _ in range(4))
+    a, b, mean, invstd = torch.empty(4, C, dtype=torch.float32, device=dev).unbind(0)   # rows of one [4, C] buffer
     if training:
         _lib.check(L.pn2_bn_stats(P, C, z.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, momentum,
                                   rm.data_ptr() if rm is not None else None,
@@ -247,6 +247,34 @@ def _dgrad(dz, W2c, n_out, wp=None):
     return out
 
 
+# BatchNorm-adjoint statistics of the layer below from the data-gradient product's epilogue (pn2_mlp_dgrad_stats)
+# instead of a separate pass over (dH_prev, Z_prev).  Measured in one call (round 2): it removes 6 of the 11 statistics
+# launches of an SSG step but the epilogue's per-thread row reads of Z_prev slow the products down by more:
+# 3.68 vs 3.64 ms per step -- off by default, kept for the tests that pin its arithmetic.
+DGRAD_STATS = os.environ.get("PN2_DGRAD_STATS", "0") == "1"
+
+
+def _dgrad_stats(dz, W2c, n_out, wp, prev, relu_prev, training):
+    """_dgrad plus (dgamma, dbeta, c1c2) of the layer below (``prev``: its z and [a | b | mean | invstd]) from the
+    product's epilogue: column sums of dY_prev and dY_prev * zhat_prev per CTA, finalised in fixed order."""
+    L = _lib.load()
+    dev = dz.device
+    P, N = dz.shape
+    s = _stream(dev)
+    if wp is None:
+        wp = _pack_dgrad(P, n_out, W2c)
+    bn, nt, grid = L.pn2_mlp_gemm_bn(P, n_out), L.pn2_mlp_gemm_n_tiles(P, n_out), L.pn2_mlp_gemm_grid(P, n_out)
+    out = torch.empty(P, n_out, dtype=torch.float32, device=dev)
+    part = torch.empty(grid, 2, nt * bn, dtype=torch.float32, device=dev)
+    _lib.check(L.pn2_mlp_dgrad_stats(P, N, n_out, dz.data_ptr(), wp.data_ptr(), out.data_ptr(), prev.z.data_ptr(),
+                                     prev.fold4.data_ptr(), relu_prev, part.data_ptr(), s), "mlp_dgrad_stats")
+    Kc = prev.cout
+    pg, pb, pc = (torch.empty(m, dtype=torch.float32, device=dev) for m in (Kc, Kc, 2 * Kc))
+    _lib.check(L.pn2_bwd_stats_finalize(P, Kc, nt * bn, grid, training, part.data_ptr(), pg.data_ptr(), pb.data_ptr(),
+                                        pc.data_ptr(), s), "bwd_stats_finalize")
+    return out, (pg, pb, pc)
+
+
 def _wgrad(dz, h, K):
     """(dz^T @ h)[:, :K] -> dense [N, K]: csrc/mlp_wgrad.cu, row-split partial images summed in fixed order
     straight into the parameter's layout (autograd takes the tensor as .grad without a copy)."""
@@ -266,7 +294,7 @@ def _wgrad(dz, h, K):
 def _bn_finalize(P, C, part, ld, nblk, gamma, beta, rm, rv, eps, momentum, nbt=None):
     L = _lib.load()
     dev = part.device
-    a, b, mean, invstd = (torch.empty(C, dtype=torch.float32, device=dev) for _ in range(4))
+    a, b, mean, invstd = torch.empty(4, C, dtype=torch.float32, device=dev).unbind(0)   # rows of one [4, C] buffer
     _lib.check(L.pn2_bn_finalize(P, C, ld, nblk, part.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps,
                                  momentum, rm.data_ptr() if rm is not None else None,
                                  rv.data_ptr() if rv is not None else None,
@@ -342,6 +370,7 @@ class SharedMLPRows(Function):
                                                                   rm, rv, eps, momentum, nbt)
                 else:
                     st.a, st.b, st.mean, st.invstd = _bn_forward(st.z, gamma, beta, rm, rv, eps, momentum, False)
+                st.fold4 = st.a._base if st.a._base is not None else None   # [a | b | mean | invstd], [4, C]
                 layers.append(st)
                 C = st.cout
                 if l < nl - 1:
@@ -482,25 +511,41 @@ class SharedMLPRows(Function):
                     dh = dh_prev
                     continue
                 # ---- split adjoint (wide layers): dZ by a streaming kernel, then two tensor-core products ----
-                pending = None
                 dz = torch.empty_like(st.z)
-                dgamma, dbeta = f32(C), f32(C)
-                ws = _ws(C, dev)
-                if pooled:
-                    _lib.check(L.pn2_pool_bn_bwd(P // ns, ns, C, training, dh.data_ptr(),
-                                                 ctx.argmax.data_ptr(), st.z.data_ptr(), st.a.data_ptr(),
-                                                 st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
-                                                 dz.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                                                 ws.data_ptr(), s), "pool_bn_bwd")
+                if pending is not None and not pooled:
+                    # this layer's statistics came out of the data-gradient product of the layer above: dZ only
+                    dgamma, dbeta, c1c2 = pending
+                    _lib.check(L.pn2_relu_bn_bwd_dz(P, C, int(ctx.relus[l]), dh.data_ptr(), st.z.data_ptr(),
+                                                    st.a.data_ptr(), st.b.data_ptr(), st.mean.data_ptr(),
+                                                    st.invstd.data_ptr(), c1c2.data_ptr(), dz.data_ptr(), s),
+                               "relu_bn_bwd_dz")
                 else:
-                    _lib.check(L.pn2_relu_bn_bwd(P, C, training, int(ctx.relus[l]), dh.data_ptr(), st.z.data_ptr(),
-                                                 st.a.data_ptr(), st.b.data_ptr(), st.mean.data_ptr(),
-                                                 st.invstd.data_ptr(), dz.data_ptr(), dgamma.data_ptr(),
-                                                 dbeta.data_ptr(), ws.data_ptr(), s), "relu_bn_bwd")
+                    dgamma, dbeta = f32(C), f32(C)
+                    ws = _ws(C, dev)
+                    if pooled:
+                        _lib.check(L.pn2_pool_bn_bwd(P // ns, ns, C, training, dh.data_ptr(),
+                                                     ctx.argmax.data_ptr(), st.z.data_ptr(), st.a.data_ptr(),
+                                                     st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
+                                                     dz.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                                     ws.data_ptr(), s), "pool_bn_bwd")
+                    else:
+                        _lib.check(L.pn2_relu_bn_bwd(P, C, training, int(ctx.relus[l]), dh.data_ptr(), st.z.data_ptr(),
+                                                     st.a.data_ptr(), st.b.data_ptr(), st.mean.data_ptr(),
+                                                     st.invstd.data_ptr(), dz.data_ptr(), dgamma.data_ptr(),
+                                                     dbeta.data_ptr(), ws.data_ptr(), s), "relu_bn_bwd")
+                pending = None
                 h_prev = hs[l]
                 # the data gradient first: the next kernel of the chain waits for it, nobody waits for dW
                 # (measured neutral for the step, 3.72 vs 3.74 ms: the two compete for the same L2 bandwidth)
-                dh = _dgrad(dz, W2.contiguous(), h_prev.shape[1], ctx.wt_packed[l]) if need_dh else None
+                dh = None
+                if need_dh:
+                    prev = layers[l - 1] if l > 0 else None
+                    if prev is not None and prev.fold4 is not None and DGRAD_STATS:
+                        # ... and the BatchNorm-adjoint statistics of the layer below from its epilogue
+                        dh, pending = _dgrad_stats(dz, W2.contiguous(), h_prev.shape[1], ctx.wt_packed[l], prev,
+                                                   int(ctx.relus[l - 1]), training)
+                    else:
+                        dh = _dgrad(dz, W2.contiguous(), h_prev.shape[1], ctx.wt_packed[l])
                 dW = _on_dw_branch(dev, (dz, h_prev), lambda: _wgrad(dz, h_prev, K))   # dense [C, K]
                 grads[3 * l] = dW.reshape(W.shape)
                 grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta

@@ -75,6 +75,8 @@ SIGNATURES = {
     "pn2_bwd_stats_finalize": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     # wide layers: data-gradient weight tiles, weight-gradient product
     "pn2_mlp_pack_weights_dgrad": [_i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "pn2_mlp_dgrad_stats": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
+    "pn2_relu_bn_bwd_dz": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_mlp_wgrad_splits": [_i, _i, _i],
     "pn2_mlp_wgrad_rows": [_i],
     "pn2_mlp_wgrad_cols": [_i],

@@ -103,17 +103,19 @@ def test_sum_partials_block_matches_flat_sum():
         assert torch.equal(out, flat[:rows, :cols])      # same order of additions: bit-identical
 
 
-def run_mlp(units, x, ns, tc_bwd):
+def run_mlp(units, x, ns, tc_bwd, dgrad_stats=False):
     import copy
     units = [copy.deepcopy(u) for u in units]
     xi = x.clone().requires_grad_(True)
     fused.TC_BWD = tc_bwd
+    saved, fused.DGRAD_STATS = fused.DGRAD_STATS, dgrad_stats
     try:
         y = fused.run_mlp_rows(units, xi, ns)
         torch.manual_seed(1)
         (y * torch.randn_like(y)).sum().backward()
     finally:
         fused.TC_BWD = True
+        fused.DGRAD_STATS = saved
     grads = [q.grad.clone() for u in units for q in u.parameters()]
     return y.detach(), xi.grad.clone(), grads
 
@@ -140,3 +142,54 @@ def test_split_adjoint_equals_one_pass_adjoint(P, ns, widths):
     assert l2(gx1, gx2) < 2e-3, l2(gx1, gx2)
     for a, b in zip(g1, g2):
         assert l2(a, b) < 2e-3, l2(a, b)
+    # ... and the split adjoint with the statistics of each layer below taken from the data-gradient epilogue
+    y3, gx3, g3 = run_mlp(units, x, ns, False, dgrad_stats=True)
+    assert torch.equal(y1, y3) and l2(gx3, gx2) < 1e-4
+    for a, b in zip(g3, g2):
+        assert l2(a, b) < 1e-4, l2(a, b)
+
+
+@pytest.mark.parametrize("P,N,K,relu", [(16384, 256, 256, True), (4100, 512, 256, True), (8192, 256, 384, True),
+                                        (3000, 128, 96, False), (2048, 256, 768, True), (1000, 196, 128, True)])
+def test_dgrad_epilogue_statistics(P, N, K, relu):
+    """pn2_mlp_dgrad_stats: the data gradient dH_prev = dZ W AND, from its epilogue, the BatchNorm-adjoint column
+    sums of the layer below -- sum_rows dY_prev and sum_rows dY_prev * zhat_prev with dY_prev = dH_prev where that
+    layer's ReLU passed -- finalised by pn2_bwd_stats_finalize: against fp64 sums over the kernel's own dH_prev
+    (1e-5 of the largest column sum) and dgamma / dbeta / c1c2 consistency."""
+    L = lib.load()
+    s = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(P + N + K + 7)
+    dz = rng.standard_normal((P, N)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    zp = rng.standard_normal((P, K)).astype(np.float32)
+    mean, var = zp.mean(0), zp.var(0)
+    invstd = (1.0 / np.sqrt(var + 1e-5)).astype(np.float32)
+    gamma = rng.uniform(0.5, 1.5, K).astype(np.float32) * rng.choice([-1, 1], K).astype(np.float32)
+    a = (gamma * invstd).astype(np.float32)
+    b = (0.3 * rng.standard_normal(K) - mean * a).astype(np.float32)
+    fold = np.stack([a, b, mean.astype(np.float32), invstd]).astype(np.float32)
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+    dz_d, W_d, zp_d, fold_d = t(dz), t(W), t(zp), t(fold)
+    wp = fused._pack_dgrad(P, K, W_d)
+    bn, nt, grid = L.pn2_mlp_gemm_bn(P, K), L.pn2_mlp_gemm_n_tiles(P, K), L.pn2_mlp_gemm_grid(P, K)
+    out = torch.full((P, K), float("nan"), device=DEV)
+    part = torch.full((grid, 2, nt * bn), float("nan"), device=DEV)
+    lib.check(L.pn2_mlp_dgrad_stats(P, N, K, dz_d.data_ptr(), wp.data_ptr(), out.data_ptr(), zp_d.data_ptr(),
+                                    fold_d.data_ptr(), int(relu), part.data_ptr(), s), "dgrad_stats")
+    dgamma, dbeta, c1c2 = (torch.full((m,), float("nan"), device=DEV) for m in (K, K, 2 * K))
+    lib.check(L.pn2_bwd_stats_finalize(P, K, nt * bn, grid, 1, part.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                       c1c2.data_ptr(), s), "finalize")
+    torch.cuda.synchronize()
+    got = out.double().cpu().numpy()
+    ref = tf32_trunc(dz).astype(np.float64) @ tf32_rna(W).astype(np.float64)
+    assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max()
+    mask = ((a * zp + b) > 0) | (not relu)
+    dy = np.where(mask, got, 0.0)
+    zhat = (zp.astype(np.float64) - mean) * invstd
+    want_s, want_q = dy.sum(0), (dy * zhat).sum(0)
+    gs, gq = dbeta.double().cpu().numpy(), dgamma.double().cpu().numpy()
+    scale = max(np.abs(want_s).max(), np.abs(want_q).max())
+    # a ReLU decision taken on fmaf(a, z, b) in fp32 can differ from the fp64 one only where a z + b ~ 0: rare, tiny
+    assert np.abs(gs - want_s).max() <= 2e-4 * scale, np.abs(gs - want_s).max() / scale
+    assert np.abs(gq - want_q).max() <= 2e-4 * scale, np.abs(gq - want_q).max() / scale
+    assert np.allclose(c1c2.cpu().numpy(), np.concatenate([gs, gq]) / P, rtol=1e-6, atol=1e-30)
