@@ -403,6 +403,53 @@ PN2_API int pn2_mlp_wgrad(int p, int n, int ldx, int ldy, const float *x, const 
                           void *stream);
 
 /* ==========================================================================
+ * First layer of a shared-MLP block applied BEFORE the gather (csrc/mlp_lead.cu; training mode).
+ * The first Conv2d 1x1 of PointnetSAModule(MSG) / PointnetFPModule acts on gathered rows
+ * (pointnet2_modules.py:60-75: QueryAndGroup -> mlp; :395-412: three_interpolate -> cat -> mlp); being linear
+ * it commutes with the gather:
+ *   SA: z[g, s, :] = u[idx[g, s], :] + W_x (xyz[idx[g, s]] - new_xyz[g]),  u = features W_f^T over the n points
+ *   FP: z[r, :]    = sum_t weight[r, t] gk[idx[r, t], :] + W_s skip[r, :], gk = known W_k^T over the m points
+ * so the gathered rows (b*npoint*nsample x (3 + C), b*n x (C2 + C1)) are never materialised.  u / gk come from
+ * pn2_mlp_gemm_fwd over the source points (weights packed with pn2_mlp_pack_weights_cols: the first k0
+ * reduction columns -- the coordinates of a [xyz | features] table -- read as zeros).
+ *
+ * c = width of the layer (a power of two in [16, 1024]; FP: [64, 1024]); z [P, c] rows; partials [pn2_lead_blocks(P, c, kind)][2][c] = per-CTA column
+ * sums of z and z^2 over fixed row ranges (finalise with pn2_bn_finalize, ld = c).  wx = &W[0][0] with row
+ * stride ldw (columns 0..2 are the coordinate weights); ws = &W[0][c2] (the c1 <= pn2_fp_lead_max_skip()
+ * skip columns).
+ * Adjoints: dh [P, c] = gradient wrt the layer's ACTIVATED output, (a, b, mean, invstd, c1c2) its BatchNorm
+ * fold and adjoint constants (pn2_relu_bn_bwd_stats / pn2_mlp_bwd_finalize); dZ is formed on the fly.
+ *   pn2_sa_lead_bwd: du [b*n, c] (zero-filled by the call) += dZ at idx; partials [blocks][3][c] = per-CTA sums
+ *     of dZ * (x, y, z of the centred coordinates): dW_x[c, k] = sum over blocks of partials[., k, c].
+ *   pn2_fp_lead_bwd: dg [b*m, c] (zero-filled by the call) += weight * dZ; partials [blocks][max_skip][c]:
+ *     dW_s[c, k] = sum over blocks of partials[., k, c].
+ * The remaining products (dW_f = du^T features, dfeatures = du W_f; dW_k = dg^T known, dknown = dg W_k) run over
+ * the source points (pn2_mlp_wgrad, pn2_mlp_gemm_fwd with pn2_mlp_pack_weights_dgrad[_cols] tiles).
+ * ========================================================================== */
+/* kind: 0 pn2_sa_lead_fwd, 1 pn2_sa_lead_bwd, 2 pn2_fp_lead_fwd, 3 pn2_fp_lead_bwd (each kernel's grid is one
+ * resident wave, sized for its own register budget) */
+PN2_API int pn2_lead_blocks(int p, int c, int kind);
+PN2_API int pn2_fp_lead_max_skip(void);
+PN2_API int pn2_mlp_pack_weights_cols(int p, int n, int k, int k0, int ldw, const float *w, float *packed,
+                                      void *stream);
+PN2_API int pn2_mlp_pack_weights_dgrad_cols(int p, int n_out, int n, int k, int k0, int ldw, const float *w,
+                                            float *packed, void *stream);
+PN2_API int pn2_sa_lead_fwd(int b, int n, int npoint, int nsample, int c, const float *u, const float *xyz,
+                            const float *new_xyz, const int *idx, const float *wx, int ldw, float *z,
+                            float *partials, void *stream);
+PN2_API int pn2_sa_lead_bwd(int b, int n, int npoint, int nsample, int c, int relu, const float *dh,
+                            const float *z, const float *a, const float *bb, const float *mean,
+                            const float *invstd, const float *c1c2, const float *xyz, const float *new_xyz,
+                            const int *idx, float *du, float *partials, void *stream);
+PN2_API int pn2_fp_lead_fwd(int b, int n, int m, int c, int c1, const float *gk, const float *skip,
+                            const int *idx, const float *weight, const float *ws, int ldw, float *z,
+                            float *partials, void *stream);
+PN2_API int pn2_fp_lead_bwd(int b, int n, int m, int c, int c1, int relu, const float *dh, const float *z,
+                            const float *a, const float *bb, const float *mean, const float *invstd,
+                            const float *c1c2, const float *skip, const int *idx, const float *weight,
+                            float *dg, float *partials, void *stream);
+
+/* ==========================================================================
  * Training-step utilities on flat fp32 buffers (the step the reference's solver
  * runs after backward, lib/solver.py:171-176, as one launch instead of one per
  * parameter tensor).

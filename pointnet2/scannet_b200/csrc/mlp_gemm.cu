@@ -440,8 +440,10 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
 // rounded to TF32, zero padded.
 // (sn, sk): strides of W along the output / reduction index -- (ldw, 1) for the forward product,
 // (1, ldw) for the transposed weight of the data-gradient product dH_prev = dZ * W.
+// (n0, k0): output / reduction indices below them read as zero weights (the coordinate columns of a layer whose
+// coordinate term is evaluated elsewhere, mlp_lead.cu).
 __global__ void pack_weights_kernel(const float *__restrict__ W, int N, int K, int sn, int sk, int BN, int n_tiles,
-                                    int k_blocks, float *__restrict__ Wp) {
+                                    int k_blocks, float *__restrict__ Wp, int n0 = 0, int k0 = 0) {
   const size_t total = static_cast<size_t>(n_tiles) * k_blocks * BN * BK;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -452,7 +454,7 @@ __global__ void pack_weights_kernel(const float *__restrict__ W, int N, int K, i
     const int kb = static_cast<int>(blk % k_blocks), nt = static_cast<int>(blk / k_blocks);
     const int n = nt * BN + r;
     const int k = kb * BK + ((pc ^ (r & 7)) * 4) + e;
-    float v = (n < N && k < K) ? W[static_cast<size_t>(n) * sn + static_cast<size_t>(k) * sk] : 0.f;
+    float v = (n >= n0 && n < N && k >= k0 && k < K) ? W[static_cast<size_t>(n) * sn + static_cast<size_t>(k) * sk] : 0.f;
     uint32_t t;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
     Wp[i] = __uint_as_float(t);
@@ -495,33 +497,54 @@ extern "C" int pn2_mlp_gemm_grid(int p, int n) {
   return m_tiles < per ? m_tiles : (per < 1 ? 1 : per);
 }
 
-extern "C" int pn2_mlp_pack_weights(int p, int n, int k, int ldw, const float *w, float *packed, void *stream) {
-  if (p <= 0 || n <= 0 || k <= 0 || ldw < k) return PN2_ERR_INVALID_ARG;
+// k0 > 0: the first k0 reduction columns of W read as zeros (pn2_mlp_pack_weights_cols)
+static int pack_fwd(int p, int n, int k, int k0, int ldw, const float *w, float *packed, void *stream) {
+  if (p <= 0 || n <= 0 || k <= 0 || ldw < k || k0 < 0 || k0 > k) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(w, packed);
   const int bn = gemm::pick_bn(p, n), nt = pn2_mlp_gemm_n_tiles(p, n), kb = pn2_mlp_gemm_k_blocks(k);
   const size_t total = static_cast<size_t>(nt) * kb * bn * gemm::BK;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-  gemm::pack_weights_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, n, k, ldw, 1, bn, nt, kb, packed);
+  gemm::pack_weights_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, n, k, ldw, 1, bn, nt, kb, packed,
+                                                                                  0, k0);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_mlp_pack_weights(int p, int n, int k, int ldw, const float *w, float *packed, void *stream) {
+  return pack_fwd(p, n, k, 0, ldw, w, packed, stream);
+}
+extern "C" int pn2_mlp_pack_weights_cols(int p, int n, int k, int k0, int ldw, const float *w, float *packed,
+                                         void *stream) {
+  return pack_fwd(p, n, k, k0, ldw, w, packed, stream);
 }
 
 // Tile images of W^T for the data-gradient product dH_prev[p, n_out] = dZ[p, n] * W[n, k] run on
 // pn2_mlp_gemm_fwd (a = dZ, reduction over the layer's n output channels): output column o < k takes
 // W[:, o]; columns k <= o < n_out (the zero padding of the rows layout) get zero weights, so the
 // product writes zeros there.  Same geometry as pn2_mlp_pack_weights(p, n_out, n).
-extern "C" int pn2_mlp_pack_weights_dgrad(int p, int n_out, int n, int k, int ldw, const float *w, float *packed,
-                                          void *stream) {
-  if (p <= 0 || n <= 0 || k <= 0 || ldw < k || n_out < k) return PN2_ERR_INVALID_ARG;
+static int pack_dgrad(int p, int n_out, int n, int k, int k0, int ldw, const float *w, float *packed, void *stream) {
+  if (p <= 0 || n <= 0 || k <= 0 || ldw < k || n_out < k || k0 < 0 || k0 > k) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(w, packed);
   const int bn = gemm::pick_bn(p, n_out), nt = pn2_mlp_gemm_n_tiles(p, n_out), kb = pn2_mlp_gemm_k_blocks(n);
   const size_t total = static_cast<size_t>(nt) * kb * bn * gemm::BK;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-  gemm::pack_weights_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, k, n, 1, ldw, bn, nt, kb, packed);
+  gemm::pack_weights_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, k, n, 1, ldw, bn, nt, kb, packed,
+                                                                                  k0, 0);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_mlp_pack_weights_dgrad(int p, int n_out, int n, int k, int ldw, const float *w, float *packed,
+                                          void *stream) {
+  return pack_dgrad(p, n_out, n, k, 0, ldw, w, packed, stream);
+}
+// ... with the first k0 OUTPUT columns written as zeros too (no gradient reaches the coordinate columns of a
+// point table through this product: their term of the layer is differentiated in mlp_lead.cu)
+extern "C" int pn2_mlp_pack_weights_dgrad_cols(int p, int n_out, int n, int k, int k0, int ldw, const float *w,
+                                               float *packed, void *stream) {
+  return pack_dgrad(p, n_out, n, k, k0, ldw, w, packed, stream);
 }
 
 extern "C" int pn2_mlp_gemm_pool_supported(int ns) { return (ns == 16 || ns == 32) ? 1 : 0; }

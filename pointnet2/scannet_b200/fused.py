@@ -303,6 +303,186 @@ def _bn_finalize(P, C, part, ld, nblk, gamma, beta, rm, rv, eps, momentum, nbt=N
     return a, b, mean, invstd
 
 
+# ---- first layer of a block applied BEFORE the gather (csrc/mlp_lead.cu) ------------------------------
+# A block's first 1x1 convolution acts on gathered rows (QueryAndGroup / three_interpolate + cat,
+# /root/reference/pointnet2/pointnet2_modules.py:60-75, 395-412); it is linear, so it commutes with the gather:
+# the product runs over the N source points (4-8x fewer rows than gathered positions) and the gather kernel
+# writes the layer's pre-BatchNorm output directly -- the gathered rows tensor is never written or re-read,
+# forward or backward.  Training mode only: inference keeps the layer-by-layer / one-kernel paths (whose
+# results are bit-identical to each other).
+LEAD = os.environ.get("PN2_LEAD", "1") != "0"
+
+
+def _gemm_plain(A, k, wp, n_out):
+    """[P, n_out] = A[:, :k] @ (packed weight tiles)^T on the tcgen05 layer kernel: no fold, no statistics."""
+    L = _lib.load()
+    P, lda = A.shape
+    out = torch.empty(P, n_out, dtype=torch.float32, device=A.device)
+    _lib.check(L.pn2_mlp_gemm_fwd(P, k, lda, n_out, n_out, A.data_ptr(), None, None, 0, None, wp.data_ptr(),
+                                  out.data_ptr(), None, None, 1.0, 0, None, None, None, None, _stream(A.device)),
+               "mlp_gemm_fwd (lead)")
+    return out
+
+
+def _sum_partials(part):
+    """[S, ...] -> [...]: fixed-order sum over the leading axis (pn2_sum_partials)."""
+    out = torch.empty(part.shape[1:], dtype=torch.float32, device=part.device)
+    _lib.check(_lib.load().pn2_sum_partials(part.shape[0], out.numel(), part.data_ptr(), out.data_ptr(),
+                                            _stream(part.device)), "sum_partials")
+    return out
+
+
+class SALead(object):
+    """QueryAndGroup + the first conv of an SA scale: z[g, s] = U[idx[g, s]] + W_x (xyz[idx[g, s]] - new_xyz[g]),
+    U = table W_f^T over the points (the coordinate columns of the [xyz | features | pad] table get zero
+    weights; their term is evaluated in fp32 on the centred differences)."""
+
+    def __init__(self, xyz, new_xyz, idx):
+        self.xyz, self.new_xyz, self.idx = xyz.contiguous(), new_xyz.contiguous(), idx
+        self.B, self.N = xyz.shape[0], xyz.shape[1]
+        self.npoint, self.ns = idx.shape[1], idx.shape[2]
+        self.P = self.B * self.npoint * self.ns
+        self.mark = False
+
+    def forward(self, table, W2, need_dx):
+        L = _lib.load()
+        dev = table.device
+        B, N, ct = table.shape
+        C, K = W2.shape
+        PN = B * N
+        W2c = W2.contiguous()
+        ldw = W2c.shape[1]
+        self.table2d, self.W2c, self.K = table.reshape(PN, ct), W2c, K
+        bn, nt, kb = L.pn2_mlp_gemm_bn(PN, C), L.pn2_mlp_gemm_n_tiles(PN, C), L.pn2_mlp_gemm_k_blocks(K)
+        wp = _packed("lead_sa", W2c, (PN, C, K), nt * kb * bn * 32, lambda ptr, st: _lib.check(
+            L.pn2_mlp_pack_weights_cols(PN, C, K, 3, ldw, W2c.data_ptr(), ptr, st), "mlp_pack_weights_cols"))
+        self.wp_dgrad = None
+        if need_dx and _pack_state["active"]:
+            self.wp_dgrad = self._pack_dgrad()
+        u = _gemm_plain(self.table2d, K, wp, C)
+        nblk = L.pn2_lead_blocks(self.P, C, 0)
+        z = torch.empty(self.P, C, dtype=torch.float32, device=dev)
+        part = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+        _lib.check(L.pn2_sa_lead_fwd(B, N, self.npoint, self.ns, C, u.data_ptr(), self.xyz.data_ptr(),
+                                     self.new_xyz.data_ptr(), self.idx.data_ptr(), W2c.data_ptr(), ldw,
+                                     z.data_ptr(), part.data_ptr(), _stream(dev)), "sa_lead_fwd")
+        return z, part, (C, nblk)
+
+    def _pack_dgrad(self):
+        L = _lib.load()
+        W2c, K = self.W2c, self.K
+        PN, ct = self.table2d.shape
+        C = W2c.shape[0]
+        bn, nt, kb = L.pn2_mlp_gemm_bn(PN, ct), L.pn2_mlp_gemm_n_tiles(PN, ct), L.pn2_mlp_gemm_k_blocks(C)
+        return _packed("lead_sa_dgrad", W2c, (PN, ct, C, K), nt * kb * bn * 32, lambda ptr, st: _lib.check(
+            L.pn2_mlp_pack_weights_dgrad_cols(PN, ct, C, K, 3, W2c.shape[1], W2c.data_ptr(), ptr, st),
+            "mlp_pack_weights_dgrad_cols"))
+
+    def backward(self, dh, st, c1c2, relu, need_dx):
+        """-> (dW [C, K] dense, d table (B, N, ct) or None)"""
+        L = _lib.load()
+        dev = dh.device
+        C, K = self.W2c.shape[0], self.K
+        PN, ct = self.table2d.shape
+        nblk = L.pn2_lead_blocks(self.P, C, 1)
+        du = torch.empty(PN, C, dtype=torch.float32, device=dev)
+        part = torch.empty(nblk, 3, C, dtype=torch.float32, device=dev)
+        _lib.check(L.pn2_sa_lead_bwd(self.B, self.N, self.npoint, self.ns, C, relu, dh.data_ptr(), st.z.data_ptr(),
+                                     st.a.data_ptr(), st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
+                                     c1c2.data_ptr(), self.xyz.data_ptr(), self.new_xyz.data_ptr(),
+                                     self.idx.data_ptr(), du.data_ptr(), part.data_ptr(), _stream(dev)), "sa_lead_bwd")
+        dtable = None
+        if need_dx:   # the data gradient first: the next kernel of the chain waits for it
+            wp = self.wp_dgrad if self.wp_dgrad is not None else self._pack_dgrad()
+            dtable = _gemm_plain(du, C, wp, ct).view(self.B, self.N, ct)
+        table2d = self.table2d
+
+        def weight_grad():
+            dW = _wgrad(du, table2d, K)          # [C, K]; its coordinate columns are replaced below
+            dW[:, :3] = _sum_partials(part).t()
+            return dW
+        dW = _on_dw_branch(dev, (du, table2d, part), weight_grad)
+        return dW, dtable
+
+
+class FPLead(object):
+    """three_interpolate + cat + the first conv of an FP block: z[r] = sum_t w[r, t] G[idx[r, t]] + W_s skip[r],
+    G = known W_k^T over the m known points; the (<= pn2_fp_lead_max_skip()) skip channels in fp32."""
+
+    def __init__(self, skip, idx, weight, mark=False):
+        self.skip = skip.contiguous() if skip is not None else None
+        self.idx, self.weight, self.mark = idx, weight.contiguous(), mark
+        self.B, self.n = idx.shape[0], idx.shape[1]
+        self.c1 = skip.shape[2] if skip is not None else 0
+        self.P = self.B * self.n
+
+    def forward(self, known, W2, need_dx):
+        L = _lib.load()
+        dev = known.device
+        B, m, c2 = known.shape
+        C = W2.shape[0]
+        PM = B * m
+        W2c = W2.contiguous()
+        ldw = W2c.shape[1]
+        assert ldw == c2 + self.c1
+        self.known2d, self.W2c, self.m, self.c2 = known.reshape(PM, c2), W2c, m, c2
+        bn, nt, kb = L.pn2_mlp_gemm_bn(PM, C), L.pn2_mlp_gemm_n_tiles(PM, C), L.pn2_mlp_gemm_k_blocks(c2)
+        wp = _packed("lead_fp", W2c, (PM, C, c2), nt * kb * bn * 32, lambda ptr, st: _lib.check(
+            L.pn2_mlp_pack_weights(PM, C, c2, ldw, W2c.data_ptr(), ptr, st), "mlp_pack_weights"))
+        self.wp_dgrad = None
+        if need_dx and _pack_state["active"]:
+            self.wp_dgrad = self._pack_dgrad()
+        gk = _gemm_plain(self.known2d, c2, wp, C)
+        nblk = L.pn2_lead_blocks(self.P, C, 2)
+        z = torch.empty(self.P, C, dtype=torch.float32, device=dev)
+        part = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+        _lib.check(L.pn2_fp_lead_fwd(B, self.n, m, C, self.c1, gk.data_ptr(),
+                                     self.skip.data_ptr() if self.skip is not None else None, self.idx.data_ptr(),
+                                     self.weight.data_ptr(), W2c.data_ptr() + 4 * c2, ldw, z.data_ptr(),
+                                     part.data_ptr(), _stream(dev)), "fp_lead_fwd")
+        return z, part, (C, nblk)
+
+    def _pack_dgrad(self):
+        L = _lib.load()
+        W2c, c2 = self.W2c, self.c2
+        PM = self.known2d.shape[0]
+        C = W2c.shape[0]
+        bn, nt, kb = L.pn2_mlp_gemm_bn(PM, c2), L.pn2_mlp_gemm_n_tiles(PM, c2), L.pn2_mlp_gemm_k_blocks(C)
+        return _packed("lead_fp_dgrad", W2c, (PM, c2, C), nt * kb * bn * 32, lambda ptr, st: _lib.check(
+            L.pn2_mlp_pack_weights_dgrad(PM, c2, C, c2, W2c.shape[1], W2c.data_ptr(), ptr, st),
+            "mlp_pack_weights_dgrad"))
+
+    def backward(self, dh, st, c1c2, relu, need_dx):
+        """-> (dW [C, c2 + c1] dense, d known (B, m, c2) or None)"""
+        L = _lib.load()
+        dev = dh.device
+        C, c2, c1 = self.W2c.shape[0], self.c2, self.c1
+        PM = self.known2d.shape[0]
+        nblk = L.pn2_lead_blocks(self.P, C, 3)
+        dg = torch.empty(PM, C, dtype=torch.float32, device=dev)
+        part = torch.empty(nblk, L.pn2_fp_lead_max_skip(), C, dtype=torch.float32, device=dev)
+        _lib.check(L.pn2_fp_lead_bwd(self.B, self.n, self.m, C, c1, relu, dh.data_ptr(), st.z.data_ptr(),
+                                     st.a.data_ptr(), st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
+                                     c1c2.data_ptr(), self.skip.data_ptr() if self.skip is not None else None,
+                                     self.idx.data_ptr(), self.weight.data_ptr(), dg.data_ptr(), part.data_ptr(),
+                                     _stream(dev)), "fp_lead_bwd")
+        dknown = None
+        if need_dx:
+            wp = self.wp_dgrad if self.wp_dgrad is not None else self._pack_dgrad()
+            dknown = _gemm_plain(dg, C, wp, c2).view(self.B, self.m, c2)
+        if self.mark and BWD_MARK_EVENT is not None:
+            BWD_MARK_EVENT.record(torch.cuda.current_stream(dev))
+        known2d = self.known2d
+
+        def weight_grad():
+            dWk = _wgrad(dg, known2d, c2)        # [C, c2]
+            if c1 == 0:
+                return dWk
+            return torch.cat([dWk, _sum_partials(part)[:c1].t()], dim=1)
+        dW = _on_dw_branch(dev, (dg, known2d, part), weight_grad)
+        return dW, dknown
+
+
 class SharedMLPRows(Function):
     """x0 [P, Cin] -> out [P/ns, C_L] (max over each run of ns rows) or [P, C_L] (ns == 0).
 
@@ -315,11 +495,11 @@ class SharedMLPRows(Function):
     """
 
     @staticmethod
-    def forward(ctx, x0, ns, training, eps, momentum, buffers, relus, drops, *params):
+    def forward(ctx, x0, ns, training, eps, momentum, buffers, relus, drops, lead, *params):
         L = _lib.load()
         dev = x0.device
         nl = len(params) // 3
-        P = x0.shape[0]
+        P = x0.shape[0] if lead is None else lead.P   # lead: x0 is the SOURCE tensor (point table / known rows)
         layers, hs = [], [x0]
         out = argmax = zsel = None
         want_grad = any(ctx.needs_input_grad)
@@ -329,6 +509,17 @@ class SharedMLPRows(Function):
             for l in range(nl):
                 W, gamma, beta = params[3 * l:3 * l + 3]
                 W2 = W.reshape(W.shape[0], -1)
+                if l == 0 and lead is not None:
+                    # the block's first conv, applied before the gather (SALead / FPLead): z and its statistics
+                    st = _BNLayer()
+                    st.cout = W2.shape[0]
+                    rm, rv, nbt = buffers[0]
+                    st.z, part, (ld, nblk) = lead.forward(x0, W2, ctx.needs_input_grad[0])
+                    st.a, st.b, st.mean, st.invstd = _bn_finalize(P, st.cout, part, ld, nblk, gamma, beta,
+                                                                  rm, rv, eps, momentum, nbt)
+                    st.fold4 = st.a._base if st.a._base is not None else None
+                    layers.append(st)
+                    continue
                 lda = x0.shape[1] if l == 0 else layers[l - 1].cout
                 bwd_fused[l] = bool(TC_BWD and want_grad and
                                     L.pn2_mlp_bwd_supported(P, W2.shape[0], W2.shape[1], lda, int(l > 0)) and
@@ -403,6 +594,7 @@ class SharedMLPRows(Function):
                                                       _stream(dev)), "bn_relu_groupmax")
         ctx.layers, ctx.hs, ctx.argmax, ctx.bwd_fused, ctx.wt_packed = layers, hs, argmax, bwd_fused, wt_packed
         ctx.zsel = zsel
+        ctx.lead = lead
         ctx.ns, ctx.training, ctx.nl, ctx.relus, ctx.drops = ns, training, nl, relus, drops
         ctx.weights = [params[3 * l] for l in range(nl)]
         return out
@@ -431,6 +623,20 @@ class SharedMLPRows(Function):
                 K = W2.shape[1]
                 pooled = l == nl - 1 and ns > 0
                 need_dh = l > 0 or ctx.needs_input_grad[0]
+                if l == 0 and ctx.lead is not None:
+                    # ---- first conv applied before the gather: dZ on the fly, scattered onto the source points ----
+                    if pending is None:
+                        dgamma, dbeta, c1c2 = f32(C), f32(C), f32(2 * C)
+                        _lib.check(L.pn2_relu_bn_bwd_stats(
+                            P, C, training, int(ctx.relus[0]), dh.data_ptr(), st.z.data_ptr(), st.a.data_ptr(),
+                            st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), dgamma.data_ptr(),
+                            dbeta.data_ptr(), c1c2.data_ptr(), _ws(C, dev).data_ptr(), s), "relu_bn_bwd_stats")
+                    else:
+                        dgamma, dbeta, c1c2 = pending
+                    dW, dh = ctx.lead.backward(dh, st, c1c2, int(ctx.relus[0]), need_dh)
+                    grads[0] = dW.reshape(W.shape)
+                    grads[1], grads[2] = dgamma, dbeta
+                    continue
                 if ctx.bwd_fused[l]:
                     # ---- one tensor-core pass: BN adjoint + dH_prev + dW + the next layer's statistics ----
                     if pending is None:
@@ -549,7 +755,7 @@ class SharedMLPRows(Function):
                 dW = _on_dw_branch(dev, (dz, h_prev), lambda: _wgrad(dz, h_prev, K))   # dense [C, K]
                 grads[3 * l] = dW.reshape(W.shape)
                 grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
-        return (dh if ctx.needs_input_grad[0] else None, None, None, None, None, None, None, None) + tuple(grads)
+        return (dh if ctx.needs_input_grad[0] else None, None, None, None, None, None, None, None, None) + tuple(grads)
 
 
 # Adjoints of the two row gathers through an inverse map (csrc/inverse_map.cu): deterministic, atomic-free --
@@ -774,9 +980,25 @@ def mlp_eligible(mlp, x_like):
     return True
 
 
-def run_mlp_rows(mlp, x0, ns, dropouts=None):
+def lead_ok(units, min_width=16):
+    """May the first unit of ``units`` be applied before the gather?  Training mode (batch statistics), at least one
+    more unit behind it (the first is never the pooled one), and a width the kernels tile exactly: a power of
+    two in [16, 1024] (SA) / [64, 1024] (FP) -- every first layer of the reference's semseg models."""
+    units = list(units)
+    if not (LEAD and ENABLED and len(units) >= 2 and units[0].training):
+        return False
+    c = units[0].conv.weight.shape[0]
+    return (c & (c - 1)) == 0 and min_width <= c <= 1024
+
+
+def fp_lead_max_skip():
+    return int(_lib.load().pn2_fp_lead_max_skip())
+
+
+def run_mlp_rows(mlp, x0, ns, dropouts=None, lead=None):
     """Apply a SharedMLP (or any sequence of conv+BN[+ReLU] units) to rows ``x0`` [P, Cin(_pad)];
-    ns > 0 pools every run of ns rows after the last layer.  ``dropouts``: {unit index: p} (or
+    ns > 0 pools every run of ns rows after the last layer.  ``lead`` (SALead / FPLead): ``x0`` is the SOURCE
+    tensor (point table (B, N, ct) / known rows (B, m, C2)) and the first unit is applied before the gather.  ``dropouts``: {unit index: p} (or
     {unit index: (p, keep mask)}) -- nn.Dropout(p) on that unit's output, applied inside the next
     unit's kernels (see ``chain_supports_dropout``); ignored in eval mode."""
     params, buffers, relus = [], [], []
@@ -794,11 +1016,12 @@ def run_mlp_rows(mlp, x0, ns, dropouts=None):
             if p <= 0.0:
                 continue
             if mask is None:  # keep mask, one byte per element
-                mask = _dropout_mask(x0.shape[0], layers[i].conv.weight.shape[0], 1.0 - p, x0.device)
+                mask = _dropout_mask(x0.shape[0] if lead is None else lead.P, layers[i].conv.weight.shape[0],
+                                     1.0 - p, x0.device)
             drops[i] = (mask, 1.0 / (1.0 - p))
     # running statistics AND num_batches_tracked are updated inside the finalise kernels
     return SharedMLPRows.apply(x0, ns, training, float(norms[0].eps), float(norms[0].momentum), buffers,
-                               tuple(relus), tuple(drops), *params)
+                               tuple(relus), tuple(drops), lead, *params)
 
 
 _drop_state = {}

@@ -81,6 +81,15 @@ SIGNATURES = {
     "pn2_mlp_wgrad_rows": [_i],
     "pn2_mlp_wgrad_cols": [_i],
     "pn2_mlp_wgrad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    # first layer of a block applied before the gather (csrc/mlp_lead.cu)
+    "pn2_lead_blocks": [_i, _i, _i],
+    "pn2_fp_lead_max_skip": [],
+    "pn2_mlp_pack_weights_cols": [_i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "pn2_mlp_pack_weights_dgrad_cols": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "pn2_sa_lead_fwd": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "pn2_sa_lead_bwd": [_i, _i, _i, _i, _i, _i] + [_vp] * 13,
+    "pn2_fp_lead_fwd": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "pn2_fp_lead_bwd": [_i, _i, _i, _i, _i, _i] + [_vp] * 13,
     # flat-buffer training-step utilities
     "pn2_sum_partials": [_i, _i, _vp, _vp, _vp],
     "pn2_sum_partials_block": [_i, _i, _i, _i, _i, _vp, _vp, _vp],

@@ -78,6 +78,9 @@ class _PointnetSAModuleBase(nn.Module):
             idx = idxs[i] if idxs is not None else pointnet2_utils.ball_query(
                 grouper.radius, grouper.nsample, xyz, new_xyz)
             out = fused.sa_chain_eval(mlp, table, new_xyz, idx)           # inference: the whole block in one kernel
+            if out is None and features is not None and fused.lead_ok(mlp):
+                # training: the first conv runs over the N points of the table, the gather writes its output
+                out = fused.run_mlp_rows(mlp, table, grouper.nsample, lead=fused.SALead(xyz, new_xyz, idx))
             if out is None:
                 inv = invs[i] if invs is not None and invs[i] is not None else (None, None)
                 rows = fused.SAGroupRows.apply(table, new_xyz, idx, inv[0], inv[1])   # (B*npoint*nsample, ct)
@@ -166,6 +169,13 @@ class PointnetFPModule(nn.Module):
             recip = 1.0 / (dist + 1e-8)                      # ref :395-397
             weight = recip / torch.sum(recip, dim=2, keepdim=True)
         skip = fused.rows_of(unknow_feats) if unknow_feats is not None else None
-        rows = fused.FPInterpRows.apply(fused.rows_of(known_feats), skip, idx, weight, mark, inv[0], inv[1])
         drops = {len(self.mlp) + i: p for i, p in (tail_dropouts or {}).items()}
-        return fused.run_mlp_rows(list(self.mlp) + list(tail), rows, 0, drops).view(B, n, -1)
+        units = list(self.mlp) + list(tail)
+        if (fused.lead_ok(units, 64) and (skip is None or (skip.size(2) <= fused.fp_lead_max_skip()
+                                                       and not skip.requires_grad))):
+            # training, few skip channels (the finest level: the input features): the first conv runs over the m
+            # known points and the interpolation writes its output
+            return fused.run_mlp_rows(units, fused.rows_of(known_feats), 0, drops,
+                                      lead=fused.FPLead(skip, idx, weight, mark)).view(B, n, -1)
+        rows = fused.FPInterpRows.apply(fused.rows_of(known_feats), skip, idx, weight, mark, inv[0], inv[1])
+        return fused.run_mlp_rows(units, rows, 0, drops).view(B, n, -1)

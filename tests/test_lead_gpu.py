@@ -1,0 +1,230 @@
+"""GPU parity of csrc/mlp_lead.cu: the first 1x1 convolution of an SA / FP block applied BEFORE the gather
+(/root/reference/pointnet2/pointnet2_modules.py:60-75, 395-412 -- QueryAndGroup / three_interpolate + cat
+followed by Conv2d 1x1; the conv is linear, so it commutes with the gather).
+
+1. the four kernels, called through the C ABI, against fp64 restatements of their formulas (the kernels are
+   fp32 SIMT code: 1e-5 of the tensor's max magnitude; statistics / weight-gradient partials 1e-4 after their
+   fixed-order sum);
+2. whole modules in training mode with the lead path on and off, as a consistency check: outputs within 5e-3
+   of the max magnitude, gradients within 5e-2 in the L2 norm (the two paths round differently -- the lead
+   path keeps the coordinate term and the interpolation weights in fp32 -- and each is within ~1e-2 of the
+   fp32 truth, which is what tests/test_fused_gpu.py bounds with the lead path on);
+3. the FP block of the finest level (6 skip channels that need no gradient: the configuration of the semseg
+   models) against the torch.nn formulation in fp32 (class_bound).
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from pointnet2.scannet_b200 import fused, lib as _lib, pointnet2_modules as M
+from test_fused_gpu import class_bound, l2_err, rel_err, run, sa_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _fold(C, g):
+    a = torch.randn(C, generator=g).to(DEV)
+    b = torch.randn(C, generator=g).to(DEV) * 0.5
+    mean = torch.randn(C, generator=g).to(DEV)
+    invstd = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    c1c2 = (torch.randn(2 * C, generator=g) * 0.1).to(DEV)
+    return a, b, mean, invstd, c1c2
+
+
+def _dz64(dh, z, a, b, mean, invstd, c1c2, relu):
+    C = z.shape[1]
+    d, v = dh.double(), z.double()
+    if relu:
+        d = torch.where(torch.addcmul(b, a, z) > 0, d, torch.zeros_like(d))   # the mask is decided in fp32
+    return a.double() * (d - c1c2[:C].double() - (v - mean.double()) * invstd.double() * c1c2[C:].double())
+
+
+@pytest.mark.parametrize("B,N,npoint,ns,C", [(2, 512, 64, 32, 32), (3, 200, 37, 16, 64), (2, 64, 16, 32, 256),
+                                             (1, 300, 50, 5, 128), (2, 128, 40, 32, 16)])
+def test_sa_lead_kernels(B, N, npoint, ns, C):
+    L = _lib.load()
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    xyz = (torch.rand(B, N, 3, generator=g) * 2 + 3).to(DEV)
+    new_xyz = (torch.rand(B, npoint, 3, generator=g) * 2 + 3).to(DEV)
+    idx = torch.randint(0, N, (B, npoint, ns), generator=g, dtype=torch.int32).to(DEV)
+    u = torch.randn(B * N, C, generator=g).to(DEV)
+    ldw = 3 + 7
+    W = torch.randn(C, ldw, generator=g).to(DEV)
+    P = B * npoint * ns
+    nblk = L.pn2_lead_blocks(P, C, 0)
+    assert nblk > 0
+    z = torch.empty(P, C, device=DEV)
+    part = torch.empty(nblk, 2, C, device=DEV)
+    _lib.check(L.pn2_sa_lead_fwd(B, N, npoint, ns, C, u.data_ptr(), xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(),
+                                 W.data_ptr(), ldw, z.data_ptr(), part.data_ptr(), _s()), "sa_lead_fwd")
+    src = (idx.long() + (torch.arange(B, device=DEV) * N).view(B, 1, 1)).reshape(-1)
+    diff = (xyz.reshape(-1, 3)[src].view(B, npoint, ns, 3) - new_xyz.view(B, npoint, 1, 3)).reshape(P, 3)  # fp32, as the kernel
+    z64 = u.double()[src] + diff.double() @ W[:, :3].double().t()
+    assert rel_err(z.double(), z64) < 1e-5
+    s = part.double().sum(0)
+    assert rel_err(s[0], z.double().sum(0)) < 1e-4 and rel_err(s[1], (z.double() ** 2).sum(0)) < 1e-4
+
+    for relu in (1, 0):
+        a, b, mean, invstd, c1c2 = _fold(C, g)
+        dh = torch.randn(P, C, generator=g).to(DEV)
+        dh[(a * z + b).abs() < 1e-4] = 0   # no gradient where fp32 rounding could decide the ReLU mask either way
+        du = torch.full((B * N, C), 7.0, device=DEV)   # the call zero-fills it
+        pw = torch.empty(L.pn2_lead_blocks(P, C, 1), 3, C, device=DEV)
+        _lib.check(L.pn2_sa_lead_bwd(B, N, npoint, ns, C, relu, dh.data_ptr(), z.data_ptr(), a.data_ptr(), b.data_ptr(),
+                                     mean.data_ptr(), invstd.data_ptr(), c1c2.data_ptr(), xyz.data_ptr(),
+                                     new_xyz.data_ptr(), idx.data_ptr(), du.data_ptr(), pw.data_ptr(), _s()), "sa_lead_bwd")
+        dz = _dz64(dh, z, a, b, mean, invstd, c1c2, relu)
+        du64 = torch.zeros(B * N, C, dtype=torch.float64, device=DEV).index_add_(0, src, dz)
+        assert rel_err(du.double(), du64) < 1e-5
+        dwx64 = dz.t() @ diff.double()                       # [C, 3]
+        assert rel_err(pw.double().sum(0).t(), dwx64) < 1e-4
+
+
+@pytest.mark.parametrize("B,n,m,C,c1", [(2, 1024, 128, 128, 6), (3, 300, 40, 64, 0), (2, 257, 16, 256, 8),
+                                        (1, 100, 3, 64, 3)])
+def test_fp_lead_kernels(B, n, m, C, c1):
+    L = _lib.load()
+    assert L.pn2_fp_lead_max_skip() == 8
+    g = torch.Generator().manual_seed(B * 1000 + C + c1)
+    gk = torch.randn(B * m, C, generator=g).to(DEV)
+    skip = torch.randn(B, n, max(c1, 1), generator=g)[:, :, :c1].contiguous().to(DEV)
+    idx = torch.randint(0, m, (B, n, 3), generator=g, dtype=torch.int32).to(DEV)
+    w = torch.rand(B, n, 3, generator=g)
+    w = (w / w.sum(-1, keepdim=True)).to(DEV)
+    c2 = 12
+    ldw = c2 + c1
+    W = torch.randn(C, ldw, generator=g).to(DEV)
+    P = B * n
+    nblk = L.pn2_lead_blocks(P, C, 2)
+    z = torch.empty(P, C, device=DEV)
+    part = torch.empty(nblk, 2, C, device=DEV)
+    _lib.check(L.pn2_fp_lead_fwd(B, n, m, C, c1, gk.data_ptr(), skip.data_ptr() if c1 else None, idx.data_ptr(),
+                                 w.data_ptr(), W.data_ptr() + 4 * c2, ldw, z.data_ptr(), part.data_ptr(), _s()),
+               "fp_lead_fwd")
+    src = (idx.long() + (torch.arange(B, device=DEV) * m).view(B, 1, 1)).reshape(P, 3)
+    z64 = (gk.double()[src] * w.double().reshape(P, 3, 1)).sum(1)
+    if c1:
+        z64 = z64 + skip.double().reshape(P, c1) @ W[:, c2:].double().t()
+    assert rel_err(z.double(), z64) < 1e-5
+    s = part.double().sum(0)
+    assert rel_err(s[0], z.double().sum(0)) < 1e-4 and rel_err(s[1], (z.double() ** 2).sum(0)) < 1e-4
+
+    for relu in (1, 0):
+        a, b, mean, invstd, c1c2 = _fold(C, g)
+        dh = torch.randn(P, C, generator=g).to(DEV)
+        dh[(a * z + b).abs() < 1e-4] = 0
+        dg = torch.full((B * m, C), -3.0, device=DEV)
+        pw = torch.empty(L.pn2_lead_blocks(P, C, 3), 8, C, device=DEV)
+        _lib.check(L.pn2_fp_lead_bwd(B, n, m, C, c1, relu, dh.data_ptr(), z.data_ptr(), a.data_ptr(), b.data_ptr(),
+                                     mean.data_ptr(), invstd.data_ptr(), c1c2.data_ptr(), skip.data_ptr() if c1 else None,
+                                     idx.data_ptr(), w.data_ptr(), dg.data_ptr(), pw.data_ptr(), _s()), "fp_lead_bwd")
+        dz = _dz64(dh, z, a, b, mean, invstd, c1c2, relu)
+        dg64 = torch.zeros(B * m, C, dtype=torch.float64, device=DEV)
+        for t in range(3):
+            dg64.index_add_(0, src[:, t], dz * w.double().reshape(P, 3)[:, t:t + 1])
+        assert rel_err(dg.double(), dg64) < 1e-5
+        if c1:
+            dws64 = dz.t() @ skip.double().reshape(P, c1)    # [C, c1]
+            assert rel_err(pw.double().sum(0)[:c1].t(), dws64) < 1e-4
+        assert float(pw[:, c1:].abs().max()) == 0.0 if c1 < 8 else True
+
+
+def test_unsupported_widths_are_refused():
+    """widths the kernels do not tile exactly (not a power of two, < 16; FP < 64) return an error status and
+    pn2_lead_blocks 0; the modules then take the rows path (fused.lead_ok)."""
+    L = _lib.load()
+    assert L.pn2_lead_blocks(4096, 96, 0) == 0 and L.pn2_lead_blocks(4096, 8, 1) == 0
+    assert L.pn2_lead_blocks(4096, 128, 4) == 0 and L.pn2_lead_blocks(4096, 128, 3) > 0
+    x = torch.zeros(4096, device=DEV)
+    p = x.data_ptr()
+    assert L.pn2_sa_lead_fwd(1, 64, 2, 2, 96, p, p, p, p, p, 3, p, p, _s()) != 0
+    assert L.pn2_fp_lead_fwd(1, 8, 4, 32, 0, p, None, p, p, None, 32, p, p, _s()) != 0
+    torch.manual_seed(0)
+    odd = M.PointnetSAModule(npoint=8, radius=0.3, nsample=8, mlp=[4, 24, 32]).to(DEV).train()
+    assert not fused.lead_ok(odd.mlps[0]) and fused.lead_ok(
+        M.PointnetSAModule(npoint=8, radius=0.3, nsample=8, mlp=[4, 32, 32]).to(DEV).train().mlps[0])
+
+
+def test_pack_weights_cols_zeroes_the_coordinate_columns():
+    """pn2_mlp_pack_weights_cols / _dgrad_cols == the plain packers on a weight whose first 3 columns are zero."""
+    L = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    P, N, K = 4096, 64, 67
+    W = torch.randn(N, K, generator=g).to(DEV)
+    Wz = W.clone()
+    Wz[:, :3] = 0
+    bn, nt, kb = L.pn2_mlp_gemm_bn(P, N), L.pn2_mlp_gemm_n_tiles(P, N), L.pn2_mlp_gemm_k_blocks(K)
+    p0, p1 = (torch.empty(nt * kb * bn * 32, device=DEV) for _ in range(2))
+    _lib.check(L.pn2_mlp_pack_weights_cols(P, N, K, 3, K, W.data_ptr(), p0.data_ptr(), _s()), "cols")
+    _lib.check(L.pn2_mlp_pack_weights(P, N, K, K, Wz.data_ptr(), p1.data_ptr(), _s()), "plain")
+    assert torch.equal(p0, p1)
+    n_out = 68
+    bn, nt, kb = L.pn2_mlp_gemm_bn(P, n_out), L.pn2_mlp_gemm_n_tiles(P, n_out), L.pn2_mlp_gemm_k_blocks(N)
+    p0, p1 = (torch.empty(nt * kb * bn * 32, device=DEV) for _ in range(2))
+    _lib.check(L.pn2_mlp_pack_weights_dgrad_cols(P, n_out, N, K, 3, K, W.data_ptr(), p0.data_ptr(), _s()), "dcols")
+    _lib.check(L.pn2_mlp_pack_weights_dgrad(P, n_out, N, K, K, Wz.data_ptr(), p1.data_ptr(), _s()), "dplain")
+    assert torch.equal(p0, p1)
+
+
+def _lead_on_off(module, inputs):
+    res = []
+    for on in (True, False):
+        fused.LEAD = on
+        try:
+            res.append(run(module, True, *inputs))
+        finally:
+            fused.LEAD = True
+    (o1, g1, b1, i1), (o0, g0, b0, i0) = res
+    assert rel_err(o1, o0) < 5e-3, rel_err(o1, o0)
+    for n in g0:
+        assert l2_err(g1[n], g0[n]) < 5e-2, (n, l2_err(g1[n], g0[n]))
+    for a, b in zip(i1, i0):
+        if b is not None:
+            assert l2_err(a, b) < 5e-2, l2_err(a, b)
+    for n in b0:
+        if b0[n].dtype != torch.long:
+            assert rel_err(b1[n], b0[n]) < 2e-3, n
+
+
+def test_sa_modules_lead_vs_rows_path():
+    torch.manual_seed(0)
+    _lead_on_off(M.PointnetSAModule(npoint=256, radius=0.2, nsample=32, mlp=[6, 32, 32, 64]).to(DEV),
+                 sa_inputs(2, 2048, 6))
+    _lead_on_off(M.PointnetSAModule(npoint=64, radius=0.4, nsample=32, mlp=[128, 128, 128, 256]).to(DEV),
+                 sa_inputs(8, 256, 128, seed=1))
+    _lead_on_off(M.PointnetSAModuleMSG(npoint=128, radii=[0.1, 0.2], nsamples=[16, 32],
+                                       mlps=[[64, 64, 96, 128], [64, 128, 196, 256]]).to(DEV), sa_inputs(2, 1024, 64, seed=3))
+
+
+def _fp0_inputs(n, m, c1, c2, seed=1):
+    xyz, _ = cases.chunk_xyz(2, npoints=n)
+    unknown = cases.t(xyz, DEV)
+    known = unknown[:, :m].contiguous()
+    rng = np.random.default_rng(seed)
+    uf = cases.t(rng.standard_normal((2, c1, n)).astype(np.float32), DEV)
+    kf = cases.t(rng.standard_normal((2, c2, m)).astype(np.float32), DEV)
+    return [(unknown, False), (known, False), (uf, False), (kf, True)]   # skip features: the network's input
+
+
+def test_fp_module_finest_level():
+    """[128 + 6, 128, 128] with input features as the skip connection (pointnet2_semseg.py:116-121): the
+    configuration that takes FPLead; against torch.nn in fp32 and against the rows path."""
+    torch.manual_seed(0)
+    fp = M.PointnetFPModule(mlp=[128 + 6, 128, 128]).to(DEV)
+    ins = _fp0_inputs(2048, 256, 6, 128)
+    calls = []
+    orig = fused.FPLead.forward
+    fused.FPLead.forward = lambda self, *a: (calls.append(1), orig(self, *a))[1]
+    try:
+        class_bound(fp, ins)
+    finally:
+        fused.FPLead.forward = orig
+    assert calls, "the finest-level configuration did not take the lead path"
+    _lead_on_off(fp, ins)
+    _lead_on_off(M.PointnetFPModule(mlp=[256 + 3, 128, 128]).to(DEV), _fp0_inputs(1500, 200, 3, 256, seed=4))
