@@ -23,6 +23,7 @@ weighted_ce_fwd_kernel(int P, int C4, long long ignore_index, const float *__res
                        const long long *__restrict__ targets, const float *__restrict__ weights,
                        float *__restrict__ lse_out, float *__restrict__ partials,
                        unsigned *__restrict__ counter, float *__restrict__ loss) {
+  pdl_enter();
   __shared__ float s_warp[kCeThreads / 32];
   __shared__ bool s_last;
   const int i = blockIdx.x * kCeThreads + threadIdx.x;
@@ -74,6 +75,7 @@ weighted_ce_bwd_kernel(size_t total4, int C4, int P, long long ignore_index, con
                        const long long *__restrict__ targets, const float *__restrict__ weights,
                        const float *__restrict__ lse, const float *__restrict__ grad_loss,
                        float *__restrict__ dlogits) {
+  pdl_enter();
   const size_t e = static_cast<size_t>(blockIdx.x) * kCeThreads + threadIdx.x;
   if (e >= total4) return;
   const unsigned i = static_cast<unsigned>(e / C4);
@@ -106,8 +108,7 @@ extern "C" int pn2_weighted_ce_fwd(int p, int c, long long ignore_index, const f
   PN2_CHECK_PTRS(logits, targets, lse, partials, counter, loss);
   if (c % 4 != 0 || c > 4096 || !aligned16(logits)) return PN2_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(targets) & 7u) != 0) return PN2_ERR_ALIGNMENT;
-  weighted_ce_fwd_kernel<<<pn2_weighted_ce_partials(p), kCeThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      p, c / 4, ignore_index, logits, targets, weights, lse, partials, counter, loss);
+  pn2::launch(weighted_ce_fwd_kernel, pn2_weighted_ce_partials(p), kCeThreads, 0, static_cast<cudaStream_t>(stream), p, c / 4, ignore_index, logits, targets, weights, lse, partials, counter, loss);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -121,8 +122,7 @@ extern "C" int pn2_weighted_ce_bwd(int p, int c, long long ignore_index, const f
   if ((reinterpret_cast<uintptr_t>(targets) & 7u) != 0) return PN2_ERR_ALIGNMENT;
   const size_t total4 = static_cast<size_t>(p) * (c / 4);
   const unsigned blocks = static_cast<unsigned>((total4 + kCeThreads - 1) / kCeThreads);
-  weighted_ce_bwd_kernel<<<blocks, kCeThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      total4, c / 4, p, ignore_index, logits, targets, weights, lse, grad_loss, dlogits);
+  pn2::launch(weighted_ce_bwd_kernel, blocks, kCeThreads, 0, static_cast<cudaStream_t>(stream), total4, c / 4, p, ignore_index, logits, targets, weights, lse, grad_loss, dlogits);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

@@ -137,6 +137,7 @@ template <bool kDrop>
 __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, const __grid_constant__ CUtensorMap tm_dh,
                                                                     const __grid_constant__ CUtensorMap tm_dw,
                                                                     const __grid_constant__ CUtensorMap tm_q) {
+  pdl_enter();
   extern __shared__ __align__(1024) unsigned char smem[];
   const long long t_entry = (p.dbg & 32) ? clock64() : 0;
   const int nb = p.nb, kb = p.kb;
@@ -629,6 +630,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
 // 16-byte chunks XOR-swizzled by (row & 7), rounded to TF32, zero padded.
 __global__ void pack_weights_t_kernel(const float *__restrict__ W, int N, int K, int ldw, int nb, int kpad16,
                                       float *__restrict__ Wp) {
+  pdl_enter();
   const size_t total = static_cast<size_t>(nb) * kpad16 * BK;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -664,6 +666,7 @@ bwd_layer_finalize_sq_kernel(int parts, int N, int K, int nb32, int kb32, const 
                              int training, float *__restrict__ dW, float *__restrict__ dgamma,
                              float *__restrict__ dbeta, float *__restrict__ c1, float *__restrict__ c2,
                              float *__restrict__ scratch, unsigned *__restrict__ counter) {
+  pdl_enter();
   __shared__ float4 s_red[kFinSlices][64][2];
   __shared__ float s_col[kFinRows][2][32];
   __shared__ bool s_last;
@@ -793,7 +796,7 @@ extern "C" int pn2_mlp_pack_weights_t(int n, int k, int lda, int ldw, const floa
   const size_t total = static_cast<size_t>(nb) * kpad16 * bwd::BK;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-  bwd::pack_weights_t_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, n, k, ldw, nb, kpad16, packed);
+  pn2::launch(bwd::pack_weights_t_kernel, blocks, 256, 0, static_cast<cudaStream_t>(stream), w, n, k, ldw, nb, kpad16, packed);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -850,7 +853,7 @@ extern "C" int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu,
   auto kern = (drop_out != nullptr || drop_in != nullptr) ? bwd::mlp_bwd_layer_kernel<true> : bwd::mlp_bwd_layer_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  kern<<<g.grid, bwd::kThreads, g.smem, static_cast<cudaStream_t>(stream)>>>(prm, tm_dh, tm_dw, tm_q);
+  pn2::launch(kern, g.grid, bwd::kThreads, g.smem, static_cast<cudaStream_t>(stream), prm, tm_dh, tm_dw, tm_q);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -868,8 +871,7 @@ extern "C" int pn2_mlp_bwd_finalize(int parts, int n, int k, int lda, const floa
   if (!aligned16(s_part) || !aligned16(q_part) || !aligned16(dw)) return PN2_ERR_UNSUPPORTED;
   const int nb32 = pn2_mlp_bwd_nb(n) * 32, kb32 = pn2_mlp_bwd_kb(lda) * 32;
   dim3 grid(kb32 / 32, nb32 / bwd::kFinRows);
-  bwd::bwd_layer_finalize_sq_kernel<<<grid, bwd::kFinThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      parts, n, k, nb32, kb32, s_part, q_part, w, a_in, b_in, mean_in, invstd_in, p, training, dw, dgamma, dbeta,
+  pn2::launch(bwd::bwd_layer_finalize_sq_kernel, grid, bwd::kFinThreads, 0, static_cast<cudaStream_t>(stream), parts, n, k, nb32, kb32, s_part, q_part, w, a_in, b_in, mean_in, invstd_in, p, training, dw, dgamma, dbeta,
       c1c2, c1c2 + k, scratch, counter);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();

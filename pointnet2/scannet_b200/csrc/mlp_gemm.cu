@@ -106,6 +106,7 @@ struct __align__(16) Barriers {
 template <bool kDrop>  // dropout keep mask on the A tile (compiled out otherwise)
 __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, const __grid_constant__ CUtensorMap tm_z,
                                                                      const __grid_constant__ CUtensorMap tm_a) {
+  pdl_enter();
   extern __shared__ __align__(1024) unsigned char smem[];
   const int STAGES = p.stages, B_STAGE_BYTES = p.b_stage_bytes;
   // The weight tiles have their OWN ring (b_slots, usually 2): they are re-read from L2 for every row tile and
@@ -444,6 +445,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
 // coordinate term is evaluated elsewhere, mlp_lead.cu).
 __global__ void pack_weights_kernel(const float *__restrict__ W, int N, int K, int sn, int sk, int BN, int n_tiles,
                                     int k_blocks, float *__restrict__ Wp, int n0 = 0, int k0 = 0) {
+  pdl_enter();
   const size_t total = static_cast<size_t>(n_tiles) * k_blocks * BN * BK;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -505,7 +507,7 @@ static int pack_fwd(int p, int n, int k, int k0, int ldw, const float *w, float 
   const size_t total = static_cast<size_t>(nt) * kb * bn * gemm::BK;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-  gemm::pack_weights_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, n, k, ldw, 1, bn, nt, kb, packed,
+  pn2::launch(gemm::pack_weights_kernel, blocks, 256, 0, static_cast<cudaStream_t>(stream), w, n, k, ldw, 1, bn, nt, kb, packed,
                                                                                   0, k0);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
@@ -530,7 +532,7 @@ static int pack_dgrad(int p, int n_out, int n, int k, int k0, int ldw, const flo
   const size_t total = static_cast<size_t>(nt) * kb * bn * gemm::BK;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-  gemm::pack_weights_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, k, n, 1, ldw, bn, nt, kb, packed,
+  pn2::launch(gemm::pack_weights_kernel, blocks, 256, 0, static_cast<cudaStream_t>(stream), w, k, n, 1, ldw, bn, nt, kb, packed,
                                                                                   k0, 0);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
@@ -622,7 +624,7 @@ static int launch_gemm(int p, int k, int lda, int n, int ldz, const float *a, co
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid(pn2_mlp_gemm_grid(p, n), prm.n_tiles);  // the partials buffer is sized by the same function
-  kern<<<grid, gemm::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(prm, tm_z, tm_a);
+  pn2::launch(kern, grid, gemm::kThreads, smem, static_cast<cudaStream_t>(stream), prm, tm_z, tm_a);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 sa_lead_fwd_kernel(Geom g, FastDiv np_ns, FastDiv ns, int n, const float *__restrict__ u,
                    const float *__restrict__ xyz, const float *__restrict__ new_xyz, const int *__restrict__ idx,
                    const float *__restrict__ wx, int ldw, float *__restrict__ z, float *__restrict__ partials) {
+  pdl_enter();
   const int c4 = threadIdx.x % g.C4, lane = threadIdx.x / g.C4;
   const int G = min(g.C4, 32), sub = threadIdx.x & (G - 1);
   float4 acc[2];
@@ -214,6 +215,7 @@ sa_lead_bwd_kernel(Geom g, FastDiv np_ns, FastDiv ns, int n, int relu, const flo
                    const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ c1c2,
                    const float *__restrict__ xyz, const float *__restrict__ new_xyz, const int *__restrict__ idx,
                    float *__restrict__ du, float *__restrict__ partials) {
+  pdl_enter();
   const int c4 = threadIdx.x % g.C4, lane = threadIdx.x / g.C4;
   const int G = min(g.C4, 32), sub = threadIdx.x & (G - 1);
   float4 acc[3];
@@ -278,6 +280,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 fp_lead_fwd_kernel(Geom g, FastDiv nn, int m, int c1, const float *__restrict__ gk, const float *__restrict__ skip,
                    const int *__restrict__ idx, const float *__restrict__ weight, const float *__restrict__ ws,
                    int ldw, float *__restrict__ z, float *__restrict__ partials) {
+  pdl_enter();
   const int c4 = threadIdx.x % g.C4, lane = threadIdx.x / g.C4;
   float4 acc[2];
   acc[0] = acc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -350,6 +353,7 @@ fp_lead_bwd_kernel(Geom g, FastDiv nn, int m, int c1, int relu, const float *__r
                    const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ c1c2,
                    const float *__restrict__ skip, const int *__restrict__ idx, const float *__restrict__ weight,
                    float *__restrict__ dg, float *__restrict__ partials) {
+  pdl_enter();
   const int c4 = threadIdx.x % g.C4, lane = threadIdx.x / g.C4;
   const int G = min(g.C4, 32), sub = threadIdx.x & (G - 1);
   float4 acc[kMaxSkip];
@@ -420,8 +424,7 @@ extern "C" int pn2_sa_lead_fwd(int b, int n, int npoint, int nsample, int c, con
   int nblk;
   const lead::Geom g = lead::geom(static_cast<int>(p), c, lead::kSaFwd, &nblk);
   const size_t smem = sizeof(float4) * 2 * g.row_lanes * g.C4;
-  lead::sa_lead_fwd_kernel<4><<<nblk, lead::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      g, lead::fast_div(npoint * nsample), lead::fast_div(nsample), n, u, xyz, new_xyz, idx, wx, ldw, z, partials);
+  pn2::launch(lead::sa_lead_fwd_kernel<4>, nblk, lead::kThreads, smem, static_cast<cudaStream_t>(stream), g, lead::fast_div(npoint * nsample), lead::fast_div(nsample), n, u, xyz, new_xyz, idx, wx, ldw, z, partials);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -444,8 +447,7 @@ extern "C" int pn2_sa_lead_bwd(int b, int n, int npoint, int nsample, int c, int
   int nblk;
   const lead::Geom g = lead::geom(static_cast<int>(p), c, lead::kSaBwd, &nblk);
   const size_t smem = sizeof(float4) * 3 * g.row_lanes * g.C4;
-  lead::sa_lead_bwd_kernel<4><<<nblk, lead::kThreads, smem, s>>>(
-      g, lead::fast_div(npoint * nsample), lead::fast_div(nsample), n, relu, dh, z, a, bb, mean, invstd, c1c2, xyz,
+  pn2::launch(lead::sa_lead_bwd_kernel<4>, nblk, lead::kThreads, smem, s, g, lead::fast_div(npoint * nsample), lead::fast_div(nsample), n, relu, dh, z, a, bb, mean, invstd, c1c2, xyz,
       new_xyz, idx, du, partials);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
@@ -462,8 +464,7 @@ extern "C" int pn2_fp_lead_fwd(int b, int n, int m, int c, int c1, const float *
   int nblk;
   const lead::Geom g = lead::geom(static_cast<int>(p), c, lead::kFpFwd, &nblk);
   const size_t smem = sizeof(float4) * (2 * g.row_lanes * g.C4 + c1 * g.C4);
-  lead::fp_lead_fwd_kernel<2><<<nblk, lead::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      g, lead::fast_div(n), m, c1, gk, skip, idx, weight, ws, ldw, z, partials);
+  pn2::launch(lead::fp_lead_fwd_kernel<2>, nblk, lead::kThreads, smem, static_cast<cudaStream_t>(stream), g, lead::fast_div(n), m, c1, gk, skip, idx, weight, ws, ldw, z, partials);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -485,8 +486,7 @@ extern "C" int pn2_fp_lead_bwd(int b, int n, int m, int c, int c1, int relu, con
   int nblk;
   const lead::Geom g = lead::geom(static_cast<int>(p), c, lead::kFpBwd, &nblk);
   const size_t smem = sizeof(float4) * lead::kMaxSkip * g.row_lanes * g.C4;
-  lead::fp_lead_bwd_kernel<2><<<nblk, lead::kThreads, smem, s>>>(
-      g, lead::fast_div(n), m, c1, relu, dh, z, a, bb, mean, invstd, c1c2, skip, idx, weight, dg, partials);
+  pn2::launch(lead::fp_lead_bwd_kernel<2>, nblk, lead::kThreads, smem, s, g, lead::fast_div(n), m, c1, relu, dh, z, a, bb, mean, invstd, c1c2, skip, idx, weight, dg, partials);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

@@ -88,6 +88,7 @@ __device__ __forceinline__ float4 ld4(const float *p, size_t i4) {
 // ------------------------------------------------------------------ forward statistics
 __global__ void __launch_bounds__(kRowThreads)
 bn_stats_partial_kernel(ColGeom g, const float *__restrict__ z, float *__restrict__ partials) {
+  pdl_enter();
   col_reduce2(g, partials, [&](int r, int c4, float4 &s, float4 &q) {
     const float4 v = ld4(z, static_cast<size_t>(r) * g.C4 + c4);
     s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
@@ -134,6 +135,7 @@ bn_stats_finalize_kernel(int P, int C, int ld, int nblk, const float *__restrict
                          float *running_var, long long *num_batches_tracked, float *__restrict__ a,
                          float *__restrict__ b, float *__restrict__ mean_out,
                          float *__restrict__ invstd_out) {
+  pdl_enter();
   const int c = blockIdx.x * kFinalizeWarps + (threadIdx.x >> 5);
   if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
   if (c >= C) return;
@@ -167,6 +169,7 @@ __global__ void bn_fold_eval_kernel(int C, const float *__restrict__ gamma, cons
                                     const float *__restrict__ running_var, float eps,
                                     float *__restrict__ a, float *__restrict__ b,
                                     float *__restrict__ mean_out, float *__restrict__ invstd_out) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float invstd = 1.0f / sqrtf(running_var[c] + eps);
@@ -181,6 +184,7 @@ __global__ void bn_fold_eval_kernel(int C, const float *__restrict__ gamma, cons
 __global__ void __launch_bounds__(kRowThreads)
 bn_relu_apply_kernel(size_t total4, int C4, const float *__restrict__ z, const float *__restrict__ a,
                      const float *__restrict__ b, float *__restrict__ h, int relu) {
+  pdl_enter();
   const size_t stride = static_cast<size_t>(gridDim.x) * kRowThreads;
   for (size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x; i < total4; i += stride) {
     const int c4 = static_cast<int>(i % C4);
@@ -196,6 +200,7 @@ bn_relu_apply_kernel(size_t total4, int C4, const float *__restrict__ z, const f
 __global__ void __launch_bounds__(kRowThreads)
 bn_relu_groupmax_kernel(int G, int ns, int C4, const float *__restrict__ z, const float *__restrict__ a,
                         const float *__restrict__ b, float *__restrict__ out, int *__restrict__ argmax) {
+  pdl_enter();
   const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
   if (i >= static_cast<size_t>(G) * C4) return;
   const int c4 = static_cast<int>(i % C4);
@@ -225,6 +230,7 @@ groupmax_from_extrema_kernel(size_t total, int C, const float *__restrict__ zmax
                              const int *__restrict__ imax, const int *__restrict__ imin,
                              const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out,
                              int *__restrict__ argmax, float *__restrict__ zsel) {
+  pdl_enter();
   const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
   if (i >= total) return;
   const int c = static_cast<int>(i % C);
@@ -245,6 +251,7 @@ pool_bwd_stats_kernel(ColGeom g, int ns, const float *__restrict__ dout, const i
                       const float *__restrict__ z, const float *__restrict__ zsel, const float *__restrict__ a,
                       const float *__restrict__ b, const float *__restrict__ mean,
                       const float *__restrict__ invstd, float *__restrict__ partials) {
+  pdl_enter();
   // rows here are GROUPS (g.P = G)
   col_reduce2(g, partials, [&](int grp, int c4, float4 &s, float4 &q) {
     const size_t i = static_cast<size_t>(grp) * g.C4 + c4;
@@ -278,6 +285,7 @@ __global__ void __launch_bounds__(32 * kFinalizeWarps)
 bwd_stats_finalize_kernel(int P, int C, int ld, int nblk, int training, const float *__restrict__ partials,
                           float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ c1,
                           float *__restrict__ c2) {
+  pdl_enter();
   const int c = blockIdx.x * kFinalizeWarps + (threadIdx.x >> 5);
   if (c >= C) return;
   double s, q;
@@ -296,6 +304,7 @@ pool_bwd_dz_kernel(int G, int ns, int C4, const float *__restrict__ dout, const 
                    const float *__restrict__ z, const float *__restrict__ a, const float *__restrict__ b,
                    const float *__restrict__ mean, const float *__restrict__ invstd,
                    const float *__restrict__ c1, const float *__restrict__ c2, float *__restrict__ dz) {
+  pdl_enter();
   const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
   if (i >= static_cast<size_t>(G) * C4) return;
   const int c4 = static_cast<int>(i % C4);
@@ -334,6 +343,7 @@ relu_bwd_stats_kernel(ColGeom g, int relu, const float *__restrict__ dh, const f
                       const float *__restrict__ a, const float *__restrict__ b,
                       const float *__restrict__ mean, const float *__restrict__ invstd,
                       float *__restrict__ partials) {
+  pdl_enter();
   col_reduce2(g, partials, [&](int r, int c4, float4 &s, float4 &q) {
     const size_t i = static_cast<size_t>(r) * g.C4 + c4;
     const float4 d = ld4(dh, i), v = ld4(z, i);
@@ -353,6 +363,7 @@ relu_bwd_dz_kernel(size_t total4, int C4, int relu, const float *__restrict__ dh
                    const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ mean,
                    const float *__restrict__ invstd, const float *__restrict__ c1,
                    const float *__restrict__ c2, float *__restrict__ dz) {
+  pdl_enter();
   const size_t stride = static_cast<size_t>(gridDim.x) * kRowThreads;
   for (size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x; i < total4; i += stride) {
     const int c4 = static_cast<int>(i % C4);
@@ -375,6 +386,7 @@ __global__ void __launch_bounds__(kRowThreads)
 sa_group_rows_kernel(size_t total4, int n, int np_ns, int ns, int ct4, const float *__restrict__ table,
                      const float *__restrict__ new_xyz, const int *__restrict__ idx,
                      float *__restrict__ rows) {
+  pdl_enter();
   const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
   if (i >= total4) return;
   const int c4 = static_cast<int>(i % ct4);
@@ -398,6 +410,7 @@ __device__ __forceinline__ void red_add_v4(float *p, float4 v) {
 __global__ void __launch_bounds__(kRowThreads)
 sa_group_rows_grad_kernel(size_t total4, int n, int np_ns, int ct4, const float *__restrict__ grad_rows,
                           const int *__restrict__ idx, float *__restrict__ grad_table) {
+  pdl_enter();
   const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
   if (i >= total4) return;
   const int c4 = static_cast<int>(i % ct4);
@@ -415,6 +428,7 @@ __global__ void __launch_bounds__(kRowThreads)
 fp_interp_rows_kernel(size_t total4, int n, int m, int c2, int c1, int ct4, const float *__restrict__ known,
                       const float *__restrict__ skip, const int *__restrict__ idx,
                       const float *__restrict__ weight, float *__restrict__ rows) {
+  pdl_enter();
   const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
   if (i >= total4) return;
   const int c4 = static_cast<int>(i % ct4);
@@ -450,6 +464,7 @@ fp_interp_rows_grad_kernel(size_t total4, int n, int m, int c2, int c1, int ct4,
                            const float *__restrict__ grad_rows, const int *__restrict__ idx,
                            const float *__restrict__ weight, float *__restrict__ grad_known,
                            float *__restrict__ grad_skip) {
+  pdl_enter();
   const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;
   if (i >= total4) return;
   const int c4 = static_cast<int>(i % ct4);
@@ -503,6 +518,7 @@ __global__ void __launch_bounds__(kRowThreads)
 sa_group_rows_kernel_u(unsigned total4, FastDiv ct4, FastDiv np_ns, FastDiv ns, int n,
                        const float *__restrict__ table, const float *__restrict__ new_xyz,
                        const int *__restrict__ idx, float *__restrict__ rows) {
+  pdl_enter();
   const unsigned base = blockIdx.x * (kRowThreads * U) + threadIdx.x;
   unsigned p[U], c4[U];
   int k[U];
@@ -538,6 +554,7 @@ __global__ void __launch_bounds__(kRowThreads)
 sa_group_rows_grad_kernel_u(unsigned total4, FastDiv ct4, FastDiv np_ns, int n,
                             const float *__restrict__ grad_rows, const int *__restrict__ idx,
                             float *__restrict__ grad_table) {
+  pdl_enter();
   const unsigned base = blockIdx.x * (kRowThreads * U) + threadIdx.x;
   unsigned p[U], c4[U];
   int k[U];
@@ -564,6 +581,7 @@ fp_interp_rows_kernel_u(unsigned total4, FastDiv ct4, FastDiv nn, int m, int c2,
                         const float *__restrict__ known, const float *__restrict__ skip,
                         const int *__restrict__ idx, const float *__restrict__ weight,
                         float *__restrict__ rows) {
+  pdl_enter();
   const unsigned base = blockIdx.x * (kRowThreads * U) + threadIdx.x;
   const unsigned k4 = c2 >> 2;
   unsigned p[U], c4[U];
@@ -617,6 +635,7 @@ fp_interp_rows_grad_kernel_u(unsigned total4, FastDiv ct4, FastDiv nn, int m, in
                              const float *__restrict__ grad_rows, const int *__restrict__ idx,
                              const float *__restrict__ weight, float *__restrict__ grad_known,
                              float *__restrict__ grad_skip) {
+  pdl_enter();
   const unsigned base = blockIdx.x * (kRowThreads * U) + threadIdx.x;
   const unsigned k4 = c2 >> 2;
   unsigned p[U], c4[U];
@@ -695,8 +714,8 @@ extern "C" int pn2_bn_stats(int p, int c, const float *z, const float *gamma, co
   int nblk;
   const ColGeom g = col_geom(p, c, &nblk);
   const size_t smem = sizeof(float4) * 2 * g.row_lanes * g.C4;
-  bn_stats_partial_kernel<<<nblk, kRowThreads, smem, s>>>(g, z, workspace);
-  bn_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(p, c, c, nblk, workspace, gamma, beta, eps, momentum,
+  pn2::launch(bn_stats_partial_kernel, nblk, kRowThreads, smem, s, g, z, workspace);
+  pn2::launch(bn_stats_finalize_kernel, (c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s, p, c, c, nblk, workspace, gamma, beta, eps, momentum,
                                                            running_mean, running_var, num_batches_tracked, a, b, mean, invstd);
   count_launch(2);
   PN2_RETURN_LAUNCH_STATUS();
@@ -707,8 +726,7 @@ extern "C" int pn2_bn_fold_eval(int c, const float *gamma, const float *beta, co
                                 float *invstd, void *stream) {
   if (c <= 0) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(gamma, beta, running_mean, running_var, a, b, mean, invstd);
-  bn_fold_eval_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      c, gamma, beta, running_mean, running_var, eps, a, b, mean, invstd);
+  pn2::launch(bn_fold_eval_kernel, (c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), c, gamma, beta, running_mean, running_var, eps, a, b, mean, invstd);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -719,8 +737,7 @@ extern "C" int pn2_bn_relu_apply(int p, int c, const float *z, const float *a, c
   PN2_CHECK_PTRS(z, a, b, h);
   if (!rows_ok(c, z) || !aligned16(h) || !aligned16(a) || !aligned16(b)) return PN2_ERR_UNSUPPORTED;
   const size_t total4 = static_cast<size_t>(p) * (c / 4);
-  bn_relu_apply_kernel<<<blocks_for(total4, 16 * kNumSMs), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      total4, c / 4, z, a, b, h, relu);
+  pn2::launch(bn_relu_apply_kernel, blocks_for(total4, 16 * kNumSMs), kRowThreads, 0, static_cast<cudaStream_t>(stream), total4, c / 4, z, a, b, h, relu);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -732,8 +749,7 @@ extern "C" int pn2_bn_relu_groupmax(int g, int ns, int c, const float *z, const 
   if (!rows_ok(c, z) || !aligned16(out) || !aligned16(argmax) || !aligned16(a) || !aligned16(b))
     return PN2_ERR_UNSUPPORTED;
   const size_t total4 = static_cast<size_t>(g) * (c / 4);
-  bn_relu_groupmax_kernel<<<blocks_for(total4), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      g, ns, c / 4, z, a, b, out, argmax);
+  pn2::launch(bn_relu_groupmax_kernel, blocks_for(total4), kRowThreads, 0, static_cast<cudaStream_t>(stream), g, ns, c / 4, z, a, b, out, argmax);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -744,8 +760,7 @@ extern "C" int pn2_groupmax_from_extrema(int g, int c, const float *zmax, const 
   if (g <= 0 || c <= 0) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(zmax, zmin, imax, imin, a, b, out, argmax);
   const size_t total = static_cast<size_t>(g) * c;
-  groupmax_from_extrema_kernel<<<blocks_for(total), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      total, c, zmax, zmin, imax, imin, a, b, out, argmax, zsel);
+  pn2::launch(groupmax_from_extrema_kernel, blocks_for(total), kRowThreads, 0, static_cast<cudaStream_t>(stream), total, c, zmax, zmin, imax, imin, a, b, out, argmax, zsel);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -763,11 +778,11 @@ extern "C" int pn2_pool_bn_bwd(int g, int ns, int c, int training, const float *
   const ColGeom geom = col_geom(g, c, &nblk);
   float *c1 = workspace + static_cast<size_t>(kMaxPartials) * 2 * c, *c2 = c1 + c;
   const size_t smem = sizeof(float4) * 2 * geom.row_lanes * geom.C4;
-  pool_bwd_stats_kernel<<<nblk, kRowThreads, smem, s>>>(geom, ns, dout, argmax, z, nullptr, a, b, mean, invstd, workspace);
-  bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(g * ns, c, c, nblk, training, workspace, dgamma,
+  pn2::launch(pool_bwd_stats_kernel, nblk, kRowThreads, smem, s, geom, ns, dout, argmax, z, nullptr, a, b, mean, invstd, workspace);
+  pn2::launch(bwd_stats_finalize_kernel, (c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s, g * ns, c, c, nblk, training, workspace, dgamma,
                                                             dbeta, c1, c2);
   const size_t total4 = static_cast<size_t>(g) * (c / 4);
-  pool_bwd_dz_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(g, ns, c / 4, dout, argmax, z, a, b, mean,
+  pn2::launch(pool_bwd_dz_kernel, blocks_for(total4), kRowThreads, 0, s, g, ns, c / 4, dout, argmax, z, a, b, mean,
                                                                invstd, c1, c2, dz);
   count_launch(3);
   PN2_RETURN_LAUNCH_STATUS();
@@ -784,11 +799,11 @@ extern "C" int pn2_relu_bn_bwd(int p, int c, int training, int relu, const float
   const ColGeom geom = col_geom(p, c, &nblk);
   float *c1 = workspace + static_cast<size_t>(kMaxPartials) * 2 * c, *c2 = c1 + c;
   const size_t smem = sizeof(float4) * 2 * geom.row_lanes * geom.C4;
-  relu_bwd_stats_kernel<<<nblk, kRowThreads, smem, s>>>(geom, relu, dh, z, a, b, mean, invstd, workspace);
-  bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(p, c, c, nblk, training, workspace, dgamma, dbeta,
+  pn2::launch(relu_bwd_stats_kernel, nblk, kRowThreads, smem, s, geom, relu, dh, z, a, b, mean, invstd, workspace);
+  pn2::launch(bwd_stats_finalize_kernel, (c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s, p, c, c, nblk, training, workspace, dgamma, dbeta,
                                                             c1, c2);
   const size_t total4 = static_cast<size_t>(p) * (c / 4);
-  relu_bwd_dz_kernel<<<blocks_for(total4, 16 * kNumSMs), kRowThreads, 0, s>>>(total4, c / 4, relu, dh, z, a, b,
+  pn2::launch(relu_bwd_dz_kernel, blocks_for(total4, 16 * kNumSMs), kRowThreads, 0, s, total4, c / 4, relu, dh, z, a, b,
                                                                              mean, invstd, c1, c2, dz);
   count_launch(3);
   PN2_RETURN_LAUNCH_STATUS();
@@ -803,8 +818,7 @@ extern "C" int pn2_relu_bn_bwd_dz(int p, int c, int relu, const float *dh, const
   PN2_CHECK_PTRS(dh, z, a, b, mean, invstd, c1c2, dz);
   if (!rows_ok(c, z) || !aligned16(dh) || !aligned16(dz) || !aligned16(c1c2)) return PN2_ERR_UNSUPPORTED;
   const size_t total4 = static_cast<size_t>(p) * (c / 4);
-  relu_bwd_dz_kernel<<<blocks_for(total4, 16 * kNumSMs), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      total4, c / 4, relu, dh, z, a, b, mean, invstd, c1c2, c1c2 + c, dz);
+  pn2::launch(relu_bwd_dz_kernel, blocks_for(total4, 16 * kNumSMs), kRowThreads, 0, static_cast<cudaStream_t>(stream), total4, c / 4, relu, dh, z, a, b, mean, invstd, c1c2, c1c2 + c, dz);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -823,9 +837,8 @@ extern "C" int pn2_pool_bn_bwd_stats(int g, int ns, int c, int training, const f
   const ColGeom geom = col_geom(g, c, &nblk);
   const size_t smem = sizeof(float4) * 2 * geom.row_lanes * geom.C4;
   if (zsel != nullptr && !aligned16(zsel)) return PN2_ERR_UNSUPPORTED;
-  pool_bwd_stats_kernel<<<nblk, kRowThreads, smem, s>>>(geom, ns, dout, argmax, z, zsel, a, b, mean, invstd, workspace);
-  bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(
-      g * ns, c, c, nblk, training, workspace, dgamma, dbeta, c1c2, c1c2 + c);
+  pn2::launch(pool_bwd_stats_kernel, nblk, kRowThreads, smem, s, geom, ns, dout, argmax, z, zsel, a, b, mean, invstd, workspace);
+  pn2::launch(bwd_stats_finalize_kernel, (c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s, g * ns, c, c, nblk, training, workspace, dgamma, dbeta, c1c2, c1c2 + c);
   count_launch(2);
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -840,9 +853,8 @@ extern "C" int pn2_relu_bn_bwd_stats(int p, int c, int training, int relu, const
   int nblk;
   const ColGeom geom = col_geom(p, c, &nblk);
   const size_t smem = sizeof(float4) * 2 * geom.row_lanes * geom.C4;
-  relu_bwd_stats_kernel<<<nblk, kRowThreads, smem, s>>>(geom, relu, dh, z, a, b, mean, invstd, workspace);
-  bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s>>>(
-      p, c, c, nblk, training, workspace, dgamma, dbeta, c1c2, c1c2 + c);
+  pn2::launch(relu_bwd_stats_kernel, nblk, kRowThreads, smem, s, geom, relu, dh, z, a, b, mean, invstd, workspace);
+  pn2::launch(bwd_stats_finalize_kernel, (c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, s, p, c, c, nblk, training, workspace, dgamma, dbeta, c1c2, c1c2 + c);
   count_launch(2);
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -853,8 +865,7 @@ extern "C" int pn2_bwd_stats_finalize(int p, int c, int ld, int nblk, int traini
                                       float *dgamma, float *dbeta, float *c1c2, void *stream) {
   if (p <= 0 || c <= 0 || ld < c || nblk <= 0) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(partials, dgamma, dbeta, c1c2);
-  bwd_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0,
-                              static_cast<cudaStream_t>(stream)>>>(p, c, ld, nblk, training, partials, dgamma,
+  pn2::launch(bwd_stats_finalize_kernel, (c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, static_cast<cudaStream_t>(stream), p, c, ld, nblk, training, partials, dgamma,
                                                                    dbeta, c1c2, c1c2 + c);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
@@ -870,14 +881,11 @@ extern "C" int pn2_sa_group_rows(int b, int n, int npoint, int nsample, int ct, 
   const int u = rows_unroll(total4);
   const FastDiv dct = fast_div(ct / 4), dcl = fast_div(npoint * nsample), dns = fast_div(nsample);
   if (u == 4)
-    sa_group_rows_kernel_u<4><<<blocks_u(total4, 4), kRowThreads, 0, s>>>(
-        static_cast<unsigned>(total4), dct, dcl, dns, n, table, new_xyz, idx, rows);
+    pn2::launch(sa_group_rows_kernel_u<4>, blocks_u(total4, 4), kRowThreads, 0, s, static_cast<unsigned>(total4), dct, dcl, dns, n, table, new_xyz, idx, rows);
   else if (u == 2)
-    sa_group_rows_kernel_u<2><<<blocks_u(total4, 2), kRowThreads, 0, s>>>(
-        static_cast<unsigned>(total4), dct, dcl, dns, n, table, new_xyz, idx, rows);
+    pn2::launch(sa_group_rows_kernel_u<2>, blocks_u(total4, 2), kRowThreads, 0, s, static_cast<unsigned>(total4), dct, dcl, dns, n, table, new_xyz, idx, rows);
   else
-    sa_group_rows_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(
-        total4, n, npoint * nsample, nsample, ct / 4, table, new_xyz, idx, rows);
+    pn2::launch(sa_group_rows_kernel, blocks_for(total4), kRowThreads, 0, s, total4, n, npoint * nsample, nsample, ct / 4, table, new_xyz, idx, rows);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -894,13 +902,11 @@ extern "C" int pn2_sa_group_rows_grad(int b, int n, int npoint, int nsample, int
   const int u = rows_unroll(total4);
   const FastDiv dct = fast_div(ct / 4), dcl = fast_div(npoint * nsample);
   if (u == 4)
-    sa_group_rows_grad_kernel_u<4><<<blocks_u(total4, 4), kRowThreads, 0, s>>>(
-        static_cast<unsigned>(total4), dct, dcl, n, grad_rows, idx, grad_table);
+    pn2::launch(sa_group_rows_grad_kernel_u<4>, blocks_u(total4, 4), kRowThreads, 0, s, static_cast<unsigned>(total4), dct, dcl, n, grad_rows, idx, grad_table);
   else if (u == 2)
-    sa_group_rows_grad_kernel_u<2><<<blocks_u(total4, 2), kRowThreads, 0, s>>>(
-        static_cast<unsigned>(total4), dct, dcl, n, grad_rows, idx, grad_table);
+    pn2::launch(sa_group_rows_grad_kernel_u<2>, blocks_u(total4, 2), kRowThreads, 0, s, static_cast<unsigned>(total4), dct, dcl, n, grad_rows, idx, grad_table);
   else
-    sa_group_rows_grad_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(total4, n, npoint * nsample, ct / 4,
+    pn2::launch(sa_group_rows_grad_kernel, blocks_for(total4), kRowThreads, 0, s, total4, n, npoint * nsample, ct / 4,
                                                                         grad_rows, idx, grad_table);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
@@ -918,14 +924,11 @@ extern "C" int pn2_fp_interp_rows(int b, int n, int m, int c2, int c1, const flo
   const int u = rows_unroll(total4);
   const FastDiv dct = fast_div(ct / 4), dn = fast_div(n);
   if (u == 4)
-    fp_interp_rows_kernel_u<4><<<blocks_u(total4, 4), kRowThreads, 0, s>>>(
-        static_cast<unsigned>(total4), dct, dn, m, c2, c1, known, skip, idx, weight, rows);
+    pn2::launch(fp_interp_rows_kernel_u<4>, blocks_u(total4, 4), kRowThreads, 0, s, static_cast<unsigned>(total4), dct, dn, m, c2, c1, known, skip, idx, weight, rows);
   else if (u == 2)
-    fp_interp_rows_kernel_u<2><<<blocks_u(total4, 2), kRowThreads, 0, s>>>(
-        static_cast<unsigned>(total4), dct, dn, m, c2, c1, known, skip, idx, weight, rows);
+    pn2::launch(fp_interp_rows_kernel_u<2>, blocks_u(total4, 2), kRowThreads, 0, s, static_cast<unsigned>(total4), dct, dn, m, c2, c1, known, skip, idx, weight, rows);
   else
-    fp_interp_rows_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(
-        total4, n, m, c2, c1, ct / 4, known, skip, idx, weight, rows);
+    pn2::launch(fp_interp_rows_kernel, blocks_for(total4), kRowThreads, 0, s, total4, n, m, c2, c1, ct / 4, known, skip, idx, weight, rows);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -945,13 +948,11 @@ extern "C" int pn2_fp_interp_rows_grad(int b, int n, int m, int c2, int c1, cons
   const int u = rows_unroll(total4);
   const FastDiv dct = fast_div(ct / 4), dn = fast_div(n);
   if (u == 4)
-    fp_interp_rows_grad_kernel_u<4><<<blocks_u(total4, 4), kRowThreads, 0, s>>>(
-        static_cast<unsigned>(total4), dct, dn, m, c2, c1, grad_rows, idx, weight, grad_known, grad_skip);
+    pn2::launch(fp_interp_rows_grad_kernel_u<4>, blocks_u(total4, 4), kRowThreads, 0, s, static_cast<unsigned>(total4), dct, dn, m, c2, c1, grad_rows, idx, weight, grad_known, grad_skip);
   else if (u == 2)
-    fp_interp_rows_grad_kernel_u<2><<<blocks_u(total4, 2), kRowThreads, 0, s>>>(
-        static_cast<unsigned>(total4), dct, dn, m, c2, c1, grad_rows, idx, weight, grad_known, grad_skip);
+    pn2::launch(fp_interp_rows_grad_kernel_u<2>, blocks_u(total4, 2), kRowThreads, 0, s, static_cast<unsigned>(total4), dct, dn, m, c2, c1, grad_rows, idx, weight, grad_known, grad_skip);
   else
-    fp_interp_rows_grad_kernel<<<blocks_for(total4), kRowThreads, 0, s>>>(total4, n, m, c2, c1, ct / 4, grad_rows,
+    pn2::launch(fp_interp_rows_grad_kernel, blocks_for(total4), kRowThreads, 0, s, total4, n, m, c2, c1, ct / 4, grad_rows,
                                                                          idx, weight, grad_known, grad_skip);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
@@ -965,8 +966,7 @@ extern "C" int pn2_bn_finalize(int p, int c, int ld, int nblk, const float *part
                                float *mean, float *invstd, void *stream) {
   if (p <= 0 || c <= 0 || ld < c || nblk <= 0) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(partials, gamma, beta, a, b, mean, invstd);
-  bn_stats_finalize_kernel<<<(c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0,
-                             static_cast<cudaStream_t>(stream)>>>(p, c, ld, nblk, partials, gamma, beta, eps,
+  pn2::launch(bn_stats_finalize_kernel, (c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, static_cast<cudaStream_t>(stream), p, c, ld, nblk, partials, gamma, beta, eps,
                                                                   momentum, running_mean, running_var,
                                                                   num_batches_tracked, a, b, mean, invstd);
   count_launch();
@@ -981,6 +981,7 @@ extern "C" int pn2_bn_finalize(int p, int c, int ld, int nblk, const float *part
 // combines the lanes, so even a 32x32 weight gradient summed over ~300 slabs uses 256 warps.
 __global__ void __launch_bounds__(kRowThreads)
 sum_partials_kernel(int S, int M4, const float *__restrict__ in, float *__restrict__ out) {
+  pdl_enter();
   const int j = blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (j >= M4) return;
@@ -1007,8 +1008,7 @@ extern "C" int pn2_sum_partials(int s, int m, const float *in, float *out, void 
   PN2_CHECK_PTRS(in, out);
   if (!aligned16(in) || !aligned16(out)) return PN2_ERR_UNSUPPORTED;
   const int warps_per_cta = kRowThreads / 32;
-  sum_partials_kernel<<<(m / 4 + warps_per_cta - 1) / warps_per_cta, kRowThreads, 0,
-                        static_cast<cudaStream_t>(stream)>>>(s, m / 4, in, out);
+  pn2::launch(sum_partials_kernel, (m / 4 + warps_per_cta - 1) / warps_per_cta, kRowThreads, 0, static_cast<cudaStream_t>(stream), s, m / 4, in, out);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -1019,6 +1019,7 @@ extern "C" int pn2_sum_partials(int s, int m, const float *in, float *out, void 
 __global__ void __launch_bounds__(kRowThreads)
 sum_partials_block_kernel(int S, int rows_in, int cols_in, int rows_out, int cols_out,
                           const float *__restrict__ in, float *__restrict__ out) {
+  pdl_enter();
   const int c4n = (cols_out + 3) / 4;
   const int j = blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -1056,8 +1057,7 @@ extern "C" int pn2_sum_partials_block(int s, int rows_in, int cols_in, int rows_
   if (!aligned16(in)) return PN2_ERR_UNSUPPORTED;
   const int warps_per_cta = kRowThreads / 32;
   const int items = rows_out * ((cols_out + 3) / 4);
-  sum_partials_block_kernel<<<(items + warps_per_cta - 1) / warps_per_cta, kRowThreads, 0,
-                              static_cast<cudaStream_t>(stream)>>>(s, rows_in, cols_in, rows_out, cols_out, in, out);
+  pn2::launch(sum_partials_block_kernel, (items + warps_per_cta - 1) / warps_per_cta, kRowThreads, 0, static_cast<cudaStream_t>(stream), s, rows_in, cols_in, rows_out, cols_out, in, out);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -1076,6 +1076,7 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 __global__ void __launch_bounds__(kRowThreads)
 dropout_mask_kernel(size_t n16, size_t n, unsigned threshold, const long long *__restrict__ state,
                     unsigned char *__restrict__ mask) {
+  pdl_enter();
   const size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x;  // 16 mask bytes per thread
   if (i >= n16) return;
   const unsigned long long key = splitmix64(static_cast<unsigned long long>(state[0]) ^
@@ -1093,7 +1094,8 @@ dropout_mask_kernel(size_t n16, size_t n, unsigned threshold, const long long *_
     for (size_t b = i * 16; b < n; ++b) mask[b] = static_cast<unsigned char>((w[(b >> 2) & 3] >> (8 * (b & 3))) & 1u);
   }
 }
-__global__ void bump_counter_kernel(long long *state) { state[1] += 1; }
+__global__ void bump_counter_kernel(long long *state) {
+  pdl_enter(); state[1] += 1; }
 
 extern "C" int pn2_dropout_mask(long long n, float keep, long long *state, unsigned char *mask, void *stream) {
   if (n <= 0 || !(keep >= 0.f && keep <= 1.f)) return PN2_ERR_INVALID_ARG;
@@ -1102,8 +1104,8 @@ extern "C" int pn2_dropout_mask(long long n, float keep, long long *state, unsig
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t n16 = (static_cast<size_t>(n) + 15) / 16;
   const unsigned threshold = static_cast<unsigned>(static_cast<double>(keep) * 65536.0 + 0.5);
-  dropout_mask_kernel<<<blocks_for(n16), kRowThreads, 0, s>>>(n16, static_cast<size_t>(n), threshold, state, mask);
-  bump_counter_kernel<<<1, 1, 0, s>>>(state);
+  pn2::launch(dropout_mask_kernel, blocks_for(n16), kRowThreads, 0, s, n16, static_cast<size_t>(n), threshold, state, mask);
+  pn2::launch(bump_counter_kernel, 1, 1, 0, s, state);
   count_launch(2);
   PN2_RETURN_LAUNCH_STATUS();
 }
@@ -1116,6 +1118,7 @@ __global__ void __launch_bounds__(kRowThreads)
 adam_flat_kernel(size_t n, float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
                  float *__restrict__ v, const long long *__restrict__ step, float lr, float beta1, float beta2,
                  float eps, float weight_decay, float grad_scale) {
+  pdl_enter();
   const double t = static_cast<double>(*step);
   const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), t));
   const float bc2s = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)));
@@ -1131,7 +1134,8 @@ adam_flat_kernel(size_t n, float *__restrict__ p, const float *__restrict__ g, f
     p[i] = w - step_size * mi / (sqrtf(vi) / bc2s + eps);
   }
 }
-__global__ void bump_step_kernel(long long *step) { *step += 1; }
+__global__ void bump_step_kernel(long long *step) {
+  pdl_enter(); *step += 1; }
 
 extern "C" int pn2_adam_flat(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
                              long long *step, float lr, float beta1, float beta2, float eps,
@@ -1140,9 +1144,8 @@ extern "C" int pn2_adam_flat(long long n, float *param, const float *grad, float
   PN2_CHECK_PTRS(param, grad, exp_avg, exp_avg_sq);
   if (step == nullptr) return PN2_ERR_INVALID_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  bump_step_kernel<<<1, 1, 0, s>>>(step);
-  adam_flat_kernel<<<blocks_for(static_cast<size_t>(n), 8 * kNumSMs), kRowThreads, 0, s>>>(
-      static_cast<size_t>(n), param, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, weight_decay,
+  pn2::launch(bump_step_kernel, 1, 1, 0, s, step);
+  pn2::launch(adam_flat_kernel, blocks_for(static_cast<size_t>(n), 8 * kNumSMs), kRowThreads, 0, s, static_cast<size_t>(n), param, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, weight_decay,
       grad_scale);
   count_launch(2);
   PN2_RETURN_LAUNCH_STATUS();

@@ -60,6 +60,7 @@ struct __align__(8) Barriers {
 
 __global__ void __launch_bounds__(kThreads, 1) wgrad_tf32_kernel(Params p, const __grid_constant__ CUtensorMap tm_x,
                                                                  const __grid_constant__ CUtensorMap tm_y) {
+  pdl_enter();
   extern __shared__ __align__(1024) unsigned char smem[];
   const int stage_bytes = (kXSlabs + p.yslabs) * SLAB;
   Barriers *bars = reinterpret_cast<Barriers *>(smem + p.stages * stage_bytes);
@@ -262,7 +263,7 @@ extern "C" int pn2_mlp_wgrad(int p, int n, int ldx, int ldy, const float *x, con
                                        static_cast<int>(g.smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid(g.splits, g.n_tiles, g.k_tiles);
-  wgrad::wgrad_tf32_kernel<<<grid, wgrad::kThreads, g.smem, static_cast<cudaStream_t>(stream)>>>(prm, tm_x, tm_y);
+  pn2::launch(wgrad::wgrad_tf32_kernel, grid, wgrad::kThreads, g.smem, static_cast<cudaStream_t>(stream), prm, tm_x, tm_y);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

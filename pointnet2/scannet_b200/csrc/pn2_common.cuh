@@ -212,8 +212,36 @@ __device__ __forceinline__ int4 ld_nc_i4(const int *p) {
   return v;
 }
 
+// ---- programmatic dependent launch --------------------------------------------------------
+// A training step is ~300 dependent launches, most of them a few microseconds long; what a kernel boundary
+// costs inside the replayed graph is the drain of the previous grid's last CTAs plus the next grid's ramp.
+// Kernels launched through pn2::launch can carry the programmatic-stream-serialization attribute: their CTAs may be
+// scheduled while the previous kernel of the stream is still draining.  Every such kernel calls pdl_enter()
+// FIRST: griddepcontrol.wait blocks until the previous grid has completed and its memory operations are visible
+// (so nothing is read or written early), then griddepcontrol.launch_dependents lets the NEXT kernel's CTAs be
+// scheduled as soon as every CTA of this grid has started.  (The trigger sits after the wait on purpose: a chain
+// of kernels cannot run more than one grid ahead.)  Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---- host side --------------------------------------------------------------
 void count_launch(int n = 1);
+bool pdl_enabled();   // PN2_PDL=1 (lib.cu; measured slower on the replayed step graph, so off by default)
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args &&>(args)...);
+}
 
 // The reference's opt_n_threads (_ext_src/include/cuda_utils.h:15-19), same
 // double-precision log quotient so that the block size -- which fixes the FPS

@@ -70,6 +70,36 @@ def test_product_never_touches_the_oracle():
                 assert "pn2o_" not in src, f
 
 
+def test_programmatic_launches_wait_first():
+    """Kernels launched through pn2::launch (programmatic dependent launch, pn2_common.cuh) may be scheduled
+    before the previous kernel of their stream has finished: each of them must call pdl_enter() --
+    griddepcontrol.wait -- as its FIRST statement, and a source file must not mix the two launch forms."""
+    csrc = os.path.join(ROOT, "pointnet2", "scannet_b200", "csrc")
+    seen = 0
+    for f in sorted(os.listdir(csrc)):
+        if not f.endswith(".cu"):
+            continue
+        src = open(os.path.join(csrc, f)).read()
+        if "pn2::launch(" not in src:
+            continue
+        seen += 1
+        assert "<<<" not in src, "%s mixes <<< >>> launches with pn2::launch" % f
+        code = re.sub(r"//[^\n]*", "", src)
+        for m in re.finditer(r"__global__", code):
+            depth, i = 0, code.index("(", m.end())
+            if "__launch_bounds__" in code[m.end():i]:       # skip its argument list
+                i = code.index(")", i) + 1
+                i = code.index("(", i)
+            for j in range(i, len(code)):
+                depth += code[j] == "("
+                depth -= code[j] == ")"
+                if depth == 0:
+                    break
+            body = code[code.index("{", j) + 1:]
+            assert body.lstrip().startswith("pdl_enter();"), "%s: %s" % (f, code[m.start():m.start() + 120])
+    assert seen >= 6
+
+
 @pytest.mark.skipif(not have_ref, reason="/root/reference not present")
 def test_reference_op_layer_resolves_to_the_dropin():
     """`import pointnet2._ext` inside the reference's unchanged pointnet2_utils.py finds this repo's."""
