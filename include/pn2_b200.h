@@ -428,6 +428,9 @@ PN2_API int pn2_mlp_wgrad(int p, int n, int ldx, int ldy, const float *x, const 
  * ========================================================================== */
 /* kind: 0 pn2_sa_lead_fwd, 1 pn2_sa_lead_bwd, 2 pn2_fp_lead_fwd, 3 pn2_fp_lead_bwd (each kernel's grid is one
  * resident wave, sized for its own register budget) */
+/* out [p, c_out] = [in [p, c_in] | 0 ...] (c_out % 4 == 0): the network's input rows (lib/dataset.py's
+ * xyz | features layout, pointnet2_semseg.py:139-146) widened to the level-0 point table in one launch */
+PN2_API int pn2_pad_rows(long long p, int c_in, int c_out, const float *in, float *out, void *stream);
 PN2_API int pn2_lead_blocks(int p, int c, int kind);
 PN2_API int pn2_fp_lead_max_skip(void);
 PN2_API int pn2_mlp_pack_weights_cols(int p, int n, int k, int k0, int ldw, const float *w, float *packed,

@@ -490,6 +490,25 @@ fp_interp_rows_grad_kernel(size_t total4, int n, int m, int c2, int c1, int ct4,
   }
 }
 
+// out[p, :] = [in[p, 0 .. c_in) | 0 ...]: the network's input rows widened to a multiple of 4 columns -- the level-0
+// point table [xyz | features | pad] in one launch (torch: contiguous copy of the features, zeros, cat)
+__global__ void __launch_bounds__(kRowThreads)
+pad_rows_kernel(size_t total4, int c_in, int c4_out, const float *__restrict__ in, float *__restrict__ out) {
+  pdl_enter();
+  const size_t stride = static_cast<size_t>(gridDim.x) * kRowThreads;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * kRowThreads + threadIdx.x; i < total4; i += stride) {
+    const size_t p = i / c4_out;
+    const int c = static_cast<int>(i - p * c4_out) * 4;
+    const float *src = in + p * c_in + c;
+    float4 v;
+    v.x = c + 0 < c_in ? __ldg(src + 0) : 0.f;
+    v.y = c + 1 < c_in ? __ldg(src + 1) : 0.f;
+    v.z = c + 2 < c_in ? __ldg(src + 2) : 0.f;
+    v.w = c + 3 < c_in ? __ldg(src + 3) : 0.f;
+    reinterpret_cast<float4 *>(out)[i] = v;
+  }
+}
+
 // ---- the four gather / scatter kernels above, U float4 elements per thread -----------------
 // One element per thread leaves a single dependent chain (index -> gathered row -> store) in
 // flight per thread and spends most of its issue slots on 64-bit divisions.  Here a thread owns
@@ -867,6 +886,17 @@ extern "C" int pn2_bwd_stats_finalize(int p, int c, int ld, int nblk, int traini
   PN2_CHECK_PTRS(partials, dgamma, dbeta, c1c2);
   pn2::launch(bwd_stats_finalize_kernel, (c + kFinalizeWarps - 1) / kFinalizeWarps, 32 * kFinalizeWarps, 0, static_cast<cudaStream_t>(stream), p, c, ld, nblk, training, partials, dgamma,
                                                                    dbeta, c1c2, c1c2 + c);
+  count_launch();
+  PN2_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pn2_pad_rows(long long p, int c_in, int c_out, const float *in, float *out, void *stream) {
+  if (p <= 0 || c_in <= 0 || c_out < c_in || c_out % 4 != 0) return PN2_ERR_INVALID_ARG;
+  PN2_CHECK_PTRS(in, out);
+  if (!aligned16(out)) return PN2_ERR_UNSUPPORTED;
+  const size_t total4 = static_cast<size_t>(p) * (c_out / 4);
+  pn2::launch(pad_rows_kernel, blocks_for(total4, 16 * kNumSMs), kRowThreads, 0, static_cast<cudaStream_t>(stream), total4,
+              c_in, c_out / 4, in, out);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

@@ -334,32 +334,40 @@ def _sum_partials(part):
 
 class SALead(object):
     """QueryAndGroup + the first conv of an SA scale: z[g, s] = U[idx[g, s]] + W_x (xyz[idx[g, s]] - new_xyz[g]),
-    U = table W_f^T over the points (the coordinate columns of the [xyz | features | pad] table get zero
-    weights; their term is evaluated in fp32 on the centred differences)."""
+    U = F W_f^T over the points; the coordinate term is evaluated in fp32 on the centred differences.  The
+    differentiable source ``x0`` (B, N, ld) holds the point features in columns [c_off, c_off + Cf): the feature
+    rows themselves (c_off = 0, ld = Cf; levels whose Cf is a multiple of 4) or the [xyz | features | pad] table
+    (c_off = 3; the coordinate columns then get zero weights and a zero gradient)."""
 
-    def __init__(self, xyz, new_xyz, idx):
+    def __init__(self, xyz, new_xyz, idx, c_off):
         self.xyz, self.new_xyz, self.idx = xyz.contiguous(), new_xyz.contiguous(), idx
         self.B, self.N = xyz.shape[0], xyz.shape[1]
         self.npoint, self.ns = idx.shape[1], idx.shape[2]
         self.P = self.B * self.npoint * self.ns
+        self.c_off = c_off
         self.mark = False
 
-    def forward(self, table, W2, need_dx):
+    def forward(self, x0, W2, need_dx):
         L = _lib.load()
-        dev = table.device
-        B, N, ct = table.shape
-        C, K = W2.shape
-        PN = B * N
+        dev = x0.device
+        B, N, ld = x0.shape
+        C, K3 = W2.shape                        # K3 = 3 + Cf
+        PN, c_off = B * N, self.c_off
         W2c = W2.contiguous()
         ldw = W2c.shape[1]
-        self.table2d, self.W2c, self.K = table.reshape(PN, ct), W2c, K
+        self.x2d, self.W2c = x0.reshape(PN, ld), W2c
+        self.K = K = c_off + K3 - 3             # columns of x2d the product reads
+        assert K <= ld
+        # column k >= c_off of x2d meets W2[:, 3 + (k - c_off)]: the weight pointer is shifted accordingly
+        self.w_ptr = W2c.data_ptr() + 4 * (3 - c_off)
         bn, nt, kb = L.pn2_mlp_gemm_bn(PN, C), L.pn2_mlp_gemm_n_tiles(PN, C), L.pn2_mlp_gemm_k_blocks(K)
-        wp = _packed("lead_sa", W2c, (PN, C, K), nt * kb * bn * 32, lambda ptr, st: _lib.check(
-            L.pn2_mlp_pack_weights_cols(PN, C, K, 3, ldw, W2c.data_ptr(), ptr, st), "mlp_pack_weights_cols"))
+        w_ptr = self.w_ptr
+        wp = _packed("lead_sa", W2c, (PN, C, K, c_off), nt * kb * bn * 32, lambda ptr, st: _lib.check(
+            L.pn2_mlp_pack_weights_cols(PN, C, K, c_off, ldw, w_ptr, ptr, st), "mlp_pack_weights_cols"))
         self.wp_dgrad = None
         if need_dx and _pack_state["active"]:
             self.wp_dgrad = self._pack_dgrad()
-        u = _gemm_plain(self.table2d, K, wp, C)
+        u = _gemm_plain(self.x2d, K, wp, C)
         nblk = L.pn2_lead_blocks(self.P, C, 0)
         z = torch.empty(self.P, C, dtype=torch.float32, device=dev)
         part = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
@@ -370,20 +378,20 @@ class SALead(object):
 
     def _pack_dgrad(self):
         L = _lib.load()
-        W2c, K = self.W2c, self.K
-        PN, ct = self.table2d.shape
+        W2c, K, c_off, w_ptr = self.W2c, self.K, self.c_off, self.w_ptr
+        PN, ld = self.x2d.shape
         C = W2c.shape[0]
-        bn, nt, kb = L.pn2_mlp_gemm_bn(PN, ct), L.pn2_mlp_gemm_n_tiles(PN, ct), L.pn2_mlp_gemm_k_blocks(C)
-        return _packed("lead_sa_dgrad", W2c, (PN, ct, C, K), nt * kb * bn * 32, lambda ptr, st: _lib.check(
-            L.pn2_mlp_pack_weights_dgrad_cols(PN, ct, C, K, 3, W2c.shape[1], W2c.data_ptr(), ptr, st),
+        bn, nt, kb = L.pn2_mlp_gemm_bn(PN, ld), L.pn2_mlp_gemm_n_tiles(PN, ld), L.pn2_mlp_gemm_k_blocks(C)
+        return _packed("lead_sa_dgrad", W2c, (PN, ld, C, K, c_off), nt * kb * bn * 32, lambda ptr, st: _lib.check(
+            L.pn2_mlp_pack_weights_dgrad_cols(PN, ld, C, K, c_off, W2c.shape[1], w_ptr, ptr, st),
             "mlp_pack_weights_dgrad_cols"))
 
     def backward(self, dh, st, c1c2, relu, need_dx):
-        """-> (dW [C, K] dense, d table (B, N, ct) or None)"""
+        """-> (dW [C, 3 + Cf] dense, d x0 (B, N, ld) or None)"""
         L = _lib.load()
         dev = dh.device
-        C, K = self.W2c.shape[0], self.K
-        PN, ct = self.table2d.shape
+        C, K, c_off = self.W2c.shape[0], self.K, self.c_off
+        PN, ld = self.x2d.shape
         nblk = L.pn2_lead_blocks(self.P, C, 1)
         du = torch.empty(PN, C, dtype=torch.float32, device=dev)
         part = torch.empty(nblk, 3, C, dtype=torch.float32, device=dev)
@@ -391,18 +399,17 @@ class SALead(object):
                                      st.a.data_ptr(), st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
                                      c1c2.data_ptr(), self.xyz.data_ptr(), self.new_xyz.data_ptr(),
                                      self.idx.data_ptr(), du.data_ptr(), part.data_ptr(), _stream(dev)), "sa_lead_bwd")
-        dtable = None
+        dx = None
         if need_dx:   # the data gradient first: the next kernel of the chain waits for it
             wp = self.wp_dgrad if self.wp_dgrad is not None else self._pack_dgrad()
-            dtable = _gemm_plain(du, C, wp, ct).view(self.B, self.N, ct)
-        table2d = self.table2d
+            dx = _gemm_plain(du, C, wp, ld).view(self.B, self.N, ld)
+        x2d = self.x2d
 
         def weight_grad():
-            dW = _wgrad(du, table2d, K)          # [C, K]; its coordinate columns are replaced below
-            dW[:, :3] = _sum_partials(part).t()
-            return dW
-        dW = _on_dw_branch(dev, (du, table2d, part), weight_grad)
-        return dW, dtable
+            wg = _wgrad(du, x2d, K)              # [C, c_off + Cf]: columns >= c_off are dW_f
+            return torch.cat([_sum_partials(part).t(), wg[:, c_off:]], dim=1)
+        dW = _on_dw_branch(dev, (du, x2d, part), weight_grad)
+        return dW, dx
 
 
 class FPLead(object):
@@ -928,6 +935,18 @@ def sa_chain_eval(mlp, table, new_xyz, idx):
         _lib.check(L.pn2_sa_chain_eval(B, N, npoint, ns, ct, table.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(),
                                        cs[0], cs[1], cs[2], packed[0].data_ptr(), packed[1].data_ptr(),
                                        packed[2].data_ptr(), fold.data_ptr(), out.data_ptr(), s), "sa_chain_eval")
+    return out
+
+
+def pad_rows(x, width):
+    """(B, N, c) contiguous rows -> (B, N, width) with zero columns appended (width % 4 == 0), one launch; ``x``
+    itself when it already has that width.  No gradient (the network's input)."""
+    B, N, c = x.shape
+    if c == width:
+        return x
+    out = torch.empty(B, N, width, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().pn2_pad_rows(B * N, c, width, x.data_ptr(), out.data_ptr(), _stream(x.device)), "pad_rows")
     return out
 
 

@@ -82,6 +82,7 @@ SIGNATURES = {
     "pn2_mlp_wgrad_cols": [_i],
     "pn2_mlp_wgrad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     # first layer of a block applied before the gather (csrc/mlp_lead.cu)
+    "pn2_pad_rows": [ctypes.c_longlong, _i, _i, _vp, _vp, _vp],
     "pn2_lead_blocks": [_i, _i, _i],
     "pn2_fp_lead_max_skip": [],
     "pn2_mlp_pack_weights_cols": [_i, _i, _i, _i, _i, _vp, _vp, _vp],

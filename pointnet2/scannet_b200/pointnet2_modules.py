@@ -28,12 +28,12 @@ class _PointnetSAModuleBase(nn.Module):
         self.groupers = None
         self.mlps = None
 
-    def forward(self, xyz, features=None, geometry=None):
+    def forward(self, xyz, features=None, geometry=None, table=None):
         """``geometry`` (optional) = (new_xyz, [idx per scale][, [inverse map of idx per scale]]) computed ahead
-        by geometry.build_plan."""
+        by geometry.build_plan; ``table`` (optional): the [xyz | features | pad] point rows (fused path only)."""
         if geometry is not None and self._fused_ok(xyz, features):
             return geometry[0], self._forward_rows(xyz, geometry[0], features, geometry[1],
-                                                   geometry[2] if len(geometry) > 2 else None)
+                                                   geometry[2] if len(geometry) > 2 else None, table)
         new_xyz = None
         if self.npoint is not None:
             # FPS on (B, N, 3); the centres are gathered from the channel-major copy
@@ -42,7 +42,7 @@ class _PointnetSAModuleBase(nn.Module):
                 xyz.transpose(1, 2).contiguous(), picked).transpose(1, 2).contiguous()
 
         if self._fused_ok(xyz, features):
-            return new_xyz, self._forward_rows(xyz, new_xyz, features)
+            return new_xyz, self._forward_rows(xyz, new_xyz, features, table=table)
 
         pooled = []
         for grouper, mlp in zip(self.groupers, self.mlps):
@@ -66,24 +66,36 @@ class _PointnetSAModuleBase(nn.Module):
                 return False
         return True
 
-    def _forward_rows(self, xyz, new_xyz, features, idxs=None, invs=None):
+    def _forward_rows(self, xyz, new_xyz, features, idxs=None, invs=None, table=None):
+        """``table`` (optional): the (B, N, pad4(3 + C)) [xyz | features | 0] rows, when the caller has them."""
         B, N, _ = xyz.shape
-        cols = [xyz] if features is None else [xyz, fused.rows_of(features)]
-        width = sum(c.size(2) for c in cols)
-        if fused.pad4(width) != width:
-            cols.append(xyz.new_zeros(B, N, fused.pad4(width) - width))
-        table = torch.cat(cols, dim=2)                       # (B, N, 3 + C [+ pad]) per-point rows
+        feat_rows = fused.rows_of(features) if features is not None else None
+
+        def the_table():   # built on first use: the training path of levels whose C is a multiple of 4 never needs it
+            nonlocal table
+            if table is None:
+                cols = [xyz] if feat_rows is None else [xyz, feat_rows]
+                width = sum(c.size(2) for c in cols)
+                if fused.pad4(width) != width:
+                    cols.append(xyz.new_zeros(B, N, fused.pad4(width) - width))
+                table = torch.cat(cols, dim=2)                   # (B, N, 3 + C [+ pad]) per-point rows
+            return table
         pooled = []
         for i, (grouper, mlp) in enumerate(zip(self.groupers, self.mlps)):
             idx = idxs[i] if idxs is not None else pointnet2_utils.ball_query(
                 grouper.radius, grouper.nsample, xyz, new_xyz)
-            out = fused.sa_chain_eval(mlp, table, new_xyz, idx)           # inference: the whole block in one kernel
-            if out is None and features is not None and fused.lead_ok(mlp):
-                # training: the first conv runs over the N points of the table, the gather writes its output
-                out = fused.run_mlp_rows(mlp, table, grouper.nsample, lead=fused.SALead(xyz, new_xyz, idx))
+            out = None
+            if feat_rows is not None and fused.lead_ok(mlp):
+                # training: the first conv runs over the N points, the gather writes its output (fused.SALead)
+                if feat_rows.size(2) % 4 == 0 and table is None:
+                    out = fused.run_mlp_rows(mlp, feat_rows, grouper.nsample, lead=fused.SALead(xyz, new_xyz, idx, 0))
+                else:
+                    out = fused.run_mlp_rows(mlp, the_table(), grouper.nsample, lead=fused.SALead(xyz, new_xyz, idx, 3))
+            if out is None:
+                out = fused.sa_chain_eval(mlp, the_table(), new_xyz, idx)    # inference: the whole block in one kernel
             if out is None:
                 inv = invs[i] if invs is not None and invs[i] is not None else (None, None)
-                rows = fused.SAGroupRows.apply(table, new_xyz, idx, inv[0], inv[1])   # (B*npoint*nsample, ct)
+                rows = fused.SAGroupRows.apply(the_table(), new_xyz, idx, inv[0], inv[1])   # (B*npoint*nsample, ct)
                 out = fused.run_mlp_rows(mlp, rows, grouper.nsample)      # (B*npoint, mlp[-1])
             pooled.append(out.view(B, self.npoint, -1))
         rows = torch.cat(pooled, dim=2) if len(pooled) > 1 else pooled[0]   # (B, npoint, sum C)

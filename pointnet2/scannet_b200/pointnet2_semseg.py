@@ -118,9 +118,15 @@ class _Pointnet2SemSeg(nn.Module):
     def _forward(self, pointcloud, plan=None):
         xyz, features = self._break_up_pc(pointcloud)
         l_xyz, l_features = [xyz], [features]
+        table0 = None
+        if (fused.LAZY_CHANNEL_MAJOR and features is not None and pointcloud.is_contiguous()
+                and not pointcloud.requires_grad and pointcloud.dtype == xyz.dtype):
+            # the level-0 point table [xyz | features | pad] IS the input, widened to a multiple of 4 columns
+            table0 = fused.pad_rows(pointcloud, fused.pad4(pointcloud.size(-1)))
         for k, sa in enumerate(self.SA_modules):
             nxt_xyz, nxt_feat = sa(l_xyz[-1], l_features[-1],
-                                   tuple(plan.sa[k]) + (plan.sa_inv[k],) if plan is not None else None)
+                                   tuple(plan.sa[k]) + (plan.sa_inv[k],) if plan is not None else None,
+                                   table0 if k == 0 else None)
             l_xyz.append(nxt_xyz)
             l_features.append(nxt_feat)
         nfp = len(self.FP_modules)

@@ -151,6 +151,41 @@ def test_unsupported_widths_are_refused():
         M.PointnetSAModule(npoint=8, radius=0.3, nsample=8, mlp=[4, 32, 32]).to(DEV).train().mlps[0])
 
 
+def test_pad_rows_is_the_level0_table():
+    g = torch.Generator().manual_seed(3)
+    for c, width in ((9, 12), (134, 136), (12, 12), (3, 4)):
+        x = torch.randn(3, 1000, c, generator=g).to(DEV)
+        t = fused.pad_rows(x, width)
+        assert t.shape == (3, 1000, width) and torch.equal(t, torch.nn.functional.pad(x, (0, width - c)))
+        if c == width:
+            assert t.data_ptr() == x.data_ptr()
+
+
+def test_sa_lead_reads_feature_rows_or_the_table():
+    """SALead with the feature rows as its source (c_off = 0, levels with C % 4 == 0) and with the
+    [xyz | features | pad] table (c_off = 3) give the same block output and gradients."""
+    torch.manual_seed(0)
+    sa = M.PointnetSAModule(npoint=128, radius=0.25, nsample=32, mlp=[64, 64, 64, 128]).to(DEV).train()
+    (xyz, _), (feats, _) = sa_inputs(2, 1024, 64, seed=5)
+    outs = []
+    for with_table in (False, True):
+        m = __import__("copy").deepcopy(sa)
+        f = feats.clone().requires_grad_(True)
+        table = None
+        if with_table:
+            table = torch.cat([xyz, f.transpose(1, 2), xyz.new_zeros(2, 1024, 1)], dim=2)
+        out = m(xyz, f, None, table)[1]
+        torch.manual_seed(1)
+        (out * torch.randn_like(out)).sum().backward()
+        outs.append((out.detach(), f.grad, {n: p.grad for n, p in m.named_parameters()}))
+    (o0, g0, p0), (o1, g1, p1) = outs
+    # (not bit-equal: the features sit in different K positions of the tensor-core product, which changes the
+    # order of its fp32 accumulation; three BatchNorm layers amplify that to ~2e-4 of the output's magnitude)
+    assert rel_err(o1, o0) < 2e-3 and l2_err(g1, g0) < 1e-2, (rel_err(o1, o0), l2_err(g1, g0))
+    for n in p0:
+        assert l2_err(p1[n], p0[n]) < 1e-2, (n, l2_err(p1[n], p0[n]))
+
+
 def test_pack_weights_cols_zeroes_the_coordinate_columns():
     """pn2_mlp_pack_weights_cols / _dgrad_cols == the plain packers on a weight whose first 3 columns are zero."""
     L = _lib.load()
