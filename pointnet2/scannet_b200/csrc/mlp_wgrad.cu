@@ -38,7 +38,7 @@ constexpr int kXSlabs = NT / 32;  // 4
 constexpr int kMaxStages = 8;
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = 32 * (kEpiWarps + 2);  // + TMA producer warp + MMA warp
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudget = 100 * 1024;   // half an SM: see geom()
 
 struct Params {
   const float *X, *Y;   // [P, ldx], [P, ldy] (fallback loader only; the TMA path uses the tensor maps)
@@ -220,7 +220,13 @@ inline bool geom(int p, int n, int ldy, Geom *g) {
   g->tmem_cols = 32;
   while (g->tmem_cols < g->KT) g->tmem_cols *= 2;
   const int stage_bytes = (kXSlabs + g->yslabs) * SLAB;
-  g->stages = kSmemBudget / stage_bytes;
+  // The pipeline's shared-memory budget (PN2_WGRAD_SMEM_KB overrides): the kernel runs on the weight-gradient branch
+  // BESIDE the critical path, and a CTA that takes a whole SM's shared memory keeps the main stream's CTAs out until
+  // it retires (ordered trace: a 41 us hole in front of the first coarse-level kernel).  Measured in one call:
+  // 3.442 / 3.446 ms per step with 200 KB, 3.434 / 3.439 ms with 100 KB, 3.441 ms with 64 KB.
+  static const int budget = getenv("PN2_WGRAD_SMEM_KB") != nullptr ? atoi(getenv("PN2_WGRAD_SMEM_KB")) * 1024 : kSmemBudget;
+  g->stages = budget / stage_bytes;
+  if (g->stages < 2) g->stages = 2;
   if (g->stages > kMaxStages) g->stages = kMaxStages;
   if (g->stages > g->per_cta) g->stages = g->per_cta < 2 ? 2 : g->per_cta;
   g->smem = static_cast<size_t>(g->stages) * stage_bytes + sizeof(Barriers);
