@@ -416,7 +416,8 @@ PN2_API int pn2_mlp_wgrad(int p, int n, int ldx, int ldy, const float *x, const 
  * c = width of the layer (a power of two in [16, 1024]; FP: [64, 1024]); z [P, c] rows; partials [pn2_lead_blocks(P, c, kind)][2][c] = per-CTA column
  * sums of z and z^2 over fixed row ranges (finalise with pn2_bn_finalize, ld = c).  wx = &W[0][0] with row
  * stride ldw (columns 0..2 are the coordinate weights); ws = &W[0][c2] (the c1 <= pn2_fp_lead_max_skip()
- * skip columns).
+ * skip columns).  xyz: point p's coordinates at xyz[p * ldx .. + 3) (ldx = 3 for a (b, n, 3) tensor, the row width
+ * when they are read out of a wider point table); skip: row r at skip[r * lds .. + c1).
  * Adjoints: dh [P, c] = gradient wrt the layer's ACTIVATED output, (a, b, mean, invstd, c1c2) its BatchNorm
  * fold and adjoint constants (pn2_relu_bn_bwd_stats / pn2_mlp_bwd_finalize); dZ is formed on the fly.
  *   pn2_sa_lead_bwd: du [b*n, c] (zero-filled by the call) += dZ at idx; partials [blocks][3][c] = per-CTA sums
@@ -426,11 +427,11 @@ PN2_API int pn2_mlp_wgrad(int p, int n, int ldx, int ldy, const float *x, const 
  * The remaining products (dW_f = du^T features, dfeatures = du W_f; dW_k = dg^T known, dknown = dg W_k) run over
  * the source points (pn2_mlp_wgrad, pn2_mlp_gemm_fwd with pn2_mlp_pack_weights_dgrad[_cols] tiles).
  * ========================================================================== */
-/* kind: 0 pn2_sa_lead_fwd, 1 pn2_sa_lead_bwd, 2 pn2_fp_lead_fwd, 3 pn2_fp_lead_bwd (each kernel's grid is one
- * resident wave, sized for its own register budget) */
 /* out [p, c_out] = [in [p, c_in] | 0 ...] (c_out % 4 == 0): the network's input rows (lib/dataset.py's
  * xyz | features layout, pointnet2_semseg.py:139-146) widened to the level-0 point table in one launch */
 PN2_API int pn2_pad_rows(long long p, int c_in, int c_out, const float *in, float *out, void *stream);
+/* kind: 0 pn2_sa_lead_fwd, 1 pn2_sa_lead_bwd, 2 pn2_fp_lead_fwd, 3 pn2_fp_lead_bwd (each kernel sizes its grid
+ * for its own register budget and for what runs beside it) */
 PN2_API int pn2_lead_blocks(int p, int c, int kind);
 PN2_API int pn2_fp_lead_max_skip(void);
 PN2_API int pn2_mlp_pack_weights_cols(int p, int n, int k, int k0, int ldw, const float *w, float *packed,
@@ -438,18 +439,18 @@ PN2_API int pn2_mlp_pack_weights_cols(int p, int n, int k, int k0, int ldw, cons
 PN2_API int pn2_mlp_pack_weights_dgrad_cols(int p, int n_out, int n, int k, int k0, int ldw, const float *w,
                                             float *packed, void *stream);
 PN2_API int pn2_sa_lead_fwd(int b, int n, int npoint, int nsample, int c, const float *u, const float *xyz,
-                            const float *new_xyz, const int *idx, const float *wx, int ldw, float *z,
+                            int ldx, const float *new_xyz, const int *idx, const float *wx, int ldw, float *z,
                             float *partials, void *stream);
 PN2_API int pn2_sa_lead_bwd(int b, int n, int npoint, int nsample, int c, int relu, const float *dh,
                             const float *z, const float *a, const float *bb, const float *mean,
-                            const float *invstd, const float *c1c2, const float *xyz, const float *new_xyz,
-                            const int *idx, float *du, float *partials, void *stream);
-PN2_API int pn2_fp_lead_fwd(int b, int n, int m, int c, int c1, const float *gk, const float *skip,
+                            const float *invstd, const float *c1c2, const float *xyz, int ldx,
+                            const float *new_xyz, const int *idx, float *du, float *partials, void *stream);
+PN2_API int pn2_fp_lead_fwd(int b, int n, int m, int c, int c1, const float *gk, const float *skip, int lds,
                             const int *idx, const float *weight, const float *ws, int ldw, float *z,
                             float *partials, void *stream);
 PN2_API int pn2_fp_lead_bwd(int b, int n, int m, int c, int c1, int relu, const float *dh, const float *z,
                             const float *a, const float *bb, const float *mean, const float *invstd,
-                            const float *c1c2, const float *skip, const int *idx, const float *weight,
+                            const float *c1c2, const float *skip, int lds, const int *idx, const float *weight,
                             float *dg, float *partials, void *stream);
 
 /* ==========================================================================

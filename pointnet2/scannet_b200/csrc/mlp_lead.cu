@@ -152,7 +152,7 @@ __device__ __forceinline__ int shfl_i(int v, int src, int width) { return __shfl
 template <int U>
 __global__ void __launch_bounds__(kThreads, 4)
 sa_lead_fwd_kernel(Geom g, FastDiv np_ns, FastDiv ns, int n, const float *__restrict__ u,
-                   const float *__restrict__ xyz, const float *__restrict__ new_xyz, const int *__restrict__ idx,
+                   const float *__restrict__ xyz, int ldx, const float *__restrict__ new_xyz, const int *__restrict__ idx,
                    const float *__restrict__ wx, int ldw, float *__restrict__ z, float *__restrict__ partials) {
   pdl_enter();
   const int c4 = threadIdx.x % g.C4, lane = threadIdx.x / g.C4;
@@ -180,7 +180,7 @@ sa_lead_fwd_kernel(Geom g, FastDiv np_ns, FastDiv ns, int n, const float *__rest
       uv[i] = ld4(u, src * g.C4 + c4);
       pc[i] = cc[i] = 0.f;
       if (sub < 3) {
-        pc[i] = __ldg(xyz + src * 3 + sub);
+        pc[i] = __ldg(xyz + src * ldx + sub);
         cc[i] = __ldg(new_xyz + static_cast<size_t>(fdiv(rr, ns)) * 3 + sub);
       }
     }
@@ -213,8 +213,8 @@ __global__ void __launch_bounds__(kThreads, 3)
 sa_lead_bwd_kernel(Geom g, FastDiv np_ns, FastDiv ns, int n, int relu, const float *__restrict__ dh,
                    const float *__restrict__ z, const float *__restrict__ a, const float *__restrict__ b,
                    const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ c1c2,
-                   const float *__restrict__ xyz, const float *__restrict__ new_xyz, const int *__restrict__ idx,
-                   float *__restrict__ du, float *__restrict__ partials) {
+                   const float *__restrict__ xyz, int ldx, const float *__restrict__ new_xyz,
+                   const int *__restrict__ idx, float *__restrict__ du, float *__restrict__ partials) {
   pdl_enter();
   const int c4 = threadIdx.x % g.C4, lane = threadIdx.x / g.C4;
   const int G = min(g.C4, 32), sub = threadIdx.x & (G - 1);
@@ -240,7 +240,7 @@ sa_lead_bwd_kernel(Geom g, FastDiv np_ns, FastDiv ns, int n, int relu, const flo
       src[i] = fdiv(rr, np_ns) * n + shfl_i(k[i], 0, G);
       pc[i] = cc[i] = 0.f;
       if (sub < 3) {
-        pc[i] = __ldg(xyz + static_cast<size_t>(src[i]) * 3 + sub);
+        pc[i] = __ldg(xyz + static_cast<size_t>(src[i]) * ldx + sub);
         cc[i] = __ldg(new_xyz + static_cast<size_t>(fdiv(rr, ns)) * 3 + sub);
       }
     }
@@ -265,11 +265,12 @@ sa_lead_bwd_kernel(Geom g, FastDiv np_ns, FastDiv ns, int n, int relu, const flo
 // the 6 + c1 scalars of row r: lane t of the row's group holds  t < 3: idx[r, t] (bits) | t < 6: weight[r, t - 3]
 // | t < 6 + c1: skip[r, t - 6]   (G >= 16 >= 6 + kMaxSkip lanes per group)
 __device__ __forceinline__ float fp_row_scalar(int sub, int c1, int rr, const int *__restrict__ idx,
-                                               const float *__restrict__ weight, const float *__restrict__ skip) {
+                                               const float *__restrict__ weight, const float *__restrict__ skip,
+                                               int lds) {
   const size_t q = static_cast<size_t>(rr) * 3;
   if (sub < 3) return __int_as_float(__ldg(idx + q + sub));
   if (sub < 6) return __ldg(weight + q + (sub - 3));
-  if (sub < 6 + c1) return __ldg(skip + static_cast<size_t>(rr) * c1 + (sub - 6));
+  if (sub < 6 + c1) return __ldg(skip + static_cast<size_t>(rr) * lds + (sub - 6));
   return 0.f;
 }
 
@@ -278,7 +279,7 @@ __device__ __forceinline__ float fp_row_scalar(int sub, int c1, int rr, const in
 template <int U>
 __global__ void __launch_bounds__(kThreads, 3)
 fp_lead_fwd_kernel(Geom g, FastDiv nn, int m, int c1, const float *__restrict__ gk, const float *__restrict__ skip,
-                   const int *__restrict__ idx, const float *__restrict__ weight, const float *__restrict__ ws,
+                   int lds, const int *__restrict__ idx, const float *__restrict__ weight, const float *__restrict__ ws,
                    int ldw, float *__restrict__ z, float *__restrict__ partials) {
   pdl_enter();
   const int c4 = threadIdx.x % g.C4, lane = threadIdx.x / g.C4;
@@ -316,7 +317,7 @@ fp_lead_fwd_kernel(Geom g, FastDiv nn, int m, int c1, const float *__restrict__ 
       const size_t q = static_cast<size_t>(rr[i]) * 3;
 #pragma unroll
       for (int t = 0; t < 3; ++t) wt[i][t] = __ldg(weight + q + t);
-      const float *sr = skip + static_cast<size_t>(rr[i]) * c1;
+      const float *sr = skip + static_cast<size_t>(rr[i]) * lds;
 #pragma unroll
       for (int k = 0; k < kMaxSkip; ++k) sk[i][k] = k < c1 ? __ldg(sr + k) : 0.f;
     }
@@ -351,8 +352,8 @@ __global__ void __launch_bounds__(kThreads, 3)
 fp_lead_bwd_kernel(Geom g, FastDiv nn, int m, int c1, int relu, const float *__restrict__ dh,
                    const float *__restrict__ z, const float *__restrict__ a, const float *__restrict__ b,
                    const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ c1c2,
-                   const float *__restrict__ skip, const int *__restrict__ idx, const float *__restrict__ weight,
-                   float *__restrict__ dg, float *__restrict__ partials) {
+                   const float *__restrict__ skip, int lds, const int *__restrict__ idx,
+                   const float *__restrict__ weight, float *__restrict__ dg, float *__restrict__ partials) {
   pdl_enter();
   const int c4 = threadIdx.x % g.C4, lane = threadIdx.x / g.C4;
   const int G = min(g.C4, 32), sub = threadIdx.x & (G - 1);
@@ -372,7 +373,7 @@ fp_lead_bwd_kernel(Geom g, FastDiv nn, int m, int c1, int relu, const float *__r
       const int rr = min(r + i * g.row_lanes, r1 - 1);
       d[i] = ld4(dh, static_cast<size_t>(rr) * g.C4 + c4);
       v[i] = ld4(z, static_cast<size_t>(rr) * g.C4 + c4);
-      sc[i] = fp_row_scalar(sub, c1, rr, idx, weight, skip);
+      sc[i] = fp_row_scalar(sub, c1, rr, idx, weight, skip, lds);
       row0[i] = static_cast<size_t>(fdiv(rr, nn)) * m;
     }
 #pragma unroll
@@ -415,26 +416,27 @@ extern "C" int pn2_lead_blocks(int p, int c, int kind) {
 extern "C" int pn2_fp_lead_max_skip(void) { return lead::kMaxSkip; }
 
 extern "C" int pn2_sa_lead_fwd(int b, int n, int npoint, int nsample, int c, const float *u, const float *xyz,
-                               const float *new_xyz, const int *idx, const float *wx, int ldw, float *z,
+                               int ldx, const float *new_xyz, const int *idx, const float *wx, int ldw, float *z,
                                float *partials, void *stream) {
   const long long p = static_cast<long long>(b) * npoint * nsample;
-  if (b <= 0 || n <= 0 || npoint <= 0 || nsample <= 0 || ldw < 3 || !lead::shape_ok(p, c)) return PN2_ERR_INVALID_ARG;
+  if (b <= 0 || n <= 0 || npoint <= 0 || nsample <= 0 || ldw < 3 || ldx < 3 || !lead::shape_ok(p, c))
+    return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(u, xyz, new_xyz, idx, wx, z, partials);
   if (!aligned16(u) || !aligned16(z) || !aligned16(partials)) return PN2_ERR_UNSUPPORTED;
   int nblk;
   const lead::Geom g = lead::geom(static_cast<int>(p), c, lead::kSaFwd, &nblk);
   const size_t smem = sizeof(float4) * 2 * g.row_lanes * g.C4;
-  pn2::launch(lead::sa_lead_fwd_kernel<4>, nblk, lead::kThreads, smem, static_cast<cudaStream_t>(stream), g, lead::fast_div(npoint * nsample), lead::fast_div(nsample), n, u, xyz, new_xyz, idx, wx, ldw, z, partials);
+  pn2::launch(lead::sa_lead_fwd_kernel<4>, nblk, lead::kThreads, smem, static_cast<cudaStream_t>(stream), g, lead::fast_div(npoint * nsample), lead::fast_div(nsample), n, u, xyz, ldx, new_xyz, idx, wx, ldw, z, partials);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
 
 extern "C" int pn2_sa_lead_bwd(int b, int n, int npoint, int nsample, int c, int relu, const float *dh,
                                const float *z, const float *a, const float *bb, const float *mean,
-                               const float *invstd, const float *c1c2, const float *xyz, const float *new_xyz,
-                               const int *idx, float *du, float *partials, void *stream) {
+                               const float *invstd, const float *c1c2, const float *xyz, int ldx,
+                               const float *new_xyz, const int *idx, float *du, float *partials, void *stream) {
   const long long p = static_cast<long long>(b) * npoint * nsample;
-  if (b <= 0 || n <= 0 || npoint <= 0 || nsample <= 0 || !lead::shape_ok(p, c) ||
+  if (b <= 0 || n <= 0 || npoint <= 0 || nsample <= 0 || ldx < 3 || !lead::shape_ok(p, c) ||
       static_cast<long long>(b) * n >= (1ll << 31))
     return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(dh, z, a, bb, mean, invstd, c1c2, xyz, new_xyz, idx, du, partials);
@@ -448,33 +450,35 @@ extern "C" int pn2_sa_lead_bwd(int b, int n, int npoint, int nsample, int c, int
   const lead::Geom g = lead::geom(static_cast<int>(p), c, lead::kSaBwd, &nblk);
   const size_t smem = sizeof(float4) * 3 * g.row_lanes * g.C4;
   pn2::launch(lead::sa_lead_bwd_kernel<4>, nblk, lead::kThreads, smem, s, g, lead::fast_div(npoint * nsample), lead::fast_div(nsample), n, relu, dh, z, a, bb, mean, invstd, c1c2, xyz,
-      new_xyz, idx, du, partials);
+      ldx, new_xyz, idx, du, partials);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
 
-extern "C" int pn2_fp_lead_fwd(int b, int n, int m, int c, int c1, const float *gk, const float *skip,
+extern "C" int pn2_fp_lead_fwd(int b, int n, int m, int c, int c1, const float *gk, const float *skip, int lds,
                                const int *idx, const float *weight, const float *ws, int ldw, float *z,
                                float *partials, void *stream) {
   const long long p = static_cast<long long>(b) * n;
-  if (b <= 0 || n <= 0 || m <= 0 || c1 < 0 || c1 > lead::kMaxSkip || c < 64 || !lead::shape_ok(p, c)) return PN2_ERR_INVALID_ARG;
+  if (b <= 0 || n <= 0 || m <= 0 || c1 < 0 || c1 > lead::kMaxSkip || lds < c1 || c < 64 || !lead::shape_ok(p, c))
+    return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(gk, idx, weight, z, partials);
   if (c1 > 0) PN2_CHECK_PTRS(skip, ws);
   if (!aligned16(gk) || !aligned16(z) || !aligned16(partials)) return PN2_ERR_UNSUPPORTED;
   int nblk;
   const lead::Geom g = lead::geom(static_cast<int>(p), c, lead::kFpFwd, &nblk);
   const size_t smem = sizeof(float4) * (2 * g.row_lanes * g.C4 + c1 * g.C4);
-  pn2::launch(lead::fp_lead_fwd_kernel<2>, nblk, lead::kThreads, smem, static_cast<cudaStream_t>(stream), g, lead::fast_div(n), m, c1, gk, skip, idx, weight, ws, ldw, z, partials);
+  pn2::launch(lead::fp_lead_fwd_kernel<2>, nblk, lead::kThreads, smem, static_cast<cudaStream_t>(stream), g, lead::fast_div(n), m, c1, gk, skip, lds, idx, weight, ws, ldw, z, partials);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }
 
 extern "C" int pn2_fp_lead_bwd(int b, int n, int m, int c, int c1, int relu, const float *dh, const float *z,
                                const float *a, const float *bb, const float *mean, const float *invstd,
-                               const float *c1c2, const float *skip, const int *idx, const float *weight,
+                               const float *c1c2, const float *skip, int lds, const int *idx, const float *weight,
                                float *dg, float *partials, void *stream) {
   const long long p = static_cast<long long>(b) * n;
-  if (b <= 0 || n <= 0 || m <= 0 || c1 < 0 || c1 > lead::kMaxSkip || c < 64 || !lead::shape_ok(p, c)) return PN2_ERR_INVALID_ARG;
+  if (b <= 0 || n <= 0 || m <= 0 || c1 < 0 || c1 > lead::kMaxSkip || lds < c1 || c < 64 || !lead::shape_ok(p, c))
+    return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(dh, z, a, bb, mean, invstd, c1c2, idx, weight, dg, partials);
   if (c1 > 0) PN2_CHECK_PTRS(skip);
   if (!aligned16(dh) || !aligned16(z) || !aligned16(a) || !aligned16(bb) || !aligned16(mean) || !aligned16(invstd) ||
@@ -486,7 +490,7 @@ extern "C" int pn2_fp_lead_bwd(int b, int n, int m, int c, int c1, int relu, con
   int nblk;
   const lead::Geom g = lead::geom(static_cast<int>(p), c, lead::kFpBwd, &nblk);
   const size_t smem = sizeof(float4) * lead::kMaxSkip * g.row_lanes * g.C4;
-  pn2::launch(lead::fp_lead_bwd_kernel<2>, nblk, lead::kThreads, smem, s, g, lead::fast_div(n), m, c1, relu, dh, z, a, bb, mean, invstd, c1c2, skip, idx, weight, dg, partials);
+  pn2::launch(lead::fp_lead_bwd_kernel<2>, nblk, lead::kThreads, smem, s, g, lead::fast_div(n), m, c1, relu, dh, z, a, bb, mean, invstd, c1c2, skip, lds, idx, weight, dg, partials);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

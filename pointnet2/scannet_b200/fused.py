@@ -340,7 +340,11 @@ class SALead(object):
     (c_off = 3; the coordinate columns then get zero weights and a zero gradient)."""
 
     def __init__(self, xyz, new_xyz, idx, c_off):
-        self.xyz, self.new_xyz, self.idx = xyz.contiguous(), new_xyz.contiguous(), idx
+        # xyz may be a column view of a wider point table (row stride ldx): read in place, no copy
+        if not (xyz.stride(2) == 1 and xyz.stride(0) == xyz.shape[1] * xyz.stride(1) and xyz.stride(1) >= 3
+                and xyz.data_ptr() % 4 == 0):
+            xyz = xyz.contiguous()
+        self.xyz, self.ldx, self.new_xyz, self.idx = xyz, xyz.stride(1), new_xyz.contiguous(), idx
         self.B, self.N = xyz.shape[0], xyz.shape[1]
         self.npoint, self.ns = idx.shape[1], idx.shape[2]
         self.P = self.B * self.npoint * self.ns
@@ -371,7 +375,7 @@ class SALead(object):
         nblk = L.pn2_lead_blocks(self.P, C, 0)
         z = torch.empty(self.P, C, dtype=torch.float32, device=dev)
         part = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
-        _lib.check(L.pn2_sa_lead_fwd(B, N, self.npoint, self.ns, C, u.data_ptr(), self.xyz.data_ptr(),
+        _lib.check(L.pn2_sa_lead_fwd(B, N, self.npoint, self.ns, C, u.data_ptr(), self.xyz.data_ptr(), self.ldx,
                                      self.new_xyz.data_ptr(), self.idx.data_ptr(), W2c.data_ptr(), ldw,
                                      z.data_ptr(), part.data_ptr(), _stream(dev)), "sa_lead_fwd")
         return z, part, (C, nblk)
@@ -397,7 +401,7 @@ class SALead(object):
         part = torch.empty(nblk, 3, C, dtype=torch.float32, device=dev)
         _lib.check(L.pn2_sa_lead_bwd(self.B, self.N, self.npoint, self.ns, C, relu, dh.data_ptr(), st.z.data_ptr(),
                                      st.a.data_ptr(), st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
-                                     c1c2.data_ptr(), self.xyz.data_ptr(), self.new_xyz.data_ptr(),
+                                     c1c2.data_ptr(), self.xyz.data_ptr(), self.ldx, self.new_xyz.data_ptr(),
                                      self.idx.data_ptr(), du.data_ptr(), part.data_ptr(), _stream(dev)), "sa_lead_bwd")
         dx = None
         if need_dx:   # the data gradient first: the next kernel of the chain waits for it
@@ -417,7 +421,11 @@ class FPLead(object):
     G = known W_k^T over the m known points; the (<= pn2_fp_lead_max_skip()) skip channels in fp32."""
 
     def __init__(self, skip, idx, weight, mark=False):
-        self.skip = skip.contiguous() if skip is not None else None
+        # skip may be a column view of a wider row tensor (the network's input): read in place, no copy
+        if skip is not None and not (skip.stride(2) == 1 and skip.stride(0) == skip.shape[1] * skip.stride(1)
+                                     and skip.stride(1) >= skip.shape[2] and skip.data_ptr() % 4 == 0):
+            skip = skip.contiguous()
+        self.skip, self.lds = skip, (skip.stride(1) if skip is not None else 0)
         self.idx, self.weight, self.mark = idx, weight.contiguous(), mark
         self.B, self.n = idx.shape[0], idx.shape[1]
         self.c1 = skip.shape[2] if skip is not None else 0
@@ -444,8 +452,8 @@ class FPLead(object):
         z = torch.empty(self.P, C, dtype=torch.float32, device=dev)
         part = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
         _lib.check(L.pn2_fp_lead_fwd(B, self.n, m, C, self.c1, gk.data_ptr(),
-                                     self.skip.data_ptr() if self.skip is not None else None, self.idx.data_ptr(),
-                                     self.weight.data_ptr(), W2c.data_ptr() + 4 * c2, ldw, z.data_ptr(),
+                                     self.skip.data_ptr() if self.skip is not None else None, self.lds,
+                                     self.idx.data_ptr(), self.weight.data_ptr(), W2c.data_ptr() + 4 * c2, ldw, z.data_ptr(),
                                      part.data_ptr(), _stream(dev)), "fp_lead_fwd")
         return z, part, (C, nblk)
 
@@ -470,7 +478,7 @@ class FPLead(object):
         part = torch.empty(nblk, L.pn2_fp_lead_max_skip(), C, dtype=torch.float32, device=dev)
         _lib.check(L.pn2_fp_lead_bwd(self.B, self.n, self.m, C, c1, relu, dh.data_ptr(), st.z.data_ptr(),
                                      st.a.data_ptr(), st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
-                                     c1c2.data_ptr(), self.skip.data_ptr() if self.skip is not None else None,
+                                     c1c2.data_ptr(), self.skip.data_ptr() if self.skip is not None else None, self.lds,
                                      self.idx.data_ptr(), self.weight.data_ptr(), dg.data_ptr(), part.data_ptr(),
                                      _stream(dev)), "fp_lead_bwd")
         dknown = None

@@ -189,5 +189,7 @@ class PointnetFPModule(nn.Module):
             # known points and the interpolation writes its output
             return fused.run_mlp_rows(units, fused.rows_of(known_feats), 0, drops,
                                       lead=fused.FPLead(skip, idx, weight, mark)).view(B, n, -1)
+        if skip is not None:
+            skip = skip.contiguous()       # (a column view of the input rows when the caller passed one)
         rows = fused.FPInterpRows.apply(fused.rows_of(known_feats), skip, idx, weight, mark, inv[0], inv[1])
         return fused.run_mlp_rows(units, rows, 0, drops).view(B, n, -1)

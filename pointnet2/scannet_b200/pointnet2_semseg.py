@@ -79,7 +79,11 @@ class _Pointnet2SemSeg(nn.Module):
         self.cls_layer = nn.Sequential(*layers)
 
     @staticmethod
-    def _break_up_pc(pc):
+    def _break_up_pc(pc, views=False):
+        """``views``: coordinates and features as column VIEWS of the input rows (no copies) -- for the fused
+        training path with a geometry plan, whose kernels read them with the input's row stride."""
+        if views and pc.size(-1) > 3:
+            return pc[..., 0:3], fused.channel_major(pc[..., 3:])
         xyz = pc[..., 0:3].contiguous()
         if pc.size(-1) <= 3:
             return xyz, None
@@ -116,7 +120,11 @@ class _Pointnet2SemSeg(nn.Module):
             for sa in self.SA_modules for g in sa.groupers)
 
     def _forward(self, pointcloud, plan=None):
-        xyz, features = self._break_up_pc(pointcloud)
+        # (column views instead of copies where every consumer reads them in place: the training path of the
+        # fused blocks with the geometry computed ahead -- SALead / FPLead take the input's row stride)
+        views = (plan is not None and fused.LAZY_CHANNEL_MAJOR and fused.LEAD and self.training
+                 and pointcloud.is_contiguous() and not pointcloud.requires_grad and pointcloud.size(-1) > 3)
+        xyz, features = self._break_up_pc(pointcloud, views)
         l_xyz, l_features = [xyz], [features]
         table0 = None
         if (fused.LAZY_CHANNEL_MAJOR and features is not None and pointcloud.is_contiguous()

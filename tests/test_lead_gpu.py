@@ -50,7 +50,8 @@ def _dz64(dh, z, a, b, mean, invstd, c1c2, relu):
 def test_sa_lead_kernels(B, N, npoint, ns, C):
     L = _lib.load()
     g = torch.Generator().manual_seed(B * 1000 + C)
-    xyz = (torch.rand(B, N, 3, generator=g) * 2 + 3).to(DEV)
+    ldx = 3 if C != 64 else 7            # coordinates read out of a wider point table (row stride ldx)
+    xyz = (torch.rand(B, N, ldx, generator=g) * 2 + 3).to(DEV)[:, :, :3]
     new_xyz = (torch.rand(B, npoint, 3, generator=g) * 2 + 3).to(DEV)
     idx = torch.randint(0, N, (B, npoint, ns), generator=g, dtype=torch.int32).to(DEV)
     u = torch.randn(B * N, C, generator=g).to(DEV)
@@ -61,10 +62,11 @@ def test_sa_lead_kernels(B, N, npoint, ns, C):
     assert nblk > 0
     z = torch.empty(P, C, device=DEV)
     part = torch.empty(nblk, 2, C, device=DEV)
-    _lib.check(L.pn2_sa_lead_fwd(B, N, npoint, ns, C, u.data_ptr(), xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(),
+    _lib.check(L.pn2_sa_lead_fwd(B, N, npoint, ns, C, u.data_ptr(), xyz.data_ptr(), ldx, new_xyz.data_ptr(), idx.data_ptr(),
                                  W.data_ptr(), ldw, z.data_ptr(), part.data_ptr(), _s()), "sa_lead_fwd")
     src = (idx.long() + (torch.arange(B, device=DEV) * N).view(B, 1, 1)).reshape(-1)
     diff = (xyz.reshape(-1, 3)[src].view(B, npoint, ns, 3) - new_xyz.view(B, npoint, 1, 3)).reshape(P, 3)  # fp32, as the kernel
+    assert xyz.stride(1) == ldx
     z64 = u.double()[src] + diff.double() @ W[:, :3].double().t()
     assert rel_err(z.double(), z64) < 1e-5
     s = part.double().sum(0)
@@ -77,7 +79,7 @@ def test_sa_lead_kernels(B, N, npoint, ns, C):
         du = torch.full((B * N, C), 7.0, device=DEV)   # the call zero-fills it
         pw = torch.empty(L.pn2_lead_blocks(P, C, 1), 3, C, device=DEV)
         _lib.check(L.pn2_sa_lead_bwd(B, N, npoint, ns, C, relu, dh.data_ptr(), z.data_ptr(), a.data_ptr(), b.data_ptr(),
-                                     mean.data_ptr(), invstd.data_ptr(), c1c2.data_ptr(), xyz.data_ptr(),
+                                     mean.data_ptr(), invstd.data_ptr(), c1c2.data_ptr(), xyz.data_ptr(), ldx,
                                      new_xyz.data_ptr(), idx.data_ptr(), du.data_ptr(), pw.data_ptr(), _s()), "sa_lead_bwd")
         dz = _dz64(dh, z, a, b, mean, invstd, c1c2, relu)
         du64 = torch.zeros(B * N, C, dtype=torch.float64, device=DEV).index_add_(0, src, dz)
@@ -93,7 +95,8 @@ def test_fp_lead_kernels(B, n, m, C, c1):
     assert L.pn2_fp_lead_max_skip() == 8
     g = torch.Generator().manual_seed(B * 1000 + C + c1)
     gk = torch.randn(B * m, C, generator=g).to(DEV)
-    skip = torch.randn(B, n, max(c1, 1), generator=g)[:, :, :c1].contiguous().to(DEV)
+    lds = c1 if C != 64 else c1 + 5      # skip channels read out of a wider row tensor (row stride lds)
+    skip = torch.randn(B, n, max(lds, 1), generator=g).to(DEV)[:, :, :c1]
     idx = torch.randint(0, m, (B, n, 3), generator=g, dtype=torch.int32).to(DEV)
     w = torch.rand(B, n, 3, generator=g)
     w = (w / w.sum(-1, keepdim=True)).to(DEV)
@@ -104,7 +107,7 @@ def test_fp_lead_kernels(B, n, m, C, c1):
     nblk = L.pn2_lead_blocks(P, C, 2)
     z = torch.empty(P, C, device=DEV)
     part = torch.empty(nblk, 2, C, device=DEV)
-    _lib.check(L.pn2_fp_lead_fwd(B, n, m, C, c1, gk.data_ptr(), skip.data_ptr() if c1 else None, idx.data_ptr(),
+    _lib.check(L.pn2_fp_lead_fwd(B, n, m, C, c1, gk.data_ptr(), skip.data_ptr() if c1 else None, lds, idx.data_ptr(),
                                  w.data_ptr(), W.data_ptr() + 4 * c2, ldw, z.data_ptr(), part.data_ptr(), _s()),
                "fp_lead_fwd")
     src = (idx.long() + (torch.arange(B, device=DEV) * m).view(B, 1, 1)).reshape(P, 3)
@@ -123,7 +126,7 @@ def test_fp_lead_kernels(B, n, m, C, c1):
         pw = torch.empty(L.pn2_lead_blocks(P, C, 3), 8, C, device=DEV)
         _lib.check(L.pn2_fp_lead_bwd(B, n, m, C, c1, relu, dh.data_ptr(), z.data_ptr(), a.data_ptr(), b.data_ptr(),
                                      mean.data_ptr(), invstd.data_ptr(), c1c2.data_ptr(), skip.data_ptr() if c1 else None,
-                                     idx.data_ptr(), w.data_ptr(), dg.data_ptr(), pw.data_ptr(), _s()), "fp_lead_bwd")
+                                     lds, idx.data_ptr(), w.data_ptr(), dg.data_ptr(), pw.data_ptr(), _s()), "fp_lead_bwd")
         dz = _dz64(dh, z, a, b, mean, invstd, c1c2, relu)
         dg64 = torch.zeros(B * m, C, dtype=torch.float64, device=DEV)
         for t in range(3):
@@ -143,8 +146,8 @@ def test_unsupported_widths_are_refused():
     assert L.pn2_lead_blocks(4096, 128, 4) == 0 and L.pn2_lead_blocks(4096, 128, 3) > 0
     x = torch.zeros(4096, device=DEV)
     p = x.data_ptr()
-    assert L.pn2_sa_lead_fwd(1, 64, 2, 2, 96, p, p, p, p, p, 3, p, p, _s()) != 0
-    assert L.pn2_fp_lead_fwd(1, 8, 4, 32, 0, p, None, p, p, None, 32, p, p, _s()) != 0
+    assert L.pn2_sa_lead_fwd(1, 64, 2, 2, 96, p, p, 3, p, p, p, 3, p, p, _s()) != 0
+    assert L.pn2_fp_lead_fwd(1, 8, 4, 32, 0, p, None, 0, p, p, None, 32, p, p, _s()) != 0
     torch.manual_seed(0)
     odd = M.PointnetSAModule(npoint=8, radius=0.3, nsample=8, mlp=[4, 24, 32]).to(DEV).train()
     assert not fused.lead_ok(odd.mlps[0]) and fused.lead_ok(
