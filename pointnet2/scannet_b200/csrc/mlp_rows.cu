@@ -1033,12 +1033,50 @@ sum_partials_kernel(int S, int M4, const float *__restrict__ in, float *__restri
   if (lane == 0) reinterpret_cast<float4 *>(out)[j] = acc;
 }
 
+// Few output columns, many partials (the [~900][3][C] coordinate-weight partials of mlp_lead.cu): one CTA per float4
+// column, its 8 warps take contiguous eighths of the partials, then warp 0 adds the eight results in order
+// (one batch of loads per lane instead of six dependent ones: 16 -> ~4 us at 888 x 96 floats).
+__global__ void __launch_bounds__(kRowThreads)
+sum_partials_wide_kernel(int S, int M4, const float *__restrict__ in, float *__restrict__ out) {
+  pdl_enter();
+  __shared__ float4 s_w[kRowThreads / 32];
+  const int j = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWarps = kRowThreads / 32;
+  const int chunk = (S + kWarps - 1) / kWarps;
+  const int s_lo = warp * chunk, s_hi = min(S, s_lo + chunk);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int kBatch = 5;
+  for (int s0 = s_lo + lane; s0 < s_hi; s0 += 32 * kBatch) {
+    float4 v[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i)
+      v[i] = s0 + 32 * i < s_hi ? ld4(in, static_cast<size_t>(s0 + 32 * i) * M4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i)
+      if (s0 + 32 * i < s_hi) acc.x += v[i].x, acc.y += v[i].y, acc.z += v[i].z, acc.w += v[i].w;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o), acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o), acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+  }
+  if (lane == 0) s_w[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float4 t = s_w[0];
+    for (int w = 1; w < kWarps; ++w) t.x += s_w[w].x, t.y += s_w[w].y, t.z += s_w[w].z, t.w += s_w[w].w;
+    reinterpret_cast<float4 *>(out)[j] = t;
+  }
+}
+
 extern "C" int pn2_sum_partials(int s, int m, const float *in, float *out, void *stream) {
   if (s <= 0 || m <= 0 || m % 4 != 0) return PN2_ERR_INVALID_ARG;
   PN2_CHECK_PTRS(in, out);
   if (!aligned16(in) || !aligned16(out)) return PN2_ERR_UNSUPPORTED;
   const int warps_per_cta = kRowThreads / 32;
-  pn2::launch(sum_partials_kernel, (m / 4 + warps_per_cta - 1) / warps_per_cta, kRowThreads, 0, static_cast<cudaStream_t>(stream), s, m / 4, in, out);
+  if (m / 4 <= 2 * kNumSMs && s >= 256)   // few columns, many partials: a CTA per column
+    pn2::launch(sum_partials_wide_kernel, m / 4, kRowThreads, 0, static_cast<cudaStream_t>(stream), s, m / 4, in, out);
+  else
+    pn2::launch(sum_partials_kernel, (m / 4 + warps_per_cta - 1) / warps_per_cta, kRowThreads, 0, static_cast<cudaStream_t>(stream), s, m / 4, in, out);
   count_launch();
   PN2_RETURN_LAUNCH_STATUS();
 }

@@ -154,6 +154,20 @@ def test_unsupported_widths_are_refused():
         M.PointnetSAModule(npoint=8, radius=0.3, nsample=8, mlp=[4, 32, 32]).to(DEV).train().mlps[0])
 
 
+@pytest.mark.parametrize("S,M", [(888, 96), (1184, 1024), (300, 64), (257, 4), (37, 6144)])
+def test_sum_partials_both_kernels(S, M):
+    """pn2_sum_partials: the CTA-per-column kernel (few columns, many partials) and the warp-per-column one
+    against an fp64 sum; repeated calls are bit-identical (fixed order)."""
+    L = _lib.load()
+    g = torch.Generator().manual_seed(S + M)
+    part = torch.randn(S, M, generator=g).to(DEV)
+    out, out2 = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    _lib.check(L.pn2_sum_partials(S, M, part.data_ptr(), out.data_ptr(), _s()), "sum")
+    _lib.check(L.pn2_sum_partials(S, M, part.data_ptr(), out2.data_ptr(), _s()), "sum")
+    assert torch.equal(out, out2)
+    assert rel_err(out.double(), part.double().sum(0)) < 1e-5
+
+
 def test_pad_rows_is_the_level0_table():
     g = torch.Generator().manual_seed(3)
     for c, width in ((9, 12), (134, 136), (12, 12), (3, 4)):
