@@ -97,17 +97,16 @@ __device__ __forceinline__ void cta_reduce(const Geom &g, int lane, int c4, floa
     for (int v = 0; v < NV; ++v) s_red[(lane * NV + v) * g.C4 + c4] = acc[v];
   }
   __syncthreads();
-  if (lane == 0) {
+  // one thread per (vector, column group) adds the row lanes in ascending order (fixed order: schedule-independent)
+  float4 *dst = reinterpret_cast<float4 *>(partials + static_cast<size_t>(blockIdx.x) * NV * g.C);
+  for (int e = threadIdx.x; e < NV * g.C4; e += kThreads) {
+    const int v = e / g.C4, cc = e - v * g.C4;
+    float4 t = s_red[v * g.C4 + cc];
     for (int l = 1; l < g.row_lanes; ++l) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const float4 t = s_red[(l * NV + v) * g.C4 + c4];
-        acc[v].x += t.x, acc[v].y += t.y, acc[v].z += t.z, acc[v].w += t.w;
-      }
+      const float4 u = s_red[(l * NV + v) * g.C4 + cc];
+      t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
     }
-    float4 *dst = reinterpret_cast<float4 *>(partials + static_cast<size_t>(blockIdx.x) * NV * g.C);
-#pragma unroll
-    for (int v = 0; v < NV; ++v) dst[v * g.C4 + c4] = acc[v];
+    dst[v * g.C4 + cc] = t;
   }
 }
 
