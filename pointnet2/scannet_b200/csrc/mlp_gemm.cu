@@ -106,7 +106,9 @@ struct __align__(16) Barriers {
 // kDrop: dropout keep mask on the A tile.  kEpi: what the epilogue does beside storing Z -- 0 column statistics (or
 // nothing), 1 group extrema of the pooled layer, 2 adjoint statistics of the layer below.  Compile-time so that each
 // instantiation carries only its own epilogue (ncu put 17 % of the plain layer's stall samples on instruction fetch).
-template <bool kDrop, int kEpi>
+// kTma: A tiles by TMA tensor loads AND Z by TMA tensor stores (the common case; the cp.async / st.global paths
+// are then not compiled in).
+template <bool kDrop, int kEpi, bool kTma>
 __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, const __grid_constant__ CUtensorMap tm_z,
                                                                      const __grid_constant__ CUtensorMap tm_a) {
   pdl_enter();
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&bars->raw[s], p.tma_load ? 1 : 32 * kLoadWarps);
+      mbar_init(&bars->raw[s], (kTma || p.tma_load) ? 1 : 32 * kLoadWarps);
       mbar_init(&bars->full[s], 32 * kLoadWarps);
       mbar_init(&bars->empty[s], 1);
     }
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
     auto issue = [&]() {                  // cp.async of the next K block into stage is_s
       const int s = is_s, tile = is_tile, kb = is_kb;
       mbar_wait(&bars->empty[s], is_par);
-      if (!kDrop && p.tma_load) {
+      if (kTma || (!kDrop && p.tma_load)) {
         // the whole 128 x 32 K block by ONE tensor load: same swizzled image as the cp.async path writes,
         // rows past P / columns past lda zero-filled by the TMA unit, no LSU wavefronts, no address math
         if (tid == 0) {
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
           float v[32];
           tc_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * acc_cols + c * 32, v);
           const int n0 = n_tile * p.BN + c * 32;
-          if (p.Z != nullptr && p.tma_store) {
+          if (p.Z != nullptr && (kTma || p.tma_store)) {
             tma_store_block32(&tm_z, smem_out + wq * kOutStageBytes, v, lane, n0, tile * BM + wq * 32);
           } else if (p.Z != nullptr && grow < p.P) {
             float *dst = p.Z + static_cast<size_t>(grow) * p.ldz + n0;
@@ -624,10 +626,12 @@ static int launch_gemm(int p, int k, int lda, int n, int ldz, const float *a, co
     if (!prm.tma_store) return PN2_ERR_UNSUPPORTED;  // the extrema are read from the staged output blocks
   }
   if (drop != nullptr && (pool_ns != 0 || zs != nullptr)) return PN2_ERR_UNSUPPORTED;
-  auto kern = drop != nullptr ? gemm::gemm_tf32_fwd_kernel<true, 0>
-              : pool_ns != 0  ? gemm::gemm_tf32_fwd_kernel<false, 1>
-              : zs != nullptr ? gemm::gemm_tf32_fwd_kernel<false, 2>
-                              : gemm::gemm_tf32_fwd_kernel<false, 0>;
+  const bool all_tma = prm.tma_load && (prm.tma_store || z == nullptr);
+  auto kern = drop != nullptr ? gemm::gemm_tf32_fwd_kernel<true, 0, false>
+              : pool_ns != 0  ? (all_tma ? gemm::gemm_tf32_fwd_kernel<false, 1, true> : gemm::gemm_tf32_fwd_kernel<false, 1, false>)
+              : zs != nullptr ? gemm::gemm_tf32_fwd_kernel<false, 2, false>
+              : all_tma       ? gemm::gemm_tf32_fwd_kernel<false, 0, true>
+                              : gemm::gemm_tf32_fwd_kernel<false, 0, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid(pn2_mlp_gemm_grid(p, n), prm.n_tiles);  // the partials buffer is sized by the same function
