@@ -50,6 +50,14 @@
 
 #include "tc_common.cuh"
 
+// Timing-experiment hooks of the backward layer (PN2_BWD_DBG: skip loads / stores, per-role wait cycles).  They are
+// compiled in only with -DPN2_BWD_DEBUG: as run-time branches they were ~10 % of the kernel's instructions.
+#ifdef PN2_BWD_DEBUG
+#define PN2_DBG(p) ((p).dbg)
+#else
+#define PN2_DBG(p) 0
+#endif
+
 namespace pn2 {
 namespace bwd {
 
@@ -133,13 +141,15 @@ __device__ __forceinline__ float4 tf32x4(float4 v) {
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 // kDrop: dropout keep masks present (the classifier head's chain); compiled out otherwise -- the loader
 // chain bounds this kernel and every instruction in it counts.
-template <bool kDrop>
+// kPooled: the pooled last layer of an SA block (gradient on the arg-max rows) -- compile-time, so that each
+// instantiation carries one loader variant only.
+template <bool kDrop, bool kPooled>
 __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, const __grid_constant__ CUtensorMap tm_dh,
                                                                     const __grid_constant__ CUtensorMap tm_dw,
                                                                     const __grid_constant__ CUtensorMap tm_q) {
   pdl_enter();
   extern __shared__ __align__(1024) unsigned char smem[];
-  const long long t_entry = (p.dbg & 32) ? clock64() : 0;
+  const long long t_entry = (PN2_DBG(p) & 32) ? clock64() : 0;
   const int nb = p.nb, kb = p.kb;
   const int nb32 = nb * 32, kb32 = kb * 32;
   const bool dgrad = p.WTp != nullptr;
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  if ((p.dbg & 32) && tid == 0) g_wait_cycles[blockIdx.x][16] = clock64() - t_entry;  // set-up
+  if ((PN2_DBG(p) & 32) && tid == 0) g_wait_cycles[blockIdx.x][16] = clock64() - t_entry;  // set-up
   // tensor memory: [acc 0 | acc 1] (kb32 columns each, only when dgrad), then dW [kb32] -- or,
   // with statistics, [S_h | Q_h] pairs of 32 columns per slab h of the layer below
   const uint32_t tm_acc = tmem_base, tm_dw_addr = tmem_base + (dgrad ? 2 * kb32 : 0);
@@ -228,13 +238,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
       off32[i] = swz_base32(row0 + i, chunk);                                                    // .._BASE32B
     }
     int w_use = 0, h_use = 0;                        // uses of this group's own slots so far
-    const bool tm = (p.dbg & 32) != 0;
+    const bool tm = (PN2_DBG(p) & 32) != 0;
     unsigned long long c_w = 0, c_dz = 0, c_h = 0, c_ld = 0, c_tot = clock64();
 
     // global loads of item (tl, j) into a register buffer: b[0..3] = dH (or dOut) / Z_prev rows,
     // b[4..7] = Z rows (dZ items only).  Rows past P load as zeros.
     auto issue = [&](int tile, int j, float4 (&b)[8], uint32_t (&mk)[4]) {
-      if (p.dbg & 16) {  // timing experiment: no global loads
+      if (PN2_DBG(p) & 16) {  // timing experiment: no global loads
 #pragma unroll
         for (int i = 0; i < 8; ++i) b[i] = zero4();
         return;
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
         const int col = j * BK + chunk * 4;
         const bool colok = col < p.N;
         const float *zp = p.Z + static_cast<size_t>(r0) * p.N + col;
-        if (p.dH != nullptr) {
+        if (!kPooled) {
           const float *dp = p.dH + static_cast<size_t>(r0) * p.N + col;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -291,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
       if (j < nb) {
         // ---------------- dZ slab c: columns [32c, 32c+32) of this layer ----------------
         const int c = j, col = c * BK + chunk * 4;
-        if (p.dH == nullptr) {  // pooled layer: the gradient lives on the arg-max row of every (group, channel)
+        if (kPooled) {  // pooled layer: the gradient lives on the arg-max row of every (group, channel)
           const int g = p.ns_shift >= 0 ? (r0 >> p.ns_shift) : r0 / p.ns;
           const int s0 = r0 - g * p.ns;
           const float4 dd = b[0];
@@ -444,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
       const uint64_t k_hi = make_desc(0);                    // K-major template
       auto addr = [](uint32_t a) { return static_cast<uint64_t>((a & 0x3ffff) >> 4); };
       uint32_t w_par = 0, h_par = 0;  // bit g: phase parity of group g's W^T / H_prev slot
-      const bool tm = (p.dbg & 32) != 0;
+      const bool tm = (PN2_DBG(p) & 32) != 0;
       unsigned long long c_acc = 0, c_dzf = 0, c_wf = 0, c_hf = 0;
       int g = 0;  // loader group of the next item (items are dealt round-robin)
       // tile scheduler: ids of the tiles tl and tl + 1 are known; tl + 2 is fetched while tile tl's MMAs are issued
@@ -541,8 +551,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
         const bool rowok = grow < p.P;
         {
           unsigned long long c_e = 0;
-          timed_wait(&bars->acc_full[acc], use & 1, (p.dbg & 32) != 0, c_e);
-          if ((p.dbg & 32) && tid == 0) g_wait_cycles[blockIdx.x][14] = (tl == 0 ? 0 : g_wait_cycles[blockIdx.x][14]) + c_e;
+          timed_wait(&bars->acc_full[acc], use & 1, (PN2_DBG(p) & 32) != 0, c_e);
+          if ((PN2_DBG(p) & 32) && tid == 0) g_wait_cycles[blockIdx.x][14] = (tl == 0 ? 0 : g_wait_cycles[blockIdx.x][14]) + c_e;
         }
         tc_fence_after();
 #pragma unroll
@@ -551,9 +561,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
             const int n0 = h * BK;
             float v[32];
             tc_ld32(tm_acc + (static_cast<uint32_t>(wq * 32) << 16) + acc * kb32 + n0, v);
-            if (p.out_bytes && !(p.dbg & 4)) {  // staged block -> one TMA tensor store (see tc_common.cuh)
+            if (p.out_bytes && !(PN2_DBG(p) & 4)) {  // staged block -> one TMA tensor store (see tc_common.cuh)
               tma_store_block32(&tm_dh, s_out + wq * 4096, v, lane, n0, tile * BM + wq * 32);
-            } else if (rowok && !(p.dbg & 4)) {
+            } else if (rowok && !(PN2_DBG(p) & 4)) {
               float *dst = p.dHprev + static_cast<size_t>(grow) * p.lda + n0;
               if (n0 + 32 <= p.lda && (p.lda & 7) == 0) {
 #pragma unroll
@@ -574,8 +584,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
     // read-out.  TMEM lanes = output channels n of this layer, columns = channels c of the layer below.
     mbar_wait(&bars->dw_full, 0);
     tc_fence_after();
-    const long long t_ro = (p.dbg & 32) ? clock64() : 0;
-    if ((p.dbg & 32) && tid == 0) g_wait_cycles[blockIdx.x][17] = t_ro - t_entry;  // entry -> all MMAs retired
+    const long long t_ro = (PN2_DBG(p) & 32) ? clock64() : 0;
+    if ((PN2_DBG(p) & 32) && tid == 0) g_wait_cycles[blockIdx.x][17] = t_ro - t_entry;  // entry -> all MMAs retired
     // With a BatchNorm below, the two accumulators S = dZ^T M and Q = dZ^T (M .* zhat) are written out
     // as they are: dW = g1 .* Q + g0 .* S and the statistics sum_n W .* S, sum_n W .* Q are linear in
     // them, so pn2_mlp_bwd_finalize forms them ONCE from the sums over all CTAs (done per CTA here,
@@ -612,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
     }
     tma_store_drain(lane);
     (void)n;
-    if ((p.dbg & 32) && tid == 0) g_wait_cycles[blockIdx.x][15] = clock64() - t_ro;  // read-out
+    if ((PN2_DBG(p) & 32) && tid == 0) g_wait_cycles[blockIdx.x][15] = clock64() - t_ro;  // read-out
   }
 
   tc_fence_before();
@@ -850,7 +860,10 @@ extern "C" int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu,
                    (stats_part == nullptr || tc::make_tmap_rows32(&tm_q, stats_part, part_rows, part_cols, part_cols)))
                       ? g.out_bytes : 0;
   if (prm.out_bytes == 0) g.smem -= g.out_bytes;
-  auto kern = (drop_out != nullptr || drop_in != nullptr) ? bwd::mlp_bwd_layer_kernel<true> : bwd::mlp_bwd_layer_kernel<false>;
+  const bool pooled = prm.dH == nullptr;
+  if (pooled && (drop_out != nullptr || drop_in != nullptr)) return PN2_ERR_UNSUPPORTED;
+  auto kern = (drop_out != nullptr || drop_in != nullptr) ? bwd::mlp_bwd_layer_kernel<true, false>
+              : pooled ? bwd::mlp_bwd_layer_kernel<false, true> : bwd::mlp_bwd_layer_kernel<false, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   pn2::launch(kern, g.grid, bwd::kThreads, g.smem, static_cast<cudaStream_t>(stream), prm, tm_dh, tm_dw, tm_q);
