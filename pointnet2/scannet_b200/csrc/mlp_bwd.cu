@@ -143,7 +143,9 @@ __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.
 // chain bounds this kernel and every instruction in it counts.
 // kPooled: the pooled last layer of an SA block (gradient on the arg-max rows) -- compile-time, so that each
 // instantiation carries one loader variant only.
-template <bool kDrop, bool kPooled>
+// kFull: data gradient AND statistics of the layer below wanted (every layer but a block's first) -- the common
+// case as compile-time constants; kFull = false reads the two flags from the parameters.
+template <bool kDrop, bool kPooled, bool kFull>
 __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, const __grid_constant__ CUtensorMap tm_dh,
                                                                     const __grid_constant__ CUtensorMap tm_dw,
                                                                     const __grid_constant__ CUtensorMap tm_q) {
@@ -152,8 +154,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, co
   const long long t_entry = (PN2_DBG(p) & 32) ? clock64() : 0;
   const int nb = p.nb, kb = p.kb;
   const int nb32 = nb * 32, kb32 = kb * 32;
-  const bool dgrad = p.WTp != nullptr;
-  const bool stats = p.stats_part != nullptr;
+  const bool dgrad = kFull || p.WTp != nullptr;
+  const bool stats = kFull || p.stats_part != nullptr;
   const int hslabs = stats ? 2 : 1;                              // per group: H_prev, or M and M .* zhat
   unsigned char *s_dz = smem;                                    // [sets][nb] slabs, MN-major image (GEMM 2)
   unsigned char *s_h = s_dz + p.sets * nb * SLAB;                // [G][hslabs] slabs
@@ -862,8 +864,11 @@ extern "C" int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu,
   if (prm.out_bytes == 0) g.smem -= g.out_bytes;
   const bool pooled = prm.dH == nullptr;
   if (pooled && (drop_out != nullptr || drop_in != nullptr)) return PN2_ERR_UNSUPPORTED;
-  auto kern = (drop_out != nullptr || drop_in != nullptr) ? bwd::mlp_bwd_layer_kernel<true, false>
-              : pooled ? bwd::mlp_bwd_layer_kernel<false, true> : bwd::mlp_bwd_layer_kernel<false, false>;
+  const bool full = prm.WTp != nullptr && prm.stats_part != nullptr;
+  const bool drop = drop_out != nullptr || drop_in != nullptr;
+  auto kern = drop ? (full ? bwd::mlp_bwd_layer_kernel<true, false, true> : bwd::mlp_bwd_layer_kernel<true, false, false>)
+              : pooled ? (full ? bwd::mlp_bwd_layer_kernel<false, true, true> : bwd::mlp_bwd_layer_kernel<false, true, false>)
+                       : (full ? bwd::mlp_bwd_layer_kernel<false, false, true> : bwd::mlp_bwd_layer_kernel<false, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   pn2::launch(kern, g.grid, bwd::kThreads, g.smem, static_cast<cudaStream_t>(stream), prm, tm_dh, tm_dw, tm_q);
