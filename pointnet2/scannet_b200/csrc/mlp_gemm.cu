@@ -108,7 +108,9 @@ struct __align__(16) Barriers {
 // instantiation carries only its own epilogue (ncu put 17 % of the plain layer's stall samples on instruction fetch).
 // kTma: A tiles by TMA tensor loads AND Z by TMA tensor stores (the common case; the cp.async / st.global paths
 // are then not compiled in).
-template <bool kDrop, int kEpi, bool kTma>
+// kVar: 1 = a layer (fold + ReLU on the A tile, column statistics, no H side output), 2 = a plain product (no fold,
+// no statistics: the lead products over the source points and the data gradients), 0 = read the flags at run time.
+template <bool kDrop, int kEpi, bool kTma, int kVar>
 __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, const __grid_constant__ CUtensorMap tm_z,
                                                                      const __grid_constant__ CUtensorMap tm_a) {
   pdl_enter();
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
       mbar_wait(&bars->raw[s], par);
       // fold constants from shared memory (staged once per CTA: as per-stage __ldg they were this
       // loop's top stall, a global-load latency in front of every transform)
-      const bool fold = p.a_in != nullptr && col < p.K;
+      const bool fold = kVar != 2 && (kVar == 1 || p.a_in != nullptr) && col < p.K;
       const float4 fa = *reinterpret_cast<const float4 *>(s_fold + col);
       const float4 fb = *reinterpret_cast<const float4 *>(s_fold + p.k_blocks * BK + col);
       unsigned char *base = smem_a + s * A_STAGE_BYTES;
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
           }
           const int grow = tile * BM + r;
           if (grow >= p.P) v = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past the end stay zero: the
-          else if (p.H_out != nullptr && n_tile == 0)             // epilogue statistics rely on it
+          else if (kVar == 0 && p.H_out != nullptr && n_tile == 0)  // epilogue statistics rely on it
             *reinterpret_cast<float4 *>(p.H_out + static_cast<size_t>(grow) * p.lda + col) = v;
           *q = v;
         }
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
             }
             csum[c] += warp_colsum32(dy, lane);
             csq[c] += warp_colsum32(dq, lane);
-          } else if (p.partials != nullptr) {  // rows past P are zero (zero-filled A): they add nothing
+          } else if (kVar != 2 && (kVar == 1 || p.partials != nullptr)) {  // rows past P are zero (zero-filled A)
             float sq[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
       mbar_arrive(&bars->acc_empty[acc]);
     }
     tma_store_drain(lane);
-    if (p.partials != nullptr) {
+    if (kVar != 2 && p.partials != nullptr) {
 #pragma unroll
       for (int c = 0; c < kMaxBN / 32; ++c)
         if (c < chunks) {
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
 
   tc_fence_before();
   __syncthreads();
-  if (p.partials != nullptr && tid < p.BN) {  // combine the four epilogue warps, fixed order
+  if (kVar != 2 && p.partials != nullptr && tid < p.BN) {  // combine the four epilogue warps, fixed order
     const int ntot = p.n_tiles * p.BN;
     float s = 0.f, q = 0.f;
     if (my_tiles > 0)
@@ -627,11 +629,17 @@ static int launch_gemm(int p, int k, int lda, int n, int ldz, const float *a, co
   }
   if (drop != nullptr && (pool_ns != 0 || zs != nullptr)) return PN2_ERR_UNSUPPORTED;
   const bool all_tma = prm.tma_load && (prm.tma_store || z == nullptr);
-  auto kern = drop != nullptr ? gemm::gemm_tf32_fwd_kernel<true, 0, false>
-              : pool_ns != 0  ? (all_tma ? gemm::gemm_tf32_fwd_kernel<false, 1, true> : gemm::gemm_tf32_fwd_kernel<false, 1, false>)
-              : zs != nullptr ? gemm::gemm_tf32_fwd_kernel<false, 2, false>
-              : all_tma       ? gemm::gemm_tf32_fwd_kernel<false, 0, true>
-                              : gemm::gemm_tf32_fwd_kernel<false, 0, false>;
+  const bool layer = a_in != nullptr && partials != nullptr && h_out == nullptr;   // fold + statistics
+  const bool plain = a_in == nullptr && partials == nullptr && h_out == nullptr;   // bare product
+  auto kern = gemm::gemm_tf32_fwd_kernel<false, 0, false, 0>;
+  if (drop != nullptr) kern = gemm::gemm_tf32_fwd_kernel<true, 0, false, 0>;
+  else if (zs != nullptr) kern = gemm::gemm_tf32_fwd_kernel<false, 2, false, 0>;
+  else if (pool_ns != 0)
+    kern = all_tma ? (layer ? gemm::gemm_tf32_fwd_kernel<false, 1, true, 1> : gemm::gemm_tf32_fwd_kernel<false, 1, true, 0>)
+                   : gemm::gemm_tf32_fwd_kernel<false, 1, false, 0>;
+  else if (all_tma)
+    kern = layer ? gemm::gemm_tf32_fwd_kernel<false, 0, true, 1>
+                 : plain ? gemm::gemm_tf32_fwd_kernel<false, 0, true, 2> : gemm::gemm_tf32_fwd_kernel<false, 0, true, 0>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid(pn2_mlp_gemm_grid(p, n), prm.n_tiles);  // the partials buffer is sized by the same function
