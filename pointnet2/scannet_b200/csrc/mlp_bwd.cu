@@ -145,14 +145,16 @@ __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.
 // instantiation carries one loader variant only.
 // kFull: data gradient AND statistics of the layer below wanted (every layer but a block's first) -- the common
 // case as compile-time constants; kFull = false reads the two flags from the parameters.
-template <bool kDrop, bool kPooled, bool kFull>
+// NB / KB: the layer's 32-column slab counts (N / 32, K / 32 rounded up) as compile-time constants for the hot
+// shapes (0 = read them from the parameters): the loaders' item bookkeeping and the slab loops then unroll.
+template <bool kDrop, bool kPooled, bool kFull, int NB, int KB>
 __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_layer_kernel(Params p, const __grid_constant__ CUtensorMap tm_dh,
                                                                     const __grid_constant__ CUtensorMap tm_dw,
                                                                     const __grid_constant__ CUtensorMap tm_q) {
   pdl_enter();
   extern __shared__ __align__(1024) unsigned char smem[];
   const long long t_entry = (PN2_DBG(p) & 32) ? clock64() : 0;
-  const int nb = p.nb, kb = p.kb;
+  const int nb = NB ? NB : p.nb, kb = KB ? KB : p.kb;
   const int nb32 = nb * 32, kb32 = kb * 32;
   const bool dgrad = kFull || p.WTp != nullptr;
   const bool stats = kFull || p.stats_part != nullptr;
@@ -866,9 +868,19 @@ extern "C" int pn2_mlp_bwd_layer(int p, int n, int k, int lda, int ns, int relu,
   if (pooled && (drop_out != nullptr || drop_in != nullptr)) return PN2_ERR_UNSUPPORTED;
   const bool full = prm.WTp != nullptr && prm.stats_part != nullptr;
   const bool drop = drop_out != nullptr || drop_in != nullptr;
-  auto kern = drop ? (full ? bwd::mlp_bwd_layer_kernel<true, false, true> : bwd::mlp_bwd_layer_kernel<true, false, false>)
-              : pooled ? (full ? bwd::mlp_bwd_layer_kernel<false, true, true> : bwd::mlp_bwd_layer_kernel<false, true, false>)
-                       : (full ? bwd::mlp_bwd_layer_kernel<false, false, true> : bwd::mlp_bwd_layer_kernel<false, false, false>);
+  auto kern = bwd::mlp_bwd_layer_kernel<false, false, false, 0, 0>;
+#define PN2_BWD_PICK(NB_, KB_)                                                                         \
+  (drop ? (full ? bwd::mlp_bwd_layer_kernel<true, false, true, NB_, KB_> : bwd::mlp_bwd_layer_kernel<true, false, false, 0, 0>) \
+        : pooled ? (full ? bwd::mlp_bwd_layer_kernel<false, true, true, NB_, KB_> : bwd::mlp_bwd_layer_kernel<false, true, false, 0, 0>) \
+                 : (full ? bwd::mlp_bwd_layer_kernel<false, false, true, NB_, KB_> : bwd::mlp_bwd_layer_kernel<false, false, false, 0, 0>))
+  // shapes of the reference's fine SA blocks: SA2's pooled layer (64 -> 128), SA1 (32 -> 32 -> 64)
+  // (measured per shape in one call, us, specialised vs not: 64 x 32 pooled 140 vs 146, 32 x 32 106 vs 114, 128 x 64 pooled 87 vs 90;
+  // 128 x 128 got SLOWER unrolled -- 155 vs 145, with dropout 182 vs 166 -- and 64 x 64 did not move: they stay generic)
+  if (prm.nb == 4 && prm.kb == 2) kern = PN2_BWD_PICK(4, 2);
+  else if (prm.nb == 2 && prm.kb == 1) kern = PN2_BWD_PICK(2, 1);
+  else if (prm.nb == 1 && prm.kb == 1) kern = PN2_BWD_PICK(1, 1);
+  else kern = PN2_BWD_PICK(0, 0);
+#undef PN2_BWD_PICK
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   pn2::launch(kern, g.grid, bwd::kThreads, g.smem, static_cast<cudaStream_t>(stream), prm, tm_dh, tm_dw, tm_q);
