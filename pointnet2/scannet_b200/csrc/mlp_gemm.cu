@@ -110,7 +110,9 @@ struct __align__(16) Barriers {
 // are then not compiled in).
 // kVar: 1 = a layer (fold + ReLU on the A tile, column statistics, no H side output), 2 = a plain product (no fold,
 // no statistics: the lead products over the source points and the data gradients), 0 = read the flags at run time.
-template <bool kDrop, int kEpi, bool kTma, int kVar>
+// kChunks: 32-column blocks of the N tile (BN / 32) as a compile-time constant for the hot widths (0 = run time, up
+// to kMaxBN / 32): the epilogue is unrolled over them, and a 32-wide layer then carries one copy of it, not eight.
+template <bool kDrop, int kEpi, bool kTma, int kVar, int kChunks>
 __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, const __grid_constant__ CUtensorMap tm_z,
                                                                      const __grid_constant__ CUtensorMap tm_a) {
   pdl_enter();
@@ -319,10 +321,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
   } else {
     // ====================================== epilogue ======================================
     const int wq = warp & 3;  // TMEM lane quarter this warp may read
-    const int chunks = p.BN / 32 + (p.BN % 32 ? 1 : 0);
-    float csum[kMaxBN / 32], csq[kMaxBN / 32];
+    constexpr int kCh = kChunks ? kChunks : kMaxBN / 32;
+    const int chunks = kChunks ? kChunks : p.BN / 32 + (p.BN % 32 ? 1 : 0);
+    float csum[kCh], csq[kCh];
 #pragma unroll
-    for (int c = 0; c < kMaxBN / 32; ++c) csum[c] = 0.f, csq[c] = 0.f;
+    for (int c = 0; c < kCh; ++c) csum[c] = 0.f, csq[c] = 0.f;
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = blockIdx.x + t * gridDim.x;
       const int acc = t & 1;
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
       tc_fence_after();
       const int grow = tile * BM + wq * 32 + lane;
 #pragma unroll
-      for (int c = 0; c < kMaxBN / 32; ++c) {
+      for (int c = 0; c < kCh; ++c) {
         if (c < chunks) {
           float v[32];
           tc_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * acc_cols + c * 32, v);
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tf32_fwd_kernel(Params p, co
     tma_store_drain(lane);
     if (kVar != 2 && p.partials != nullptr) {
 #pragma unroll
-      for (int c = 0; c < kMaxBN / 32; ++c)
+      for (int c = 0; c < kCh; ++c)
         if (c < chunks) {
           s_stats[(wq * 2 + 0) * kMaxBN + c * 32 + lane] = csum[c];
           s_stats[(wq * 2 + 1) * kMaxBN + c * 32 + lane] = csq[c];
@@ -631,15 +634,20 @@ static int launch_gemm(int p, int k, int lda, int n, int ldz, const float *a, co
   const bool all_tma = prm.tma_load && (prm.tma_store || z == nullptr);
   const bool layer = a_in != nullptr && partials != nullptr && h_out == nullptr;   // fold + statistics
   const bool plain = a_in == nullptr && partials == nullptr && h_out == nullptr;   // bare product
-  auto kern = gemm::gemm_tf32_fwd_kernel<false, 0, false, 0>;
-  if (drop != nullptr) kern = gemm::gemm_tf32_fwd_kernel<true, 0, false, 0>;
-  else if (zs != nullptr) kern = gemm::gemm_tf32_fwd_kernel<false, 2, false, 0>;
+  auto kern = gemm::gemm_tf32_fwd_kernel<false, 0, false, 0, 0>;
+  const int ch = prm.BN % 32 == 0 ? prm.BN / 32 : 0;   // 32-column blocks of the N tile (0: partial block, run time)
+#define PN2_GEMM_CH(E_, V_)                                                                     \
+  (ch == 1 ? gemm::gemm_tf32_fwd_kernel<false, E_, true, V_, 1>                                  \
+           : ch == 2 ? gemm::gemm_tf32_fwd_kernel<false, E_, true, V_, 2>                        \
+                     : ch == 4 ? gemm::gemm_tf32_fwd_kernel<false, E_, true, V_, 4> : gemm::gemm_tf32_fwd_kernel<false, E_, true, V_, 0>)
+  if (drop != nullptr) kern = gemm::gemm_tf32_fwd_kernel<true, 0, false, 0, 0>;
+  else if (zs != nullptr) kern = gemm::gemm_tf32_fwd_kernel<false, 2, false, 0, 0>;
   else if (pool_ns != 0)
-    kern = all_tma ? (layer ? gemm::gemm_tf32_fwd_kernel<false, 1, true, 1> : gemm::gemm_tf32_fwd_kernel<false, 1, true, 0>)
-                   : gemm::gemm_tf32_fwd_kernel<false, 1, false, 0>;
+    kern = all_tma ? (layer ? PN2_GEMM_CH(1, 1) : gemm::gemm_tf32_fwd_kernel<false, 1, true, 0, 0>)
+                   : gemm::gemm_tf32_fwd_kernel<false, 1, false, 0, 0>;
   else if (all_tma)
-    kern = layer ? gemm::gemm_tf32_fwd_kernel<false, 0, true, 1>
-                 : plain ? gemm::gemm_tf32_fwd_kernel<false, 0, true, 2> : gemm::gemm_tf32_fwd_kernel<false, 0, true, 0>;
+    kern = layer ? PN2_GEMM_CH(0, 1) : plain ? PN2_GEMM_CH(0, 2) : gemm::gemm_tf32_fwd_kernel<false, 0, true, 0, 0>;
+#undef PN2_GEMM_CH
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid(pn2_mlp_gemm_grid(p, n), prm.n_tiles);  // the partials buffer is sized by the same function
