@@ -60,8 +60,21 @@ __device__ __forceinline__ void col_reduce2(const ColGeom &g, float *__restrict_
   for (int c4 = threadIdx.x % g.C4; c4 < g.C4; c4 += kRowThreads) {  // C4 > 256 only if C > 1024
     const int lane = threadIdx.x / g.C4;
     float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-    if (lane < g.row_lanes)
-      for (int r = r0 + lane; r < r1; r += g.row_lanes) f(r, c4, s0, s1);
+    if (lane < g.row_lanes) {
+      // four rows per trip: their loads are independent of each other and of the accumulators, so the compiler
+      // issues all of them before the first add (same order of additions as the plain loop); one row per trip
+      // left a single global-load round trip in flight per thread
+      int r = r0 + lane;
+      for (; r + 3 * g.row_lanes < r1; r += 4 * g.row_lanes) {
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0, c0 = a0, c1 = a0, d0 = a0, d1 = a0;
+        f(r, c4, a0, a1), f(r + g.row_lanes, c4, b0, b1), f(r + 2 * g.row_lanes, c4, c0, c1), f(r + 3 * g.row_lanes, c4, d0, d1);
+        s0.x += a0.x, s0.y += a0.y, s0.z += a0.z, s0.w += a0.w, s1.x += a1.x, s1.y += a1.y, s1.z += a1.z, s1.w += a1.w;
+        s0.x += b0.x, s0.y += b0.y, s0.z += b0.z, s0.w += b0.w, s1.x += b1.x, s1.y += b1.y, s1.z += b1.z, s1.w += b1.w;
+        s0.x += c0.x, s0.y += c0.y, s0.z += c0.z, s0.w += c0.w, s1.x += c1.x, s1.y += c1.y, s1.z += c1.z, s1.w += c1.w;
+        s0.x += d0.x, s0.y += d0.y, s0.z += d0.z, s0.w += d0.w, s1.x += d1.x, s1.y += d1.y, s1.z += d1.z, s1.w += d1.w;
+      }
+      for (; r < r1; r += g.row_lanes) f(r, c4, s0, s1);
+    }
     if (lane < g.row_lanes) {
       s_red[(lane * 2 + 0) * g.C4 + c4] = s0;
       s_red[(lane * 2 + 1) * g.C4 + c4] = s1;
