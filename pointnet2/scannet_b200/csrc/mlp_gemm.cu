@@ -640,7 +640,8 @@ static int launch_gemm(int p, int k, int lda, int n, int ldz, const float *a, co
   (ch == 1 ? gemm::gemm_tf32_fwd_kernel<false, E_, true, V_, 1>                                  \
            : ch == 2 ? gemm::gemm_tf32_fwd_kernel<false, E_, true, V_, 2>                        \
                      : ch == 4 ? gemm::gemm_tf32_fwd_kernel<false, E_, true, V_, 4> : gemm::gemm_tf32_fwd_kernel<false, E_, true, V_, 0>)
-  if (drop != nullptr) kern = gemm::gemm_tf32_fwd_kernel<true, 0, false, 0, 0>;
+  if (drop != nullptr)   // (the keep mask arrives by cp.async beside the A tile: no TMA variant)
+    kern = (layer && ch == 1) ? gemm::gemm_tf32_fwd_kernel<true, 0, false, 1, 1> : gemm::gemm_tf32_fwd_kernel<true, 0, false, 0, 0>;
   else if (zs != nullptr) kern = gemm::gemm_tf32_fwd_kernel<false, 2, false, 0, 0>;
   else if (pool_ns != 0)
     kern = all_tma ? (layer ? PN2_GEMM_CH(1, 1) : gemm::gemm_tf32_fwd_kernel<false, 1, true, 0, 0>)
