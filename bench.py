@@ -348,8 +348,13 @@ def run_product(args, world, rank, local):
                 eager.optimizer.step()
             return loss
 
+        # The eager pass is bound by the host (one C-ABI call per launch): with an idle GPU every pair of events
+        # would also time the wait for its own launch to arrive.  A busy-wait kernel in front of each step lets the
+        # host run ahead, so the launches are already queued and the events bracket the kernels alone.
+        sleep_cycles = int(6e-3 * 1e6 * float(clocks.get("sm_max_mhz") or 1965.0))   # ~6 ms
         with profiling.LibTimer() as timer:
             for i in range(nprof):
+                torch.cuda._sleep(sleep_cycles)
                 local_step(*dev[i % len(dev)])
         rows = timer.summary(nprof)
         for r in rows:

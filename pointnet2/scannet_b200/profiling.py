@@ -162,6 +162,22 @@ def _lib_bytes(name, a):
         return 8 * a[0] * a[1], 0
     if name == "pn2_pool_bn_bwd_stats":   # dout, arg-max and z at the arg-max rows (gathered, or kept by the forward pass)
         return 12 * a[0] * a[2], 0
+    if name == "pn2_sa_lead_fwd":      # idx, u rows (or the table if smaller), coordinates; z out
+        b, n, npoint, ns, c = a[:5]
+        rows = b * npoint * ns
+        return 4 * rows + (4 * c + 12) * min(b * n, rows) + 12 * b * npoint + 4 * rows * c, 0
+    if name == "pn2_sa_lead_bwd":      # dh, z, idx, coordinates in; du out
+        b, n, npoint, ns, c = a[:5]
+        rows = b * npoint * ns
+        return 8 * rows * c + 4 * rows + 12 * min(b * n, rows) + 12 * b * npoint + 4 * b * n * c, 0
+    if name == "pn2_fp_lead_fwd":      # idx + weights, gk rows (or the table), skip; z out
+        b, n, m, c, c1 = a[:5]
+        return 24 * b * n + 4 * b * min(m, 3 * n) * c + 4 * b * n * c1 + 4 * b * n * c, 0
+    if name == "pn2_fp_lead_bwd":      # dh, z, idx + weights, skip in; dg out
+        b, n, m, c, c1 = a[:5]
+        return 8 * b * n * c + 24 * b * n + 4 * b * n * c1 + 4 * b * m * c, 0
+    if name == "pn2_pad_rows":
+        return 4 * a[0] * (a[1] + a[2]), 0
     if name == "pn2_weighted_ce_fwd":                          # logits, targets (int64), weights; lse out
         return 4 * a[0] * a[1] + 16 * a[0], 0
     if name == "pn2_weighted_ce_bwd":                          # logits in, d logits out, targets, weights, lse
