@@ -3,6 +3,8 @@ stream, start, duration and the idle gap in front of it on the same stream -- wh
 tools/timeline.py cannot show: the critical path of the step and where the main stream waits.
 
     python tools/trace_step.py [tag] [--msg]      -> gpurun_out/trace_<tag>.txt
+    torchrun --nproc-per-node N tools/trace_step.py [tag]     data parallel: rank 0 writes its trace (where the gradient
+                                                              all-reduce and Adam sit relative to the last backward kernel)
 """
 import os, sys
 import torch
@@ -13,10 +15,18 @@ from pointnet2.scannet_b200 import pointnet2_semseg, synthetic, train
 
 tag = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "step"
 msg = "--msg" in sys.argv
-batches = [tuple(torch.from_numpy(a).cuda() for a in synthetic.make_batch(2, 32, first_chunk=32 * i)) for i in range(2)]
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+if world > 1:
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+batches = [tuple(torch.from_numpy(a).cuda() for a in synthetic.make_batch(2, 32, first_chunk=32 * (i + 2 * rank)))
+           for i in range(2)]
 torch.manual_seed(0)
 model = pointnet2_semseg.get_model(20, is_msg=msg, input_channels=6).cuda().train()
-step = train.PipelinedTrainStep(train.TrainStep(model, lr=1e-3), batches[0], scope="step")
+# (as bench.py: one GPU captures the whole step; data parallel captures forward + backward, NCCL + Adam run after it)
+step = train.PipelinedTrainStep(train.TrainStep(model, lr=1e-3), batches[0], scope="step" if world == 1 else "fwd_bwd")
 for i in range(8):
     step(*batches[i % 2])
 torch.cuda.synchronize()
@@ -27,6 +37,9 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
         step()
         step.prefetch(*batches[(i + 1) % 2])
     torch.cuda.synchronize()
+if rank != 0:
+    dist.barrier()
+    sys.exit(0)
 import json, tempfile
 tmp = os.path.join(tempfile.gettempdir(), "pn2_trace.json")
 prof.export_chrome_trace(tmp)
@@ -55,3 +68,5 @@ with open(path, "w") as f:
     f.write("# strm  start_us   dur_us  gap_us  kernel\n")
     f.write("\n".join(lines) + "\n")
 print(open(path).read()[:1500])
+if world > 1:
+    dist.barrier()
