@@ -70,6 +70,32 @@ def test_product_never_touches_the_oracle():
                 assert "pn2o_" not in src, f
 
 
+def test_lead_path_eligibility_and_byte_models():
+    """Host logic of csrc/mlp_lead.cu's path: the first conv of a block is applied before the gather only in
+    training mode, with at least one more unit behind it and a power-of-two width the kernels tile exactly;
+    the per-kernel table models the lead kernels' algorithmic bytes."""
+    from pointnet2.scannet_b200 import fused, profiling, pytorch_utils as pt_utils
+    ok = pt_utils.SharedMLP([9, 32, 32, 64], bn=True).train()
+    assert fused.lead_ok(ok) and fused.lead_ok(ok, 16) and not fused.lead_ok(ok, 64)
+    assert not fused.lead_ok(pt_utils.SharedMLP([9, 32, 32, 64], bn=True).eval())
+    assert not fused.lead_ok(pt_utils.SharedMLP([9, 24, 32], bn=True).train())       # 24: not a power of two
+    assert not fused.lead_ok(pt_utils.SharedMLP([9, 32], bn=True).train())           # nothing behind the first unit
+    assert fused.lead_ok(pt_utils.SharedMLP([134, 128, 128], bn=True).train(), 64)
+    saved = fused.LEAD
+    try:
+        fused.LEAD = False
+        assert not fused.lead_ok(ok)
+    finally:
+        fused.LEAD = saved
+    b, n, m, c, c1 = 32, 8192, 1024, 128, 6
+    fwd, _ = profiling._lib_bytes("pn2_fp_lead_fwd", (b, n, m, c, c1))
+    bwd, _ = profiling._lib_bytes("pn2_fp_lead_bwd", (b, n, m, c, c1, 1))
+    assert fwd == 24 * b * n + 4 * b * m * c + 4 * b * n * c1 + 4 * b * n * c
+    assert bwd == 8 * b * n * c + 24 * b * n + 4 * b * n * c1 + 4 * b * m * c
+    sa, _ = profiling._lib_bytes("pn2_sa_lead_bwd", (32, 8192, 1024, 32, 32, 1))
+    assert sa > 8 * 32 * 1024 * 32 * 32              # dH and z of 2^20 rows x 32 channels, read once each
+
+
 def test_programmatic_launches_wait_first():
     """Kernels launched through pn2::launch (programmatic dependent launch, pn2_common.cuh) may be scheduled
     before the previous kernel of their stream has finished: each of them must call pdl_enter() --
