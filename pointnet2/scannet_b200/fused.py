@@ -13,6 +13,10 @@ Numerics: BatchNorm statistics fp32 partials + fp64 finalise; every 1x1 convolut
 adjoint products run on the hand-written tcgen05 kernels (csrc/mlp_gemm.cu, mlp_bwd.cu, mlp_wgrad.cu)
 with TF32 operands and fp32 accumulation -- the arithmetic class of the reference's own cuDNN convs,
 whose ``cudnn.allow_tf32`` defaults to True.  There is no library GEMM on this path.
+
+In training mode the FIRST conv of a block does not see gathered rows at all: it is linear, so it is applied to
+the source points and the gather / interpolation kernel writes its output directly (``SALead`` / ``FPLead``,
+csrc/mlp_lead.cu); the rows kernels (``SAGroupRows`` / ``FPInterpRows``) remain the inference / fallback path.
 """
 import os
 
