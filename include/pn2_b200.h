@@ -420,9 +420,10 @@ PN2_API int pn2_mlp_wgrad(int p, int n, int ldx, int ldy, const float *x, const 
  * when they are read out of a wider point table); skip: row r at skip[r * lds .. + c1).
  * Adjoints: dh [P, c] = gradient wrt the layer's ACTIVATED output, (a, b, mean, invstd, c1c2) its BatchNorm
  * fold and adjoint constants (pn2_relu_bn_bwd_stats / pn2_mlp_bwd_finalize); dZ is formed on the fly.
- *   pn2_sa_lead_bwd: du [b*n, c] (zero-filled by the call) += dZ at idx; partials [blocks][3][c] = per-CTA sums
+ *   (zero_fill != 0: the call zero-fills its reduction target first; 0: the caller did, ahead of time)
+ *   pn2_sa_lead_bwd: du [b*n, c] += dZ at idx; partials [blocks][3][c] = per-CTA sums
  *     of dZ * (x, y, z of the centred coordinates): dW_x[c, k] = sum over blocks of partials[., k, c].
- *   pn2_fp_lead_bwd: dg [b*m, c] (zero-filled by the call) += weight * dZ; partials [blocks][max_skip][c]:
+ *   pn2_fp_lead_bwd: dg [b*m, c] += weight * dZ; partials [blocks][max_skip][c]:
  *     dW_s[c, k] = sum over blocks of partials[., k, c].
  * The remaining products (dW_f = du^T features, dfeatures = du W_f; dW_k = dg^T known, dknown = dg W_k) run over
  * the source points (pn2_mlp_wgrad, pn2_mlp_gemm_fwd with pn2_mlp_pack_weights_dgrad[_cols] tiles).
@@ -444,14 +445,15 @@ PN2_API int pn2_sa_lead_fwd(int b, int n, int npoint, int nsample, int c, const 
 PN2_API int pn2_sa_lead_bwd(int b, int n, int npoint, int nsample, int c, int relu, const float *dh,
                             const float *z, const float *a, const float *bb, const float *mean,
                             const float *invstd, const float *c1c2, const float *xyz, int ldx,
-                            const float *new_xyz, const int *idx, float *du, float *partials, void *stream);
+                            const float *new_xyz, const int *idx, float *du, int zero_fill, float *partials,
+                            void *stream);
 PN2_API int pn2_fp_lead_fwd(int b, int n, int m, int c, int c1, const float *gk, const float *skip, int lds,
                             const int *idx, const float *weight, const float *ws, int ldw, float *z,
                             float *partials, void *stream);
 PN2_API int pn2_fp_lead_bwd(int b, int n, int m, int c, int c1, int relu, const float *dh, const float *z,
                             const float *a, const float *bb, const float *mean, const float *invstd,
                             const float *c1c2, const float *skip, int lds, const int *idx, const float *weight,
-                            float *dg, float *partials, void *stream);
+                            float *dg, int zero_fill, float *partials, void *stream);
 
 /* ==========================================================================
  * Training-step utilities on flat fp32 buffers (the step the reference's solver

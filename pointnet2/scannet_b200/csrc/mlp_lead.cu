@@ -433,7 +433,8 @@ extern "C" int pn2_sa_lead_fwd(int b, int n, int npoint, int nsample, int c, con
 extern "C" int pn2_sa_lead_bwd(int b, int n, int npoint, int nsample, int c, int relu, const float *dh,
                                const float *z, const float *a, const float *bb, const float *mean,
                                const float *invstd, const float *c1c2, const float *xyz, int ldx,
-                               const float *new_xyz, const int *idx, float *du, float *partials, void *stream) {
+                               const float *new_xyz, const int *idx, float *du, int zero_fill, float *partials,
+                               void *stream) {
   const long long p = static_cast<long long>(b) * npoint * nsample;
   if (b <= 0 || n <= 0 || npoint <= 0 || nsample <= 0 || ldx < 3 || !lead::shape_ok(p, c) ||
       static_cast<long long>(b) * n >= (1ll << 31))
@@ -443,8 +444,10 @@ extern "C" int pn2_sa_lead_bwd(int b, int n, int npoint, int nsample, int c, int
       !aligned16(c1c2) || !aligned16(du) || !aligned16(partials))
     return PN2_ERR_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(du, 0, sizeof(float) * static_cast<size_t>(b) * n * c, s);
-  if (e != cudaSuccess) return static_cast<int>(e);
+  if (zero_fill) {   // (0: the caller zeroed du ahead of time, off the critical path)
+    cudaError_t e = cudaMemsetAsync(du, 0, sizeof(float) * static_cast<size_t>(b) * n * c, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   int nblk;
   const lead::Geom g = lead::geom(static_cast<int>(p), c, lead::kSaBwd, &nblk);
   const size_t smem = sizeof(float4) * 3 * g.row_lanes * g.C4;
@@ -474,7 +477,7 @@ extern "C" int pn2_fp_lead_fwd(int b, int n, int m, int c, int c1, const float *
 extern "C" int pn2_fp_lead_bwd(int b, int n, int m, int c, int c1, int relu, const float *dh, const float *z,
                                const float *a, const float *bb, const float *mean, const float *invstd,
                                const float *c1c2, const float *skip, int lds, const int *idx, const float *weight,
-                               float *dg, float *partials, void *stream) {
+                               float *dg, int zero_fill, float *partials, void *stream) {
   const long long p = static_cast<long long>(b) * n;
   if (b <= 0 || n <= 0 || m <= 0 || c1 < 0 || c1 > lead::kMaxSkip || lds < c1 || c < 64 || !lead::shape_ok(p, c))
     return PN2_ERR_INVALID_ARG;
@@ -484,8 +487,10 @@ extern "C" int pn2_fp_lead_bwd(int b, int n, int m, int c, int c1, int relu, con
       !aligned16(c1c2) || !aligned16(dg) || !aligned16(partials))
     return PN2_ERR_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(dg, 0, sizeof(float) * static_cast<size_t>(b) * m * c, s);
-  if (e != cudaSuccess) return static_cast<int>(e);
+  if (zero_fill) {
+    cudaError_t e = cudaMemsetAsync(dg, 0, sizeof(float) * static_cast<size_t>(b) * m * c, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   int nblk;
   const lead::Geom g = lead::geom(static_cast<int>(p), c, lead::kFpBwd, &nblk);
   const size_t smem = sizeof(float4) * lead::kMaxSkip * g.row_lanes * g.C4;

@@ -76,6 +76,7 @@ class pack_branch(object):
             _pack_state["stream"].wait_stream(torch.cuda.current_stream(self.dev))
             _pack_state["active"] = True
             _pack_state["n_drop"] = 0
+            _pack_state["n_zero"] = 0
         return self
 
     def __exit__(self, *exc):
@@ -317,6 +318,24 @@ def _bn_finalize(P, C, part, ld, nblk, gamma, beta, rm, rv, eps, momentum, nbt=N
 LEAD = os.environ.get("PN2_LEAD", "1") != "0"
 
 
+def _prezeroed(rows, cols, dev):
+    """A zero [rows, cols] reduction target for the BACKWARD pass, zero-filled now -- during the forward pass, on the
+    packing branch -- so that the memset is off the backward pass's critical path (5 memsets, ~18 us per SSG step).
+    Persistent buffers, one per call site of the step (as the dropout masks); None outside a pack_branch."""
+    if not _pack_state["active"]:
+        return None
+    n = _pack_state["n_zero"] = _pack_state.get("n_zero", 0) + 1
+    key = ("zero", n, rows, cols, dev)
+    buf = _pack_state["bufs"].get(key)
+    if buf is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        buf = _pack_state["bufs"][key] = torch.empty(rows, cols, dtype=torch.float32, device=dev)
+    with torch.cuda.stream(_pack_state["stream"]):
+        buf.zero_()
+    return buf      # the branch is joined when the forward pass ends (pack_branch.__exit__)
+
+
 def _gemm_plain(A, k, wp, n_out):
     """[P, n_out] = A[:, :k] @ (packed weight tiles)^T on the tcgen05 layer kernel: no fold, no statistics."""
     L = _lib.load()
@@ -375,6 +394,7 @@ class SALead(object):
         self.wp_dgrad = None
         if need_dx and _pack_state["active"]:
             self.wp_dgrad = self._pack_dgrad()
+        self.du0 = _prezeroed(PN, C, dev) if getattr(self, "want_grad", False) else None
         u = _gemm_plain(self.x2d, K, wp, C)
         nblk = L.pn2_lead_blocks(self.P, C, 0)
         z = torch.empty(self.P, C, dtype=torch.float32, device=dev)
@@ -401,12 +421,13 @@ class SALead(object):
         C, K, c_off = self.W2c.shape[0], self.K, self.c_off
         PN, ld = self.x2d.shape
         nblk = L.pn2_lead_blocks(self.P, C, 1)
-        du = torch.empty(PN, C, dtype=torch.float32, device=dev)
+        du = self.du0 if self.du0 is not None else torch.empty(PN, C, dtype=torch.float32, device=dev)
         part = torch.empty(nblk, 3, C, dtype=torch.float32, device=dev)
         _lib.check(L.pn2_sa_lead_bwd(self.B, self.N, self.npoint, self.ns, C, relu, dh.data_ptr(), st.z.data_ptr(),
                                      st.a.data_ptr(), st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
                                      c1c2.data_ptr(), self.xyz.data_ptr(), self.ldx, self.new_xyz.data_ptr(),
-                                     self.idx.data_ptr(), du.data_ptr(), part.data_ptr(), _stream(dev)), "sa_lead_bwd")
+                                     self.idx.data_ptr(), du.data_ptr(), int(self.du0 is None), part.data_ptr(),
+                                     _stream(dev)), "sa_lead_bwd")
         dx = None
         if need_dx:   # the data gradient first: the next kernel of the chain waits for it
             wp = self.wp_dgrad if self.wp_dgrad is not None else self._pack_dgrad()
@@ -451,6 +472,7 @@ class FPLead(object):
         self.wp_dgrad = None
         if need_dx and _pack_state["active"]:
             self.wp_dgrad = self._pack_dgrad()
+        self.dg0 = _prezeroed(PM, C, dev) if getattr(self, "want_grad", False) else None
         gk = _gemm_plain(self.known2d, c2, wp, C)
         nblk = L.pn2_lead_blocks(self.P, C, 2)
         z = torch.empty(self.P, C, dtype=torch.float32, device=dev)
@@ -478,13 +500,13 @@ class FPLead(object):
         C, c2, c1 = self.W2c.shape[0], self.c2, self.c1
         PM = self.known2d.shape[0]
         nblk = L.pn2_lead_blocks(self.P, C, 3)
-        dg = torch.empty(PM, C, dtype=torch.float32, device=dev)
+        dg = self.dg0 if self.dg0 is not None else torch.empty(PM, C, dtype=torch.float32, device=dev)
         part = torch.empty(nblk, L.pn2_fp_lead_max_skip(), C, dtype=torch.float32, device=dev)
         _lib.check(L.pn2_fp_lead_bwd(self.B, self.n, self.m, C, c1, relu, dh.data_ptr(), st.z.data_ptr(),
                                      st.a.data_ptr(), st.b.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
                                      c1c2.data_ptr(), self.skip.data_ptr() if self.skip is not None else None, self.lds,
-                                     self.idx.data_ptr(), self.weight.data_ptr(), dg.data_ptr(), part.data_ptr(),
-                                     _stream(dev)), "fp_lead_bwd")
+                                     self.idx.data_ptr(), self.weight.data_ptr(), dg.data_ptr(), int(self.dg0 is None),
+                                     part.data_ptr(), _stream(dev)), "fp_lead_bwd")
         dknown = None
         if need_dx:
             wp = self.wp_dgrad if self.wp_dgrad is not None else self._pack_dgrad()
@@ -533,6 +555,7 @@ class SharedMLPRows(Function):
                     st = _BNLayer()
                     st.cout = W2.shape[0]
                     rm, rv, nbt = buffers[0]
+                    lead.want_grad = want_grad     # (a backward pass will follow: reserve its reduction target now)
                     st.z, part, (ld, nblk) = lead.forward(x0, W2, ctx.needs_input_grad[0])
                     st.a, st.b, st.mean, st.invstd = _bn_finalize(P, st.cout, part, ld, nblk, gamma, beta,
                                                                   rm, rv, eps, momentum, nbt)

@@ -88,9 +88,9 @@ SIGNATURES = {
     "pn2_mlp_pack_weights_cols": [_i, _i, _i, _i, _i, _vp, _vp, _vp],
     "pn2_mlp_pack_weights_dgrad_cols": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "pn2_sa_lead_fwd": [_i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
-    "pn2_sa_lead_bwd": [_i, _i, _i, _i, _i, _i] + [_vp] * 8 + [_i] + [_vp] * 5,
+    "pn2_sa_lead_bwd": [_i, _i, _i, _i, _i, _i] + [_vp] * 8 + [_i] + [_vp] * 3 + [_i, _vp, _vp],
     "pn2_fp_lead_fwd": [_i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
-    "pn2_fp_lead_bwd": [_i, _i, _i, _i, _i, _i] + [_vp] * 8 + [_i] + [_vp] * 5,
+    "pn2_fp_lead_bwd": [_i, _i, _i, _i, _i, _i] + [_vp] * 8 + [_i] + [_vp] * 3 + [_i, _vp, _vp],
     # flat-buffer training-step utilities
     "pn2_sum_partials": [_i, _i, _vp, _vp, _vp],
     "pn2_sum_partials_block": [_i, _i, _i, _i, _i, _vp, _vp, _vp],

@@ -80,7 +80,14 @@ def test_sa_lead_kernels(B, N, npoint, ns, C):
         pw = torch.empty(L.pn2_lead_blocks(P, C, 1), 3, C, device=DEV)
         _lib.check(L.pn2_sa_lead_bwd(B, N, npoint, ns, C, relu, dh.data_ptr(), z.data_ptr(), a.data_ptr(), b.data_ptr(),
                                      mean.data_ptr(), invstd.data_ptr(), c1c2.data_ptr(), xyz.data_ptr(), ldx,
-                                     new_xyz.data_ptr(), idx.data_ptr(), du.data_ptr(), pw.data_ptr(), _s()), "sa_lead_bwd")
+                                     new_xyz.data_ptr(), idx.data_ptr(), du.data_ptr(), 1, pw.data_ptr(), _s()), "sa_lead_bwd")
+        if relu:   # zero_fill = 0: the caller's zeros are kept, the result is the same
+            du2 = torch.zeros(B * N, C, device=DEV)
+            _lib.check(L.pn2_sa_lead_bwd(B, N, npoint, ns, C, relu, dh.data_ptr(), z.data_ptr(), a.data_ptr(),
+                                         b.data_ptr(), mean.data_ptr(), invstd.data_ptr(), c1c2.data_ptr(),
+                                         xyz.data_ptr(), ldx, new_xyz.data_ptr(), idx.data_ptr(), du2.data_ptr(), 0,
+                                         pw.data_ptr(), _s()), "sa_lead_bwd")
+            assert rel_err(du2.double(), du.double()) < 1e-5
         dz = _dz64(dh, z, a, b, mean, invstd, c1c2, relu)
         du64 = torch.zeros(B * N, C, dtype=torch.float64, device=DEV).index_add_(0, src, dz)
         assert rel_err(du.double(), du64) < 1e-5
@@ -126,7 +133,7 @@ def test_fp_lead_kernels(B, n, m, C, c1):
         pw = torch.empty(L.pn2_lead_blocks(P, C, 3), 8, C, device=DEV)
         _lib.check(L.pn2_fp_lead_bwd(B, n, m, C, c1, relu, dh.data_ptr(), z.data_ptr(), a.data_ptr(), b.data_ptr(),
                                      mean.data_ptr(), invstd.data_ptr(), c1c2.data_ptr(), skip.data_ptr() if c1 else None,
-                                     lds, idx.data_ptr(), w.data_ptr(), dg.data_ptr(), pw.data_ptr(), _s()), "fp_lead_bwd")
+                                     lds, idx.data_ptr(), w.data_ptr(), dg.data_ptr(), 1, pw.data_ptr(), _s()), "fp_lead_bwd")
         dz = _dz64(dh, z, a, b, mean, invstd, c1c2, relu)
         dg64 = torch.zeros(B * m, C, dtype=torch.float64, device=DEV)
         for t in range(3):
